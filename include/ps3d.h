@@ -1,0 +1,188 @@
+/* ps3d.h — the C-ABI drop-in boundary of puresoft3d_b200.
+ *
+ * Puresoft3D has no FFI of its own: its boundary is the C++ class surface `PuresoftPipeline`
+ * (src/puresoft3d/pipeline.h:27-66) plus `PuresoftVBO` (src/puresoft3d/vbo.h:16-21), linked statically by
+ * the demos. Every entry point below replaces one of those member functions (cited beside it); a C++
+ * mirror of the class that forwards to these symbols is in include/puresoft3d_b200.hpp, and
+ * INTEGRATION.md shows how the reference's demos bind to it.
+ *
+ * The SAME header is implemented by three shared libraries so that the parity tests drive them with one
+ * script:
+ *   puresoft3d_b200/libps3d_b200.so   the product: hand-written sm_100a CUDA (no CPU fallback)
+ *   oracle/libps3d_oracle.so          the CPU restatement (oracle/ps3d_oracle.c) — test infrastructure
+ *   oracle/_ref/libps3d_ref.so        the unmodified reference built through oracle/ref_shim — test infrastructure
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 (PS3D_OK) or a negative PS3D_ERR_*.
+ * Where the reference throws std::out_of_range / std::invalid_argument / std::bad_alloc the C-ABI returns
+ * PS3D_ERR_OUT_OF_RANGE / PS3D_ERR_INVALID_ARGUMENT / PS3D_ERR_BAD_ALLOC and the C++ mirror re-throws the
+ * same exception type. The API is single-threaded per pipe, like the reference's.
+ */
+#ifndef PS3D_H
+#define PS3D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PS3D_OK                      0
+#define PS3D_ERR_OUT_OF_RANGE       (-1)
+#define PS3D_ERR_INVALID_ARGUMENT   (-2)
+#define PS3D_ERR_BAD_ALLOC          (-3)
+#define PS3D_ERR_DEVICE             (-4)   /* CUDA error; ps3d_last_error() has the text */
+#define PS3D_ERR_UNSUPPORTED        (-5)   /* e.g. a processor triple with no device functor */
+
+/* limits: src/puresoft3d/config.h:3-9 */
+#define PS3D_MAX_VBOS      16
+#define PS3D_MAX_UNIFORMS  1024
+#define PS3D_MAX_TEXTURES  16
+
+/* behaviour bits: src/puresoft3d/pipeline.h:17-20 */
+#define PS3D_BEHAVIOR_UPDATE_DEPTH  0x1
+#define PS3D_BEHAVIOR_TEST_DEPTH    0x2
+#define PS3D_BEHAVIOR_FACE_CULLING  0x4
+#define PS3D_BEHAVIOR_ALPHABLEND    0x8
+
+/* PuresoftFBO::WRAPMODE, PuresoftFBO::LAYER: src/puresoft3d/fbo.h:18-19 */
+#define PS3D_WRAP_CLAMP 0
+#define PS3D_WRAP_WRAP  1
+#define PS3D_LAYER_XPOS 0
+#define PS3D_LAYER_XNEG 1
+#define PS3D_LAYER_YPOS 2
+#define PS3D_LAYER_YNEG 3
+#define PS3D_LAYER_ZPOS 4
+#define PS3D_LAYER_ZNEG 5
+
+/* processor kinds (the three abstract classes of src/puresoft3d/proc.h:27-71) */
+#define PS3D_PROC_VERTEX        0
+#define PS3D_PROC_INTERPOLATION 1
+#define PS3D_PROC_FRAGMENT      2
+
+/* Device functor ids. In the reference a "processor" is a C++ object with virtual methods; here it is the id
+ * of a device functor compiled into the library (puresoft3d_b200/csrc/shaders.cuh). One id names the
+ * V/I/F triple of one reference shader file; ps3d_processor_add(kind, id) selects the member of the triple. */
+#define PS3D_FN_DEF01  1   /* tex1light1.cpp      textured Blinn-Phong                      */
+#define PS3D_FN_DEF02  2   /* colr1light1.cpp     vertex-colour Blinn-Phong                 */
+#define PS3D_FN_DEF03  3   /* tex1bump1light1.cpp + tangent-space normal map                */
+#define PS3D_FN_DEF04  4   /* skybox.cpp          cube-map skybox                           */
+#define PS3D_FN_DEF05  5   /* shadow.cpp          depth-only, 0.9 shrink                    */
+#define PS3D_FN_PLANET       16  /* src/test/testproc.cpp  VP_Planet / IP_Planet / FP_Earth      */
+#define PS3D_FN_SATELLITE    17  /*                        FP_Satellite (V/I = Planet)           */
+#define PS3D_FN_CLOUD        18  /*                        VP_Cloud / IP_Cloud / FP_Cloud        */
+#define PS3D_FN_CLOUDSHADOW  19  /*                        VP/IP/FP_CloudShadow                  */
+#define PS3D_FN_NULL         20  /*                        VP_Null? (see shaders.cuh)            */
+#define PS3D_FN_FLATID       64  /* parity-test functor (not in the reference): writes a per-triangle id */
+
+typedef struct ps3d_pipe ps3d_pipe;
+
+/* "cuda-sm100a", "oracle-c" or "reference-shim" */
+const char* ps3d_backend_name(void);
+/* text of the last error on this pipe (never NULL) */
+const char* ps3d_last_error(const ps3d_pipe* p);
+
+/* PuresoftPipeline::PuresoftPipeline(hwnd, W, H, rndr) / dtor — pipeline.cpp:24-116.
+ * Creates the default float depth target (scanline round(W/4)*16 bytes, bottom-up) and the top-down BGRA8
+ * display target W x H; behaviour = UPDATE_DEPTH|TEST_DEPTH|FACE_CULLING. `device` = CUDA ordinal (ignored by
+ * the CPU libraries). */
+int ps3d_create(int width, int height, int device, ps3d_pipe** out);
+int ps3d_destroy(ps3d_pipe* p);
+
+/* createTexture / getTexture / destroyTexture — pipeline.h:31-33, tex.cpp:4-58.
+ * First-free-slot handle; elemLen must be 1 or 4 (fbo.cpp:21-24); copies scanline*height bytes when pixels
+ * != NULL. getTexture() exposes writable storage in the reference; here upload/download copy one layer. */
+int ps3d_texture_create(ps3d_pipe* p, unsigned width, unsigned scanline, unsigned height, unsigned elemLen,
+                        const void* pixels, int extraLayers, int wrapMode, int* idx);
+int ps3d_texture_upload(ps3d_pipe* p, int idx, int layer, const void* pixels);
+int ps3d_texture_download(ps3d_pipe* p, int idx, int layer, void* pixels);
+int ps3d_texture_destroy(ps3d_pipe* p, int idx);
+
+/* new PuresoftVBO(unitBytes, unitCount) / updateContent / delete — vbo.h:16-18, vbo.cpp:8-31 */
+int ps3d_vbo_create(ps3d_pipe* p, size_t unitBytes, size_t unitCount, int* vbo);
+int ps3d_vbo_update(ps3d_pipe* p, int vbo, const void* src);
+int ps3d_vbo_destroy(ps3d_pipe* p, int vbo);
+
+/* createVAO / attachVBO / detachVBO / getVBO / destroyVAO — pipeline.h:43-47, pipeline.cpp:118-205.
+ * attach/detach hand the displaced VBO back (-1 = none); destroyVAO destroys the VBOs still attached. */
+int ps3d_vao_create(ps3d_pipe* p, int* vao);
+int ps3d_vao_attach(ps3d_pipe* p, int vao, int slot, int vbo, int* displaced);
+int ps3d_vao_detach(ps3d_pipe* p, int vao, int slot, int* displaced);
+int ps3d_vao_get(ps3d_pipe* p, int vao, int slot, int* vbo);
+int ps3d_vao_destroy(ps3d_pipe* p, int vao);
+
+/* addProcessor / destroyProcessor / createProgramme / destroyProgramme / useProgramme — pipeline.h:36-40,
+ * prog.cpp:3-131. */
+int ps3d_processor_add(ps3d_pipe* p, int kind, int functor, int* idx);
+int ps3d_processor_destroy(ps3d_pipe* p, int idx);
+int ps3d_programme_create(ps3d_pipe* p, int vid, int iid, int fid, int* idx);
+int ps3d_programme_destroy(ps3d_pipe* p, int idx);
+int ps3d_programme_use(ps3d_pipe* p, int idx);
+
+/* setViewport / setDepth / setUniform / enable / disable / clearDepth / clearColour — pipeline.h:50-61,
+ * pipeline.cpp:207-342. setDepth(idx) requires elemLen==4 && scanline%4==0 (pipeline.cpp:232-235).
+ * setUniform copies the bytes; data==NULL releases the slot; values are latched at draw time. */
+int ps3d_set_viewport(ps3d_pipe* p, int width, int height);
+int ps3d_set_depth(ps3d_pipe* p, int textureIdx /* -1 = default depth */);
+int ps3d_set_uniform(ps3d_pipe* p, int idx, const void* data, size_t len);
+int ps3d_enable(ps3d_pipe* p, int behaviorBits);
+int ps3d_disable(ps3d_pipe* p, int behaviorBits);
+int ps3d_clear_depth(ps3d_pipe* p, float furthest);
+int ps3d_clear_colour(ps3d_pipe* p, uint32_t bgra);
+
+/* drawVAO(vao, callerThrdForFragProc) — drawvao.cpp:3-133. Silently returns OK when no programme is in use
+ * or vao is out of range (drawvao.cpp:12-15). The reference call is synchronous; the CUDA library enqueues
+ * on the pipe's stream and ps3d_finish() waits. `callerThread` only matters to the reference build. */
+int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread);
+int ps3d_finish(ps3d_pipe* p);
+
+/* swapBuffers — pipeline.cpp:314-322 (headless: flips the two display buffers). */
+int ps3d_swap_buffers(ps3d_pipe* p);
+
+/* Read-back (replaces the debug dumps saveTexture(-2)/saveTexture(-1), dbg.cpp:3-43).
+ * Colour: the display target's current back buffer exactly as stored — top-down, memory row 0 = raster row
+ * H-1 — `pitchBytes` >= W*4 per row. Depth: the default depth target as stored — bottom-up floats. */
+int ps3d_read_colour(ps3d_pipe* p, void* bgra, size_t pitchBytes);
+int ps3d_read_depth(ps3d_pipe* p, float* depth, size_t pitchBytes);
+/* Host -> device copies of the same two targets (lets a caller restore state; used by the sort-first composite). */
+int ps3d_write_colour(ps3d_pipe* p, const void* bgra, size_t pitchBytes);
+int ps3d_write_depth(ps3d_pipe* p, const float* depth, size_t pitchBytes);
+
+/* Counters (replace getTaskQCounters, dbg.cpp:45-61, with quantities that exist on both sides). */
+typedef struct ps3d_stats
+{
+	uint64_t triangles_submitted;   /* iterations of the per-triangle loop, drawvao.cpp:36 */
+	uint64_t triangles_rasterised;  /* survived cull, z reject and pushTriangle (drawvao.cpp:46-63) */
+	uint64_t spans;                 /* scanline tasks pushed, drawvao.cpp:66-110 */
+	uint64_t fragments_tested;      /* interpolateNextStep calls, fragthrd.cpp:214 */
+	uint64_t fragments_shaded;      /* FragmentProcessor::process calls, fragthrd.cpp:231 — THE metric's unit */
+	uint64_t draws;
+} ps3d_stats;
+int ps3d_get_stats(ps3d_pipe* p, ps3d_stats* out);
+int ps3d_reset_stats(ps3d_pipe* p);
+
+/* Parity hook: when enabled, a width x height uint32 image counts FragmentProcessor::process invocations per
+ * raster pixel (row 0 = raster row 0 = bottom). ps3d_debug_capture(p, 0, 0) turns it off. */
+int ps3d_debug_capture(ps3d_pipe* p, int width, int height);
+int ps3d_debug_read_shade_counts(ps3d_pipe* p, uint32_t* counts /* height*width */);
+int ps3d_debug_clear_shade_counts(ps3d_pipe* p);
+
+/* Sort-first sharding (new; the reference has no multi-device path): restrict rasterisation to raster rows
+ * [row0, row1) of the viewport. Geometry still runs for every triangle; spans outside the band are dropped
+ * before binning. (-1,-1) = whole viewport. */
+int ps3d_set_row_band(ps3d_pipe* p, int row0, int row1);
+
+/* Device-resident access for the benchmark and the multi-GPU composite (CUDA library only; the CPU
+ * libraries return PS3D_ERR_UNSUPPORTED). Pointers are CUDA device pointers owned by the pipe. */
+int ps3d_device_colour_ptr(ps3d_pipe* p, void** devPtr, size_t* pitchBytes);
+int ps3d_device_depth_ptr(ps3d_pipe* p, void** devPtr, size_t* pitchBytes);
+int ps3d_device_stream(ps3d_pipe* p, void** cudaStream);
+/* Same as ps3d_vbo_update / ps3d_texture_upload but the source is a device pointer (HBM-resident inputs). */
+int ps3d_vbo_update_device(ps3d_pipe* p, int vbo, const void* devSrc);
+/* number of kernels this pipe has launched since creation (bench.py's gpu_launches) */
+int ps3d_device_launch_count(ps3d_pipe* p, uint64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PS3D_H */

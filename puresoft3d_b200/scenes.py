@@ -1,0 +1,484 @@
+"""Seeded synthetic scenes for the BASELINE.json configs, and the replay that feeds one scene to a pipeline.
+
+A scene is plain data (numpy arrays + a command list) so that the CUDA library, the CPU oracle and the shimmed
+reference all consume identical bytes — including the uniform matrices, which are built ONCE here in float32
+ and never recomputed per backend. The command vocabulary is the reference's frame loop
+(src/test/puresoft.cpp:162-206): setUniform / setDepth / clearDepth / setViewport / enable / disable /
+useProgramme / drawVAO.
+
+Vertex layout follows the demos (src/test/scenobj.cpp:135-158): slot 0 position float4 (w=1), 1 tangent float4,
+2 binormal float4, 3 normal float4, 4 uv float2. Matrices are column-major like mcemath (m[col*4+row]).
+"""
+import math
+
+import numpy as np
+
+from . import _capi as K
+
+F32 = np.float32
+
+
+# ---- float32 matrix helpers (host-side uniform builders; both renderers receive the same bytes) ---------------
+
+def mat_identity():
+    return np.eye(4, dtype=F32)
+
+
+def mat_perspective(znear, zfar, aspect, fov_rad):
+    """Same layout as mcemaths_make_proj_perspective (src/mcemath/matrxgl.cpp:9-22)."""
+    h = F32(1.0 / math.tan(fov_rad / 2.0))
+    nd = F32(znear - zfar)
+    m = np.zeros((4, 4), dtype=F32)  # m[row, col]
+    m[0, 0] = h / F32(aspect)
+    m[1, 1] = h
+    m[2, 2] = F32(zfar + znear) / nd
+    m[3, 2] = F32(-1.0)
+    m[2, 3] = F32(2.0) * F32(znear * zfar) / nd
+    return m
+
+
+def mat_translation(x, y, z):
+    m = np.eye(4, dtype=F32)
+    m[0, 3], m[1, 3], m[2, 3] = x, y, z
+    return m
+
+
+def mat_scaling(x, y, z):
+    m = np.eye(4, dtype=F32)
+    m[0, 0], m[1, 1], m[2, 2] = x, y, z
+    return m
+
+
+def mat_rotation(axis, rad):
+    a = np.asarray(axis, dtype=np.float64)
+    a = a / np.linalg.norm(a)
+    c, s = math.cos(rad), math.sin(rad)
+    x, y, z = a
+    r = np.array([[c + x * x * (1 - c), x * y * (1 - c) - z * s, x * z * (1 - c) + y * s, 0],
+                  [y * x * (1 - c) + z * s, c + y * y * (1 - c), y * z * (1 - c) - x * s, 0],
+                  [z * x * (1 - c) - y * s, z * y * (1 - c) + x * s, c + z * z * (1 - c), 0],
+                  [0, 0, 0, 1]])
+    return r.astype(F32)
+
+
+def mat_look_at(eye, target, up=(0, 1, 0)):
+    e = np.asarray(eye, dtype=np.float64)
+    f = np.asarray(target, dtype=np.float64) - e
+    f /= np.linalg.norm(f)
+    s = np.cross(f, np.asarray(up, dtype=np.float64))
+    s /= np.linalg.norm(s)
+    u = np.cross(s, f)
+    m = np.eye(4)
+    m[0, :3], m[1, :3], m[2, :3] = s, u, -f
+    m[:3, 3] = -m[:3, :3] @ e
+    return m.astype(F32)
+
+
+def colmajor(m):
+    """(4,4) row/col matrix -> the 16 floats mcemath expects (column-major)."""
+    return np.ascontiguousarray(np.asarray(m, dtype=F32).T).reshape(16)
+
+
+def vec4(x, y, z, w=0.0):
+    return np.array([x, y, z, w], dtype=F32)
+
+
+def i32(v):
+    return np.array([v], dtype=np.int32)
+
+
+# ---- scene container ------------------------------------------------------------------------------------------
+
+class Scene:
+    def __init__(self, name, width, height):
+        self.name = name
+        self.width = width
+        self.height = height
+        self.textures = []    # dict(width, height, elemLen, layers=[arrays], wrap)
+        self.vaos = []        # dict(slot -> (unitBytes, array))
+        self.programmes = []  # (fnV, fnI, fnF)
+        self.commands = []    # tuples, see replay()
+        self.meta = {}
+
+    def add_texture(self, width, height, elemLen=4, pixels=None, layers=None, wrap=K.WRAP_CLAMP):
+        lay = layers if layers is not None else [pixels]
+        self.textures.append(dict(width=width, height=height, elemLen=elemLen, layers=lay, wrap=wrap))
+        return len(self.textures) - 1
+
+    def add_vao(self, slots):
+        self.vaos.append(slots)
+        return len(self.vaos) - 1
+
+    def add_programme(self, fn_v, fn_i=None, fn_f=None):
+        self.programmes.append((fn_v, fn_i if fn_i is not None else fn_v, fn_f if fn_f is not None else fn_v))
+        return len(self.programmes) - 1
+
+    def cmd(self, *c):
+        self.commands.append(c)
+
+    def vertex_bytes_read(self):
+        """Σ over draws of the bytes the bound vertex functor reads."""
+        slots_read = {K.FN_DEF01: (0, 3, 4), K.FN_DEF02: (0, 1, 2), K.FN_DEF03: (0, 1, 2, 3, 4), K.FN_DEF04: (0,),
+                      K.FN_DEF05: (0,), K.FN_FLATID: (0, 6)}
+        total, prog = 0, None
+        for c in self.commands:
+            if c[0] == "use":
+                prog = c[1]
+            elif c[0] == "draw":
+                fn = self.programmes[prog][0]
+                for s in slots_read.get(fn, ()):
+                    if s in self.vaos[c[1]]:
+                        total += self.vaos[c[1]][s][1].nbytes
+        return total
+
+
+class Uploaded:
+    def __init__(self):
+        self.textures, self.vaos, self.programmes, self.vbos = [], [], [], []
+
+
+def upload(pipe, scene):
+    """Create the scene's resources on `pipe` (one-time; outside any timed region)."""
+    up = Uploaded()
+    for t in scene.textures:
+        first = t["layers"][0]
+        idx = pipe.createTexture(t["width"], t["height"], t["elemLen"], pixels=first,
+                                 extraLayers=len(t["layers"]) - 1, mode=t["wrap"])
+        for li in range(1, len(t["layers"])):
+            pipe.uploadTexture(idx, t["layers"][li], layer=li)
+        up.textures.append(idx)
+    for slots in scene.vaos:
+        vao = pipe.createVAO()
+        for slot, (unit, arr) in sorted(slots.items()):
+            a = np.ascontiguousarray(arr)
+            vbo = pipe.createVBO(unit, a.nbytes // unit)
+            vbo.updateContent(a)
+            pipe.attachVBO(vao, slot, vbo)
+            up.vbos.append((vbo, a))
+        up.vaos.append(vao)
+    procs = {}
+    from .pipeline import PuresoftProcessor
+
+    def proc(kind, fn):
+        if (kind, fn) not in procs:
+            p = PuresoftProcessor()
+            p.kind, p.functor = kind, fn
+            procs[(kind, fn)] = pipe.addProcessor(p)
+        return procs[(kind, fn)]
+
+    for (fv, fi, ff) in scene.programmes:
+        up.programmes.append(pipe.createProgramme(proc(K.PROC_VERTEX, fv), proc(K.PROC_INTERPOLATION, fi),
+                                                  proc(K.PROC_FRAGMENT, ff)))
+    return up
+
+
+def replay(pipe, scene, up):
+    """One frame: run the command list. ("tex_uniform", slot, sceneTexIdx) sets an int uniform to the pipe's handle."""
+    for c in scene.commands:
+        op = c[0]
+        if op == "uniform":
+            pipe.setUniform(c[1], c[2])
+        elif op == "tex_uniform":
+            pipe.setUniform(c[1], i32(up.textures[c[2]]))
+        elif op == "viewport":
+            pipe.setViewport(c[1], c[2])
+        elif op == "depth":
+            pipe.setDepth(-1 if c[1] < 0 else up.textures[c[1]])
+        elif op == "clearDepth":
+            pipe.clearDepth(c[1])
+        elif op == "clearColour":
+            pipe.clearColour(c[1])
+        elif op == "enable":
+            pipe.enable(c[1])
+        elif op == "disable":
+            pipe.disable(c[1])
+        elif op == "use":
+            pipe.useProgramme(up.programmes[c[1]])
+        elif op == "draw":
+            pipe.drawVAO(up.vaos[c[1]], bool(c[2]) if len(c) > 2 else False)
+        else:
+            raise ValueError("unknown scene command %r" % (op,))
+    pipe.finish()
+
+
+def render(pipe, scene):
+    up = upload(pipe, scene)
+    replay(pipe, scene, up)
+    return up
+
+
+# ---- texture generators ---------------------------------------------------------------------------------------
+
+def tex_random_bgra(rng, w, h):
+    return rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+
+
+def tex_smooth_bgra(rng, w, h, octaves=4, normal_map=False):
+    """Smooth noise: neighbouring texels differ by a few /255 (keeps nearest-texel flips inside the colour gate)."""
+    acc = np.zeros((h, w, 3), dtype=np.float64)
+    amp_sum = 0.0
+    for o in range(octaves):
+        n = 4 << o
+        g = rng.random((n + 1, n + 1, 3))
+        ys = np.linspace(0, n, h, endpoint=False)
+        xs = np.linspace(0, n, w, endpoint=False)
+        y0, x0 = ys.astype(int), xs.astype(int)
+        fy, fx = (ys - y0)[:, None, None], (xs - x0)[None, :, None]
+        a = g[y0][:, x0] * (1 - fx) + g[y0][:, x0 + 1] * fx
+        b = g[y0 + 1][:, x0] * (1 - fx) + g[y0 + 1][:, x0 + 1] * fx
+        amp = 0.5 ** o
+        acc += amp * (a * (1 - fy) + b * fy)
+        amp_sum += amp
+    acc /= amp_sum
+    out = np.zeros((h, w, 4), dtype=np.uint8)
+    if normal_map:
+        nx, ny = (acc[..., 0] - 0.5) * 0.6, (acc[..., 1] - 0.5) * 0.6
+        nz = np.sqrt(np.maximum(1.0 - nx * nx - ny * ny, 0.0))
+        # FragmentProcessorDEF03 reads r,g,b = x,y,z (tex1bump1light1.cpp:193-196); memory order is B,G,R,A
+        out[..., 2] = np.clip((nx * 0.5 + 0.5) * 255.0, 0, 255)
+        out[..., 1] = np.clip((ny * 0.5 + 0.5) * 255.0, 0, 255)
+        out[..., 0] = np.clip((nz * 0.5 + 0.5) * 255.0, 0, 255)
+    else:
+        out[..., :3] = np.clip(40 + acc * 200.0, 0, 255)
+    out[..., 3] = 255
+    return out
+
+
+# ---- geometry generators --------------------------------------------------------------------------------------
+
+def cube_mesh():
+    """Unit cube, 12 triangles / 36 un-indexed vertices, CCW outward faces."""
+    faces = [  # normal, tangent(u), bitangent(v)
+        ((0, 0, 1), (1, 0, 0), (0, 1, 0)), ((0, 0, -1), (-1, 0, 0), (0, 1, 0)),
+        ((1, 0, 0), (0, 0, -1), (0, 1, 0)), ((-1, 0, 0), (0, 0, 1), (0, 1, 0)),
+        ((0, 1, 0), (1, 0, 0), (0, 0, -1)), ((0, -1, 0), (1, 0, 0), (0, 0, 1)),
+    ]
+    pos, nrm, tan, bin_, uv = [], [], [], [], []
+    for n, t, b in faces:
+        n, t, b = np.array(n, float), np.array(t, float), np.array(b, float)
+        corners = [(-1, -1), (1, -1), (1, 1), (-1, 1)]
+        quad = [0.5 * (n + cu * t + cv * b) for cu, cv in corners]
+        quv = [((cu + 1) / 2, (cv + 1) / 2) for cu, cv in corners]
+        for i in (0, 1, 2, 0, 2, 3):
+            pos.append(list(quad[i]) + [1.0])
+            nrm.append(list(n) + [0.0])
+            tan.append(list(t) + [0.0])
+            bin_.append(list(b) + [0.0])
+            uv.append(quv[i])
+    return (np.array(pos, F32), np.array(tan, F32), np.array(bin_, F32), np.array(nrm, F32), np.array(uv, F32))
+
+
+def heightfield_mesh(rng, nx, ny, layers, extent=1.0, z_jitter=0.05, shuffle=True):
+    """`layers` stacked height-field grids of nx*ny quads (2 triangles each) in the z=const planes facing +z,
+    jittered in z, optionally shuffled so submission order is not depth order (C2 / C5 geometry)."""
+    tris_pos, tris_uv = [], []
+    for L in range(layers):
+        z0 = -0.3 * L
+        gx = np.linspace(-extent, extent, nx + 1)
+        gy = np.linspace(-extent, extent, ny + 1)
+        X, Y = np.meshgrid(gx, gy)
+        Z = z0 + (rng.random(X.shape) * 2 - 1) * z_jitter
+        U = (X + extent) / (2 * extent)
+        V = (Y + extent) / (2 * extent)
+        P = np.stack([X, Y, Z, np.ones_like(X)], axis=-1)
+        T = np.stack([U, V], axis=-1)
+        a, b, c, d = P[:-1, :-1], P[:-1, 1:], P[1:, 1:], P[1:, :-1]
+        ta, tb, tc, td = T[:-1, :-1], T[:-1, 1:], T[1:, 1:], T[1:, :-1]
+        t1 = np.stack([a, b, c], axis=2).reshape(-1, 3, 4)
+        t2 = np.stack([a, c, d], axis=2).reshape(-1, 3, 4)
+        u1 = np.stack([ta, tb, tc], axis=2).reshape(-1, 3, 2)
+        u2 = np.stack([ta, tc, td], axis=2).reshape(-1, 3, 2)
+        tris_pos.append(np.concatenate([t1, t2]))
+        tris_uv.append(np.concatenate([u1, u2]))
+    pos = np.concatenate(tris_pos)
+    uv = np.concatenate(tris_uv)
+    if shuffle:
+        perm = rng.permutation(pos.shape[0])
+        pos, uv = pos[perm], uv[perm]
+    # per-triangle geometric normal -> smooth enough for lighting; tangent along +x, binormal along +y
+    e1 = pos[:, 1, :3] - pos[:, 0, :3]
+    e2 = pos[:, 2, :3] - pos[:, 0, :3]
+    n = np.cross(e1, e2)
+    n /= np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-20)
+    nrm = np.repeat(np.concatenate([n, np.zeros((n.shape[0], 1))], axis=1)[:, None, :], 3, axis=1)
+    tan = np.zeros_like(nrm)
+    tan[..., 0] = 1.0
+    bin_ = np.zeros_like(nrm)
+    bin_[..., 1] = 1.0
+    nv = pos.shape[0] * 3
+    return (pos.reshape(nv, 4).astype(F32), tan.reshape(nv, 4).astype(F32), bin_.reshape(nv, 4).astype(F32),
+            nrm.reshape(nv, 4).astype(F32), uv.reshape(nv, 2).astype(F32))
+
+
+def _std_slots(mesh):
+    pos, tan, bin_, nrm, uv = mesh
+    return {0: (16, pos), 1: (16, tan), 2: (16, bin_), 3: (16, nrm), 4: (8, uv)}
+
+
+def _camera_uniforms(sc, width, height, eye, model, mrot, light):
+    proj = mat_perspective(0.1, 10.0, width / height, math.radians(60.0))
+    view = mat_look_at(eye, (0, 0, 0))
+    pv = (proj.astype(np.float64) @ view.astype(np.float64)).astype(F32)
+    sc.cmd("uniform", 0, colmajor(proj))
+    sc.cmd("uniform", 1, colmajor(view))
+    sc.cmd("uniform", 3, colmajor(pv))
+    sc.cmd("uniform", 4, colmajor(model))
+    sc.cmd("uniform", 5, colmajor(mrot))
+    sc.cmd("uniform", 7, vec4(*light))
+    sc.cmd("uniform", 8, vec4(*eye))
+    return proj, view, pv
+
+
+# ---- the BASELINE.json configs --------------------------------------------------------------------------------
+
+def scene_cube(width=640, height=480, seed=1, functor=K.FN_DEF01):
+    """C1: textured cube, 12 triangles, DEF01 (per-pixel Blinn-Phong), 256² BGRA texture, depth test on."""
+    rng = np.random.default_rng(seed)
+    sc = Scene("C1-cube", width, height)
+    tex = sc.add_texture(256, 256, 4, tex_random_bgra(rng, 256, 256))
+    vao = sc.add_vao(_std_slots(cube_mesh()))
+    prog = sc.add_programme(functor)
+    rot = (mat_rotation((0, 1, 0), math.radians(30.0)).astype(np.float64) @ mat_rotation((1, 0, 0), math.radians(20.0)).astype(np.float64)).astype(F32)
+    sc.cmd("viewport", width, height)
+    sc.cmd("depth", -1)
+    sc.cmd("clearDepth", 1.0)
+    sc.cmd("clearColour", 0xFF202020)
+    _camera_uniforms(sc, width, height, (0.0, 0.0, 3.0), rot, rot, (-3.0, 2.0, 3.0))
+    sc.cmd("tex_uniform", 9, tex)
+    if functor == K.FN_DEF03:
+        bump = sc.add_texture(256, 256, 4, tex_smooth_bgra(rng, 256, 256, normal_map=True))
+        sc.cmd("tex_uniform", 10, bump)
+    sc.cmd("use", prog)
+    sc.cmd("draw", vao)
+    return sc
+
+
+def scene_heightfield(width=1920, height=1080, grid=354, layers=4, seed=2, tex_size=2048, functor=K.FN_DEF03,
+                      shuffle=True):
+    """C2 (and C5 at larger sizes): `layers` stacked grids of grid² quads -> 2*grid²*layers triangles; DEF03 with
+    a smooth diffuse texture and a normal map (tex_size²)."""
+    rng = np.random.default_rng(seed)
+    sc = Scene("C2-heightfield-%dx%d-g%d-l%d" % (width, height, grid, layers), width, height)
+    diffuse = sc.add_texture(tex_size, tex_size, 4, tex_smooth_bgra(rng, tex_size, tex_size))
+    bump = sc.add_texture(tex_size, tex_size, 4, tex_smooth_bgra(rng, tex_size, tex_size, normal_map=True))
+    aspect = width / height
+    mesh = heightfield_mesh(rng, grid, grid, layers, extent=1.0, shuffle=shuffle)
+    vao = sc.add_vao(_std_slots(mesh))
+    prog = sc.add_programme(functor)
+    model = mat_scaling(1.55 * aspect, 1.55, 1.0)
+    sc.cmd("viewport", width, height)
+    sc.cmd("depth", -1)
+    sc.cmd("clearDepth", 1.0)
+    sc.cmd("clearColour", 0xFF000000)
+    _camera_uniforms(sc, width, height, (0.0, 0.0, 2.6), model, mat_identity(), (-2.0, 1.5, 3.0))
+    sc.cmd("tex_uniform", 9, diffuse)
+    sc.cmd("tex_uniform", 10, bump)
+    sc.cmd("use", prog)
+    sc.cmd("draw", vao)
+    sc.meta["triangles"] = mesh[0].shape[0] // 3
+    return sc
+
+
+def scene_blend_overdraw(width=1920, height=1080, seed=4, quads=10, randoms=2000):
+    """C4: `quads` full-viewport quads at descending z (back-to-front) then `randoms` mid-size triangles, all
+    through the skybox functor's write4 path with ALPHABLEND on (FBOBridge::write4 -> blend4, fragthrd.cpp:70-82),
+    depth test + write on (as the cloud draw, src/test/testobjs.cpp:110-112). The cube-map texels carry random
+    alpha so blend4's integer formula is exercised over its whole domain."""
+    rng = np.random.default_rng(seed)
+    sc = Scene("C4-blend-overdraw", width, height)
+    layers = [tex_random_bgra(rng, 64, 64) for _ in range(6)]
+    tex = sc.add_texture(64, 64, 4, layers=layers)
+    pos = []
+    for q in range(quads):
+        z = 0.9 - 0.15 * q
+        sx = 1.0 - 0.02 * q  # shrink slightly so every layer keeps a visible border
+        for (x, y) in ((-sx, sx), (-sx, -sx), (sx, -sx), (sx, -sx), (sx, sx), (-sx, sx)):
+            pos.append((x, y, z, 1.0))
+    for _ in range(randoms):
+        c = rng.uniform(-0.9, 0.9, size=2)
+        r = rng.uniform(0.02, 0.25)
+        ang = rng.uniform(0, 2 * math.pi) + np.array([0.0, 2.1, 4.2]) + rng.uniform(-0.5, 0.5, size=3)
+        z = rng.uniform(-0.9, 0.9)
+        tri = [(c[0] + r * math.cos(a), c[1] + r * math.sin(a), z + rng.uniform(-0.05, 0.05), 1.0) for a in ang]
+        pos.extend(tri)
+    pos = np.array(pos, dtype=F32)
+    vao = sc.add_vao({0: (16, pos)})
+    prog = sc.add_programme(K.FN_DEF04)
+    sc.cmd("viewport", width, height)
+    sc.cmd("depth", -1)
+    sc.cmd("clearDepth", 1.0)
+    sc.cmd("clearColour", 0xFF404040)
+    sc.cmd("uniform", 0, colmajor(mat_identity()))
+    sc.cmd("uniform", 1, colmajor(mat_rotation((0, 1, 0), 0.3)))
+    sc.cmd("tex_uniform", 2, tex)
+    sc.cmd("disable", K.BEHAVIOR_FACE_CULLING)
+    sc.cmd("enable", K.BEHAVIOR_ALPHABLEND)
+    sc.cmd("use", prog)
+    sc.cmd("draw", vao)
+    sc.cmd("disable", K.BEHAVIOR_ALPHABLEND)
+    sc.cmd("enable", K.BEHAVIOR_FACE_CULLING)
+    sc.meta["triangles"] = pos.shape[0] // 3
+    return sc
+
+
+def scene_soup(width=320, height=240, seed=7, count=400, functor=K.FN_DEF02, cull=True):
+    """Edge-case soup in NDC space (identity matrices): sub-pixel slivers, exact flat tops/bottoms, triangles
+    straddling every screen edge, far off-screen ones, z outside [-1,1] (whole-triangle reject, drawvao.cpp:51-56),
+    zero-area (NaN normal => not culled, vertthrd.cpp:59-64), mixed winding, w != 1."""
+    rng = np.random.default_rng(seed)
+    sc = Scene("soup-%d" % seed, width, height)
+    pos, col, nrm = [], [], []
+
+    def tri(p, w=(1.0, 1.0, 1.0)):
+        for (x, y, z), ww in zip(p, w):
+            pos.append((x * ww, y * ww, z * ww, ww))
+            col.append(tuple(rng.uniform(30, 255, size=3)) + (255.0,))
+            nrm.append((0.0, 0.0, 1.0, 0.0))
+
+    for i in range(count):
+        kind = i % 10
+        c = rng.uniform(-1.1, 1.1, size=2)
+        z = rng.uniform(-0.95, 0.95, size=3)
+        if kind == 0:    # tiny sliver
+            d = rng.uniform(-0.01, 0.01, size=(3, 2))
+        elif kind == 1:  # large
+            d = rng.uniform(-1.2, 1.2, size=(3, 2))
+        else:
+            d = rng.uniform(-0.2, 0.2, size=(3, 2))
+        p = [(c[0] + d[k, 0], c[1] + d[k, 1], z[k]) for k in range(3)]
+        if kind == 2:    # exact flat bottom on a pixel row
+            yy = (rng.integers(0, height) - height // 2) / (height // 2)
+            p[0] = (p[0][0], yy, p[0][2])
+            p[1] = (p[1][0], yy, p[1][2])
+        elif kind == 3:  # exact flat top, fractional y
+            p[2] = (p[2][0], p[1][1], p[2][2])
+        elif kind == 4:  # z out of range on one vertex
+            p[1] = (p[1][0], p[1][1], rng.choice([-1.5, 1.5]))
+        elif kind == 5:  # degenerate: repeated vertex
+            p[2] = p[1]
+        elif kind == 6:  # perspective w
+            tri(p, w=tuple(rng.uniform(0.5, 3.0, size=3)))
+            continue
+        elif kind == 7:  # far off-screen
+            p = [(x + 3.0, y, zz) for (x, y, zz) in p]
+        tri(p)
+    # DEF02 reads slot 0 position, 1 normal, 2 colour (colr1light1.cpp:24-26)
+    vao = sc.add_vao({0: (16, np.array(pos, F32)), 1: (16, np.array(nrm, F32)), 2: (16, np.array(col, F32))})
+    prog = sc.add_programme(functor)
+    ident = colmajor(mat_identity())
+    sc.cmd("viewport", width, height)
+    sc.cmd("depth", -1)
+    sc.cmd("clearDepth", 1.0)
+    sc.cmd("clearColour", 0xFF101010)
+    sc.cmd("uniform", 3, ident)
+    sc.cmd("uniform", 4, ident)
+    sc.cmd("uniform", 5, ident)
+    sc.cmd("uniform", 7, vec4(0.3, 0.4, 2.0))
+    sc.cmd("uniform", 8, vec4(0.0, 0.0, 3.0))
+    if not cull:
+        sc.cmd("disable", K.BEHAVIOR_FACE_CULLING)
+    sc.cmd("use", prog)
+    sc.cmd("draw", vao)
+    if not cull:
+        sc.cmd("enable", K.BEHAVIOR_FACE_CULLING)
+    return sc
