@@ -39,8 +39,15 @@ typedef struct { float v[4]; } f4;
 
 static float hsum4(float p0, float p1, float p2, float p3) { return (p0 + p1) + (p2 + p3); } /* haddps x2: vector.cpp:97-98 */
 static float dot4(const float* a, const float* b) { return hsum4(a[0] * b[0], a[1] * b[1], a[2] * b[2], a[3] * b[3]); } /* vector.cpp:85-112 */
+#ifndef PS3D_ORACLE_IEEE_APPROX
 static float rcp_approx(float x) { return _mm_cvtss_f32(_mm_rcp_ps(_mm_set1_ps(x))); }   /* rcpps, vector.cpp:165 */
 static float rsqrt_approx(float x) { return _mm_cvtss_f32(_mm_rsqrt_ss(_mm_set_ss(x))); } /* rsqrtss, vector.cpp:245 */
+#else
+/* experiment switch (never the parity pin): correctly rounded 1/x and 1/sqrt(x), i.e. what a GPU computes, to
+ * measure how far the x86 approximations move the colours ("approximate instructions") */
+static float rcp_approx(float x) { return 1.0f / x; }
+static float rsqrt_approx(float x) { return (float)(1.0 / sqrt((double)x)); }
+#endif
 static void sub4(float* r, const float* a, const float* b) { for(int i = 0; i < 4; i++) r[i] = a[i] - b[i]; }
 static void add4(float* r, const float* a, const float* b) { for(int i = 0; i < 4; i++) r[i] = a[i] + b[i]; }
 static void mul4s(float* r, float s) { for(int i = 0; i < 4; i++) r[i] = r[i] * s; }       /* vector.cpp:146-156 */

@@ -1,0 +1,74 @@
+// device_types.cuh — data that crosses the host/device boundary of one draw.
+//
+// HBM layout (DESIGN.md "Data layout"):
+//   attribute streams   one contiguous buffer per VBO, fixed stride, un-indexed (vbo.cpp:8-31): read once by geom_setup
+//   TriHeader[ntris]    64 B per triangle (4 x 16-B quads): screen xy, 1/w, NDC z, row range, edge plan
+//   vary[ntris][3][NV]  float4 varyings exactly as the vertex functor wrote them (PROCDATA_* order)
+//   bins                (tile id, triangle id) pairs, stably sorted by tile => per-tile lists in submission order
+//   targets             colour BGRA8 top-down, depth float bottom-up — the reference's own memory layout (fbo.cpp:98-110)
+#pragma once
+#include <stdint.h>
+#include "exact_math.cuh"
+
+#define PS_TILE 16            // screen tile edge in pixels; one warp owns one tile
+#define PS_SEG 8              // a lane owns one row segment of PS_SEG pixels: 16 rows x 2 segments = 32 lanes
+#define PS_MAX_VARY 6         // float4 varyings per vertex (PROCDATA_PLANET, src/test/testproc.h:7-16, has 6)
+#define PS_UNIFORM_SLOTS 32   // slots latched per draw, first 64 bytes each (a mat4)
+#define PS_MAX_BOUND_TEX 6
+
+#define PS_BEHAVIOR_UPDATE_DEPTH 0x1
+#define PS_BEHAVIOR_TEST_DEPTH 0x2
+#define PS_BEHAVIOR_FACE_CULLING 0x4
+#define PS_BEHAVIOR_ALPHABLEND 0x8
+
+struct TexDesc
+{
+	const uint8_t* layer[6];
+	int width, height, scanline, wrap, nLayers, elemLen;
+};
+
+struct TargetDesc
+{
+	uint8_t* ptr;
+	int width, height, scanline, topDown;
+};
+
+struct alignas(16) TriHeader
+{
+	float vx0, vy0, vx1, vy1;   // viewport-space vertices (rasterizer.cpp:73-77)
+	float vx2, vy2, rw0, rw1;   // rw = 1/w per vertex ("correction factor 1", vertthrd.cpp:37-47)
+	float rw2, z0, z1, z2;      // NDC z per vertex
+	uint32_t rows;              // firstRow | lastRow << 16
+	uint32_t half0, half1;      // y0 | y1 << 16 of the upper / lower half (flat triangles: half0 only)
+	uint32_t plan;              // 2-bit vertex ids: eL0.i0,eL0.i1,eR0.i0,eR0.i1,eL1.i0,eL1.i1,eR1.i0,eR1.i1 ; bit 16: two halves
+};
+
+struct DeviceStats
+{
+	unsigned long long triangles_rasterised;
+	unsigned long long spans;
+	unsigned long long fragments_tested;
+	unsigned long long fragments_shaded;
+};
+
+struct DrawParams
+{
+	const uint8_t* slot[16];
+	uint32_t stride[16];
+	uint32_t ntris;
+	int vpW, vpH, halfW, halfH;
+	int behavior;
+	int band0, band1;           // raster rows [band0, band1) are rendered (sort-first sharding)
+	int tilesX, tilesY;
+	float u[PS_UNIFORM_SLOTS][16];
+	TexDesc tex[PS_MAX_BOUND_TEX];
+	TargetDesc colour, depth;
+	ApproxTables approx;
+	TriHeader* hdr;
+	F4* vary;
+	uint32_t* triCount;         // bin entries per triangle (0 = culled / rejected / empty)
+	uint32_t* triRect;          // tx0 | tx1<<8... packed as 4 x uint16 in two words (see geom_setup)
+	DeviceStats* stats;
+	uint32_t* cap;              // per-pixel FragmentProcessor::process counts (parity hook) or NULL
+	int capW, capH;
+};

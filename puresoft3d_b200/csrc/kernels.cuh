@@ -1,0 +1,559 @@
+// kernels.cuh — the hot path: geom_setup -> ordered binning -> tile_raster_shade.
+//
+// Reference call stack replaced: PuresoftPipeline::drawVAO (drawvao.cpp:3-133) with
+// processVertices / isBackFace (vertthrd.cpp), PuresoftRasterizer::pushTriangle (rasterizer.cpp),
+// PuresoftInterpolater (interp.cpp), the per-scanline ring queues (rinque.h) and fragmentThread (fragthrd.cpp).
+//
+//   geom_setup<PROG>          one thread per triangle: vertex functor x3, perspective divide, back-face, whole-triangle z
+//                             reject, pushTriangle's setup; writes the 64-byte TriHeader + the varyings, and the
+//                             rectangle of 16x16 tiles its spans touch.
+//   scan / emit / radix sort  (tile, triangle) pairs emitted in triangle order and stably sorted by tile id: every tile
+//                             gets its triangles in SUBMISSION ORDER, which the depth dead-band and blend4 require (§9.7).
+//   tile_raster_shade<PROG>   one warp per 16x16 tile, depth + colour tile staged in shared memory. Per chunk of 32
+//                             triangles: phase A (lane = triangle) evaluates the reference's per-row spans and ORs a
+//                             per-row bitmask; phase B (lane = row segment of 8 pixels) walks its row's spans in bit
+//                             order = submission order, replaying the exact serial float chains (§9.6), depth-tests
+//                             against shared memory, runs the fragment functor, blends. One coalesced write-back.
+#pragma once
+#include "shaders.cuh"
+#include "raster.cuh"
+
+#define PS_WARPS_PER_BLOCK 4
+#define PS_FULL 0xffffffffu
+
+PS_D unsigned long long warpSumU64(unsigned v)
+{
+	v += __shfl_xor_sync(PS_FULL, v, 16);
+	v += __shfl_xor_sync(PS_FULL, v, 8);
+	v += __shfl_xor_sync(PS_FULL, v, 4);
+	v += __shfl_xor_sync(PS_FULL, v, 2);
+	v += __shfl_xor_sync(PS_FULL, v, 1);
+	return v;
+}
+
+// ======================================================================================================================
+// geometry
+// ======================================================================================================================
+
+// vertthrd.cpp:56-65 isBackFace — sign of the NDC cross product's z after mcemaths_norm_3_4; NaN (zero area) => keep
+PS_D bool isBackFace(F4 v0, F4 v1, F4 v2, const ApproxTables& ap)
+{
+	const F4 a = f4sub(v1, v0), b = f4sub(v2, v1);
+	F4 c; // mcemaths_cross_3, vector.cpp:114-144
+	c.x = fsub(fmul(a.y, b.z), fmul(a.z, b.y));
+	c.y = fsub(fmul(a.z, b.x), fmul(a.x, b.z));
+	c.z = fsub(fmul(a.x, b.y), fmul(a.y, b.x));
+	c.w = fsub(fmul(a.w, b.w), fmul(a.w, b.w));
+	c = f4norm(c, ap);
+	return f4dot(f4(0, 0, 1.0f, 0), c) < 0;
+}
+
+template<class PROG>
+__global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__ DrawParams P)
+{
+	constexpr int NV = PROG::NV;
+	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned rasterised = 0, spans = 0;
+	if(tri < P.ntris)
+	{
+		VertexProcessorOutput<NV> vo[3];
+		float ndcX[3], ndcY[3], rw[3], pz[3];
+		F4 pos[3];
+#pragma unroll
+		for(int i = 0; i < 3; i++)
+		{
+			// processVertices, vertthrd.cpp:14-51 : all attached slots advance in lock-step, un-indexed
+			VertexProcessorInput in;
+#pragma unroll
+			for(int s = 0; s < 16; s++)
+				in.data[s] = (PROG::V::SLOTS >> s) & 1 ? P.slot[s] + (size_t)(tri * 3 + i) * P.stride[s] : nullptr;
+			PROG::V::process(in, vo[i], P);
+			const float reciprocalW = fdiv(1.0f, vo[i].position.w);       // vertthrd.cpp:37 (true divide)
+			pos[i] = f4muls(vo[i].position, reciprocalW);                  // :38 all four lanes
+			ndcX[i] = pos[i].x; ndcY[i] = pos[i].y; pz[i] = pos[i].z; rw[i] = reciprocalW;
+		}
+		bool alive = true;
+		if((P.behavior & PS_BEHAVIOR_FACE_CULLING) && isBackFace(pos[0], pos[1], pos[2], P.approx)) alive = false; // drawvao.cpp:46
+		// drawvao.cpp:51-56 : the only "clipping" — drop the whole triangle
+		if(pz[0] < -1.0f || pz[0] > 1.0f || pz[1] < -1.0f || pz[1] > 1.0f || pz[2] < -1.0f || pz[2] > 1.0f) alive = false;
+
+		uint32_t count = 0, rect0 = 0, rect1 = 0;
+		if(alive)
+		{
+			TriHeader h;
+			float vx[3], vy[3];
+			const int code = setupTriangle(P.vpW, P.vpH, P.halfW, P.halfH, ndcX, ndcY, h, vx, vy);
+			rasterised = code != 0;
+			if(1 == code)
+			{
+				const int firstRow = (int)(h.rows & 0xffff), lastRow = (int)(h.rows >> 16);
+				int minX = 0x7fffffff, maxX = -1, minY = 0x7fffffff, maxY = -1;
+				for(int iy = firstRow; iy <= lastRow; iy++) // drawvao.cpp:66-75
+				{
+					RowSpan r;
+					if(!rowOf(h, vx, vy, iy, r)) continue;
+					if(r.left == r.right) continue;
+					spans++;
+					if(iy < P.band0 || iy >= P.band1) continue;
+					const int x1 = r.left < 0 ? 0 : r.left;                 // RESULT_ROW::leftClamped
+					const int x2 = r.right >= P.vpW ? P.vpW - 1 : r.right;  // RESULT_ROW::rightClamped
+					if(x1 > x2) continue;
+					minX = min(minX, x1); maxX = max(maxX, x2);
+					minY = min(minY, iy); maxY = max(maxY, iy);
+				}
+				if(maxX >= 0)
+				{
+					const int tx0 = minX / PS_TILE, tx1 = maxX / PS_TILE, ty0 = minY / PS_TILE, ty1 = maxY / PS_TILE;
+					count = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+					rect0 = (uint32_t)tx0 | ((uint32_t)tx1 << 16);
+					rect1 = (uint32_t)ty0 | ((uint32_t)ty1 << 16);
+					h.rw0 = rw[0]; h.rw1 = rw[1]; h.rw2 = rw[2];
+					h.z0 = pz[0]; h.z1 = pz[1]; h.z2 = pz[2];
+					// 64-byte record as four 16-byte stores
+					uint4* dst = (uint4*)(P.hdr + tri);
+					const uint4* src = (const uint4*)&h;
+					dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+					if(NV > 0)
+					{
+						float4* vd = (float4*)(P.vary + (size_t)tri * 3 * NV);
+#pragma unroll
+						for(int i = 0; i < 3; i++)
+#pragma unroll
+							for(int k = 0; k < NV; k++)
+								vd[i * NV + k] = make_float4(vo[i].user[k].x, vo[i].user[k].y, vo[i].user[k].z, vo[i].user[k].w);
+					}
+				}
+			}
+		}
+		P.triCount[tri] = count;
+		P.triRect[2 * tri] = rect0;
+		P.triRect[2 * tri + 1] = rect1;
+	}
+	const unsigned long long r = warpSumU64(rasterised), s = warpSumU64(spans);
+	if(0 == (threadIdx.x & 31))
+	{
+		if(r) atomicAdd(&P.stats->triangles_rasterised, r);
+		if(s) atomicAdd(&P.stats->spans, s);
+	}
+}
+
+// ======================================================================================================================
+// exclusive scan (uint32), three small kernels
+// ======================================================================================================================
+
+#define PS_SCAN_THREADS 256
+#define PS_SCAN_ITEMS 8
+#define PS_SCAN_BLOCK (PS_SCAN_THREADS * PS_SCAN_ITEMS)
+
+__global__ void __launch_bounds__(PS_SCAN_THREADS) scan_local_kernel(const uint32_t* in, uint32_t* out,
+                                                                    uint32_t* __restrict__ blockSums, uint32_t n)
+{
+	__shared__ uint32_t warpTotals[PS_SCAN_THREADS / 32];
+	const uint32_t base = blockIdx.x * PS_SCAN_BLOCK + threadIdx.x * PS_SCAN_ITEMS;
+	uint32_t v[PS_SCAN_ITEMS], sum = 0;
+#pragma unroll
+	for(int i = 0; i < PS_SCAN_ITEMS; i++)
+	{
+		v[i] = (base + i < n) ? in[base + i] : 0;
+		sum += v[i];
+	}
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t incl = sum;
+#pragma unroll
+	for(int d = 1; d < 32; d <<= 1)
+	{
+		uint32_t t = __shfl_up_sync(PS_FULL, incl, d);
+		if(lane >= d) incl += t;
+	}
+	if(31 == lane) warpTotals[warp] = incl;
+	__syncthreads();
+	uint32_t warpBase = 0;
+	for(int w = 0; w < warp; w++) warpBase += warpTotals[w];
+	uint32_t run = warpBase + incl - sum;
+#pragma unroll
+	for(int i = 0; i < PS_SCAN_ITEMS; i++)
+	{
+		if(base + i < n) out[base + i] = run;
+		run += v[i];
+	}
+	if(PS_SCAN_THREADS - 1 == threadIdx.x) blockSums[blockIdx.x] = run;
+}
+
+// one block: exclusive scan of blockSums[nb] in place; total -> *total
+__global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t* __restrict__ blockSums, uint32_t nb, uint32_t* __restrict__ total)
+{
+	__shared__ uint32_t warpTotals[32];
+	__shared__ uint32_t carryS;
+	if(0 == threadIdx.x) carryS = 0;
+	__syncthreads();
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for(uint32_t base = 0; base < nb; base += 1024)
+	{
+		const uint32_t i = base + threadIdx.x;
+		const uint32_t v = i < nb ? blockSums[i] : 0;
+		uint32_t incl = v;
+#pragma unroll
+		for(int d = 1; d < 32; d <<= 1)
+		{
+			uint32_t t = __shfl_up_sync(PS_FULL, incl, d);
+			if(lane >= d) incl += t;
+		}
+		if(31 == lane) warpTotals[warp] = incl;
+		__syncthreads();
+		uint32_t warpBase = 0;
+		for(int w = 0; w < warp; w++) warpBase += warpTotals[w];
+		const uint32_t carry = carryS;
+		if(i < nb) blockSums[i] = carry + warpBase + incl - v;
+		__syncthreads();
+		if(1023 == threadIdx.x) carryS = carry + warpBase + incl;
+		__syncthreads();
+	}
+	if(0 == threadIdx.x) *total = carryS;
+}
+
+__global__ void __launch_bounds__(PS_SCAN_THREADS) scan_add_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ blockSums, uint32_t n)
+{
+	const uint32_t base = blockIdx.x * PS_SCAN_BLOCK + threadIdx.x * PS_SCAN_ITEMS;
+	const uint32_t add = blockSums[blockIdx.x];
+#pragma unroll
+	for(int i = 0; i < PS_SCAN_ITEMS; i++)
+		if(base + i < n) out[base + i] += add;
+}
+
+// ======================================================================================================================
+// binning: emit (tile, triangle) pairs in triangle order, then a stable LSD radix sort on the tile id
+// ======================================================================================================================
+
+__global__ void __launch_bounds__(128) emit_pairs_kernel(const uint32_t* __restrict__ triCount, const uint32_t* __restrict__ triOffset,
+                                                        const uint32_t* __restrict__ triRect, uint32_t* __restrict__ keys,
+                                                        uint32_t* __restrict__ vals, uint32_t* __restrict__ tileCount, uint32_t ntris, int tilesX)
+{
+	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+	if(tri >= ntris) return;
+	if(0 == triCount[tri]) return;
+	uint32_t o = triOffset[tri];
+	const uint32_t r0 = triRect[2 * tri], r1 = triRect[2 * tri + 1];
+	const int tx0 = (int)(r0 & 0xffff), tx1 = (int)(r0 >> 16), ty0 = (int)(r1 & 0xffff), ty1 = (int)(r1 >> 16);
+	for(int ty = ty0; ty <= ty1; ty++)
+		for(int tx = tx0; tx <= tx1; tx++)
+		{
+			const uint32_t tile = (uint32_t)(ty * tilesX + tx);
+			keys[o] = tile;
+			vals[o] = tri;
+			o++;
+			atomicAdd(&tileCount[tile], 1u);
+		}
+}
+
+#define PS_SORT_ITEMS_PER_WARP 1024
+
+// counts[digit * nwarps + warp]
+__global__ void __launch_bounds__(128) sort_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ counts, uint32_t nwarps)
+{
+	__shared__ uint32_t hist[PS_WARPS_PER_BLOCK][256];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const uint32_t wg = blockIdx.x * PS_WARPS_PER_BLOCK + w;
+	for(int d = lane; d < 256; d += 32) hist[w][d] = 0;
+	__syncwarp();
+	if(wg < nwarps)
+	{
+		const uint32_t base = wg * PS_SORT_ITEMS_PER_WARP;
+		for(int s = 0; s < PS_SORT_ITEMS_PER_WARP / 32; s++)
+		{
+			const uint32_t i = base + s * 32 + lane;
+			if(i < n) atomicAdd(&hist[w][(keys[i] >> shift) & 0xff], 1u);
+		}
+		__syncwarp();
+		for(int d = lane; d < 256; d += 32) counts[(size_t)d * nwarps + wg] = hist[w][d];
+	}
+}
+
+__global__ void __launch_bounds__(128) sort_scatter_kernel(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
+                                                          uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut, uint32_t n, int shift,
+                                                          const uint32_t* __restrict__ offsets, uint32_t nwarps)
+{
+	__shared__ uint32_t off[PS_WARPS_PER_BLOCK][256];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const uint32_t wg = blockIdx.x * PS_WARPS_PER_BLOCK + w;
+	if(wg >= nwarps) return;
+	for(int d = lane; d < 256; d += 32) off[w][d] = offsets[(size_t)d * nwarps + wg];
+	__syncwarp();
+	const uint32_t base = wg * PS_SORT_ITEMS_PER_WARP;
+	const uint32_t ltMask = (1u << lane) - 1;
+	for(int s = 0; s < PS_SORT_ITEMS_PER_WARP / 32; s++)
+	{
+		const uint32_t i = base + s * 32 + lane;
+		const bool valid = i < n;
+		uint32_t k = 0, v = 0;
+		if(valid) { k = keysIn[i]; v = valsIn[i]; }
+		const uint32_t d = valid ? ((k >> shift) & 0xff) : 0x100u; // invalid lanes form their own group
+		const uint32_t peers = __match_any_sync(PS_FULL, d);
+		const uint32_t rank = __popc(peers & ltMask);
+		uint32_t pos = 0;
+		if(valid) pos = off[w][d] + rank; // lanes ascend with item index => stable
+		__syncwarp();
+		if(valid && 0 == rank) off[w][d] += __popc(peers);
+		__syncwarp();
+		if(valid) { keysOut[pos] = k; valsOut[pos] = v; }
+	}
+}
+
+// ======================================================================================================================
+// clears (pipeline.cpp:334-342 -> fbo.cpp:332-371)
+// ======================================================================================================================
+
+// clear16: fills m_bytes/16 whole quads with the value
+__global__ void clear_depth_kernel(float4* __restrict__ buf, size_t quads, float v)
+{
+	const float4 q = make_float4(v, v, v, v);
+	for(size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < quads; i += (size_t)gridDim.x * blockDim.x) buf[i] = q;
+}
+// clear4: every pixel of every buffer row EXCEPT the last one (fbo.cpp:336: `y < m_height - 1`)
+__global__ void clear_colour_kernel(uint8_t* __restrict__ buf, int width, int rows, int scanline, uint32_t v)
+{
+	const size_t total = (size_t)width * rows;
+	for(size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+	{
+		const size_t y = i / width, x = i - y * width;
+		*(uint32_t*)(buf + y * scanline + x * 4) = v;
+	}
+}
+
+// ======================================================================================================================
+// tile raster + shade
+// ======================================================================================================================
+
+// fbo.cpp:208-229 blend4 : per channel dst + ((sat_u16(src - dst) * srcA) >> 8), 16-bit lanes, unsigned-saturating pack
+PS_D uint32_t blend4(uint32_t src, uint32_t dst)
+{
+	const uint32_t a = src >> 24;
+	uint32_t out = 0;
+#pragma unroll
+	for(int ch = 0; ch < 4; ch++)
+	{
+		const uint32_t s = (src >> (8 * ch)) & 0xff, d = (dst >> (8 * ch)) & 0xff;
+		const uint32_t diff = s > d ? s - d : 0;           // _mm_subs_pu16
+		const uint32_t prod = (diff * a) & 0xffff;          // _mm_mullo_pi16
+		const uint32_t sum = ((prod >> 8) + d) & 0xffff;    // _mm_srli_pi16 + _mm_add_pi16
+		const int ssum = (int)(short)sum;                   // _mm_packs_pu16 saturates a SIGNED 16-bit value to 0..255
+		const uint32_t byte = ssum < 0 ? 0u : (ssum > 255 ? 255u : (uint32_t)ssum);
+		out |= byte << (8 * ch);
+	}
+	return out;
+}
+
+struct TileSmem
+{
+	float depth[PS_TILE][PS_TILE];
+	uint32_t colour[PS_TILE][PS_TILE];
+	TriHeader hdr[32];
+	int spanL[PS_TILE][32];
+	int spanR[PS_TILE][32];
+	uint8_t spanE[PS_TILE][32];
+	uint32_t rowMask[PS_TILE];
+	uint32_t triId[32];
+};
+
+template<class PROG>
+__global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_kernel(const __grid_constant__ DrawParams P,
+                                                                                  const uint32_t* __restrict__ tileStart,
+                                                                                  const uint32_t* __restrict__ sortedTris)
+{
+	constexpr int NV = PROG::NV;
+	typedef typename PROG::I IP;
+	__shared__ TileSmem smem[PS_WARPS_PER_BLOCK];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int tile = blockIdx.x * PS_WARPS_PER_BLOCK + w;
+	if(tile >= P.tilesX * P.tilesY) return;
+	const uint32_t listBegin = tileStart[tile], listEnd = tileStart[tile + 1];
+	if(listBegin == listEnd) return;
+	TileSmem& S = smem[w];
+
+	const int tx0 = (tile % P.tilesX) * PS_TILE, ty0 = (tile / P.tilesX) * PS_TILE;
+	const int rr = lane >> 1, seg = lane & 1;          // phase-B ownership: row rr, pixels [sx0, sx0+7]
+	const int y = ty0 + rr, sx0 = tx0 + seg * PS_SEG;
+	const bool testDepth = 0 != (P.behavior & PS_BEHAVIOR_TEST_DEPTH);
+	const bool updateDepth = 0 != (P.behavior & PS_BEHAVIOR_UPDATE_DEPTH);
+	const bool useDepth = testDepth || updateDepth;
+	const bool alphaBlend = 0 != (P.behavior & PS_BEHAVIOR_ALPHABLEND);
+
+	// ---- stage the tile: each lane loads the 8-pixel segment it owns (fbo.cpp:98-110: colour top-down, depth bottom-up)
+	const bool depthRowOk = y < P.depth.height, colourRowOk = y < P.colour.height;
+	uint8_t* depthRow = P.depth.ptr + (size_t)(P.depth.topDown ? P.depth.height - 1 - y : y) * P.depth.scanline;
+	uint8_t* colourRow = P.colour.ptr + (size_t)(P.colour.topDown ? P.colour.height - 1 - y : y) * P.colour.scanline;
+#pragma unroll
+	for(int i = 0; i < PS_SEG; i++)
+	{
+		const int x = sx0 + i;
+		float d = 1.0f;
+		uint32_t c = 0;
+		if(useDepth && depthRowOk && x < P.depth.width) d = *(const float*)(depthRow + (size_t)x * 4);
+		if(colourRowOk && x < P.colour.width) c = *(const uint32_t*)(colourRow + (size_t)x * 4);
+		S.depth[rr][seg * PS_SEG + i] = d;
+		S.colour[rr][seg * PS_SEG + i] = c;
+	}
+	if(lane < PS_TILE) S.rowMask[lane] = 0;
+	__syncwarp();
+
+	unsigned tested = 0, shaded = 0;
+	bool depthDirty = false, colourDirty = false;
+	// the reference reads a clamped column/row when the viewport exceeds the depth target (fbo.cpp:101,150); that
+	// behaviour is not reproducible tile-locally, such fragments are dropped (DESIGN.md "divergences")
+	const int depthLimitX = useDepth ? P.depth.width - 1 : 0x7fffffff;
+	const bool rowDrawable = !useDepth || depthRowOk;
+
+	for(uint32_t chunk = listBegin; chunk < listEnd; chunk += 32)
+	{
+		// ---- phase A: lane = triangle of the chunk (submission order). Evaluate its rows inside this tile. ----
+		const uint32_t li = chunk + lane;
+		if(li < listEnd)
+		{
+			const uint32_t tri = sortedTris[li];
+			S.triId[lane] = tri;
+			const uint4* src = (const uint4*)(P.hdr + tri);
+			uint4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
+			uint4* dst = (uint4*)&S.hdr[lane];
+			dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3;
+			TriHeader h;
+			*(uint4*)&h = q0; *((uint4*)&h + 1) = q1; *((uint4*)&h + 2) = q2; *((uint4*)&h + 3) = q3;
+			const float vx[3] = { h.vx0, h.vx1, h.vx2 }, vy[3] = { h.vy0, h.vy1, h.vy2 };
+			int r0 = (int)(h.rows & 0xffff), r1 = (int)(h.rows >> 16);
+			r0 = max(max(r0, ty0), P.band0);
+			r1 = min(min(r1, ty0 + PS_TILE - 1), P.band1 - 1);
+			for(int iy = r0; iy <= r1; iy++)
+			{
+				RowSpan r;
+				if(!rowOf(h, vx, vy, iy, r)) continue;
+				if(r.left == r.right) continue;                           // drawvao.cpp:72
+				const int x1 = r.left < 0 ? 0 : r.left;
+				const int x2 = r.right >= P.vpW ? P.vpW - 1 : r.right;
+				if(x1 > x2 || x2 < tx0 || x1 > tx0 + PS_TILE - 1) continue;
+				S.spanL[iy - ty0][lane] = r.left;
+				S.spanR[iy - ty0][lane] = r.right;
+				S.spanE[iy - ty0][lane] = (uint8_t)r.edges;
+				atomicOr(&S.rowMask[iy - ty0], 1u << lane);
+			}
+		}
+		__syncwarp();
+
+		// ---- phase B: lane = (row, 8-pixel segment). Spans of my row in bit order = submission order. ----
+		uint32_t mask = rowDrawable ? S.rowMask[rr] : 0;
+		while(mask)
+		{
+			const int t = __ffs(mask) - 1;
+			mask &= mask - 1;
+			const int left = S.spanL[rr][t], right = S.spanR[rr][t];
+			const int x1 = left < 0 ? 0 : left;
+			const int x2 = right >= P.vpW ? P.vpW - 1 : right;
+			const int xs = max(x1, sx0), xe = min(min(x2, sx0 + PS_SEG - 1), depthLimitX);
+			if(xs > xe) continue;
+			const int e = S.spanE[rr][t];
+			const TriHeader& h = S.hdr[t];
+			const float vx[3] = { h.vx0, h.vx1, h.vx2 }, vy[3] = { h.vy0, h.vy1, h.vy2 };
+
+			// interpolateStartAndStep, interp.cpp:26-80
+			float cl[3], cr[3];
+			edgeContrib(vx, vy, e & 3, (e >> 2) & 3, (float)left, (float)y, cl);
+			edgeContrib(vx, vy, (e >> 4) & 3, (e >> 6) & 3, (float)right, (float)y, cr);
+			cl[0] = fmul(cl[0], h.rw0); cl[1] = fmul(cl[1], h.rw1); cl[2] = fmul(cl[2], h.rw2); // mulvec_3_4 (:40-41); lane 3 is 0*0
+			cr[0] = fmul(cr[0], h.rw0); cr[1] = fmul(cr[1], h.rw1); cr[2] = fmul(cr[2], h.rw2);
+			const int stepCount = right - left;
+			const float rcpLen = fdiv(1.0f, (float)stepCount);                                   // :47
+			float zStart = hsum4(fmul(cl[0], h.z0), fmul(cl[1], h.z1), fmul(cl[2], h.z2), 0.0f);  // :49 dot_3_4
+			float zStep = hsum4(fmul(cr[0], h.z0), fmul(cr[1], h.z1), fmul(cr[2], h.z2), 0.0f);   // :50
+			zStep = fmul(fsub(zStep, zStart), rcpLen);                                           // :51
+			float cf2Start = hsum4(cl[0], cl[1], cl[2], 0.0f);                                   // :55-68
+			float cf2Step = hsum4(cr[0], cr[1], cr[2], 0.0f);
+			cf2Step = fmul(fsub(cf2Step, cf2Start), rcpLen);                                     // :72
+			const int skip = x1 - left;                                                          // drawvao.cpp:90
+			if(skip > 0)                                                                         // interp.cpp:74-79
+			{
+				cf2Start = fadd(cf2Start, fmul(cf2Step, (float)skip));
+				zStart = fadd(zStart, fmul(zStep, (float)skip));
+			}
+			// the k-th pixel's value is k rounded additions from the span start (§9.6): replay them up to my segment
+			for(int x = x1; x < xs; x++)
+			{
+				cf2Start = fadd(cf2Start, cf2Step);
+				zStart = fadd(zStart, zStep);
+			}
+
+			F4 vStart[NV > 0 ? NV : 1], vStep[NV > 0 ? NV : 1];
+			bool varyReady = false;
+			for(int x = xs; x <= xe; x++)
+			{
+				// interpolateNextStep, interp.cpp:82-92
+				const float inv = fdiv(1.0f, cf2Start);
+				cf2Start = fadd(cf2Start, cf2Step);
+				const float z = fmul(zStart, inv);
+				zStart = fadd(zStart, zStep);
+				tested++;
+				const int px = x - tx0;
+				const float cur = testDepth ? S.depth[rr][px] : 1.0f;            // fragthrd.cpp:217-225
+				if(-1.0f < z && fsub(z, cur) < -0.0001f)                         // fragthrd.cpp:227
+				{
+					if(NV > 0 && !varyReady)
+					{
+						// IP::interpolateByContributes x2, calcStep, and the left-clip skip, then catch the chain up to x
+						const F4* v = P.vary + (size_t)S.triId[t] * 3 * NV;
+						F4 v0[NV > 0 ? NV : 1], v1[NV > 0 ? NV : 1], v2[NV > 0 ? NV : 1], vEnd[NV > 0 ? NV : 1];
+#pragma unroll
+						for(int k = 0; k < NV; k++)
+						{
+							const float4 a = __ldg((const float4*)(v + k)), b = __ldg((const float4*)(v + NV + k)), c = __ldg((const float4*)(v + 2 * NV + k));
+							v0[k] = f4(a.x, a.y, a.z, a.w); v1[k] = f4(b.x, b.y, b.z, b.w); v2[k] = f4(c.x, c.y, c.z, c.w);
+						}
+						IP::interpolateByContributes(vStart, v0, v1, v2, cl[0], cl[1], cl[2]);
+						IP::interpolateByContributes(vEnd, v0, v1, v2, cr[0], cr[1], cr[2]);
+						IP::calcStep(vStep, vStart, vEnd, stepCount);
+						if(skip > 0) IP::stepForward(vStart, vStep, skip);
+						for(int k = x1; k < x; k++) IP::stepForward(vStart, vStep, 1);
+						varyReady = true;
+					}
+					F4 frag[NV > 0 ? NV : 1];
+					IP::correctInterpolation(frag, vStart, inv);
+					FragmentProcessorOutput out;
+					out.discarded = false; out.wrote = false; out.blendable = false; out.bgra = 0;
+					PROG::F::process(frag, out, P);                              // fragthrd.cpp:231
+					shaded++;
+					if(P.cap && x < P.capW && y < P.capH) atomicAdd(&P.cap[(size_t)y * P.capW + x], 1u);
+					if(out.wrote && colourRowOk && x < P.colour.width)
+					{
+						// FBOBridge::write4 -> blend4 under ALPHABLEND, FBOBridge::write -> plain store (fragthrd.cpp:54-82)
+						S.colour[rr][px] = (out.blendable && alphaBlend) ? blend4(out.bgra, S.colour[rr][px]) : out.bgra;
+						colourDirty = true;
+					}
+					if(!out.discarded && updateDepth)                            // fragthrd.cpp:234-237
+					{
+						S.depth[rr][px] = z;
+						depthDirty = true;
+					}
+				}
+				if(NV > 0 && varyReady) IP::stepForward(vStart, vStep, 1);       // interp.cpp:88
+			}
+		}
+		__syncwarp();
+		if(lane < PS_TILE) S.rowMask[lane] = 0;
+		__syncwarp();
+	}
+
+	// ---- write back the segments this lane dirtied
+	if(depthDirty)
+	{
+#pragma unroll
+		for(int i = 0; i < PS_SEG; i++)
+			if(sx0 + i < P.depth.width) *(float*)(depthRow + (size_t)(sx0 + i) * 4) = S.depth[rr][seg * PS_SEG + i];
+	}
+	if(colourDirty)
+	{
+#pragma unroll
+		for(int i = 0; i < PS_SEG; i++)
+			if(sx0 + i < P.colour.width) *(uint32_t*)(colourRow + (size_t)(sx0 + i) * 4) = S.colour[rr][seg * PS_SEG + i];
+	}
+	const unsigned long long t = warpSumU64(tested), s = warpSumU64(shaded);
+	if(0 == lane)
+	{
+		if(t) atomicAdd(&P.stats->fragments_tested, t);
+		if(s) atomicAdd(&P.stats->fragments_shaded, s);
+	}
+}

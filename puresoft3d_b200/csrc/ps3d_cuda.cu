@@ -1,0 +1,770 @@
+// ps3d_cuda.cu — include/ps3d.h implemented on one B200 (sm_100a). The product library.
+//
+// Host side = the reference's resource tables (pipeline.cpp, tex.cpp, prog.cpp, vao.cpp, vbo.cpp) with storage in
+// device memory, plus the per-draw enqueue of the kernels in kernels.cuh on the pipe's CUDA stream (the reference's
+// ring queues and worker threads, rinque.h / fragthrd.cpp, have no counterpart: CUDA streams order the draws).
+// There is NO CPU rendering path in this file: every ps3d_draw_vao either launches the kernels or returns an error.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <mutex>
+#include "ps3d.h"
+#include "kernels.cuh"
+#include "x86_approx.h"
+
+namespace
+{
+
+struct Texture
+{
+	int width, height, scanline, elemLen, wrap, nLayers;
+	uint8_t* layer[6];
+};
+struct Vbo { size_t unitBytes, unitCount; uint8_t* data; bool alive; };
+struct Vao { bool alive; int vbo[PS3D_MAX_VBOS]; };
+struct Proc { bool alive; int kind, functor; };
+struct Prog { int vp, ip, fp; };
+
+typedef void (*LaunchGeom)(const DrawParams&, cudaStream_t);
+typedef void (*LaunchTile)(const DrawParams&, const uint32_t*, const uint32_t*, cudaStream_t);
+
+struct ProgEntry
+{
+	int fnV, fnI, fnF;
+	int nv;
+	uint32_t slots, uniforms;
+	int ntex;
+	int texSlot[PS_MAX_BOUND_TEX];
+	LaunchGeom geom;
+	LaunchTile tile;
+};
+
+template<class PROG> void launchGeom(const DrawParams& P, cudaStream_t s)
+{
+	const unsigned blocks = (P.ntris + 127) / 128;
+	geom_setup_kernel<PROG><<<blocks, 128, 0, s>>>(P);
+}
+template<class PROG> void launchTile(const DrawParams& P, const uint32_t* tileStart, const uint32_t* sortedTris, cudaStream_t s)
+{
+	const unsigned tiles = (unsigned)(P.tilesX * P.tilesY);
+	const unsigned blocks = (tiles + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK;
+	tile_raster_shade_kernel<PROG><<<blocks, 32 * PS_WARPS_PER_BLOCK, 0, s>>>(P, tileStart, sortedTris);
+}
+template<class PROG> ProgEntry makeEntry(int fnV, int fnI, int fnF)
+{
+	ProgEntry e;
+	e.fnV = fnV; e.fnI = fnI; e.fnF = fnF;
+	e.nv = PROG::NV;
+	e.slots = PROG::V::SLOTS;
+	e.uniforms = PROG::V::UNIFORMS | PROG::F::UNIFORMS;
+	e.ntex = PROG::F::NTEX;
+	for(int i = 0; i < PS_MAX_BOUND_TEX; i++) e.texSlot[i] = i < e.ntex ? PROG::F::texSlot(i) : -1;
+	e.geom = launchGeom<PROG>;
+	e.tile = launchTile<PROG>;
+	return e;
+}
+
+const std::vector<ProgEntry>& programmeTable()
+{
+	static std::vector<ProgEntry> t;
+	if(t.empty())
+	{
+		t.push_back(makeEntry<ProgDEF01>(PS3D_FN_DEF01, PS3D_FN_DEF01, PS3D_FN_DEF01));
+		t.push_back(makeEntry<ProgDEF02>(PS3D_FN_DEF02, PS3D_FN_DEF02, PS3D_FN_DEF02));
+		t.push_back(makeEntry<ProgDEF03>(PS3D_FN_DEF03, PS3D_FN_DEF03, PS3D_FN_DEF03));
+		t.push_back(makeEntry<ProgDEF04>(PS3D_FN_DEF04, PS3D_FN_DEF04, PS3D_FN_DEF04));
+		t.push_back(makeEntry<ProgDEF05>(PS3D_FN_DEF05, PS3D_FN_DEF05, PS3D_FN_DEF05));
+		t.push_back(makeEntry<ProgFLATID>(PS3D_FN_FLATID, PS3D_FN_FLATID, PS3D_FN_FLATID));
+	}
+	return t;
+}
+
+bool functorKnown(int kind, int fn)
+{
+	for(const ProgEntry& e : programmeTable())
+		if((kind == PS3D_PROC_VERTEX && e.fnV == fn) || (kind == PS3D_PROC_INTERPOLATION && e.fnI == fn) || (kind == PS3D_PROC_FRAGMENT && e.fnF == fn))
+			return true;
+	return false;
+}
+
+template<typename T> struct DevBuf
+{
+	T* p = nullptr;
+	size_t cap = 0;
+	cudaError_t ensure(size_t n)
+	{
+		if(n <= cap) return cudaSuccess;
+		if(p) cudaFree(p);
+		p = nullptr;
+		size_t want = n + n / 4 + 1024;
+		cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+		cap = e == cudaSuccess ? want : 0;
+		return e;
+	}
+	void release() { if(p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+} // namespace
+
+struct ps3d_pipe
+{
+	int device;
+	cudaStream_t stream;
+	int width, height;
+	int vpW, vpH;
+	int behavior;
+	int band0, band1;
+	uint8_t* display[2];
+	int back;
+	uint8_t* defaultDepth;
+	int depthScanline;
+	int depthTex;
+	std::vector<Texture*> textures;
+	std::vector<Vbo> vbos;
+	std::vector<Vao> vaos;
+	std::vector<Proc> procs;
+	std::vector<Prog> progs;
+	int curProg;
+	std::vector<uint8_t> uniforms[PS3D_MAX_UNIFORMS];
+	bool uniformSet[PS3D_MAX_UNIFORMS];
+	// per-draw scratch
+	DevBuf<TriHeader> hdr;
+	DevBuf<F4> vary;
+	DevBuf<uint32_t> triCount, triOffset, triRect, scanSums, keysA, valsA, keysB, valsB, tileCount, tileStart, sortCounts;
+	uint32_t* totalDev;
+	uint32_t* totalHost; // pinned
+	DeviceStats* statsDev;
+	ps3d_stats stats;
+	uint32_t* capDev;
+	int capW, capH;
+	uint32_t* rcpDev;
+	uint32_t* rsqrtDev;
+	ApproxTables approx;
+	uint64_t launches;
+	std::string err;
+};
+
+#define CK(p, call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { (p)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return PS3D_ERR_DEVICE; } } while(0)
+
+static int fail(ps3d_pipe* p, int code, const char* msg) { p->err = msg; return code; }
+
+static const Ps3dHostApprox& hostApprox()
+{
+	static Ps3dHostApprox a;
+	static std::once_flag once;
+	std::call_once(once, [] { ps3d_measure_x86_approx(&a); });
+	return a;
+}
+
+static int exclusiveScan(ps3d_pipe* p, const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* totalDev)
+{
+	const uint32_t nb = (n + PS_SCAN_BLOCK - 1) / PS_SCAN_BLOCK;
+	CK(p, p->scanSums.ensure(nb + 1));
+	scan_local_kernel<<<nb, PS_SCAN_THREADS, 0, p->stream>>>(in, out, p->scanSums.p, n);
+	scan_sums_kernel<<<1, 1024, 0, p->stream>>>(p->scanSums.p, nb, totalDev);
+	scan_add_kernel<<<nb, PS_SCAN_THREADS, 0, p->stream>>>(out, p->scanSums.p, n);
+	p->launches += 3;
+	CK(p, cudaGetLastError());
+	return PS3D_OK;
+}
+
+static TargetDesc depthTarget(ps3d_pipe* p)
+{
+	TargetDesc d;
+	if(p->depthTex < 0)
+	{
+		d.ptr = p->defaultDepth; d.width = p->width; d.height = p->height; d.scanline = p->depthScanline; d.topDown = 0;
+	}
+	else
+	{
+		Texture* t = p->textures[p->depthTex];
+		d.ptr = t->layer[0]; d.width = t->width; d.height = t->height; d.scanline = t->scanline; d.topDown = 0;
+	}
+	return d;
+}
+
+extern "C" {
+
+const char* ps3d_backend_name(void) { return "cuda-sm100a"; }
+const char* ps3d_last_error(const ps3d_pipe* p) { return p ? p->err.c_str() : ""; }
+
+int ps3d_create(int width, int height, int device, ps3d_pipe** out)
+{
+	if(!out || width <= 0 || height <= 0) return PS3D_ERR_INVALID_ARGUMENT;
+	int ndev = 0;
+	if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return PS3D_ERR_DEVICE; // no GPU, no renderer
+	if(cudaSetDevice(device) != cudaSuccess) return PS3D_ERR_DEVICE;
+	ps3d_pipe* p = new ps3d_pipe();
+	p->device = device;
+	p->width = width; p->height = height; p->vpW = width; p->vpH = height;
+	p->behavior = PS3D_BEHAVIOR_UPDATE_DEPTH | PS3D_BEHAVIOR_TEST_DEPTH | PS3D_BEHAVIOR_FACE_CULLING; // pipeline.cpp:34
+	p->band0 = 0; p->band1 = 0x7fffffff;
+	p->back = 1; p->depthTex = -1; p->curProg = -1;
+	p->capDev = nullptr; p->capW = p->capH = 0;
+	p->launches = 0;
+	memset(&p->stats, 0, sizeof(p->stats));
+	memset(p->uniformSet, 0, sizeof(p->uniformSet));
+	p->depthScanline = ((int)(width / 4.0f + 0.5f) * 4) * (int)sizeof(float); // pipeline.cpp:31
+	if(p->depthScanline < width * 4) p->depthScanline = width * 4;           // the reference under-allocates when W%4==1
+	bool ok = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) == cudaSuccess;
+	const size_t cbytes = (size_t)width * 4 * height, dbytes = (size_t)p->depthScanline * height;
+	ok = ok && cudaMalloc((void**)&p->display[0], cbytes) == cudaSuccess && cudaMalloc((void**)&p->display[1], cbytes) == cudaSuccess;
+	ok = ok && cudaMalloc((void**)&p->defaultDepth, dbytes + 16) == cudaSuccess;
+	ok = ok && cudaMalloc((void**)&p->totalDev, 16) == cudaSuccess && cudaMallocHost((void**)&p->totalHost, 16) == cudaSuccess;
+	ok = ok && cudaMalloc((void**)&p->statsDev, sizeof(DeviceStats)) == cudaSuccess;
+	if(ok)
+	{
+		cudaMemsetAsync(p->display[0], 0, cbytes, p->stream);
+		cudaMemsetAsync(p->display[1], 0, cbytes, p->stream);
+		cudaMemsetAsync(p->defaultDepth, 0, dbytes, p->stream);
+		cudaMemsetAsync(p->statsDev, 0, sizeof(DeviceStats), p->stream);
+	}
+	p->rcpDev = p->rsqrtDev = nullptr;
+	p->approx.rcp = p->approx.rsqrt = nullptr; p->approx.rcpBits = p->approx.rsqrtBits = 0;
+	const Ps3dHostApprox& ha = hostApprox();
+	if(ok && ha.rcpBits && ha.rsqrtBits)
+	{
+		ok = cudaMalloc((void**)&p->rcpDev, ha.rcp.size() * 4) == cudaSuccess && cudaMalloc((void**)&p->rsqrtDev, ha.rsqrt.size() * 4) == cudaSuccess;
+		if(ok)
+		{
+			cudaMemcpyAsync(p->rcpDev, ha.rcp.data(), ha.rcp.size() * 4, cudaMemcpyHostToDevice, p->stream);
+			cudaMemcpyAsync(p->rsqrtDev, ha.rsqrt.data(), ha.rsqrt.size() * 4, cudaMemcpyHostToDevice, p->stream);
+			p->approx.rcp = p->rcpDev; p->approx.rsqrt = p->rsqrtDev; p->approx.rcpBits = ha.rcpBits; p->approx.rsqrtBits = ha.rsqrtBits;
+		}
+	}
+	if(!ok || cudaStreamSynchronize(p->stream) != cudaSuccess)
+	{
+		delete p;
+		return PS3D_ERR_DEVICE;
+	}
+	*out = p;
+	return PS3D_OK;
+}
+
+int ps3d_destroy(ps3d_pipe* p)
+{
+	if(!p) return PS3D_ERR_INVALID_ARGUMENT;
+	cudaSetDevice(p->device);
+	cudaStreamSynchronize(p->stream);
+	for(Texture* t : p->textures) if(t) { for(int i = 0; i < 6; i++) if(t->layer[i]) cudaFree(t->layer[i]); delete t; }
+	for(Vbo& v : p->vbos) if(v.alive && v.data) cudaFree(v.data);
+	cudaFree(p->display[0]); cudaFree(p->display[1]); cudaFree(p->defaultDepth);
+	cudaFree(p->totalDev); cudaFreeHost(p->totalHost); cudaFree(p->statsDev);
+	if(p->capDev) cudaFree(p->capDev);
+	if(p->rcpDev) cudaFree(p->rcpDev);
+	if(p->rsqrtDev) cudaFree(p->rsqrtDev);
+	p->hdr.release(); p->vary.release(); p->triCount.release(); p->triOffset.release(); p->triRect.release(); p->scanSums.release();
+	p->keysA.release(); p->valsA.release(); p->keysB.release(); p->valsB.release(); p->tileCount.release(); p->tileStart.release(); p->sortCounts.release();
+	cudaStreamDestroy(p->stream);
+	delete p;
+	return PS3D_OK;
+}
+
+// ---- textures (tex.cpp) ------------------------------------------------------------------------------------------
+
+int ps3d_texture_create(ps3d_pipe* p, unsigned width, unsigned scanline, unsigned height, unsigned elemLen,
+                        const void* pixels, int extraLayers, int wrapMode, int* idx)
+{
+	cudaSetDevice(p->device);
+	if(1 != elemLen && 4 != elemLen) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "PuresoftFBO: elemLen must be 1 or 4"); // fbo.cpp:21-24
+	if(extraLayers < 0 || extraLayers > 5) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftFBO: extraLayers");
+	if(!width || !height || scanline < width * elemLen) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "texture geometry");
+	size_t slot = 0;
+	for(; slot < p->textures.size(); slot++) if(!p->textures[slot]) break; // tex.cpp:6-16 first free slot
+	Texture* t = new Texture();
+	memset(t, 0, sizeof(*t));
+	t->width = (int)width; t->height = (int)height; t->scanline = (int)scanline; t->elemLen = (int)elemLen; t->wrap = wrapMode; t->nLayers = 1 + extraLayers;
+	const size_t bytes = (size_t)scanline * height;
+	for(int i = 0; i < t->nLayers; i++)
+	{
+		if(cudaMalloc((void**)&t->layer[i], bytes + 16) != cudaSuccess)
+		{
+			for(int j = 0; j < i; j++) cudaFree(t->layer[j]);
+			delete t;
+			return fail(p, PS3D_ERR_BAD_ALLOC, "texture");
+		}
+		cudaMemsetAsync(t->layer[i], 0, bytes, p->stream);
+	}
+	if(pixels) CK(p, cudaMemcpyAsync(t->layer[0], pixels, bytes, cudaMemcpyHostToDevice, p->stream)); // tex.cpp:20-23
+	CK(p, cudaStreamSynchronize(p->stream));
+	if(slot == p->textures.size()) p->textures.push_back(nullptr);
+	p->textures[slot] = t;
+	*idx = (int)slot;
+	return PS3D_OK;
+}
+
+static Texture* texLayer(ps3d_pipe* p, int idx, int layer)
+{
+	if(idx < 0 || idx >= (int)p->textures.size() || !p->textures[idx]) return nullptr;
+	if(layer < 0 || layer >= p->textures[idx]->nLayers) return nullptr;
+	return p->textures[idx];
+}
+int ps3d_texture_upload(ps3d_pipe* p, int idx, int layer, const void* pixels)
+{
+	cudaSetDevice(p->device);
+	Texture* t = texLayer(p, idx, layer);
+	if(!t) return fail(p, PS3D_ERR_OUT_OF_RANGE, "getTexture: index/layer out of range");
+	CK(p, cudaMemcpyAsync(t->layer[layer], pixels, (size_t)t->scanline * t->height, cudaMemcpyHostToDevice, p->stream));
+	CK(p, cudaStreamSynchronize(p->stream));
+	return PS3D_OK;
+}
+int ps3d_texture_download(ps3d_pipe* p, int idx, int layer, void* pixels)
+{
+	cudaSetDevice(p->device);
+	Texture* t = texLayer(p, idx, layer);
+	if(!t) return fail(p, PS3D_ERR_OUT_OF_RANGE, "getTexture: index/layer out of range");
+	CK(p, cudaMemcpyAsync(pixels, t->layer[layer], (size_t)t->scanline * t->height, cudaMemcpyDeviceToHost, p->stream));
+	CK(p, cudaStreamSynchronize(p->stream));
+	return PS3D_OK;
+}
+int ps3d_texture_destroy(ps3d_pipe* p, int idx)
+{
+	cudaSetDevice(p->device);
+	if(idx < 0 || idx >= (int)p->textures.size()) return fail(p, PS3D_ERR_OUT_OF_RANGE, "destroyTexture: index out of range"); // tex.cpp:48-51
+	if(p->textures[idx])
+	{
+		cudaStreamSynchronize(p->stream);
+		for(int i = 0; i < 6; i++) if(p->textures[idx]->layer[i]) cudaFree(p->textures[idx]->layer[i]);
+		delete p->textures[idx];
+		p->textures[idx] = nullptr;
+		if(p->depthTex == idx) p->depthTex = -1;
+	}
+	return PS3D_OK;
+}
+
+// ---- VBO / VAO (vbo.cpp, vao.cpp, pipeline.cpp:118-205) --------------------------------------------------------------
+
+int ps3d_vbo_create(ps3d_pipe* p, size_t unitBytes, size_t unitCount, int* vbo)
+{
+	cudaSetDevice(p->device);
+	size_t slot = 0;
+	for(; slot < p->vbos.size(); slot++) if(!p->vbos[slot].alive) break;
+	Vbo v;
+	v.unitBytes = unitBytes; v.unitCount = unitCount; v.alive = true; v.data = nullptr;
+	if(cudaMalloc((void**)&v.data, unitBytes * unitCount + 64) != cudaSuccess) return fail(p, PS3D_ERR_BAD_ALLOC, "vbo"); // vbo.cpp:14
+	cudaMemsetAsync(v.data, 0, unitBytes * unitCount + 64, p->stream);
+	if(slot == p->vbos.size()) p->vbos.push_back(v); else p->vbos[slot] = v;
+	*vbo = (int)slot;
+	return PS3D_OK;
+}
+static bool vboOk(ps3d_pipe* p, int v) { return v >= 0 && v < (int)p->vbos.size() && p->vbos[v].alive; }
+int ps3d_vbo_update(ps3d_pipe* p, int vbo, const void* src)
+{
+	cudaSetDevice(p->device);
+	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
+	// vbo.cpp:28-31 copies synchronously: the caller may free `src` on return
+	CK(p, cudaMemcpyAsync(p->vbos[vbo].data, src, p->vbos[vbo].unitBytes * p->vbos[vbo].unitCount, cudaMemcpyHostToDevice, p->stream));
+	CK(p, cudaStreamSynchronize(p->stream));
+	return PS3D_OK;
+}
+int ps3d_vbo_update_device(ps3d_pipe* p, int vbo, const void* devSrc)
+{
+	cudaSetDevice(p->device);
+	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
+	CK(p, cudaMemcpyAsync(p->vbos[vbo].data, devSrc, p->vbos[vbo].unitBytes * p->vbos[vbo].unitCount, cudaMemcpyDeviceToDevice, p->stream));
+	return PS3D_OK;
+}
+int ps3d_vbo_destroy(ps3d_pipe* p, int vbo)
+{
+	cudaSetDevice(p->device);
+	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
+	cudaStreamSynchronize(p->stream);
+	cudaFree(p->vbos[vbo].data);
+	p->vbos[vbo].data = nullptr; p->vbos[vbo].alive = false;
+	for(Vao& a : p->vaos) if(a.alive) for(int s = 0; s < PS3D_MAX_VBOS; s++) if(a.vbo[s] == vbo) a.vbo[s] = -1;
+	return PS3D_OK;
+}
+
+int ps3d_vao_create(ps3d_pipe* p, int* vao)
+{
+	size_t slot = 0;
+	for(; slot < p->vaos.size(); slot++) if(!p->vaos[slot].alive) break; // pipeline.cpp:120-134
+	Vao a;
+	a.alive = true;
+	for(int s = 0; s < PS3D_MAX_VBOS; s++) a.vbo[s] = -1;
+	if(slot == p->vaos.size()) p->vaos.push_back(a); else p->vaos[slot] = a;
+	*vao = (int)slot;
+	return PS3D_OK;
+}
+static int vaoCheck(ps3d_pipe* p, int vao, int slot) // pipeline.cpp:140-148
+{
+	if(vao < 0 || vao >= (int)p->vaos.size() || !p->vaos[vao].alive) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::attachVBO vao");
+	if(slot < 0 || slot >= PS3D_MAX_VBOS) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::attachVBO idx");
+	return PS3D_OK;
+}
+int ps3d_vao_attach(ps3d_pipe* p, int vao, int slot, int vbo, int* displaced)
+{
+	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
+	int rc = vaoCheck(p, vao, slot); if(rc) return rc;
+	if(displaced) *displaced = p->vaos[vao].vbo[slot];
+	p->vaos[vao].vbo[slot] = vbo;
+	return PS3D_OK;
+}
+int ps3d_vao_detach(ps3d_pipe* p, int vao, int slot, int* displaced)
+{
+	int rc = vaoCheck(p, vao, slot); if(rc) return rc;
+	if(displaced) *displaced = p->vaos[vao].vbo[slot];
+	p->vaos[vao].vbo[slot] = -1;
+	return PS3D_OK;
+}
+int ps3d_vao_get(ps3d_pipe* p, int vao, int slot, int* vbo)
+{
+	int rc = vaoCheck(p, vao, slot); if(rc) return rc;
+	*vbo = p->vaos[vao].vbo[slot];
+	return PS3D_OK;
+}
+int ps3d_vao_destroy(ps3d_pipe* p, int vao)
+{
+	cudaSetDevice(p->device);
+	if(vao < 0 || vao >= (int)p->vaos.size()) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::attachVBO vao"); // pipeline.cpp:185-188
+	if(!p->vaos[vao].alive) return PS3D_OK;
+	cudaStreamSynchronize(p->stream);
+	for(int s = 0; s < PS3D_MAX_VBOS; s++) // pipeline.cpp:194-201: the pipeline owns attached VBOs
+	{
+		const int v = p->vaos[vao].vbo[s];
+		if(v >= 0 && p->vbos[v].alive) { cudaFree(p->vbos[v].data); p->vbos[v].data = nullptr; p->vbos[v].alive = false; }
+	}
+	p->vaos[vao].alive = false;
+	return PS3D_OK;
+}
+
+// ---- processors / programmes (prog.cpp) --------------------------------------------------------------------------------
+
+int ps3d_processor_add(ps3d_pipe* p, int kind, int functor, int* idx)
+{
+	if(kind < 0 || kind > 2) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "processor kind");
+	if(!functorKnown(kind, functor)) return fail(p, PS3D_ERR_UNSUPPORTED, "no device functor with this id for this processor kind");
+	size_t slot = 0;
+	for(; slot < p->procs.size(); slot++) if(!p->procs[slot].alive) break; // prog.cpp:5-17
+	Proc pr; pr.alive = true; pr.kind = kind; pr.functor = functor;
+	if(slot == p->procs.size()) p->procs.push_back(pr); else p->procs[slot] = pr;
+	*idx = (int)slot;
+	return PS3D_OK;
+}
+int ps3d_processor_destroy(ps3d_pipe* p, int idx)
+{
+	if(idx < 0 || idx >= (int)p->procs.size()) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::destroyProcessor"); // prog.cpp:24-27
+	if(p->procs[idx].alive)
+	{
+		if(p->curProg >= 0 && (p->progs[p->curProg].vp == idx || p->progs[p->curProg].ip == idx || p->progs[p->curProg].fp == idx)) p->curProg = -1; // prog.cpp:32-37
+		p->procs[idx].alive = false;
+	}
+	return PS3D_OK;
+}
+static const ProgEntry* findEntry(ps3d_pipe* p, const Prog& pg)
+{
+	for(const ProgEntry& e : programmeTable())
+		if(e.fnV == p->procs[pg.vp].functor && e.fnI == p->procs[pg.ip].functor && e.fnF == p->procs[pg.fp].functor) return &e;
+	return nullptr;
+}
+int ps3d_programme_create(ps3d_pipe* p, int vid, int iid, int fid, int* idx)
+{
+	const int n = (int)p->procs.size();
+	if(vid < 0 || vid >= n) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::createProgramme, vid"); // prog.cpp:45-58
+	if(iid < 0 || iid >= n) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::createProgramme, iid");
+	if(fid < 0 || fid >= n) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::createProgramme, fid");
+	if(!p->procs[vid].alive || !p->procs[iid].alive || !p->procs[fid].alive || p->procs[vid].kind != PS3D_PROC_VERTEX ||
+	   p->procs[iid].kind != PS3D_PROC_INTERPOLATION || p->procs[fid].kind != PS3D_PROC_FRAGMENT)
+		return fail(p, PS3D_ERR_INVALID_ARGUMENT, "createProgramme: processor kind mismatch");
+	Prog pg; pg.vp = vid; pg.ip = iid; pg.fp = fid;
+	if(!findEntry(p, pg)) return fail(p, PS3D_ERR_UNSUPPORTED, "no kernel instantiation for this vertex/interpolation/fragment functor triple");
+	size_t slot = 0;
+	for(; slot < p->progs.size(); slot++) if(-1 == p->progs[slot].vp) break; // prog.cpp:60-71
+	if(slot == p->progs.size()) p->progs.push_back(pg); else p->progs[slot] = pg;
+	*idx = (int)slot;
+	return PS3D_OK;
+}
+int ps3d_programme_destroy(ps3d_pipe* p, int idx)
+{
+	if(idx < 0 || idx >= (int)p->progs.size()) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::destroyProgramme"); // prog.cpp:112-115
+	p->progs[idx].vp = p->progs[idx].ip = p->progs[idx].fp = -1;
+	if(p->curProg == idx) p->curProg = -1;
+	return PS3D_OK;
+}
+int ps3d_programme_use(ps3d_pipe* p, int idx)
+{
+	if(idx < 0 || idx >= (int)p->progs.size() || -1 == p->progs[idx].vp) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::useProgramme"); // prog.cpp:123-126
+	p->curProg = idx;
+	return PS3D_OK;
+}
+
+// ---- state (pipeline.cpp:207-342) ------------------------------------------------------------------------------------
+
+int ps3d_set_viewport(ps3d_pipe* p, int width, int height)
+{
+	if(width <= 0 || height <= 0 || width > 32767 || height > 32767) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "viewport");
+	p->vpW = width; p->vpH = height;
+	return PS3D_OK;
+}
+int ps3d_set_depth(ps3d_pipe* p, int textureIdx) // pipeline.cpp:218-239
+{
+	if(-1 == textureIdx) { p->depthTex = -1; return PS3D_OK; }
+	if(textureIdx < 0 || textureIdx >= (int)p->textures.size() || !p->textures[textureIdx]) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::setDepth");
+	if(4 != p->textures[textureIdx]->elemLen || 0 != p->textures[textureIdx]->scanline % 4) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "PuresoftPipeline::setDepth");
+	p->depthTex = textureIdx;
+	return PS3D_OK;
+}
+int ps3d_set_uniform(ps3d_pipe* p, int idx, const void* data, size_t len) // pipeline.cpp:277-312
+{
+	if(idx < 0 || idx >= PS3D_MAX_UNIFORMS) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::setUniform");
+	if(!data) { p->uniforms[idx].clear(); p->uniformSet[idx] = false; return PS3D_OK; }
+	if(p->uniforms[idx].size() < len) p->uniforms[idx].resize(len, 0);
+	memcpy(p->uniforms[idx].data(), data, len);
+	p->uniformSet[idx] = true;
+	return PS3D_OK;
+}
+int ps3d_enable(ps3d_pipe* p, int bits) { p->behavior |= bits; return PS3D_OK; }
+int ps3d_disable(ps3d_pipe* p, int bits) { p->behavior &= ~bits; return PS3D_OK; }
+
+int ps3d_clear_depth(ps3d_pipe* p, float furthest) // pipeline.cpp:334-338 -> clear16 (fbo.cpp:348-371)
+{
+	cudaSetDevice(p->device);
+	TargetDesc d = depthTarget(p);
+	const size_t quads = ((size_t)d.scanline * d.height) >> 4;
+	const int blocks = (int)((quads + 255) / 256 < 148 * 16 ? (quads + 255) / 256 : 148 * 16);
+	clear_depth_kernel<<<blocks ? blocks : 1, 256, 0, p->stream>>>((float4*)d.ptr, quads, furthest);
+	p->launches++;
+	CK(p, cudaGetLastError());
+	return PS3D_OK;
+}
+int ps3d_clear_colour(ps3d_pipe* p, uint32_t bgra) // pipeline.cpp:340-343 -> clear4 skips the last buffer row (fbo.cpp:332-346)
+{
+	cudaSetDevice(p->device);
+	if(p->height < 2) return PS3D_OK;
+	clear_colour_kernel<<<148 * 8, 256, 0, p->stream>>>(p->display[p->back], p->width, p->height - 1, p->width * 4, bgra);
+	p->launches++;
+	CK(p, cudaGetLastError());
+	return PS3D_OK;
+}
+
+// ---- the draw (drawvao.cpp:3-133) ------------------------------------------------------------------------------------
+
+int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
+{
+	(void)callerThread;
+	cudaSetDevice(p->device);
+	if(p->curProg < 0 || vao < 0 || vao >= (int)p->vaos.size() || !p->vaos[vao].alive) return PS3D_OK; // drawvao.cpp:12-15
+	const Prog pg = p->progs[p->curProg];
+	if(pg.vp < 0) return PS3D_OK;
+	const ProgEntry* pe = findEntry(p, pg);
+	if(!pe) return fail(p, PS3D_ERR_UNSUPPORTED, "no kernel instantiation for this programme");
+
+	DrawParams P;
+	memset(&P, 0, sizeof(P));
+	// vertex streams: all attached slots advance in lock-step; the draw ends when any runs out (vertthrd.cpp:21-31)
+	const Vao& va = p->vaos[vao];
+	size_t nverts = (size_t)-1;
+	bool any = false;
+	for(int s = 0; s < PS3D_MAX_VBOS; s++)
+		if(va.vbo[s] >= 0)
+		{
+			const Vbo& v = p->vbos[va.vbo[s]];
+			any = true;
+			if(v.unitCount < nverts) nverts = v.unitCount;
+			P.slot[s] = v.data;
+			P.stride[s] = (uint32_t)v.unitBytes;
+		}
+	if(!any) return PS3D_OK;
+	for(int s = 0; s < PS3D_MAX_VBOS; s++)
+		if(((pe->slots >> s) & 1) && !P.slot[s]) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "vertex functor reads a VBO slot that is not attached");
+	const size_t ntris = nverts / 3;
+	if(ntris > 0x7fffffffu / 3) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "too many triangles in one draw");
+	// uniforms are latched now (the reference latches pointers in preprocess(), drawvao.cpp:18-20)
+	for(int u = 0; u < PS_UNIFORM_SLOTS; u++)
+	{
+		if(((pe->uniforms >> u) & 1) && !p->uniformSet[u]) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "a uniform slot the programme reads is unset");
+		if(p->uniformSet[u]) memcpy(P.u[u], p->uniforms[u].data(), p->uniforms[u].size() < 64 ? p->uniforms[u].size() : 64);
+	}
+	for(int k = 0; k < pe->ntex; k++)
+	{
+		const int us = pe->texSlot[k];
+		int id = -1;
+		if(p->uniforms[us].size() >= 4) memcpy(&id, p->uniforms[us].data(), 4);
+		if(id < 0 || id >= (int)p->textures.size() || !p->textures[id]) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "a texture uniform does not name a live texture");
+		const Texture* t = p->textures[id];
+		if(4 != t->elemLen) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "sampler needs a 4-byte texture");
+		for(int l = 0; l < 6; l++) P.tex[k].layer[l] = t->layer[l];
+		P.tex[k].width = t->width; P.tex[k].height = t->height; P.tex[k].scanline = t->scanline; P.tex[k].wrap = t->wrap;
+		P.tex[k].nLayers = t->nLayers; P.tex[k].elemLen = t->elemLen;
+	}
+	p->stats.draws++;
+	p->stats.triangles_submitted += ntris;
+	if(0 == ntris) return PS3D_OK;
+
+	P.ntris = (uint32_t)ntris;
+	P.vpW = p->vpW; P.vpH = p->vpH; P.halfW = p->vpW / 2; P.halfH = p->vpH / 2; // rasterizer.cpp:28-31
+	P.behavior = p->behavior;
+	P.band0 = p->band0 < 0 ? 0 : p->band0;
+	P.band1 = p->band1 > p->vpH ? p->vpH : p->band1;
+	P.tilesX = (p->vpW + PS_TILE - 1) / PS_TILE;
+	P.tilesY = (p->vpH + PS_TILE - 1) / PS_TILE;
+	P.colour.ptr = p->display[p->back]; P.colour.width = p->width; P.colour.height = p->height; P.colour.scanline = p->width * 4; P.colour.topDown = 1;
+	P.depth = depthTarget(p);
+	P.approx = p->approx;
+	P.stats = p->statsDev;
+	P.cap = p->capDev; P.capW = p->capW; P.capH = p->capH;
+
+	CK(p, p->hdr.ensure(ntris));
+	CK(p, p->vary.ensure(ntris * 3 * (size_t)(pe->nv > 0 ? pe->nv : 1)));
+	CK(p, p->triCount.ensure(ntris));
+	CK(p, p->triOffset.ensure(ntris));
+	CK(p, p->triRect.ensure(ntris * 2));
+	P.hdr = p->hdr.p; P.vary = p->vary.p; P.triCount = p->triCount.p; P.triRect = p->triRect.p;
+
+	pe->geom(P, p->stream);
+	p->launches++;
+	CK(p, cudaGetLastError());
+	int rc = exclusiveScan(p, p->triCount.p, p->triOffset.p, P.ntris, p->totalDev);
+	if(rc) return rc;
+	// the number of (tile, triangle) pairs sizes the bins: one 4-byte read-back per draw
+	CK(p, cudaMemcpyAsync(p->totalHost, p->totalDev, 4, cudaMemcpyDeviceToHost, p->stream));
+	CK(p, cudaStreamSynchronize(p->stream));
+	const uint32_t total = *p->totalHost;
+	if(0 == total) return PS3D_OK;
+
+	const uint32_t ntiles = (uint32_t)(P.tilesX * P.tilesY);
+	CK(p, p->keysA.ensure(total)); CK(p, p->valsA.ensure(total)); CK(p, p->keysB.ensure(total)); CK(p, p->valsB.ensure(total));
+	CK(p, p->tileCount.ensure(ntiles + 1)); CK(p, p->tileStart.ensure(ntiles + 1));
+	CK(p, cudaMemsetAsync(p->tileCount.p, 0, (size_t)(ntiles + 1) * 4, p->stream));
+	emit_pairs_kernel<<<(P.ntris + 127) / 128, 128, 0, p->stream>>>(p->triCount.p, p->triOffset.p, p->triRect.p, p->keysA.p, p->valsA.p, p->tileCount.p, P.ntris, P.tilesX);
+	p->launches++;
+	CK(p, cudaGetLastError());
+
+	// stable LSD radix sort of the pairs by tile id, 8 bits per pass
+	int bits = 0;
+	while((1u << bits) < ntiles) bits++;
+	uint32_t *kIn = p->keysA.p, *vIn = p->valsA.p, *kOut = p->keysB.p, *vOut = p->valsB.p;
+	const uint32_t nwarps = (total + PS_SORT_ITEMS_PER_WARP - 1) / PS_SORT_ITEMS_PER_WARP;
+	CK(p, p->sortCounts.ensure((size_t)256 * nwarps));
+	for(int shift = 0; shift < bits; shift += 8)
+	{
+		const unsigned blocks = (nwarps + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK;
+		sort_hist_kernel<<<blocks, 128, 0, p->stream>>>(kIn, total, shift, p->sortCounts.p, nwarps);
+		p->launches++;
+		rc = exclusiveScan(p, p->sortCounts.p, p->sortCounts.p, 256 * nwarps, p->totalDev);
+		if(rc) return rc;
+		sort_scatter_kernel<<<blocks, 128, 0, p->stream>>>(kIn, vIn, kOut, vOut, total, shift, p->sortCounts.p, nwarps);
+		p->launches++;
+		CK(p, cudaGetLastError());
+		uint32_t* t;
+		t = kIn; kIn = kOut; kOut = t;
+		t = vIn; vIn = vOut; vOut = t;
+	}
+	rc = exclusiveScan(p, p->tileCount.p, p->tileStart.p, ntiles + 1, p->totalDev);
+	if(rc) return rc;
+
+	pe->tile(P, p->tileStart.p, vIn, p->stream);
+	p->launches++;
+	CK(p, cudaGetLastError());
+	return PS3D_OK;
+}
+
+int ps3d_finish(ps3d_pipe* p)
+{
+	cudaSetDevice(p->device);
+	CK(p, cudaStreamSynchronize(p->stream));
+	return PS3D_OK;
+}
+int ps3d_swap_buffers(ps3d_pipe* p) { p->back ^= 1; return PS3D_OK; } // pipeline.cpp:314-322
+
+int ps3d_read_colour(ps3d_pipe* p, void* bgra, size_t pitch)
+{
+	cudaSetDevice(p->device);
+	if(pitch < (size_t)p->width * 4) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "pitch");
+	CK(p, cudaMemcpy2DAsync(bgra, pitch, p->display[p->back], (size_t)p->width * 4, (size_t)p->width * 4, p->height, cudaMemcpyDeviceToHost, p->stream));
+	CK(p, cudaStreamSynchronize(p->stream));
+	return PS3D_OK;
+}
+int ps3d_read_depth(ps3d_pipe* p, float* depth, size_t pitch)
+{
+	cudaSetDevice(p->device);
+	if(pitch < (size_t)p->width * 4) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "pitch");
+	CK(p, cudaMemcpy2DAsync(depth, pitch, p->defaultDepth, p->depthScanline, (size_t)p->width * 4, p->height, cudaMemcpyDeviceToHost, p->stream));
+	CK(p, cudaStreamSynchronize(p->stream));
+	return PS3D_OK;
+}
+int ps3d_write_colour(ps3d_pipe* p, const void* bgra, size_t pitch)
+{
+	cudaSetDevice(p->device);
+	if(pitch < (size_t)p->width * 4) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "pitch");
+	CK(p, cudaMemcpy2DAsync(p->display[p->back], (size_t)p->width * 4, bgra, pitch, (size_t)p->width * 4, p->height, cudaMemcpyHostToDevice, p->stream));
+	CK(p, cudaStreamSynchronize(p->stream));
+	return PS3D_OK;
+}
+int ps3d_write_depth(ps3d_pipe* p, const float* depth, size_t pitch)
+{
+	cudaSetDevice(p->device);
+	if(pitch < (size_t)p->width * 4) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "pitch");
+	CK(p, cudaMemcpy2DAsync(p->defaultDepth, p->depthScanline, depth, pitch, (size_t)p->width * 4, p->height, cudaMemcpyHostToDevice, p->stream));
+	CK(p, cudaStreamSynchronize(p->stream));
+	return PS3D_OK;
+}
+
+int ps3d_get_stats(ps3d_pipe* p, ps3d_stats* out)
+{
+	cudaSetDevice(p->device);
+	DeviceStats d;
+	CK(p, cudaMemcpyAsync(&d, p->statsDev, sizeof(d), cudaMemcpyDeviceToHost, p->stream));
+	CK(p, cudaStreamSynchronize(p->stream));
+	*out = p->stats;
+	out->triangles_rasterised = d.triangles_rasterised;
+	out->spans = d.spans;
+	out->fragments_tested = d.fragments_tested;
+	out->fragments_shaded = d.fragments_shaded;
+	return PS3D_OK;
+}
+int ps3d_reset_stats(ps3d_pipe* p)
+{
+	cudaSetDevice(p->device);
+	memset(&p->stats, 0, sizeof(p->stats));
+	CK(p, cudaMemsetAsync(p->statsDev, 0, sizeof(DeviceStats), p->stream));
+	return PS3D_OK;
+}
+
+int ps3d_debug_capture(ps3d_pipe* p, int width, int height)
+{
+	cudaSetDevice(p->device);
+	if(width < 0 || height < 0) return PS3D_ERR_INVALID_ARGUMENT;
+	CK(p, cudaStreamSynchronize(p->stream));
+	if(p->capDev) cudaFree(p->capDev);
+	p->capDev = nullptr; p->capW = p->capH = 0;
+	if(width > 0 && height > 0)
+	{
+		CK(p, cudaMalloc((void**)&p->capDev, (size_t)width * height * 4));
+		CK(p, cudaMemsetAsync(p->capDev, 0, (size_t)width * height * 4, p->stream));
+		p->capW = width; p->capH = height;
+	}
+	return PS3D_OK;
+}
+int ps3d_debug_read_shade_counts(ps3d_pipe* p, uint32_t* counts)
+{
+	cudaSetDevice(p->device);
+	if(!p->capDev) return PS3D_ERR_INVALID_ARGUMENT;
+	CK(p, cudaMemcpyAsync(counts, p->capDev, (size_t)p->capW * p->capH * 4, cudaMemcpyDeviceToHost, p->stream));
+	CK(p, cudaStreamSynchronize(p->stream));
+	return PS3D_OK;
+}
+int ps3d_debug_clear_shade_counts(ps3d_pipe* p)
+{
+	cudaSetDevice(p->device);
+	if(p->capDev) CK(p, cudaMemsetAsync(p->capDev, 0, (size_t)p->capW * p->capH * 4, p->stream));
+	return PS3D_OK;
+}
+
+int ps3d_set_row_band(ps3d_pipe* p, int row0, int row1)
+{
+	if(row0 == -1 && row1 == -1) { p->band0 = 0; p->band1 = 0x7fffffff; return PS3D_OK; }
+	if(row0 < 0 || row1 < row0) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "row band");
+	p->band0 = row0; p->band1 = row1;
+	return PS3D_OK;
+}
+
+int ps3d_device_colour_ptr(ps3d_pipe* p, void** devPtr, size_t* pitch) { *devPtr = p->display[p->back]; *pitch = (size_t)p->width * 4; return PS3D_OK; }
+int ps3d_device_depth_ptr(ps3d_pipe* p, void** devPtr, size_t* pitch) { *devPtr = p->defaultDepth; *pitch = (size_t)p->depthScanline; return PS3D_OK; }
+int ps3d_device_stream(ps3d_pipe* p, void** s) { *s = (void*)p->stream; return PS3D_OK; }
+int ps3d_device_launch_count(ps3d_pipe* p, uint64_t* n) { *n = p->launches; return PS3D_OK; }
+
+} // extern "C"

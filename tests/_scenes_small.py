@@ -1,0 +1,17 @@
+"""The seeded scene set shared by the oracle pin, the golden fixtures and the GPU parity tests (sizes the CPU
+checkers finish in well under a second each)."""
+from puresoft3d_b200 import _capi as K
+from puresoft3d_b200 import scenes
+
+SMALL = {
+    "c1_cube_def01": lambda: scenes.scene_cube(320, 240),
+    "c1_cube_def03": lambda: scenes.scene_cube(320, 240, functor=K.FN_DEF03),
+    "c1_cube_640": lambda: scenes.scene_cube(640, 480),
+    "soup_def02": lambda: scenes.scene_soup(320, 240, seed=7),
+    "soup_nocull": lambda: scenes.scene_soup(200, 150, seed=9, cull=False),
+    # odd, non-tile-aligned size; not W%4==1, where pipeline.cpp:31 under-allocates the depth rows
+    "soup_odd_size": lambda: scenes.scene_soup(238, 131, seed=11, count=300),
+    "c2_heightfield_small": lambda: scenes.scene_heightfield(480, 270, grid=40, layers=2, tex_size=256),
+    "c2_heightfield_tiny_tris": lambda: scenes.scene_heightfield(256, 144, grid=96, layers=3, tex_size=128),
+    "c4_blend_overdraw": lambda: scenes.scene_blend_overdraw(480, 270, randoms=200),
+}
