@@ -151,6 +151,10 @@ struct ps3d_pipe
 
 static int fail(ps3d_pipe* p, int code, const char* msg) { p->err = msg; return code; }
 
+// PS3D_TRACE=1 prints every C-ABI entry to stderr (debug aid)
+static bool traceOn() { static int on = -1; if(on < 0) { const char* e = getenv("PS3D_TRACE"); on = (e && e[0] == '1') ? 1 : 0; } return on == 1; }
+#define TRACE() do { if(traceOn()) { fprintf(stderr, "[ps3d] %s\n", __func__); fflush(stderr); } } while(0)
+
 static const Ps3dHostApprox& hostApprox()
 {
 	static Ps3dHostApprox a;
@@ -193,6 +197,7 @@ const char* ps3d_last_error(const ps3d_pipe* p) { return p ? p->err.c_str() : ""
 
 int ps3d_create(int width, int height, int device, ps3d_pipe** out)
 {
+	TRACE();
 	if(!out || width <= 0 || height <= 0) return PS3D_ERR_INVALID_ARGUMENT;
 	int ndev = 0;
 	if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return PS3D_ERR_DEVICE; // no GPU, no renderer
@@ -246,6 +251,7 @@ int ps3d_create(int width, int height, int device, ps3d_pipe** out)
 
 int ps3d_destroy(ps3d_pipe* p)
 {
+	TRACE();
 	if(!p) return PS3D_ERR_INVALID_ARGUMENT;
 	cudaSetDevice(p->device);
 	cudaStreamSynchronize(p->stream);
@@ -268,6 +274,7 @@ int ps3d_destroy(ps3d_pipe* p)
 int ps3d_texture_create(ps3d_pipe* p, unsigned width, unsigned scanline, unsigned height, unsigned elemLen,
                         const void* pixels, int extraLayers, int wrapMode, int* idx)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	if(1 != elemLen && 4 != elemLen) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "PuresoftFBO: elemLen must be 1 or 4"); // fbo.cpp:21-24
 	if(extraLayers < 0 || extraLayers > 5) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftFBO: extraLayers");
@@ -304,6 +311,7 @@ static Texture* texLayer(ps3d_pipe* p, int idx, int layer)
 }
 int ps3d_texture_upload(ps3d_pipe* p, int idx, int layer, const void* pixels)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	Texture* t = texLayer(p, idx, layer);
 	if(!t) return fail(p, PS3D_ERR_OUT_OF_RANGE, "getTexture: index/layer out of range");
@@ -313,6 +321,7 @@ int ps3d_texture_upload(ps3d_pipe* p, int idx, int layer, const void* pixels)
 }
 int ps3d_texture_download(ps3d_pipe* p, int idx, int layer, void* pixels)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	Texture* t = texLayer(p, idx, layer);
 	if(!t) return fail(p, PS3D_ERR_OUT_OF_RANGE, "getTexture: index/layer out of range");
@@ -322,6 +331,7 @@ int ps3d_texture_download(ps3d_pipe* p, int idx, int layer, void* pixels)
 }
 int ps3d_texture_destroy(ps3d_pipe* p, int idx)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	if(idx < 0 || idx >= (int)p->textures.size()) return fail(p, PS3D_ERR_OUT_OF_RANGE, "destroyTexture: index out of range"); // tex.cpp:48-51
 	if(p->textures[idx])
@@ -339,6 +349,7 @@ int ps3d_texture_destroy(ps3d_pipe* p, int idx)
 
 int ps3d_vbo_create(ps3d_pipe* p, size_t unitBytes, size_t unitCount, int* vbo)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	size_t slot = 0;
 	for(; slot < p->vbos.size(); slot++) if(!p->vbos[slot].alive) break;
@@ -353,6 +364,7 @@ int ps3d_vbo_create(ps3d_pipe* p, size_t unitBytes, size_t unitCount, int* vbo)
 static bool vboOk(ps3d_pipe* p, int v) { return v >= 0 && v < (int)p->vbos.size() && p->vbos[v].alive; }
 int ps3d_vbo_update(ps3d_pipe* p, int vbo, const void* src)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
 	// vbo.cpp:28-31 copies synchronously: the caller may free `src` on return
@@ -362,6 +374,7 @@ int ps3d_vbo_update(ps3d_pipe* p, int vbo, const void* src)
 }
 int ps3d_vbo_update_device(ps3d_pipe* p, int vbo, const void* devSrc)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
 	CK(p, cudaMemcpyAsync(p->vbos[vbo].data, devSrc, p->vbos[vbo].unitBytes * p->vbos[vbo].unitCount, cudaMemcpyDeviceToDevice, p->stream));
@@ -369,6 +382,7 @@ int ps3d_vbo_update_device(ps3d_pipe* p, int vbo, const void* devSrc)
 }
 int ps3d_vbo_destroy(ps3d_pipe* p, int vbo)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
 	cudaStreamSynchronize(p->stream);
@@ -380,6 +394,7 @@ int ps3d_vbo_destroy(ps3d_pipe* p, int vbo)
 
 int ps3d_vao_create(ps3d_pipe* p, int* vao)
 {
+	TRACE();
 	size_t slot = 0;
 	for(; slot < p->vaos.size(); slot++) if(!p->vaos[slot].alive) break; // pipeline.cpp:120-134
 	Vao a;
@@ -397,6 +412,7 @@ static int vaoCheck(ps3d_pipe* p, int vao, int slot) // pipeline.cpp:140-148
 }
 int ps3d_vao_attach(ps3d_pipe* p, int vao, int slot, int vbo, int* displaced)
 {
+	TRACE();
 	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
 	int rc = vaoCheck(p, vao, slot); if(rc) return rc;
 	if(displaced) *displaced = p->vaos[vao].vbo[slot];
@@ -405,6 +421,7 @@ int ps3d_vao_attach(ps3d_pipe* p, int vao, int slot, int vbo, int* displaced)
 }
 int ps3d_vao_detach(ps3d_pipe* p, int vao, int slot, int* displaced)
 {
+	TRACE();
 	int rc = vaoCheck(p, vao, slot); if(rc) return rc;
 	if(displaced) *displaced = p->vaos[vao].vbo[slot];
 	p->vaos[vao].vbo[slot] = -1;
@@ -412,12 +429,14 @@ int ps3d_vao_detach(ps3d_pipe* p, int vao, int slot, int* displaced)
 }
 int ps3d_vao_get(ps3d_pipe* p, int vao, int slot, int* vbo)
 {
+	TRACE();
 	int rc = vaoCheck(p, vao, slot); if(rc) return rc;
 	*vbo = p->vaos[vao].vbo[slot];
 	return PS3D_OK;
 }
 int ps3d_vao_destroy(ps3d_pipe* p, int vao)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	if(vao < 0 || vao >= (int)p->vaos.size()) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::attachVBO vao"); // pipeline.cpp:185-188
 	if(!p->vaos[vao].alive) return PS3D_OK;
@@ -435,6 +454,7 @@ int ps3d_vao_destroy(ps3d_pipe* p, int vao)
 
 int ps3d_processor_add(ps3d_pipe* p, int kind, int functor, int* idx)
 {
+	TRACE();
 	if(kind < 0 || kind > 2) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "processor kind");
 	if(!functorKnown(kind, functor)) return fail(p, PS3D_ERR_UNSUPPORTED, "no device functor with this id for this processor kind");
 	size_t slot = 0;
@@ -446,6 +466,7 @@ int ps3d_processor_add(ps3d_pipe* p, int kind, int functor, int* idx)
 }
 int ps3d_processor_destroy(ps3d_pipe* p, int idx)
 {
+	TRACE();
 	if(idx < 0 || idx >= (int)p->procs.size()) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::destroyProcessor"); // prog.cpp:24-27
 	if(p->procs[idx].alive)
 	{
@@ -462,6 +483,7 @@ static const ProgEntry* findEntry(ps3d_pipe* p, const Prog& pg)
 }
 int ps3d_programme_create(ps3d_pipe* p, int vid, int iid, int fid, int* idx)
 {
+	TRACE();
 	const int n = (int)p->procs.size();
 	if(vid < 0 || vid >= n) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::createProgramme, vid"); // prog.cpp:45-58
 	if(iid < 0 || iid >= n) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::createProgramme, iid");
@@ -479,6 +501,7 @@ int ps3d_programme_create(ps3d_pipe* p, int vid, int iid, int fid, int* idx)
 }
 int ps3d_programme_destroy(ps3d_pipe* p, int idx)
 {
+	TRACE();
 	if(idx < 0 || idx >= (int)p->progs.size()) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::destroyProgramme"); // prog.cpp:112-115
 	p->progs[idx].vp = p->progs[idx].ip = p->progs[idx].fp = -1;
 	if(p->curProg == idx) p->curProg = -1;
@@ -486,6 +509,7 @@ int ps3d_programme_destroy(ps3d_pipe* p, int idx)
 }
 int ps3d_programme_use(ps3d_pipe* p, int idx)
 {
+	TRACE();
 	if(idx < 0 || idx >= (int)p->progs.size() || -1 == p->progs[idx].vp) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::useProgramme"); // prog.cpp:123-126
 	p->curProg = idx;
 	return PS3D_OK;
@@ -495,12 +519,14 @@ int ps3d_programme_use(ps3d_pipe* p, int idx)
 
 int ps3d_set_viewport(ps3d_pipe* p, int width, int height)
 {
+	TRACE();
 	if(width <= 0 || height <= 0 || width > 32767 || height > 32767) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "viewport");
 	p->vpW = width; p->vpH = height;
 	return PS3D_OK;
 }
 int ps3d_set_depth(ps3d_pipe* p, int textureIdx) // pipeline.cpp:218-239
 {
+	TRACE();
 	if(-1 == textureIdx) { p->depthTex = -1; return PS3D_OK; }
 	if(textureIdx < 0 || textureIdx >= (int)p->textures.size() || !p->textures[textureIdx]) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::setDepth");
 	if(4 != p->textures[textureIdx]->elemLen || 0 != p->textures[textureIdx]->scanline % 4) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "PuresoftPipeline::setDepth");
@@ -509,6 +535,7 @@ int ps3d_set_depth(ps3d_pipe* p, int textureIdx) // pipeline.cpp:218-239
 }
 int ps3d_set_uniform(ps3d_pipe* p, int idx, const void* data, size_t len) // pipeline.cpp:277-312
 {
+	TRACE();
 	if(idx < 0 || idx >= PS3D_MAX_UNIFORMS) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::setUniform");
 	if(!data) { p->uniforms[idx].clear(); p->uniformSet[idx] = false; return PS3D_OK; }
 	if(p->uniforms[idx].size() < len) p->uniforms[idx].resize(len, 0);
@@ -521,6 +548,7 @@ int ps3d_disable(ps3d_pipe* p, int bits) { p->behavior &= ~bits; return PS3D_OK;
 
 int ps3d_clear_depth(ps3d_pipe* p, float furthest) // pipeline.cpp:334-338 -> clear16 (fbo.cpp:348-371)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	TargetDesc d = depthTarget(p);
 	const size_t quads = ((size_t)d.scanline * d.height) >> 4;
@@ -532,6 +560,7 @@ int ps3d_clear_depth(ps3d_pipe* p, float furthest) // pipeline.cpp:334-338 -> cl
 }
 int ps3d_clear_colour(ps3d_pipe* p, uint32_t bgra) // pipeline.cpp:340-343 -> clear4 skips the last buffer row (fbo.cpp:332-346)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	if(p->height < 2) return PS3D_OK;
 	clear_colour_kernel<<<148 * 8, 256, 0, p->stream>>>(p->display[p->back], p->width, p->height - 1, p->width * 4, bgra);
@@ -544,6 +573,7 @@ int ps3d_clear_colour(ps3d_pipe* p, uint32_t bgra) // pipeline.cpp:340-343 -> cl
 
 int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 {
+	TRACE();
 	(void)callerThread;
 	cudaSetDevice(p->device);
 	if(p->curProg < 0 || vao < 0 || vao >= (int)p->vaos.size() || !p->vaos[vao].alive) return PS3D_OK; // drawvao.cpp:12-15
@@ -664,6 +694,7 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 
 int ps3d_finish(ps3d_pipe* p)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	CK(p, cudaStreamSynchronize(p->stream));
 	return PS3D_OK;
@@ -672,6 +703,7 @@ int ps3d_swap_buffers(ps3d_pipe* p) { p->back ^= 1; return PS3D_OK; } // pipelin
 
 int ps3d_read_colour(ps3d_pipe* p, void* bgra, size_t pitch)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	if(pitch < (size_t)p->width * 4) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "pitch");
 	CK(p, cudaMemcpy2DAsync(bgra, pitch, p->display[p->back], (size_t)p->width * 4, (size_t)p->width * 4, p->height, cudaMemcpyDeviceToHost, p->stream));
@@ -680,6 +712,7 @@ int ps3d_read_colour(ps3d_pipe* p, void* bgra, size_t pitch)
 }
 int ps3d_read_depth(ps3d_pipe* p, float* depth, size_t pitch)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	if(pitch < (size_t)p->width * 4) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "pitch");
 	CK(p, cudaMemcpy2DAsync(depth, pitch, p->defaultDepth, p->depthScanline, (size_t)p->width * 4, p->height, cudaMemcpyDeviceToHost, p->stream));
@@ -688,6 +721,7 @@ int ps3d_read_depth(ps3d_pipe* p, float* depth, size_t pitch)
 }
 int ps3d_write_colour(ps3d_pipe* p, const void* bgra, size_t pitch)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	if(pitch < (size_t)p->width * 4) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "pitch");
 	CK(p, cudaMemcpy2DAsync(p->display[p->back], (size_t)p->width * 4, bgra, pitch, (size_t)p->width * 4, p->height, cudaMemcpyHostToDevice, p->stream));
@@ -696,6 +730,7 @@ int ps3d_write_colour(ps3d_pipe* p, const void* bgra, size_t pitch)
 }
 int ps3d_write_depth(ps3d_pipe* p, const float* depth, size_t pitch)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	if(pitch < (size_t)p->width * 4) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "pitch");
 	CK(p, cudaMemcpy2DAsync(p->defaultDepth, p->depthScanline, depth, pitch, (size_t)p->width * 4, p->height, cudaMemcpyHostToDevice, p->stream));
@@ -705,6 +740,7 @@ int ps3d_write_depth(ps3d_pipe* p, const float* depth, size_t pitch)
 
 int ps3d_get_stats(ps3d_pipe* p, ps3d_stats* out)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	DeviceStats d;
 	CK(p, cudaMemcpyAsync(&d, p->statsDev, sizeof(d), cudaMemcpyDeviceToHost, p->stream));
@@ -718,6 +754,7 @@ int ps3d_get_stats(ps3d_pipe* p, ps3d_stats* out)
 }
 int ps3d_reset_stats(ps3d_pipe* p)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	memset(&p->stats, 0, sizeof(p->stats));
 	CK(p, cudaMemsetAsync(p->statsDev, 0, sizeof(DeviceStats), p->stream));
@@ -726,6 +763,7 @@ int ps3d_reset_stats(ps3d_pipe* p)
 
 int ps3d_debug_capture(ps3d_pipe* p, int width, int height)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	if(width < 0 || height < 0) return PS3D_ERR_INVALID_ARGUMENT;
 	CK(p, cudaStreamSynchronize(p->stream));
@@ -741,6 +779,7 @@ int ps3d_debug_capture(ps3d_pipe* p, int width, int height)
 }
 int ps3d_debug_read_shade_counts(ps3d_pipe* p, uint32_t* counts)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	if(!p->capDev) return PS3D_ERR_INVALID_ARGUMENT;
 	CK(p, cudaMemcpyAsync(counts, p->capDev, (size_t)p->capW * p->capH * 4, cudaMemcpyDeviceToHost, p->stream));
@@ -749,6 +788,7 @@ int ps3d_debug_read_shade_counts(ps3d_pipe* p, uint32_t* counts)
 }
 int ps3d_debug_clear_shade_counts(ps3d_pipe* p)
 {
+	TRACE();
 	cudaSetDevice(p->device);
 	if(p->capDev) CK(p, cudaMemsetAsync(p->capDev, 0, (size_t)p->capW * p->capH * 4, p->stream));
 	return PS3D_OK;
@@ -756,6 +796,7 @@ int ps3d_debug_clear_shade_counts(ps3d_pipe* p)
 
 int ps3d_set_row_band(ps3d_pipe* p, int row0, int row1)
 {
+	TRACE();
 	if(row0 == -1 && row1 == -1) { p->band0 = 0; p->band1 = 0x7fffffff; return PS3D_OK; }
 	if(row0 < 0 || row1 < row0) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "row band");
 	p->band0 = row0; p->band1 = row1;

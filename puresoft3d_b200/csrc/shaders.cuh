@@ -245,7 +245,7 @@ struct FragmentProcessorDEF01
 {
 	static constexpr uint32_t UNIFORMS = (1u << 7) | (1u << 8) | (1u << 9);
 	static constexpr int NTEX = 1;
-	PS_D static int texSlot(int i) { return 9; }
+	__host__ __device__ static constexpr int texSlot(int i) { return 9; }
 	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P) // :152-193
 	{
 		F4 colour = unpackBGRA(PuresoftSampler2D::get4(P.tex[0], in[2].x, in[2].y));
@@ -273,7 +273,7 @@ struct FragmentProcessorDEF02
 {
 	static constexpr uint32_t UNIFORMS = (1u << 7) | (1u << 8);
 	static constexpr int NTEX = 0;
-	PS_D static int texSlot(int i) { return -1; }
+	__host__ __device__ static constexpr int texSlot(int i) { return -1; }
 	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P) // :150-190
 	{
 		out.write(blinnPhong(P, in[2], in[1], in[0]));
@@ -304,7 +304,7 @@ struct FragmentProcessorDEF03
 {
 	static constexpr uint32_t UNIFORMS = (1u << 7) | (1u << 8) | (1u << 9) | (1u << 10);
 	static constexpr int NTEX = 2;
-	PS_D static int texSlot(int i) { return i == 0 ? 9 : 10; }
+	__host__ __device__ static constexpr int texSlot(int i) { return i == 0 ? 9 : 10; }
 	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P) // :180-239
 	{
 		F4 colour = unpackBGRA(PuresoftSampler2D::get4(P.tex[0], in[4].x, in[4].y));
@@ -353,7 +353,7 @@ struct FragmentProcessorDEF04
 {
 	static constexpr uint32_t UNIFORMS = (1u << 2);
 	static constexpr int NTEX = 1;
-	PS_D static int texSlot(int i) { return 2; }
+	__host__ __device__ static constexpr int texSlot(int i) { return 2; }
 	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P) // :127-134
 	{
 		out.write4(PuresoftSamplerCube::get4(P.tex[0], in[0]));
@@ -385,7 +385,7 @@ struct FragmentProcessorDEF05
 {
 	static constexpr uint32_t UNIFORMS = 0;
 	static constexpr int NTEX = 0;
-	PS_D static int texSlot(int i) { return -1; }
+	__host__ __device__ static constexpr int texSlot(int i) { return -1; }
 	PS_D static void process(const F4*, FragmentProcessorOutput&, const DrawParams&) {} // shadow.cpp:76-77
 };
 
@@ -405,7 +405,7 @@ struct FragmentProcessorFLATID
 {
 	static constexpr uint32_t UNIFORMS = 0;
 	static constexpr int NTEX = 0;
-	PS_D static int texSlot(int i) { return -1; }
+	__host__ __device__ static constexpr int texSlot(int i) { return -1; }
 	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams&)
 	{
 		uint32_t b = (uint32_t)(cvtt(fadd(in[0].x, 0.5f)) & 0xff), g = (uint32_t)(cvtt(fadd(in[0].y, 0.5f)) & 0xff);
