@@ -1,0 +1,344 @@
+#!/usr/bin/env python3
+"""bench.py — BASELINE.json's metric on BASELINE.json's config, one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload = "C2"): BASELINE.json configs[1] — 1080p synthetic 1M-triangle mesh (4 stacked 354x354
+height-field grids, shuffled so submission order matters), DEF03 = per-pixel Blinn-Phong + tangent-space normal map,
+two 2048^2 BGRA textures, depth test + write, back-face culling. Synthetic, seed 2 (puresoft3d_b200/scenes.py).
+A step = one frame of the hot path: clearDepth + clearColour + uniforms + drawVAO (+ the sort-first composite at N>1).
+
+metric/value : shaded fragments/s, whole job. A shaded fragment is one FragmentProcessor::process invocation
+               (fragthrd.cpp:231) — counted on the device; identical on every backend because parity is bit-exact.
+value        : inputs resident in HBM when the timed region starts; CUDA events on the pipe's own stream, max over ranks.
+e2e          : same metric through the public API with HOST buffers: every step re-uploads the five vertex streams
+               from pinned host memory (updateContent), renders, and reads the colour target back.
+roofline     : the dominant kernel class, live CUDA-event time on its launching stream (ps3d_profile_*), against
+               MEASURED_PEAKS.json; frame_roofline is SURVEY.md §8(d)'s whole-frame formula.
+cpu_baseline : the reference's own renderer (oracle/_ref, the unmodified sources through the shim) on this host's cores.
+
+N > 1 (torchrun): sort-first — rank r renders raster rows [r*H/N, (r+1)*H/N) of the SAME frame (strong scaling); every
+rank runs the geometry stage for all triangles; finished colour bands are gathered to rank 0 over NCCL (NVLink).
+--impl reference: the reference's CPU renderer alone (rank 0 only), same scene, same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only when MEASURED_PEAKS.json is absent
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md's clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene(args):
+    from puresoft3d_b200 import scenes
+    if args.workload == "C2":
+        return scenes.scene_heightfield(1920, 1080, grid=354, layers=4, seed=2, tex_size=2048)
+    if args.workload == "C2-small":  # developer smoke of this script, not a bench line
+        return scenes.scene_heightfield(1920, 1080, grid=100, layers=4, seed=2, tex_size=512)
+    raise SystemExit("unknown workload")
+
+
+def algorithmic_bytes(scene, tex_samples):
+    """vertex bytes read once + every bound target written once + targets loaded because the clear is a
+    separate pass here? No: the formula counts clears as fused (0 B) — kept as specified — + min(texture bytes, 4 B x samples)."""
+    vertex = scene.vertex_bytes_read()
+    targets = 2 * scene.width * scene.height * 4
+    tex = 0
+    for t in scene.textures:
+        tex += min(sum(a.nbytes for a in t["layers"]), 4 * tex_samples)
+    return vertex, targets, tex
+
+
+def run_reference(args, rank):
+    """The reference's own CPU renderer (unmodified sources, oracle/_ref) with every host thread it can use."""
+    if rank != 0:
+        return 0
+    from puresoft3d_b200 import _capi, scenes
+    from puresoft3d_b200.pipeline import PuresoftPipeline
+    so = os.path.join(ROOT, "oracle", "_ref", "libps3d_ref.so")
+    kind = "reference"
+    if not os.path.exists(so):
+        so = os.path.join(ROOT, "oracle", "libps3d_oracle.so")  # the restatement, single-threaded
+        kind = "port"
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("PS3D_REF_THREADS", str(cores))
+    sc = build_scene(args)
+    lib = _capi.bind(so)
+    # pass 1 (untimed, counting decorators on): fragments per frame
+    os.environ["PS3D_REF_COUNTING"] = "1"
+    p = PuresoftPipeline(sc.width, sc.height, lib=lib)
+    up = scenes.upload(p, sc)
+    scenes.replay(p, sc, up)
+    frags = p.getStats()["fragments_shaded"]
+    p.close()
+    # pass 2 (timed, decorators off): the stock code path
+    os.environ["PS3D_REF_COUNTING"] = "0"
+    p = PuresoftPipeline(sc.width, sc.height, lib=lib)
+    up = scenes.upload(p, sc)
+    for _ in range(args.warmup):
+        scenes.replay(p, sc, up)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        scenes.replay(p, sc, up)
+        p.swapBuffers()
+    dt = time.perf_counter() - t0
+    p.close()
+    ms = dt * 1000.0 / args.steps
+    value = frags * args.steps / dt
+    threads = cores if kind == "reference" else 1
+    line = {
+        "impl": "reference", "metric": "shaded_fragments_per_s", "value": value, "unit": "fragments/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "frames_per_s": 1000.0 / ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "scene": sc.name, "triangles": sc.meta.get("triangles"), "resolution": [sc.width, sc.height],
+                   "shader": "DEF03", "fragments_per_frame": frags},
+        "cpu_baseline": {"value": value, "unit": "fragments/s", "cores": threads, "kind": kind,
+                         "sample": "%d full frames of the workload, %d warm-up" % (args.steps, args.warmup)},
+        "e2e": {"value": value, "unit": "fragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 3
+        args.warmup = args.warmup if args.warmup is not None else 1
+        return run_reference(args, rank)
+    args.steps = args.steps if args.steps is not None else 50
+    args.warmup = args.warmup if args.warmup is not None else 5
+
+    import torch
+    import torch.distributed as dist
+    from puresoft3d_b200 import scenes
+    from puresoft3d_b200.pipeline import PuresoftPipeline
+    from puresoft3d_b200 import sortfirst
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    sc = build_scene(args)
+    pipe = PuresoftPipeline(sc.width, sc.height, device=local_rank)
+    up = scenes.upload(pipe, sc)
+    ext = torch.cuda.ExternalStream(pipe.deviceStream(), device=dev)
+    comp = sortfirst.Compositor(pipe, rank, world, dev, ext) if world > 1 else None
+    if comp:
+        pipe.setRowBand(*comp.band)
+
+    def frame():
+        scenes.replay(pipe, sc, up, finish=False)
+        if comp:
+            comp.gather_to_rank0()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-only: inputs resident in HBM ------------------------------------------------------------------
+    for _ in range(args.warmup):
+        frame()
+    pipe.finish()
+    pipe.resetStats()
+    pipe.profileEnable(True)
+    launches0 = pipe.deviceLaunchCount()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0.record(ext)
+    for _ in range(args.steps):
+        frame()
+    ev1.record(ext)
+    ev1.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    prof = pipe.profileRead()
+    pipe.profileEnable(False)
+    launches = pipe.deviceLaunchCount() - launches0
+    stats = pipe.getStats()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    frag_t = torch.tensor([float(stats["fragments_shaded"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(frag_t, op=dist.ReduceOp.SUM)
+    ms_total = float(t.item())
+    frags_total = float(frag_t.item())
+    ms_step = ms_total / args.steps
+    value = frags_total / (ms_total / 1000.0)
+    frags_per_frame = frags_total / args.steps
+
+    # ---- end to end: host buffers in, colour image out, every step ----------------------------------------------
+    host_streams = []
+    for (vbo, arr) in up.vbos:
+        tsr = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+        host_streams.append((vbo, tsr))
+    host_colour = torch.empty((sc.height, sc.width), dtype=torch.int32).pin_memory()
+    h2d = sum(tsr.numel() * tsr.element_size() for _, tsr in host_streams)
+    d2h = host_colour.numel() * 4
+
+    def frame_e2e():
+        for vbo, tsr in host_streams:
+            pipe._check(pipe._lib.ps3d_vbo_update(pipe._h, vbo.handle, tsr.data_ptr()))
+        frame()
+        if rank == 0:
+            pipe._check(pipe._lib.ps3d_read_colour(pipe._h, host_colour.data_ptr(), sc.width * 4))
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        frame_e2e()
+    pipe.resetStats()
+    barrier()
+    ev0.record(ext)
+    for _ in range(e2e_steps):
+        frame_e2e()
+    ev1.record(ext)
+    ev1.synchronize()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    frag_t = torch.tensor([float(pipe.getStats()["fragments_shaded"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(frag_t, op=dist.ReduceOp.SUM)
+    e2e_value = float(frag_t.item()) / (float(t.item()) / 1000.0)
+
+    # ---- roofline ------------------------------------------------------------------------------------------------
+    peak, peak_src = load_peaks()
+    vertex_b, target_b, tex_b = algorithmic_bytes(sc, int(2 * frags_per_frame))
+    classes = {
+        # algorithmic bytes per launch of each kernel class (DESIGN.md "Kernels"): what an ideal implementation must move
+        "geom_setup": (prof["geom_ms"], prof["geom_launches"], vertex_b),
+        "binning": (prof["bin_ms"], prof["bin_launches"], 0),
+        "tile_raster_shade": (prof["tile_ms"], prof["tile_launches"], target_b + tex_b),
+    }
+    dominant = max(classes, key=lambda k: classes[k][0])
+    dom_ms, dom_launches, dom_bytes = classes[dominant]
+    draws = max(1, stats["draws"])
+    dom_ms_per_launch = dom_ms / draws if dom_ms > 0 else float("nan")
+    achieved = (dom_bytes / 1e9) / (dom_ms_per_launch / 1e3) if dom_ms > 0 else 0.0
+    frame_bytes = vertex_b + target_b + tex_b
+    frame_achieved = (frame_bytes / 1e9) / (ms_step / 1e3)
+
+    if rank == 0:
+        line = {
+            "metric": "shaded_fragments_per_s", "value": value, "unit": "fragments/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "frames_per_s": 1000.0 / ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "scene": sc.name, "triangles": sc.meta.get("triangles"), "resolution": [sc.width, sc.height],
+                       "shader": "DEF03 (Blinn-Phong + normal map)", "textures": "2 x 2048^2 BGRA nearest", "fragments_per_frame": frags_per_frame,
+                       "parallelism": "sort-first row bands x%d, NCCL gather to rank 0" % world if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (216 MB vertex streams + 34 MB textures + 350 MB intermediates per frame vs 126 MB L2)",
+                       "approx": "x86 rcpps/rsqrtss tables bits=%s" % (pipe.hostApproxInfo(),)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(t.item()) / e2e_steps, "steps": e2e_steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "ms_per_launch": dom_ms_per_launch, "algorithmic_bytes": dom_bytes},
+            "frame_roofline": {"achieved": frame_achieved, "peak": peak, "unit": "GB/s", "frac": frame_achieved / peak,
+                               "algorithmic_bytes": frame_bytes, "roofline_us": frame_bytes / (peak * 1e3)},
+            "kernel_ms_per_frame": {k: v[0] / args.steps for k, v in classes.items()},
+            "bin_pairs_per_frame": prof["bin_pairs"] / args.steps,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, frags_per_frame)
+        print(json.dumps(line), flush=True)
+    pipe.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def cpu_baseline(args, frags_per_frame):
+    """The reference's renderer on this box's host cores, a bounded sample (about 10-30 s): whole frames of the same scene."""
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                          "--workload", args.workload], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    for ln in out.stdout.splitlines()[::-1]:
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    return {"value": None, "unit": "fragments/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: " + out.stderr[-200:]}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

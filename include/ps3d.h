@@ -182,6 +182,20 @@ int ps3d_vbo_update_device(ps3d_pipe* p, int vbo, const void* devSrc);
 /* number of kernels this pipe has launched since creation (bench.py's gpu_launches) */
 int ps3d_device_launch_count(ps3d_pipe* p, uint64_t* launches);
 
+/* Per-kernel-class device timing with CUDA events recorded on the pipe's own stream (bench.py's roofline figures).
+ * While enabled every draw brackets its geometry kernel, its binning kernels and its tile kernel with event pairs;
+ * ps3d_profile_read() waits for the stream, sums the elapsed times since the last read and resets. */
+typedef struct ps3d_profile
+{
+	double geom_ms, bin_ms, tile_ms;
+	uint64_t geom_launches, bin_launches, tile_launches;
+	uint64_t bin_pairs;            /* (tile, triangle) pairs sorted */
+} ps3d_profile;
+int ps3d_profile_enable(ps3d_pipe* p, int on);
+int ps3d_profile_read(ps3d_pipe* p, ps3d_profile* out);
+/* which rcpps / rsqrtss emulation the kernels use: table index bits measured on this host (0,0 = IEEE 1/x, 1/sqrt) */
+int ps3d_host_approx_info(int* rcpBits, int* rsqrtBits);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1126,3 +1126,6 @@ int ps3d_device_depth_ptr(ps3d_pipe* p, void** d, size_t* pitch) { (void)p; (voi
 int ps3d_device_stream(ps3d_pipe* p, void** s) { (void)p; (void)s; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_vbo_update_device(ps3d_pipe* p, int vbo, const void* src) { (void)p; (void)vbo; (void)src; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_device_launch_count(ps3d_pipe* p, uint64_t* n) { (void)p; if(n) *n = 0; return PS3D_OK; }
+int ps3d_profile_enable(ps3d_pipe* p, int on) { (void)p; (void)on; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_profile_read(ps3d_pipe* p, ps3d_profile* out) { (void)p; (void)out; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_host_approx_info(int* rcpBits, int* rsqrtBits) { *rcpBits = -1; *rsqrtBits = -1; return PS3D_OK; } /* the hardware instructions themselves */

@@ -573,5 +573,8 @@ int ps3d_device_depth_ptr(ps3d_pipe*, void**, size_t*) { return PS3D_ERR_UNSUPPO
 int ps3d_device_stream(ps3d_pipe*, void**) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_vbo_update_device(ps3d_pipe*, int, const void*) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_device_launch_count(ps3d_pipe*, uint64_t* n) { if(n) *n = 0; return PS3D_OK; }
+int ps3d_profile_enable(ps3d_pipe*, int) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_profile_read(ps3d_pipe*, ps3d_profile*) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_host_approx_info(int* rcpBits, int* rsqrtBits) { *rcpBits = -1; *rsqrtBits = -1; return PS3D_OK; } // the hardware instructions themselves
 
 } // extern "C"

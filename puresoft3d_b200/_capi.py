@@ -45,6 +45,15 @@ class Stats(C.Structure):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
+class Profile(C.Structure):
+    _fields_ = [("geom_ms", C.c_double), ("bin_ms", C.c_double), ("tile_ms", C.c_double),
+                ("geom_launches", C.c_uint64), ("bin_launches", C.c_uint64), ("tile_launches", C.c_uint64),
+                ("bin_pairs", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 _P = C.c_void_p
 _INT_P = C.POINTER(C.c_int)
 
@@ -96,6 +105,9 @@ PROTOTYPES = {
     "ps3d_device_stream": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
     "ps3d_vbo_update_device": (C.c_int, [_P, C.c_int, C.c_void_p]),
     "ps3d_device_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "ps3d_profile_enable": (C.c_int, [_P, C.c_int]),
+    "ps3d_profile_read": (C.c_int, [_P, C.POINTER(Profile)]),
+    "ps3d_host_approx_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
 }
 
 

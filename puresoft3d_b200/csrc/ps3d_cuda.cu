@@ -144,7 +144,40 @@ struct ps3d_pipe
 	uint32_t* rsqrtDev;
 	ApproxTables approx;
 	uint64_t launches;
+	// per-kernel-class event timing (ps3d_profile_*)
+	bool profiling;
+	struct Span { cudaEvent_t a, b; int cls; };
+	std::vector<Span> spans;
+	std::vector<cudaEvent_t> eventPool;
+	uint64_t profLaunches[3];
+	uint64_t profPairs;
 	std::string err;
+};
+
+enum { CLS_GEOM = 0, CLS_BIN = 1, CLS_TILE = 2 };
+
+static cudaEvent_t takeEvent(ps3d_pipe* p)
+{
+	cudaEvent_t e;
+	if(!p->eventPool.empty()) { e = p->eventPool.back(); p->eventPool.pop_back(); return e; }
+	cudaEventCreate(&e);
+	return e;
+}
+struct ProfScope
+{
+	ps3d_pipe* p; int cls; cudaEvent_t a; uint64_t launches0;
+	ProfScope(ps3d_pipe* p_, int cls_) : p(p_), cls(cls_), a(nullptr), launches0(p_->launches)
+	{
+		if(p->profiling) { a = takeEvent(p); cudaEventRecord(a, p->stream); }
+	}
+	~ProfScope()
+	{
+		if(!a) return;
+		ps3d_pipe::Span s; s.a = a; s.b = takeEvent(p); s.cls = cls;
+		cudaEventRecord(s.b, p->stream);
+		p->spans.push_back(s);
+		p->profLaunches[cls] += p->launches - launches0;
+	}
 };
 
 #define CK(p, call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { (p)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return PS3D_ERR_DEVICE; } } while(0)
@@ -210,6 +243,7 @@ int ps3d_create(int width, int height, int device, ps3d_pipe** out)
 	p->back = 1; p->depthTex = -1; p->curProg = -1;
 	p->capDev = nullptr; p->capW = p->capH = 0;
 	p->launches = 0;
+	p->profiling = false; p->profPairs = 0; p->profLaunches[0] = p->profLaunches[1] = p->profLaunches[2] = 0;
 	memset(&p->stats, 0, sizeof(p->stats));
 	memset(p->uniformSet, 0, sizeof(p->uniformSet));
 	p->depthScanline = ((int)(width / 4.0f + 0.5f) * 4) * (int)sizeof(float); // pipeline.cpp:31
@@ -264,6 +298,8 @@ int ps3d_destroy(ps3d_pipe* p)
 	if(p->rsqrtDev) cudaFree(p->rsqrtDev);
 	p->hdr.release(); p->vary.release(); p->triCount.release(); p->triOffset.release(); p->triRect.release(); p->scanSums.release();
 	p->keysA.release(); p->valsA.release(); p->keysB.release(); p->valsB.release(); p->tileCount.release(); p->tileStart.release(); p->sortCounts.release();
+	for(auto& s : p->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+	for(auto& e : p->eventPool) cudaEventDestroy(e);
 	cudaStreamDestroy(p->stream);
 	delete p;
 	return PS3D_OK;
@@ -644,10 +680,17 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	CK(p, p->triRect.ensure(ntris * 2));
 	P.hdr = p->hdr.p; P.vary = p->vary.p; P.triCount = p->triCount.p; P.triRect = p->triRect.p;
 
-	pe->geom(P, p->stream);
-	p->launches++;
+	{
+		ProfScope ps(p, CLS_GEOM);
+		pe->geom(P, p->stream);
+		p->launches++;
+	}
 	CK(p, cudaGetLastError());
-	int rc = exclusiveScan(p, p->triCount.p, p->triOffset.p, P.ntris, p->totalDev);
+	int rc;
+	{
+		ProfScope ps(p, CLS_BIN);
+		rc = exclusiveScan(p, p->triCount.p, p->triOffset.p, P.ntris, p->totalDev);
+	}
 	if(rc) return rc;
 	// the number of (tile, triangle) pairs sizes the bins: one 4-byte read-back per draw
 	CK(p, cudaMemcpyAsync(p->totalHost, p->totalDev, 4, cudaMemcpyDeviceToHost, p->stream));
@@ -656,6 +699,9 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	if(0 == total) return PS3D_OK;
 
 	const uint32_t ntiles = (uint32_t)(P.tilesX * P.tilesY);
+	p->profPairs += p->profiling ? total : 0;
+	ProfScope* binScope = new ProfScope(p, CLS_BIN);
+	struct ScopeGuard { ProfScope*& s; ~ScopeGuard() { delete s; s = nullptr; } } binGuard{binScope};
 	CK(p, p->keysA.ensure(total)); CK(p, p->valsA.ensure(total)); CK(p, p->keysB.ensure(total)); CK(p, p->valsB.ensure(total));
 	CK(p, p->tileCount.ensure(ntiles + 1)); CK(p, p->tileStart.ensure(ntiles + 1));
 	CK(p, cudaMemsetAsync(p->tileCount.p, 0, (size_t)(ntiles + 1) * 4, p->stream));
@@ -685,9 +731,13 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	}
 	rc = exclusiveScan(p, p->tileCount.p, p->tileStart.p, ntiles + 1, p->totalDev);
 	if(rc) return rc;
+	delete binScope; binScope = nullptr;
 
-	pe->tile(P, p->tileStart.p, vIn, p->stream);
-	p->launches++;
+	{
+		ProfScope ps(p, CLS_TILE);
+		pe->tile(P, p->tileStart.p, vIn, p->stream);
+		p->launches++;
+	}
 	CK(p, cudaGetLastError());
 	return PS3D_OK;
 }
@@ -807,5 +857,43 @@ int ps3d_device_colour_ptr(ps3d_pipe* p, void** devPtr, size_t* pitch) { *devPtr
 int ps3d_device_depth_ptr(ps3d_pipe* p, void** devPtr, size_t* pitch) { *devPtr = p->defaultDepth; *pitch = (size_t)p->depthScanline; return PS3D_OK; }
 int ps3d_device_stream(ps3d_pipe* p, void** s) { *s = (void*)p->stream; return PS3D_OK; }
 int ps3d_device_launch_count(ps3d_pipe* p, uint64_t* n) { *n = p->launches; return PS3D_OK; }
+
+int ps3d_profile_enable(ps3d_pipe* p, int on)
+{
+	TRACE();
+	cudaSetDevice(p->device);
+	CK(p, cudaStreamSynchronize(p->stream));
+	for(auto& s : p->spans) { p->eventPool.push_back(s.a); p->eventPool.push_back(s.b); }
+	p->spans.clear();
+	p->profiling = on != 0;
+	p->profPairs = 0; p->profLaunches[0] = p->profLaunches[1] = p->profLaunches[2] = 0;
+	return PS3D_OK;
+}
+int ps3d_profile_read(ps3d_pipe* p, ps3d_profile* out)
+{
+	TRACE();
+	cudaSetDevice(p->device);
+	CK(p, cudaStreamSynchronize(p->stream));
+	double ms[3] = { 0, 0, 0 };
+	for(auto& s : p->spans)
+	{
+		float t = 0;
+		cudaEventElapsedTime(&t, s.a, s.b);
+		ms[s.cls] += t;
+		p->eventPool.push_back(s.a); p->eventPool.push_back(s.b);
+	}
+	p->spans.clear();
+	out->geom_ms = ms[0]; out->bin_ms = ms[1]; out->tile_ms = ms[2];
+	out->geom_launches = p->profLaunches[0]; out->bin_launches = p->profLaunches[1]; out->tile_launches = p->profLaunches[2];
+	out->bin_pairs = p->profPairs;
+	p->profPairs = 0; p->profLaunches[0] = p->profLaunches[1] = p->profLaunches[2] = 0;
+	return PS3D_OK;
+}
+int ps3d_host_approx_info(int* rcpBits, int* rsqrtBits)
+{
+	const Ps3dHostApprox& a = hostApprox();
+	*rcpBits = a.rcpBits; *rsqrtBits = a.rsqrtBits;
+	return PS3D_OK;
+}
 
 } // extern "C"

@@ -299,6 +299,19 @@ class PuresoftPipeline:
         self._check(self._lib.ps3d_device_stream(self._h, C.byref(s)))
         return s.value or 0
 
+    def profileEnable(self, on=True):
+        self._check(self._lib.ps3d_profile_enable(self._h, 1 if on else 0))
+
+    def profileRead(self):
+        pr = _capi.Profile()
+        self._check(self._lib.ps3d_profile_read(self._h, C.byref(pr)))
+        return pr.as_dict()
+
+    def hostApproxInfo(self):
+        a, b = C.c_int(), C.c_int()
+        self._lib.ps3d_host_approx_info(C.byref(a), C.byref(b))
+        return a.value, b.value
+
     def deviceLaunchCount(self):
         n = C.c_uint64()
         self._check(self._lib.ps3d_device_launch_count(self._h, C.byref(n)))

@@ -172,8 +172,9 @@ def upload(pipe, scene):
     return up
 
 
-def replay(pipe, scene, up):
-    """One frame: run the command list. ("tex_uniform", slot, sceneTexIdx) sets an int uniform to the pipe's handle."""
+def replay(pipe, scene, up, finish=True):
+    """One frame: run the command list. ("tex_uniform", slot, sceneTexIdx) sets an int uniform to the pipe's handle.
+    finish=False leaves the frame in flight on the pipe's stream (the reference's drawVAO is synchronous)."""
     for c in scene.commands:
         op = c[0]
         if op == "uniform":
@@ -198,7 +199,8 @@ def replay(pipe, scene, up):
             pipe.drawVAO(up.vaos[c[1]], bool(c[2]) if len(c) > 2 else False)
         else:
             raise ValueError("unknown scene command %r" % (op,))
-    pipe.finish()
+    if finish:
+        pipe.finish()
 
 
 def render(pipe, scene):
