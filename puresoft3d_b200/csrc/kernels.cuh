@@ -9,11 +9,21 @@
 //                             rectangle of 16x16 tiles its spans touch.
 //   scan / emit / radix sort  (tile, triangle) pairs emitted in triangle order and stably sorted by tile id: every tile
 //                             gets its triangles in SUBMISSION ORDER, which the depth dead-band and blend4 require (§9.7).
-//   tile_raster_shade<PROG>   one warp per 16x16 tile, depth + colour tile staged in shared memory. Per chunk of 32
-//                             triangles: phase A (lane = triangle) evaluates the reference's per-row spans and ORs a
-//                             per-row bitmask; phase B (lane = row segment of 8 pixels) walks its row's spans in bit
-//                             order = submission order, replaying the exact serial float chains (§9.6), depth-tests
-//                             against shared memory, runs the fragment functor, blends. One coalesced write-back.
+//   tile_raster_shade<PROG>   one warp per 16x16 tile, depth + colour tile staged in shared memory for the whole draw.
+//                             Per chunk of 32 triangles (submission order):
+//                               A1  lane = triangle: header -> shared memory, rows inside the tile, warp scan => span list
+//                               A2  lane = span (triangle,row), dense: the reference's RESULT_ROW arithmetic, the span's
+//                                   interpolation set-up (interp.cpp:26-80) and the chain advanced to the tile's edge
+//                               B   lane = pixel owner (row, 8-pixel segment): walks the spans of its row in submission
+//                                   order replaying the exact serial chains (§9.6), depth-tests against shared memory,
+//                                   pushes every survivor into a shared-memory queue
+//                               C   lane = survivor, dense, 32 at a time: varyings, fragment functor, ordered commit
+//                             One write-back per tile.
+//   tile_raster_shade_immediate<PROG>
+//                             the first version (lane = row segment does everything, fragment functor called inside
+//                             the pixel loop). Kept for functors that may discard() while depth writes are on — there
+//                             the depth write depends on the functor's result (fragthrd.cpp:234-237) — and as an A/B
+//                             switch (PS3D_TILE_IMMEDIATE=1).
 #pragma once
 #include "shaders.cuh"
 #include "raster.cuh"
@@ -355,7 +365,7 @@ struct TileSmem
 };
 
 template<class PROG>
-__global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_kernel(const __grid_constant__ DrawParams P,
+__global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_immediate_kernel(const __grid_constant__ DrawParams P,
                                                                                   const uint32_t* __restrict__ tileStart,
                                                                                   const uint32_t* __restrict__ sortedTris)
 {
@@ -555,5 +565,337 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_ker
 	{
 		if(t) atomicAdd(&P.stats->fragments_tested, t);
 		if(s) atomicAdd(&P.stats->fragments_shaded, s);
+	}
+}
+
+// ======================================================================================================================
+// tile raster + shade, v2: dense span set-up, pixel-owner depth pass, survivors shaded 32 at a time
+// ======================================================================================================================
+
+#define PS_QCAP 288   // < 32 left over from the previous flush + at most 32 lanes x 8 pixels pushed by one B step
+
+struct TileSmem2
+{
+	float depth[PS_TILE][PS_TILE];
+	uint32_t colour[PS_TILE][PS_TILE];
+	TriHeader hdr[32];          // the chunk's triangles, submission order
+	uint32_t triId[32];
+	uint32_t spanBase[33];      // exclusive scan of "rows of triangle t inside this tile"
+	int triRow0[32];
+	// span records of the current pass; slot order = (triangle, row) order = submission order on every row
+	float rCf2[32], rCf2Step[32], rZ[32], rZStep[32];   // the two depth chains, already advanced to the span's first pixel in the tile
+	int rLeft[32], rRight[32];                          // RESULT_ROW::left / right (unclamped)
+	uint32_t rMisc[32];                                 // xs | xe << 4 (tile-relative, inclusive) | edges << 8 | triLocal << 16
+	uint32_t rowMask[PS_TILE];
+	// survivors of the depth test waiting to be shaded; per pixel the queue order is submission order
+	uint32_t qTri[PS_QCAP];
+	int qLeft[PS_QCAP], qRight[PS_QCAP];
+	float qInv[PS_QCAP];        // 1 / correctionFactor2 at the pixel (interp.cpp:85)
+	uint32_t qMisc[PS_QCAP];    // px | row << 4 | edges << 8
+	uint32_t qCount;
+};
+
+// Phase C: shade queue entries [0, n) in batches of 32 (only full batches unless `final`), keep the remainder.
+template<class PROG>
+PS_D void shadeSurvivors(const DrawParams& P, TileSmem2& S, int lane, int tx0, int ty0, bool alphaBlend, bool final,
+                         unsigned& shaded, bool& colourDirty)
+{
+	constexpr int NV = PROG::NV;
+	typedef typename PROG::I IP;
+	const uint32_t n = S.qCount;
+	uint32_t head = 0;
+	const uint32_t ltMask = (1u << lane) - 1;
+	while(head + 32 <= n || (final && head < n))
+	{
+		const uint32_t i = head + lane;
+		const bool active = i < n;
+		bool wants = false;
+		uint32_t bgra = 0, pix = 0x1000u + lane;
+		bool blend = false;
+		if(active)
+		{
+			const uint32_t tri = S.qTri[i];
+			const int left = S.qLeft[i], right = S.qRight[i];
+			const float inv = S.qInv[i];
+			const uint32_t misc = S.qMisc[i];
+			const int px = (int)(misc & 15), row = (int)((misc >> 4) & 15), e = (int)((misc >> 8) & 0xff);
+			const int x = tx0 + px, y = ty0 + row;
+			const uint4* src = (const uint4*)(P.hdr + tri);
+			const uint4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
+			const float vx[3] = { __uint_as_float(q0.x), __uint_as_float(q0.z), __uint_as_float(q1.x) };
+			const float vy[3] = { __uint_as_float(q0.y), __uint_as_float(q0.w), __uint_as_float(q1.y) };
+			const float rw0 = __uint_as_float(q1.z), rw1 = __uint_as_float(q1.w), rw2 = __uint_as_float(q2.x);
+			// interpolateStartAndStep, interp.cpp:26-80 (the varyings' half; the depth half ran in phase A2)
+			float cl[3], cr[3];
+			edgeContrib(vx, vy, e & 3, (e >> 2) & 3, (float)left, (float)y, cl);
+			edgeContrib(vx, vy, (e >> 4) & 3, (e >> 6) & 3, (float)right, (float)y, cr);
+			cl[0] = fmul(cl[0], rw0); cl[1] = fmul(cl[1], rw1); cl[2] = fmul(cl[2], rw2);
+			cr[0] = fmul(cr[0], rw0); cr[1] = fmul(cr[1], rw1); cr[2] = fmul(cr[2], rw2);
+			F4 frag[NV > 0 ? NV : 1];
+			if(NV > 0)
+			{
+				const int stepCount = right - left;
+				const int x1 = left < 0 ? 0 : left;
+				const int skip = x1 - left;
+				const F4* v = P.vary + (size_t)tri * 3 * NV;
+				F4 v0[NV > 0 ? NV : 1], v1[NV > 0 ? NV : 1], v2[NV > 0 ? NV : 1];
+				F4 vStart[NV > 0 ? NV : 1], vEnd[NV > 0 ? NV : 1], vStep[NV > 0 ? NV : 1];
+#pragma unroll
+				for(int k = 0; k < NV; k++)
+				{
+					const float4 a = __ldg((const float4*)(v + k)), b = __ldg((const float4*)(v + NV + k)), c = __ldg((const float4*)(v + 2 * NV + k));
+					v0[k] = f4(a.x, a.y, a.z, a.w); v1[k] = f4(b.x, b.y, b.z, b.w); v2[k] = f4(c.x, c.y, c.z, c.w);
+				}
+				IP::interpolateByContributes(vStart, v0, v1, v2, cl[0], cl[1], cl[2]);
+				IP::interpolateByContributes(vEnd, v0, v1, v2, cr[0], cr[1], cr[2]);
+				IP::calcStep(vStep, vStart, vEnd, stepCount);
+				if(skip > 0) IP::stepForward(vStart, vStep, skip);               // interp.cpp:74-79
+				for(int k = x1; k < x; k++) IP::stepForward(vStart, vStep, 1);    // interp.cpp:88, one rounded add per pixel
+				IP::correctInterpolation(frag, vStart, inv);
+			}
+			FragmentProcessorOutput out;
+			out.discarded = false; out.wrote = false; out.blendable = false; out.bgra = 0;
+			PROG::F::process(frag, out, P);                                      // fragthrd.cpp:231
+			shaded++;
+			if(P.cap && x < P.capW && y < P.capH) atomicAdd(&P.cap[(size_t)y * P.capW + x], 1u);
+			if(out.wrote && y < P.colour.height && x < P.colour.width)
+			{
+				wants = true; bgra = out.bgra; pix = (uint32_t)(row * PS_TILE + px);
+				blend = out.blendable && alphaBlend;
+			}
+		}
+		// ordered commit: entries of one pixel are applied in queue order (= submission order)
+		const uint32_t peers = __match_any_sync(PS_FULL, pix);
+		const int rank = __popc(peers & ltMask);
+		const int maxRank = __reduce_max_sync(PS_FULL, wants ? rank : 0);
+		for(int r = 0; r <= maxRank; r++)
+		{
+			if(wants && rank == r)
+			{
+				uint32_t* dst = &S.colour[0][0] + pix;
+				// FBOBridge::write4 -> blend4 under ALPHABLEND, FBOBridge::write -> plain store (fragthrd.cpp:54-82)
+				*dst = blend ? blend4(bgra, *dst) : bgra;
+			}
+			__syncwarp();
+		}
+		if(__any_sync(PS_FULL, wants)) colourDirty = true;
+		head += 32;
+	}
+	if(head > 0)
+	{
+		// keep the remainder (< 32 entries) at the front of the queue
+		const uint32_t rem = n > head ? n - head : 0;
+		uint32_t a = 0, d = 0; int b = 0, c = 0; float f = 0;
+		if((uint32_t)lane < rem) { a = S.qTri[head + lane]; b = S.qLeft[head + lane]; c = S.qRight[head + lane]; f = S.qInv[head + lane]; d = S.qMisc[head + lane]; }
+		__syncwarp();
+		if((uint32_t)lane < rem) { S.qTri[lane] = a; S.qLeft[lane] = b; S.qRight[lane] = c; S.qInv[lane] = f; S.qMisc[lane] = d; }
+		if(0 == lane) S.qCount = rem;
+		__syncwarp();
+	}
+}
+
+template<class PROG>
+__global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_kernel(const __grid_constant__ DrawParams P,
+                                                                                  const uint32_t* __restrict__ tileStart,
+                                                                                  const uint32_t* __restrict__ sortedTris)
+{
+	__shared__ TileSmem2 smem[PS_WARPS_PER_BLOCK];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int tile = blockIdx.x * PS_WARPS_PER_BLOCK + w;
+	if(tile >= P.tilesX * P.tilesY) return;
+	const uint32_t listBegin = tileStart[tile], listEnd = tileStart[tile + 1];
+	if(listBegin == listEnd) return;
+	TileSmem2& S = smem[w];
+
+	const int tx0 = (tile % P.tilesX) * PS_TILE, ty0 = (tile / P.tilesX) * PS_TILE;
+	const int rr = lane >> 1, seg = lane & 1;          // phase-B ownership: row rr, pixels [sx0, sx0+7]
+	const int y = ty0 + rr, sx0 = tx0 + seg * PS_SEG;
+	const bool testDepth = 0 != (P.behavior & PS_BEHAVIOR_TEST_DEPTH);
+	const bool updateDepth = 0 != (P.behavior & PS_BEHAVIOR_UPDATE_DEPTH);
+	const bool useDepth = testDepth || updateDepth;
+	const bool alphaBlend = 0 != (P.behavior & PS_BEHAVIOR_ALPHABLEND);
+
+	// ---- stage the tile: each lane loads the 8-pixel segment it owns (fbo.cpp:98-110: colour top-down, depth bottom-up)
+	const bool depthRowOk = y < P.depth.height, colourRowOk = y < P.colour.height;
+	uint8_t* depthRow = P.depth.ptr + (size_t)(P.depth.topDown ? P.depth.height - 1 - y : y) * P.depth.scanline;
+	uint8_t* colourRow = P.colour.ptr + (size_t)(P.colour.topDown ? P.colour.height - 1 - y : y) * P.colour.scanline;
+#pragma unroll
+	for(int i = 0; i < PS_SEG; i++)
+	{
+		const int x = sx0 + i;
+		float d = 1.0f;
+		uint32_t c = 0;
+		if(useDepth && depthRowOk && x < P.depth.width) d = *(const float*)(depthRow + (size_t)x * 4);
+		if(colourRowOk && x < P.colour.width) c = *(const uint32_t*)(colourRow + (size_t)x * 4);
+		S.depth[rr][seg * PS_SEG + i] = d;
+		S.colour[rr][seg * PS_SEG + i] = c;
+	}
+	if(lane < PS_TILE) S.rowMask[lane] = 0;
+	if(0 == lane) S.qCount = 0;
+	__syncwarp();
+
+	unsigned tested = 0, shaded = 0;
+	bool depthDirty = false, colourDirty = false;
+	// the reference reads a clamped column/row when the viewport exceeds the depth target (fbo.cpp:101,150); that
+	// behaviour is not reproducible tile-locally, such fragments are dropped (DESIGN.md "divergences")
+	const int depthLimitX = useDepth ? P.depth.width - 1 : 0x7fffffff;
+	const bool rowDrawable = !useDepth || depthRowOk;
+	const int tileX1 = tx0 + PS_TILE - 1;
+
+	for(uint32_t chunk = listBegin; chunk < listEnd; chunk += 32)
+	{
+		// ---- A1: lane = triangle of the chunk. Header to shared memory; rows of the triangle inside tile and band. ----
+		const uint32_t li = chunk + lane;
+		int nrows = 0, r0 = 0;
+		if(li < listEnd)
+		{
+			const uint32_t tri = sortedTris[li];
+			S.triId[lane] = tri;
+			const uint4* src = (const uint4*)(P.hdr + tri);
+			const uint4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
+			uint4* dst = (uint4*)&S.hdr[lane];
+			dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3;
+			r0 = max(max((int)(q3.x & 0xffff), ty0), P.band0);
+			const int r1 = min(min((int)(q3.x >> 16), ty0 + PS_TILE - 1), P.band1 - 1);
+			nrows = r1 >= r0 ? r1 - r0 + 1 : 0;
+		}
+		uint32_t incl = (uint32_t)nrows;
+#pragma unroll
+		for(int d = 1; d < 32; d <<= 1)
+		{
+			const uint32_t t = __shfl_up_sync(PS_FULL, incl, d);
+			if(lane >= d) incl += t;
+		}
+		S.spanBase[lane] = incl - (uint32_t)nrows;
+		S.triRow0[lane] = r0;
+		const uint32_t total = __shfl_sync(PS_FULL, incl, 31);
+		__syncwarp();
+
+		for(uint32_t s0 = 0; s0 < total; s0 += 32)
+		{
+			// ---- A2: lane = span (triangle, row), dense. RESULT_ROW + interpolateStartAndStep's depth half. ----
+			const uint32_t s = s0 + lane;
+			if(s < total)
+			{
+				int t = 0; // the last triangle whose base <= s
+#pragma unroll
+				for(int b = 16; b > 0; b >>= 1)
+					if(t + b < 32 && S.spanBase[t + b] <= s) t += b;
+				const int iy = S.triRow0[t] + (int)(s - S.spanBase[t]);
+				const TriHeader& h = S.hdr[t];
+				const float vx[3] = { h.vx0, h.vx1, h.vx2 }, vy[3] = { h.vy0, h.vy1, h.vy2 };
+				RowSpan r;
+				if(rowOf(h, vx, vy, iy, r) && r.left != r.right)                  // drawvao.cpp:72
+				{
+					const int x1 = r.left < 0 ? 0 : r.left;                       // RESULT_ROW::leftClamped
+					const int x2 = r.right >= P.vpW ? P.vpW - 1 : r.right;        // RESULT_ROW::rightClamped
+					const int xs = max(x1, tx0), xe = min(min(x2, tileX1), depthLimitX);
+					if(x1 <= x2 && xs <= xe)
+					{
+						const int e = r.edges;
+						// interpolateStartAndStep, interp.cpp:26-80
+						float cl[3], cr[3];
+						edgeContrib(vx, vy, e & 3, (e >> 2) & 3, (float)r.left, (float)iy, cl);
+						edgeContrib(vx, vy, (e >> 4) & 3, (e >> 6) & 3, (float)r.right, (float)iy, cr);
+						cl[0] = fmul(cl[0], h.rw0); cl[1] = fmul(cl[1], h.rw1); cl[2] = fmul(cl[2], h.rw2); // mulvec_3_4 (:40-41); lane 3 is 0*0
+						cr[0] = fmul(cr[0], h.rw0); cr[1] = fmul(cr[1], h.rw1); cr[2] = fmul(cr[2], h.rw2);
+						const float rcpLen = fdiv(1.0f, (float)(r.right - r.left));                          // :47
+						float zStart = hsum4(fmul(cl[0], h.z0), fmul(cl[1], h.z1), fmul(cl[2], h.z2), 0.0f);  // :49 dot_3_4
+						float zStep = hsum4(fmul(cr[0], h.z0), fmul(cr[1], h.z1), fmul(cr[2], h.z2), 0.0f);   // :50
+						zStep = fmul(fsub(zStep, zStart), rcpLen);                                           // :51
+						float cf2Start = hsum4(cl[0], cl[1], cl[2], 0.0f);                                   // :55-68
+						float cf2Step = hsum4(cr[0], cr[1], cr[2], 0.0f);
+						cf2Step = fmul(fsub(cf2Step, cf2Start), rcpLen);                                     // :72
+						const int skip = x1 - r.left;                                                        // drawvao.cpp:90
+						if(skip > 0)                                                                         // interp.cpp:74-79
+						{
+							cf2Start = fadd(cf2Start, fmul(cf2Step, (float)skip));
+							zStart = fadd(zStart, fmul(zStep, (float)skip));
+						}
+						// the k-th pixel's value is k rounded additions from the span start (§9.6): replay them up to the tile
+						for(int x = x1; x < xs; x++)
+						{
+							cf2Start = fadd(cf2Start, cf2Step);
+							zStart = fadd(zStart, zStep);
+						}
+						S.rCf2[lane] = cf2Start; S.rCf2Step[lane] = cf2Step; S.rZ[lane] = zStart; S.rZStep[lane] = zStep;
+						S.rLeft[lane] = r.left; S.rRight[lane] = r.right;
+						S.rMisc[lane] = (uint32_t)(xs - tx0) | ((uint32_t)(xe - tx0) << 4) | ((uint32_t)e << 8) | ((uint32_t)t << 16);
+						atomicOr(&S.rowMask[iy - ty0], 1u << lane);
+					}
+				}
+			}
+			__syncwarp();
+
+			// ---- B: lane = (row, 8-pixel segment). Spans of my row in slot order = submission order. ----
+			uint32_t mask = rowDrawable ? S.rowMask[rr] : 0;
+			while(__any_sync(PS_FULL, mask != 0))
+			{
+				if(mask)
+				{
+					const int slot = __ffs(mask) - 1;
+					mask &= mask - 1;
+					const uint32_t misc = S.rMisc[slot];
+					const int sxs = tx0 + (int)(misc & 15), sxe = tx0 + (int)((misc >> 4) & 15);
+					const int xs = max(sxs, sx0), xe = min(sxe, sx0 + PS_SEG - 1);
+					if(xs <= xe)
+					{
+						float cf2 = S.rCf2[slot], z0 = S.rZ[slot];
+						const float cf2Step = S.rCf2Step[slot], zStep = S.rZStep[slot];
+						for(int x = sxs; x < xs; x++)
+						{
+							cf2 = fadd(cf2, cf2Step);
+							z0 = fadd(z0, zStep);
+						}
+						for(int x = xs; x <= xe; x++)
+						{
+							// interpolateNextStep, interp.cpp:82-92
+							const float inv = fdiv(1.0f, cf2);
+							cf2 = fadd(cf2, cf2Step);
+							const float z = fmul(z0, inv);
+							z0 = fadd(z0, zStep);
+							tested++;
+							const int px = x - tx0;
+							const float cur = testDepth ? S.depth[rr][px] : 1.0f;        // fragthrd.cpp:217-225
+							if(-1.0f < z && fsub(z, cur) < -0.0001f)                     // fragthrd.cpp:227
+							{
+								// no functor on this path discards, so the depth write does not wait for the shading (fragthrd.cpp:234-237)
+								if(updateDepth) { S.depth[rr][px] = z; depthDirty = true; }
+								const uint32_t q = atomicAdd(&S.qCount, 1u);
+								S.qTri[q] = S.triId[misc >> 16];
+								S.qLeft[q] = S.rLeft[slot]; S.qRight[q] = S.rRight[slot];
+								S.qInv[q] = inv;
+								S.qMisc[q] = (uint32_t)px | ((uint32_t)rr << 4) | (((misc >> 8) & 0xff) << 8);
+							}
+						}
+					}
+				}
+				__syncwarp();
+				if(S.qCount >= 32) shadeSurvivors<PROG>(P, S, lane, tx0, ty0, alphaBlend, false, shaded, colourDirty);
+			}
+			if(lane < PS_TILE) S.rowMask[lane] = 0;
+			__syncwarp();
+		}
+	}
+	shadeSurvivors<PROG>(P, S, lane, tx0, ty0, alphaBlend, true, shaded, colourDirty);
+
+	// ---- write back
+	if(depthDirty)
+	{
+#pragma unroll
+		for(int i = 0; i < PS_SEG; i++)
+			if(sx0 + i < P.depth.width) *(float*)(depthRow + (size_t)(sx0 + i) * 4) = S.depth[rr][seg * PS_SEG + i];
+	}
+	if(colourDirty && colourRowOk)
+	{
+#pragma unroll
+		for(int i = 0; i < PS_SEG; i++)
+			if(sx0 + i < P.colour.width) *(uint32_t*)(colourRow + (size_t)(sx0 + i) * 4) = S.colour[rr][seg * PS_SEG + i];
+	}
+	const unsigned long long t = warpSumU64(tested), sh = warpSumU64(shaded);
+	if(0 == lane)
+	{
+		if(t) atomicAdd(&P.stats->fragments_tested, t);
+		if(sh) atomicAdd(&P.stats->fragments_shaded, sh);
 	}
 }

@@ -42,6 +42,9 @@ struct ProgEntry
 	LaunchTile tile;
 };
 
+// PS3D_TILE_IMMEDIATE=1 selects the first tile kernel for every programme (A/B checks)
+bool tileImmediateForced() { static int on = -1; if(on < 0) { const char* e = getenv("PS3D_TILE_IMMEDIATE"); on = (e && e[0] == '1') ? 1 : 0; } return on == 1; }
+
 template<class PROG> void launchGeom(const DrawParams& P, cudaStream_t s)
 {
 	const unsigned blocks = (P.ntris + 127) / 128;
@@ -51,7 +54,11 @@ template<class PROG> void launchTile(const DrawParams& P, const uint32_t* tileSt
 {
 	const unsigned tiles = (unsigned)(P.tilesX * P.tilesY);
 	const unsigned blocks = (tiles + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK;
-	tile_raster_shade_kernel<PROG><<<blocks, 32 * PS_WARPS_PER_BLOCK, 0, s>>>(P, tileStart, sortedTris);
+	// a functor that may discard() makes the depth write wait for the shading (fragthrd.cpp:234-237): immediate kernel
+	if(PROG::F::MAY_DISCARD || tileImmediateForced())
+		tile_raster_shade_immediate_kernel<PROG><<<blocks, 32 * PS_WARPS_PER_BLOCK, 0, s>>>(P, tileStart, sortedTris);
+	else
+		tile_raster_shade_kernel<PROG><<<blocks, 32 * PS_WARPS_PER_BLOCK, 0, s>>>(P, tileStart, sortedTris);
 }
 template<class PROG> ProgEntry makeEntry(int fnV, int fnI, int fnF)
 {

@@ -244,6 +244,7 @@ struct VertexProcesserDEF01
 struct FragmentProcessorDEF01
 {
 	static constexpr uint32_t UNIFORMS = (1u << 7) | (1u << 8) | (1u << 9);
+	static constexpr bool MAY_DISCARD = false;
 	static constexpr int NTEX = 1;
 	__host__ __device__ static constexpr int texSlot(int i) { return 9; }
 	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P) // :152-193
@@ -272,6 +273,7 @@ struct VertexProcesserDEF02
 struct FragmentProcessorDEF02
 {
 	static constexpr uint32_t UNIFORMS = (1u << 7) | (1u << 8);
+	static constexpr bool MAY_DISCARD = false;
 	static constexpr int NTEX = 0;
 	__host__ __device__ static constexpr int texSlot(int i) { return -1; }
 	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P) // :150-190
@@ -303,6 +305,7 @@ struct VertexProcesserDEF03
 struct FragmentProcessorDEF03
 {
 	static constexpr uint32_t UNIFORMS = (1u << 7) | (1u << 8) | (1u << 9) | (1u << 10);
+	static constexpr bool MAY_DISCARD = false;
 	static constexpr int NTEX = 2;
 	__host__ __device__ static constexpr int texSlot(int i) { return i == 0 ? 9 : 10; }
 	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P) // :180-239
@@ -352,6 +355,7 @@ struct VertexProcesserDEF04
 struct FragmentProcessorDEF04
 {
 	static constexpr uint32_t UNIFORMS = (1u << 2);
+	static constexpr bool MAY_DISCARD = false;
 	static constexpr int NTEX = 1;
 	__host__ __device__ static constexpr int texSlot(int i) { return 2; }
 	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P) // :127-134
@@ -384,6 +388,7 @@ struct VertexProcesserDEF05
 struct FragmentProcessorDEF05
 {
 	static constexpr uint32_t UNIFORMS = 0;
+	static constexpr bool MAY_DISCARD = false;
 	static constexpr int NTEX = 0;
 	__host__ __device__ static constexpr int texSlot(int i) { return -1; }
 	PS_D static void process(const F4*, FragmentProcessorOutput&, const DrawParams&) {} // shadow.cpp:76-77
@@ -404,6 +409,7 @@ struct VertexProcesserFLATID
 struct FragmentProcessorFLATID
 {
 	static constexpr uint32_t UNIFORMS = 0;
+	static constexpr bool MAY_DISCARD = false;
 	static constexpr int NTEX = 0;
 	__host__ __device__ static constexpr int texSlot(int i) { return -1; }
 	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams&)
