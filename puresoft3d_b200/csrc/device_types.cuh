@@ -49,6 +49,21 @@ struct DeviceStats
 	unsigned long long spans;
 	unsigned long long fragments_tested;
 	unsigned long long fragments_shaded;
+	unsigned long long fragBound;   // this draw: sum of clamped span lengths = upper bound of its depth-test survivors
+};
+
+// Survivors of the depth test, one record per FragmentProcessor::process call still to make (split path): structure of
+// arrays in HBM, appended 32 at a time by the raster/depth kernel, consumed in any order by the shade kernel.
+struct SurvivorStream
+{
+	uint32_t* tri;        // triangle id of the draw
+	int* left;            // RESULT_ROW::left / right of the span (unclamped)
+	int* right;
+	float* inv;           // 1 / correctionFactor2 at the pixel (interp.cpp:85)
+	uint32_t* misc;       // x | y << 13 | edge code << 26 (two 3-bit ordered vertex pairs)
+	uint32_t* count;      // records appended so far
+	uint32_t* winner;     // vpW x vpH: index of the LAST record of each pixel (only that one's colour lands)
+	uint32_t capacity;
 };
 
 struct DrawParams

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 {
 	constexpr int NV = PROG::NV;
 	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
-	unsigned rasterised = 0, spans = 0;
+	unsigned rasterised = 0, spans = 0, frags = 0;
 	if(tri < P.ntris)
 	{
 		VertexProcessorOutput<NV> vo[3];
@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 					const int x1 = r.left < 0 ? 0 : r.left;                 // RESULT_ROW::leftClamped
 					const int x2 = r.right >= P.vpW ? P.vpW - 1 : r.right;  // RESULT_ROW::rightClamped
 					if(x1 > x2) continue;
+					frags += (unsigned)(x2 - x1 + 1);
 					minX = min(minX, x1); maxX = max(maxX, x2);
 					minY = min(minY, iy); maxY = max(maxY, iy);
 				}
@@ -140,10 +141,14 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 		P.triRect[2 * tri + 1] = rect1;
 	}
 	const unsigned long long r = warpSumU64(rasterised), s = warpSumU64(spans);
+	unsigned long long f = frags;
+#pragma unroll
+	for(int d = 16; d > 0; d >>= 1) f += __shfl_xor_sync(PS_FULL, f, d);
 	if(0 == (threadIdx.x & 31))
 	{
 		if(r) atomicAdd(&P.stats->triangles_rasterised, r);
 		if(s) atomicAdd(&P.stats->spans, s);
+		if(f) atomicAdd(&P.stats->fragBound, f);
 	}
 }
 
@@ -569,10 +574,11 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_imm
 }
 
 // ======================================================================================================================
-// tile raster + shade, v2: dense span set-up, pixel-owner depth pass, survivors shaded 32 at a time
+// tile raster + shade, ordered (one kernel): lane = span for set-up AND depth test, lane = survivor for shading, colour
+// committed in submission order in shared memory. Used when the draw blends (blend4 is not commutative).
 // ======================================================================================================================
 
-#define PS_QCAP 288   // < 32 left over from the previous flush + at most 32 lanes x 8 pixels pushed by one B step
+#define PS_QCAP 192   // survivor queue entries per warp; a flush leaves < 32 behind, a round admits what fits
 
 struct TileSmem2
 {
@@ -582,29 +588,30 @@ struct TileSmem2
 	uint32_t triId[32];
 	uint32_t spanBase[33];      // exclusive scan of "rows of triangle t inside this tile"
 	int triRow0[32];
-	// span records of the current pass; slot order = (triangle, row) order = submission order on every row
-	float rCf2[32], rCf2Step[32], rZ[32], rZStep[32];   // the two depth chains, already advanced to the span's first pixel in the tile
-	int rLeft[32], rRight[32];                          // RESULT_ROW::left / right (unclamped)
-	uint32_t rMisc[32];                                 // xs | xe << 4 (tile-relative, inclusive) | edges << 8 | triLocal << 16
-	uint32_t rowMask[PS_TILE];
+	uint32_t rExtent[32];       // spans of the current pass: xs | xe << 4 (tile-relative, inclusive); slot order = submission order
+	uint32_t rowMask[PS_TILE];  // slots of the current pass per tile row
 	// survivors of the depth test waiting to be shaded; per pixel the queue order is submission order
 	uint32_t qTri[PS_QCAP];
-	int qLeft[PS_QCAP], qRight[PS_QCAP];
-	float qInv[PS_QCAP];        // 1 / correctionFactor2 at the pixel (interp.cpp:85)
-	uint32_t qMisc[PS_QCAP];    // px | row << 4 | edges << 8
+	int qLeft[PS_QCAP], qRight[PS_QCAP];   // RESULT_ROW::left / right (unclamped)
+	float qInv[PS_QCAP];                   // 1 / correctionFactor2 at the pixel (interp.cpp:85)
+	uint32_t qMisc[PS_QCAP];               // px | row << 4 | edges << 8
 	uint32_t qCount;
 };
 
 // Phase C: shade queue entries [0, n) in batches of 32 (only full batches unless `final`), keep the remainder.
+// One copy of the fragment functor in the kernel (the instruction footprint matters: see profiles/).
 template<class PROG>
-PS_D void shadeSurvivors(const DrawParams& P, TileSmem2& S, int lane, int tx0, int ty0, bool alphaBlend, bool final,
-                         unsigned& shaded, bool& colourDirty)
+__device__ __noinline__ void shadeSurvivors(const DrawParams& P, TileSmem2& S, int tx0, int ty0, bool final, unsigned& shadedOut, bool& colourDirtyOut)
 {
 	constexpr int NV = PROG::NV;
 	typedef typename PROG::I IP;
+	const int lane = threadIdx.x & 31;
+	const bool alphaBlend = 0 != (P.behavior & PS_BEHAVIOR_ALPHABLEND);
 	const uint32_t n = S.qCount;
 	uint32_t head = 0;
 	const uint32_t ltMask = (1u << lane) - 1;
+	unsigned shaded = 0;
+	bool colourDirty = false;
 	while(head + 32 <= n || (final && head < n))
 	{
 		const uint32_t i = head + lane;
@@ -625,30 +632,33 @@ PS_D void shadeSurvivors(const DrawParams& P, TileSmem2& S, int lane, int tx0, i
 			const float vx[3] = { __uint_as_float(q0.x), __uint_as_float(q0.z), __uint_as_float(q1.x) };
 			const float vy[3] = { __uint_as_float(q0.y), __uint_as_float(q0.w), __uint_as_float(q1.y) };
 			const float rw0 = __uint_as_float(q1.z), rw1 = __uint_as_float(q1.w), rw2 = __uint_as_float(q2.x);
-			// interpolateStartAndStep, interp.cpp:26-80 (the varyings' half; the depth half ran in phase A2)
-			float cl[3], cr[3];
-			edgeContrib(vx, vy, e & 3, (e >> 2) & 3, (float)left, (float)y, cl);
-			edgeContrib(vx, vy, (e >> 4) & 3, (e >> 6) & 3, (float)right, (float)y, cr);
-			cl[0] = fmul(cl[0], rw0); cl[1] = fmul(cl[1], rw1); cl[2] = fmul(cl[2], rw2);
-			cr[0] = fmul(cr[0], rw0); cr[1] = fmul(cr[1], rw1); cr[2] = fmul(cr[2], rw2);
 			F4 frag[NV > 0 ? NV : 1];
 			if(NV > 0)
 			{
+				// interpolateStartAndStep, interp.cpp:26-80 (the varyings' half; the depth half ran with the span set-up)
+				float cl[3], cr[3];
+				edgeContrib(vx, vy, e & 3, (e >> 2) & 3, (float)left, (float)y, cl);
+				edgeContrib(vx, vy, (e >> 4) & 3, (e >> 6) & 3, (float)right, (float)y, cr);
+				cl[0] = fmul(cl[0], rw0); cl[1] = fmul(cl[1], rw1); cl[2] = fmul(cl[2], rw2);
+				cr[0] = fmul(cr[0], rw0); cr[1] = fmul(cr[1], rw1); cr[2] = fmul(cr[2], rw2);
 				const int stepCount = right - left;
 				const int x1 = left < 0 ? 0 : left;
 				const int skip = x1 - left;
 				const F4* v = P.vary + (size_t)tri * 3 * NV;
-				F4 v0[NV > 0 ? NV : 1], v1[NV > 0 ? NV : 1], v2[NV > 0 ? NV : 1];
-				F4 vStart[NV > 0 ? NV : 1], vEnd[NV > 0 ? NV : 1], vStep[NV > 0 ? NV : 1];
+				F4 vStart[NV > 0 ? NV : 1], vStep[NV > 0 ? NV : 1];
+				// every varying is an independent float4 (the IP's methods are per-field loops, tex1light1.cpp:60-135): one at a
+				// time keeps the three vertex values of only one field live
+				typedef InterpolationProcessorVec4<1> IP1;
 #pragma unroll
 				for(int k = 0; k < NV; k++)
 				{
 					const float4 a = __ldg((const float4*)(v + k)), b = __ldg((const float4*)(v + NV + k)), c = __ldg((const float4*)(v + 2 * NV + k));
-					v0[k] = f4(a.x, a.y, a.z, a.w); v1[k] = f4(b.x, b.y, b.z, b.w); v2[k] = f4(c.x, c.y, c.z, c.w);
+					const F4 v0 = f4(a.x, a.y, a.z, a.w), v1 = f4(b.x, b.y, b.z, b.w), v2 = f4(c.x, c.y, c.z, c.w);
+					F4 vEnd;
+					IP1::interpolateByContributes(&vStart[k], &v0, &v1, &v2, cl[0], cl[1], cl[2]);
+					IP1::interpolateByContributes(&vEnd, &v0, &v1, &v2, cr[0], cr[1], cr[2]);
+					IP1::calcStep(&vStep[k], &vStart[k], &vEnd, stepCount);
 				}
-				IP::interpolateByContributes(vStart, v0, v1, v2, cl[0], cl[1], cl[2]);
-				IP::interpolateByContributes(vEnd, v0, v1, v2, cr[0], cr[1], cr[2]);
-				IP::calcStep(vStep, vStart, vEnd, stepCount);
 				if(skip > 0) IP::stepForward(vStart, vStep, skip);               // interp.cpp:74-79
 				for(int k = x1; k < x; k++) IP::stepForward(vStart, vStep, 1);    // interp.cpp:88, one rounded add per pixel
 				IP::correctInterpolation(frag, vStart, inv);
@@ -692,10 +702,12 @@ PS_D void shadeSurvivors(const DrawParams& P, TileSmem2& S, int lane, int tx0, i
 		if(0 == lane) S.qCount = rem;
 		__syncwarp();
 	}
+	shadedOut += shaded;
+	colourDirtyOut = colourDirtyOut || colourDirty;
 }
 
 template<class PROG>
-__global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_kernel(const __grid_constant__ DrawParams P,
+__global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_ordered_kernel(const __grid_constant__ DrawParams P,
                                                                                   const uint32_t* __restrict__ tileStart,
                                                                                   const uint32_t* __restrict__ sortedTris)
 {
@@ -708,14 +720,13 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_ker
 	TileSmem2& S = smem[w];
 
 	const int tx0 = (tile % P.tilesX) * PS_TILE, ty0 = (tile / P.tilesX) * PS_TILE;
-	const int rr = lane >> 1, seg = lane & 1;          // phase-B ownership: row rr, pixels [sx0, sx0+7]
+	const int rr = lane >> 1, seg = lane & 1;          // staging / write-back ownership: row rr, pixels [sx0, sx0+7]
 	const int y = ty0 + rr, sx0 = tx0 + seg * PS_SEG;
 	const bool testDepth = 0 != (P.behavior & PS_BEHAVIOR_TEST_DEPTH);
 	const bool updateDepth = 0 != (P.behavior & PS_BEHAVIOR_UPDATE_DEPTH);
 	const bool useDepth = testDepth || updateDepth;
-	const bool alphaBlend = 0 != (P.behavior & PS_BEHAVIOR_ALPHABLEND);
 
-	// ---- stage the tile: each lane loads the 8-pixel segment it owns (fbo.cpp:98-110: colour top-down, depth bottom-up)
+	// ---- stage the tile: each lane loads one 8-pixel segment (fbo.cpp:98-110: colour top-down, depth bottom-up)
 	const bool depthRowOk = y < P.depth.height, colourRowOk = y < P.colour.height;
 	uint8_t* depthRow = P.depth.ptr + (size_t)(P.depth.topDown ? P.depth.height - 1 - y : y) * P.depth.scanline;
 	uint8_t* colourRow = P.colour.ptr + (size_t)(P.colour.topDown ? P.colour.height - 1 - y : y) * P.colour.scanline;
@@ -735,12 +746,13 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_ker
 	__syncwarp();
 
 	unsigned tested = 0, shaded = 0;
-	bool depthDirty = false, colourDirty = false;
+	bool depthWrote = false, colourDirty = false;
 	// the reference reads a clamped column/row when the viewport exceeds the depth target (fbo.cpp:101,150); that
 	// behaviour is not reproducible tile-locally, such fragments are dropped (DESIGN.md "divergences")
 	const int depthLimitX = useDepth ? P.depth.width - 1 : 0x7fffffff;
-	const bool rowDrawable = !useDepth || depthRowOk;
+	const int depthLimitY = useDepth ? P.depth.height - 1 : 0x7fffffff;
 	const int tileX1 = tx0 + PS_TILE - 1;
+	const uint32_t ltMask = (1u << lane) - 1;
 
 	for(uint32_t chunk = listBegin; chunk < listEnd; chunk += 32)
 	{
@@ -756,7 +768,7 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_ker
 			uint4* dst = (uint4*)&S.hdr[lane];
 			dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3;
 			r0 = max(max((int)(q3.x & 0xffff), ty0), P.band0);
-			const int r1 = min(min((int)(q3.x >> 16), ty0 + PS_TILE - 1), P.band1 - 1);
+			const int r1 = min(min(min((int)(q3.x >> 16), ty0 + PS_TILE - 1), P.band1 - 1), depthLimitY);
 			nrows = r1 >= r0 ? r1 - r0 + 1 : 0;
 		}
 		uint32_t incl = (uint32_t)nrows;
@@ -775,6 +787,10 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_ker
 		{
 			// ---- A2: lane = span (triangle, row), dense. RESULT_ROW + interpolateStartAndStep's depth half. ----
 			const uint32_t s = s0 + lane;
+			bool valid = false;
+			int row = 0, xs = 0, xe = -1, left = 0, right = 0, edges = 0;
+			uint32_t tri = 0;
+			float cf2 = 0, cf2Step = 0, z0 = 0, zStep = 0;
 			if(s < total)
 			{
 				int t = 0; // the last triangle whose base <= s
@@ -789,8 +805,8 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_ker
 				{
 					const int x1 = r.left < 0 ? 0 : r.left;                       // RESULT_ROW::leftClamped
 					const int x2 = r.right >= P.vpW ? P.vpW - 1 : r.right;        // RESULT_ROW::rightClamped
-					const int xs = max(x1, tx0), xe = min(min(x2, tileX1), depthLimitX);
-					if(x1 <= x2 && xs <= xe)
+					const int xsA = max(x1, tx0), xeA = min(min(x2, tileX1), depthLimitX);
+					if(x1 <= x2 && xsA <= xeA)
 					{
 						const int e = r.edges;
 						// interpolateStartAndStep, interp.cpp:26-80
@@ -800,87 +816,98 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_ker
 						cl[0] = fmul(cl[0], h.rw0); cl[1] = fmul(cl[1], h.rw1); cl[2] = fmul(cl[2], h.rw2); // mulvec_3_4 (:40-41); lane 3 is 0*0
 						cr[0] = fmul(cr[0], h.rw0); cr[1] = fmul(cr[1], h.rw1); cr[2] = fmul(cr[2], h.rw2);
 						const float rcpLen = fdiv(1.0f, (float)(r.right - r.left));                          // :47
-						float zStart = hsum4(fmul(cl[0], h.z0), fmul(cl[1], h.z1), fmul(cl[2], h.z2), 0.0f);  // :49 dot_3_4
-						float zStep = hsum4(fmul(cr[0], h.z0), fmul(cr[1], h.z1), fmul(cr[2], h.z2), 0.0f);   // :50
-						zStep = fmul(fsub(zStep, zStart), rcpLen);                                           // :51
-						float cf2Start = hsum4(cl[0], cl[1], cl[2], 0.0f);                                   // :55-68
-						float cf2Step = hsum4(cr[0], cr[1], cr[2], 0.0f);
-						cf2Step = fmul(fsub(cf2Step, cf2Start), rcpLen);                                     // :72
+						z0 = hsum4(fmul(cl[0], h.z0), fmul(cl[1], h.z1), fmul(cl[2], h.z2), 0.0f);            // :49 dot_3_4
+						zStep = hsum4(fmul(cr[0], h.z0), fmul(cr[1], h.z1), fmul(cr[2], h.z2), 0.0f);         // :50
+						zStep = fmul(fsub(zStep, z0), rcpLen);                                               // :51
+						cf2 = hsum4(cl[0], cl[1], cl[2], 0.0f);                                              // :55-68
+						cf2Step = hsum4(cr[0], cr[1], cr[2], 0.0f);
+						cf2Step = fmul(fsub(cf2Step, cf2), rcpLen);                                          // :72
 						const int skip = x1 - r.left;                                                        // drawvao.cpp:90
 						if(skip > 0)                                                                         // interp.cpp:74-79
 						{
-							cf2Start = fadd(cf2Start, fmul(cf2Step, (float)skip));
-							zStart = fadd(zStart, fmul(zStep, (float)skip));
+							cf2 = fadd(cf2, fmul(cf2Step, (float)skip));
+							z0 = fadd(z0, fmul(zStep, (float)skip));
 						}
 						// the k-th pixel's value is k rounded additions from the span start (§9.6): replay them up to the tile
-						for(int x = x1; x < xs; x++)
+						for(int x = x1; x < xsA; x++)
 						{
-							cf2Start = fadd(cf2Start, cf2Step);
-							zStart = fadd(zStart, zStep);
+							cf2 = fadd(cf2, cf2Step);
+							z0 = fadd(z0, zStep);
 						}
-						S.rCf2[lane] = cf2Start; S.rCf2Step[lane] = cf2Step; S.rZ[lane] = zStart; S.rZStep[lane] = zStep;
-						S.rLeft[lane] = r.left; S.rRight[lane] = r.right;
-						S.rMisc[lane] = (uint32_t)(xs - tx0) | ((uint32_t)(xe - tx0) << 4) | ((uint32_t)e << 8) | ((uint32_t)t << 16);
-						atomicOr(&S.rowMask[iy - ty0], 1u << lane);
+						valid = true;
+						row = iy - ty0; xs = xsA - tx0; xe = xeA - tx0;
+						left = r.left; right = r.right; edges = e; tri = S.triId[t];
+						S.rExtent[lane] = (uint32_t)xs | ((uint32_t)xe << 4);
+						atomicOr(&S.rowMask[row], 1u << lane);
 					}
 				}
 			}
 			__syncwarp();
-
-			// ---- B: lane = (row, 8-pixel segment). Spans of my row in slot order = submission order. ----
-			uint32_t mask = rowDrawable ? S.rowMask[rr] : 0;
-			while(__any_sync(PS_FULL, mask != 0))
+			// earlier spans of this pass that touch a pixel of mine must be tested before me (§9.7)
+			uint32_t deps = 0;
+			if(valid)
 			{
-				if(mask)
+				uint32_t m = S.rowMask[row] & ltMask;
+				while(m)
 				{
-					const int slot = __ffs(mask) - 1;
-					mask &= mask - 1;
-					const uint32_t misc = S.rMisc[slot];
-					const int sxs = tx0 + (int)(misc & 15), sxe = tx0 + (int)((misc >> 4) & 15);
-					const int xs = max(sxs, sx0), xe = min(sxe, sx0 + PS_SEG - 1);
-					if(xs <= xe)
-					{
-						float cf2 = S.rCf2[slot], z0 = S.rZ[slot];
-						const float cf2Step = S.rCf2Step[slot], zStep = S.rZStep[slot];
-						for(int x = sxs; x < xs; x++)
-						{
-							cf2 = fadd(cf2, cf2Step);
-							z0 = fadd(z0, zStep);
-						}
-						for(int x = xs; x <= xe; x++)
-						{
-							// interpolateNextStep, interp.cpp:82-92
-							const float inv = fdiv(1.0f, cf2);
-							cf2 = fadd(cf2, cf2Step);
-							const float z = fmul(z0, inv);
-							z0 = fadd(z0, zStep);
-							tested++;
-							const int px = x - tx0;
-							const float cur = testDepth ? S.depth[rr][px] : 1.0f;        // fragthrd.cpp:217-225
-							if(-1.0f < z && fsub(z, cur) < -0.0001f)                     // fragthrd.cpp:227
-							{
-								// no functor on this path discards, so the depth write does not wait for the shading (fragthrd.cpp:234-237)
-								if(updateDepth) { S.depth[rr][px] = z; depthDirty = true; }
-								const uint32_t q = atomicAdd(&S.qCount, 1u);
-								S.qTri[q] = S.triId[misc >> 16];
-								S.qLeft[q] = S.rLeft[slot]; S.qRight[q] = S.rRight[slot];
-								S.qInv[q] = inv;
-								S.qMisc[q] = (uint32_t)px | ((uint32_t)rr << 4) | (((misc >> 8) & 0xff) << 8);
-							}
-						}
-					}
+					const int j = __ffs(m) - 1;
+					m &= m - 1;
+					const uint32_t o = S.rExtent[j];
+					if((int)(o & 15) <= xe && xs <= (int)(o >> 4)) deps |= 1u << j;
 				}
-				__syncwarp();
-				if(S.qCount >= 32) shadeSurvivors<PROG>(P, S, lane, tx0, ty0, alphaBlend, false, shaded, colourDirty);
 			}
+			__syncwarp();
 			if(lane < PS_TILE) S.rowMask[lane] = 0;
 			__syncwarp();
+
+			// ---- B: lane = span still. Rounds: a span runs when every earlier overlapping span has run and the queue has room.
+			uint32_t pending = __ballot_sync(PS_FULL, valid);
+			while(pending)
+			{
+				const bool ready = valid && 0 == (deps & pending);
+				uint32_t room = (uint32_t)(ready ? xe - xs + 1 : 0);
+#pragma unroll
+				for(int d = 1; d < 32; d <<= 1)
+				{
+					const uint32_t t = __shfl_up_sync(PS_FULL, room, d);
+					if(lane >= d) room += t;
+				}
+				const bool admit = ready && room <= PS_QCAP - S.qCount;
+				__syncwarp();
+				if(admit)
+				{
+					for(int px = xs; px <= xe; px++)
+					{
+						// interpolateNextStep, interp.cpp:82-92
+						const float inv = fdiv(1.0f, cf2);
+						cf2 = fadd(cf2, cf2Step);
+						const float z = fmul(z0, inv);
+						z0 = fadd(z0, zStep);
+						tested++;
+						const float cur = testDepth ? S.depth[row][px] : 1.0f;           // fragthrd.cpp:217-225
+						if(-1.0f < z && fsub(z, cur) < -0.0001f)                         // fragthrd.cpp:227
+						{
+							// no functor on this path discards, so the depth write does not wait for the shading (fragthrd.cpp:234-237)
+							if(updateDepth) { S.depth[row][px] = z; depthWrote = true; }
+							const uint32_t q = atomicAdd(&S.qCount, 1u);
+							S.qTri[q] = tri;
+							S.qLeft[q] = left; S.qRight[q] = right;
+							S.qInv[q] = inv;
+							S.qMisc[q] = (uint32_t)px | ((uint32_t)row << 4) | ((uint32_t)edges << 8);
+						}
+					}
+					valid = false;
+				}
+				__syncwarp();
+				pending &= ~__ballot_sync(PS_FULL, admit);
+				if(S.qCount >= 32) shadeSurvivors<PROG>(P, S, tx0, ty0, false, shaded, colourDirty);
+			}
 		}
 	}
-	shadeSurvivors<PROG>(P, S, lane, tx0, ty0, alphaBlend, true, shaded, colourDirty);
+	shadeSurvivors<PROG>(P, S, tx0, ty0, true, shaded, colourDirty);
 
 	// ---- write back
-	if(depthDirty)
+	if(__any_sync(PS_FULL, depthWrote) && depthRowOk)
 	{
 #pragma unroll
 		for(int i = 0; i < PS_SEG; i++)
@@ -897,5 +924,367 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_ker
 	{
 		if(t) atomicAdd(&P.stats->fragments_tested, t);
 		if(sh) atomicAdd(&P.stats->fragments_shaded, sh);
+	}
+}
+
+
+// ======================================================================================================================
+// the split path (default): raster + depth kernel -> survivor stream in HBM -> shade kernel
+//
+// Without blending only the LAST survivor of a pixel decides its colour, so shading needs no order at all: the raster
+// kernel resolves the order-dependent part (the depth test with its dead band, §9.7) tile by tile and appends every
+// survivor to a stream; when a tile is finished it publishes, per pixel, which record was the last one. The shade kernel
+// is then a flat loop over the stream with every lane busy, each record running the fragment functor exactly once
+// (fragthrd.cpp:231) and only the winner storing its colour. Two kernels also keep each instruction footprint inside the
+// SM's instruction cache, which the one-kernel version did not (profiles/r01c).
+// ======================================================================================================================
+
+PS_D uint32_t edgeCode3(int v0, int v1) { return (uint32_t)(v0 * 2 + (v1 > v0 ? v1 - 1 : v1)); }   // ordered pair of distinct vertex ids -> 0..5
+PS_D void edgeDecode3(uint32_t c, int& v0, int& v1) { v0 = (int)(c >> 1); const int t = (int)(c & 1); v1 = t + (t >= v0 ? 1 : 0); }
+
+#define PS_RQCAP 64   // raster kernel's staging queue: < 32 left by a flush + at most 32 pushed by one pixel batch
+
+struct RasterSmem
+{
+	float depth[PS_TILE * PS_TILE];
+	uint32_t lastIdx[PS_TILE * PS_TILE];   // stream index of the last survivor of each pixel
+	TriHeader hdr[32];                     // the chunk's triangles, submission order
+	uint32_t triId[32];
+	uint32_t spanBase[33];
+	int triRow0[32];
+	// spans of the current pass (slot = lane of phase A2; slot order = submission order on every row)
+	float rCf2[32], rCf2Step[32], rZ[32], rZStep[32];
+	int rLeft[32], rRight[32];
+	uint32_t rMisc[32];                    // xs | row << 4 | edge code << 8 (xs, row tile-relative)
+	uint32_t rTri[32];
+	uint32_t pixBase[33];                  // exclusive scan of span lengths inside the tile
+	// staging queue of survivors
+	uint32_t qTri[PS_RQCAP];
+	int qLeft[PS_RQCAP], qRight[PS_RQCAP];
+	float qInv[PS_RQCAP];
+	uint32_t qMisc[PS_RQCAP];              // px | row << 4 | edge code << 8
+};
+
+// append queue entries [0, n) (n <= 32) to the stream; remember the last record of every pixel
+PS_D void flushSurvivors(const SurvivorStream& Q, RasterSmem& S, int lane, uint32_t n, int tx0, int ty0)
+{
+	uint32_t base = 0;
+	if(0 == lane) base = atomicAdd(Q.count, n);
+	base = __shfl_sync(PS_FULL, base, 0);
+	const bool act = (uint32_t)lane < n;
+	uint32_t pix = 0x1000u + lane;
+	if(act)
+	{
+		const uint32_t i = base + lane;
+		const uint32_t m = S.qMisc[lane];
+		pix = m & 0xff;
+		if(i < Q.capacity)
+		{
+			Q.tri[i] = S.qTri[lane]; Q.left[i] = S.qLeft[lane]; Q.right[i] = S.qRight[lane]; Q.inv[i] = S.qInv[lane];
+			Q.misc[i] = (uint32_t)(tx0 + (int)(m & 15)) | ((uint32_t)(ty0 + (int)((m >> 4) & 15)) << 13) | ((m >> 8) << 26);
+		}
+	}
+	const uint32_t peers = __match_any_sync(PS_FULL, pix);
+	if(act && 0 == (peers >> lane >> 1)) S.lastIdx[pix] = base + lane;   // the highest lane of a pixel = the latest in submission order
+	__syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_depth_kernel(const __grid_constant__ DrawParams P, const SurvivorStream Q,
+                                                                                  const uint32_t* __restrict__ tileStart,
+                                                                                  const uint32_t* __restrict__ sortedTris)
+{
+	__shared__ RasterSmem smem[PS_WARPS_PER_BLOCK];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int tile = blockIdx.x * PS_WARPS_PER_BLOCK + w;
+	if(tile >= P.tilesX * P.tilesY) return;
+	const uint32_t listBegin = tileStart[tile], listEnd = tileStart[tile + 1];
+	if(listBegin == listEnd) return;
+	RasterSmem& S = smem[w];
+
+	const int tx0 = (tile % P.tilesX) * PS_TILE, ty0 = (tile / P.tilesX) * PS_TILE;
+	const int rr = lane >> 1, seg = lane & 1;          // staging / write-back ownership: row rr, pixels [sx0, sx0+7]
+	const int y = ty0 + rr, sx0 = tx0 + seg * PS_SEG;
+	const bool testDepth = 0 != (P.behavior & PS_BEHAVIOR_TEST_DEPTH);
+	const bool updateDepth = 0 != (P.behavior & PS_BEHAVIOR_UPDATE_DEPTH);
+	const bool useDepth = testDepth || updateDepth;
+
+	const bool depthRowOk = y < P.depth.height;
+	uint8_t* depthRow = P.depth.ptr + (size_t)(P.depth.topDown ? P.depth.height - 1 - y : y) * P.depth.scanline;
+#pragma unroll
+	for(int i = 0; i < PS_SEG; i++)
+	{
+		const int x = sx0 + i;
+		float d = 1.0f;
+		if(useDepth && depthRowOk && x < P.depth.width) d = *(const float*)(depthRow + (size_t)x * 4);
+		S.depth[rr * PS_TILE + seg * PS_SEG + i] = d;
+		S.lastIdx[rr * PS_TILE + seg * PS_SEG + i] = 0xffffffffu;
+	}
+	__syncwarp();
+
+	unsigned tested = 0, survived = 0;
+	bool depthWrote = false;
+	uint32_t qCount = 0;                               // warp-uniform
+	// the reference reads a clamped column/row when the viewport exceeds the depth target (fbo.cpp:101,150); that
+	// behaviour is not reproducible tile-locally, such fragments are dropped (DESIGN.md "divergences")
+	const int depthLimitX = useDepth ? P.depth.width - 1 : 0x7fffffff;
+	const int depthLimitY = useDepth ? P.depth.height - 1 : 0x7fffffff;
+	const int tileX1 = tx0 + PS_TILE - 1;
+	const uint32_t ltMask = (1u << lane) - 1;
+
+	for(uint32_t chunk = listBegin; chunk < listEnd; chunk += 32)
+	{
+		// ---- A1: lane = triangle of the chunk. Header to shared memory; rows of the triangle inside tile and band. ----
+		const uint32_t li = chunk + lane;
+		int nrows = 0, r0 = 0;
+		if(li < listEnd)
+		{
+			const uint32_t tri = sortedTris[li];
+			S.triId[lane] = tri;
+			const uint4* src = (const uint4*)(P.hdr + tri);
+			const uint4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
+			uint4* dst = (uint4*)&S.hdr[lane];
+			dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3;
+			r0 = max(max((int)(q3.x & 0xffff), ty0), P.band0);
+			const int r1 = min(min(min((int)(q3.x >> 16), ty0 + PS_TILE - 1), P.band1 - 1), depthLimitY);
+			nrows = r1 >= r0 ? r1 - r0 + 1 : 0;
+		}
+		uint32_t incl = (uint32_t)nrows;
+#pragma unroll
+		for(int d = 1; d < 32; d <<= 1)
+		{
+			const uint32_t t = __shfl_up_sync(PS_FULL, incl, d);
+			if(lane >= d) incl += t;
+		}
+		S.spanBase[lane] = incl - (uint32_t)nrows;
+		S.triRow0[lane] = r0;
+		const uint32_t total = __shfl_sync(PS_FULL, incl, 31);
+		__syncwarp();
+
+		for(uint32_t s0 = 0; s0 < total; s0 += 32)
+		{
+			// ---- A2: lane = span (triangle, row), dense. RESULT_ROW + interpolateStartAndStep's depth half. ----
+			const uint32_t s = s0 + lane;
+			int len = 0;
+			if(s < total)
+			{
+				int t = 0; // the last triangle whose base <= s
+#pragma unroll
+				for(int b = 16; b > 0; b >>= 1)
+					if(t + b < 32 && S.spanBase[t + b] <= s) t += b;
+				const int iy = S.triRow0[t] + (int)(s - S.spanBase[t]);
+				const TriHeader& h = S.hdr[t];
+				const float vx[3] = { h.vx0, h.vx1, h.vx2 }, vy[3] = { h.vy0, h.vy1, h.vy2 };
+				RowSpan r;
+				if(rowOf(h, vx, vy, iy, r) && r.left != r.right)                  // drawvao.cpp:72
+				{
+					const int x1 = r.left < 0 ? 0 : r.left;                       // RESULT_ROW::leftClamped
+					const int x2 = r.right >= P.vpW ? P.vpW - 1 : r.right;        // RESULT_ROW::rightClamped
+					const int xsA = max(x1, tx0), xeA = min(min(x2, tileX1), depthLimitX);
+					if(x1 <= x2 && xsA <= xeA)
+					{
+						const int e = r.edges;
+						// interpolateStartAndStep, interp.cpp:26-80
+						float cl[3], cr[3];
+						edgeContrib(vx, vy, e & 3, (e >> 2) & 3, (float)r.left, (float)iy, cl);
+						edgeContrib(vx, vy, (e >> 4) & 3, (e >> 6) & 3, (float)r.right, (float)iy, cr);
+						cl[0] = fmul(cl[0], h.rw0); cl[1] = fmul(cl[1], h.rw1); cl[2] = fmul(cl[2], h.rw2); // mulvec_3_4 (:40-41); lane 3 is 0*0
+						cr[0] = fmul(cr[0], h.rw0); cr[1] = fmul(cr[1], h.rw1); cr[2] = fmul(cr[2], h.rw2);
+						const float rcpLen = fdiv(1.0f, (float)(r.right - r.left));                          // :47
+						float z0 = hsum4(fmul(cl[0], h.z0), fmul(cl[1], h.z1), fmul(cl[2], h.z2), 0.0f);      // :49 dot_3_4
+						float zStep = hsum4(fmul(cr[0], h.z0), fmul(cr[1], h.z1), fmul(cr[2], h.z2), 0.0f);   // :50
+						zStep = fmul(fsub(zStep, z0), rcpLen);                                               // :51
+						float cf2 = hsum4(cl[0], cl[1], cl[2], 0.0f);                                        // :55-68
+						float cf2Step = hsum4(cr[0], cr[1], cr[2], 0.0f);
+						cf2Step = fmul(fsub(cf2Step, cf2), rcpLen);                                          // :72
+						const int skip = x1 - r.left;                                                        // drawvao.cpp:90
+						if(skip > 0)                                                                         // interp.cpp:74-79
+						{
+							cf2 = fadd(cf2, fmul(cf2Step, (float)skip));
+							z0 = fadd(z0, fmul(zStep, (float)skip));
+						}
+						// the k-th pixel's value is k rounded additions from the span start (§9.6): replay them up to the tile
+#pragma unroll 1
+						for(int x = x1; x < xsA; x++)
+						{
+							cf2 = fadd(cf2, cf2Step);
+							z0 = fadd(z0, zStep);
+						}
+						len = xeA - xsA + 1;
+						S.rCf2[lane] = cf2; S.rCf2Step[lane] = cf2Step; S.rZ[lane] = z0; S.rZStep[lane] = zStep;
+						S.rLeft[lane] = r.left; S.rRight[lane] = r.right; S.rTri[lane] = S.triId[t];
+						S.rMisc[lane] = (uint32_t)(xsA - tx0) | ((uint32_t)(iy - ty0) << 4)
+						              | ((edgeCode3(e & 3, (e >> 2) & 3) | (edgeCode3((e >> 4) & 3, (e >> 6) & 3) << 3)) << 8);
+					}
+				}
+			}
+			uint32_t pincl = (uint32_t)len;
+#pragma unroll
+			for(int d = 1; d < 32; d <<= 1)
+			{
+				const uint32_t t = __shfl_up_sync(PS_FULL, pincl, d);
+				if(lane >= d) pincl += t;
+			}
+			S.pixBase[lane] = pincl - (uint32_t)len;
+			const uint32_t totalPix = __shfl_sync(PS_FULL, pincl, 31);
+			__syncwarp();
+
+			// ---- B: lane = pixel of a span, dense; spans in slot order, pixels left to right. ----
+			for(uint32_t p0 = 0; p0 < totalPix; p0 += 32)
+			{
+				const uint32_t p = p0 + lane;
+				const bool act = p < totalPix;
+				uint32_t pix = 0x1000u + lane, misc = 0;
+				int slot = 0;
+				float z = 0, inv = 0;
+				if(act)
+				{
+#pragma unroll
+					for(int b = 16; b > 0; b >>= 1)
+						if(slot + b < 32 && S.pixBase[slot + b] <= p) slot += b;
+					const int k = (int)(p - S.pixBase[slot]);
+					misc = S.rMisc[slot];
+					float cf2 = S.rCf2[slot], z0 = S.rZ[slot];
+					const float cf2Step = S.rCf2Step[slot], zStep = S.rZStep[slot];
+#pragma unroll 1
+					for(int j = 0; j < k; j++)
+					{
+						cf2 = fadd(cf2, cf2Step);
+						z0 = fadd(z0, zStep);
+					}
+					// interpolateNextStep, interp.cpp:82-92
+					inv = fdiv(1.0f, cf2);
+					z = fmul(z0, inv);
+					pix = (((misc >> 4) & 15) << 4) | ((misc & 15) + (uint32_t)k);
+					tested++;
+				}
+				// fragments of one pixel are tested in lane order = submission order (§9.7)
+				const uint32_t peers = __match_any_sync(PS_FULL, pix);
+				const int rank = __popc(peers & ltMask);
+				const int maxRank = __reduce_max_sync(PS_FULL, act ? rank : 0);
+				bool pass = false;
+				for(int r = 0; r <= maxRank; r++)
+				{
+					if(act && rank == r)
+					{
+						const float cur = testDepth ? S.depth[pix] : 1.0f;               // fragthrd.cpp:217-225
+						if(-1.0f < z && fsub(z, cur) < -0.0001f)                         // fragthrd.cpp:227
+						{
+							pass = true;
+							// no functor on this path discards, so the depth write does not wait for the shading (fragthrd.cpp:234-237)
+							if(updateDepth) { S.depth[pix] = z; depthWrote = true; }
+						}
+					}
+					__syncwarp();
+				}
+				const uint32_t b = __ballot_sync(PS_FULL, pass);
+				if(pass)
+				{
+					const uint32_t q = qCount + __popc(b & ltMask);
+					S.qTri[q] = S.rTri[slot]; S.qLeft[q] = S.rLeft[slot]; S.qRight[q] = S.rRight[slot]; S.qInv[q] = inv;
+					S.qMisc[q] = pix | ((misc >> 8) << 8);
+				}
+				qCount += __popc(b);
+				__syncwarp();
+				if(qCount >= 32)
+				{
+					flushSurvivors(Q, S, lane, 32, tx0, ty0);
+					survived += 32;
+					const uint32_t rem = qCount - 32;
+					uint32_t a = 0, d = 0; int bb = 0, c = 0; float f = 0;
+					if((uint32_t)lane < rem) { a = S.qTri[32 + lane]; bb = S.qLeft[32 + lane]; c = S.qRight[32 + lane]; f = S.qInv[32 + lane]; d = S.qMisc[32 + lane]; }
+					__syncwarp();
+					if((uint32_t)lane < rem) { S.qTri[lane] = a; S.qLeft[lane] = bb; S.qRight[lane] = c; S.qInv[lane] = f; S.qMisc[lane] = d; }
+					qCount = rem;
+					__syncwarp();
+				}
+			}
+		}
+	}
+	if(qCount) { flushSurvivors(Q, S, lane, qCount, tx0, ty0); survived += qCount; }
+
+	// ---- write back: depth tile, and which record won each pixel
+	if(__any_sync(PS_FULL, depthWrote) && depthRowOk)
+	{
+#pragma unroll
+		for(int i = 0; i < PS_SEG; i++)
+			if(sx0 + i < P.depth.width) *(float*)(depthRow + (size_t)(sx0 + i) * 4) = S.depth[rr * PS_TILE + seg * PS_SEG + i];
+	}
+	if(survived && y < P.vpH)
+	{
+#pragma unroll
+		for(int i = 0; i < PS_SEG; i++)
+			if(sx0 + i < P.vpW) Q.winner[(size_t)y * P.vpW + sx0 + i] = S.lastIdx[rr * PS_TILE + seg * PS_SEG + i];
+	}
+	const unsigned long long t = warpSumU64(tested);
+	if(0 == lane)
+	{
+		if(t) atomicAdd(&P.stats->fragments_tested, t);
+		if(survived) atomicAdd(&P.stats->fragments_shaded, (unsigned long long)survived);   // every survivor is shaded exactly once by shade_kernel
+	}
+}
+
+// lane = survivor record, any order: varyings (interp.cpp:26-92), fragment functor (fragthrd.cpp:231), winner stores its colour
+template<class PROG>
+__global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ DrawParams P, const SurvivorStream Q)
+{
+	constexpr int NV = PROG::NV;
+	const uint32_t n = min(*Q.count, Q.capacity);
+	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+		const uint32_t tri = Q.tri[i];
+		const int left = Q.left[i], right = Q.right[i];
+		const float inv = Q.inv[i];
+		const uint32_t misc = Q.misc[i];
+		const int x = (int)(misc & 0x1fff), y = (int)((misc >> 13) & 0x1fff);
+		F4 frag[NV > 0 ? NV : 1];
+		if(NV > 0)
+		{
+			const uint4* src = (const uint4*)(P.hdr + tri);
+			const uint4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
+			const float vx[3] = { __uint_as_float(q0.x), __uint_as_float(q0.z), __uint_as_float(q1.x) };
+			const float vy[3] = { __uint_as_float(q0.y), __uint_as_float(q0.w), __uint_as_float(q1.y) };
+			const float rw0 = __uint_as_float(q1.z), rw1 = __uint_as_float(q1.w), rw2 = __uint_as_float(q2.x);
+			int l0, l1, r0, r1;
+			edgeDecode3((misc >> 26) & 7, l0, l1);
+			edgeDecode3((misc >> 29) & 7, r0, r1);
+			// interpolateStartAndStep, interp.cpp:26-80 (the varyings' half; the depth half ran in the raster kernel)
+			float cl[3], cr[3];
+			edgeContrib(vx, vy, l0, l1, (float)left, (float)y, cl);
+			edgeContrib(vx, vy, r0, r1, (float)right, (float)y, cr);
+			cl[0] = fmul(cl[0], rw0); cl[1] = fmul(cl[1], rw1); cl[2] = fmul(cl[2], rw2);
+			cr[0] = fmul(cr[0], rw0); cr[1] = fmul(cr[1], rw1); cr[2] = fmul(cr[2], rw2);
+			const int stepCount = right - left;
+			const int x1 = left < 0 ? 0 : left;
+			const int skip = x1 - left;
+			const F4* v = P.vary + (size_t)tri * 3 * NV;
+			F4 vStart[NV > 0 ? NV : 1], vStep[NV > 0 ? NV : 1];
+			// every varying is an independent float4 (the IP's methods are per-field loops, tex1light1.cpp:60-135)
+			typedef InterpolationProcessorVec4<1> IP1;
+			typedef typename PROG::I IP;
+#pragma unroll
+			for(int k = 0; k < NV; k++)
+			{
+				const float4 a = __ldg((const float4*)(v + k)), b = __ldg((const float4*)(v + NV + k)), c = __ldg((const float4*)(v + 2 * NV + k));
+				const F4 v0 = f4(a.x, a.y, a.z, a.w), v1 = f4(b.x, b.y, b.z, b.w), v2 = f4(c.x, c.y, c.z, c.w);
+				F4 vEnd;
+				IP1::interpolateByContributes(&vStart[k], &v0, &v1, &v2, cl[0], cl[1], cl[2]);
+				IP1::interpolateByContributes(&vEnd, &v0, &v1, &v2, cr[0], cr[1], cr[2]);
+				IP1::calcStep(&vStep[k], &vStart[k], &vEnd, stepCount);
+			}
+			if(skip > 0) IP::stepForward(vStart, vStep, skip);               // interp.cpp:74-79
+#pragma unroll 1
+			for(int k = x1; k < x; k++) IP::stepForward(vStart, vStep, 1);    // interp.cpp:88, one rounded add per pixel
+			IP::correctInterpolation(frag, vStart, inv);
+		}
+		FragmentProcessorOutput out;
+		out.discarded = false; out.wrote = false; out.blendable = false; out.bgra = 0;
+		PROG::F::process(frag, out, P);                                      // fragthrd.cpp:231
+		if(P.cap && x < P.capW && y < P.capH) atomicAdd(&P.cap[(size_t)y * P.capW + x], 1u);
+		if(out.wrote && y < P.colour.height && x < P.colour.width && Q.winner[(size_t)y * P.vpW + x] == i)
+		{
+			// FBOBridge::write / write4 without ALPHABLEND: a plain store (fragthrd.cpp:54-82); later survivors of the pixel overwrite
+			uint8_t* row = P.colour.ptr + (size_t)(P.colour.topDown ? P.colour.height - 1 - y : y) * P.colour.scanline;
+			*(uint32_t*)(row + (size_t)x * 4) = out.bgra;
+		}
 	}
 }

@@ -30,6 +30,7 @@ struct Prog { int vp, ip, fp; };
 
 typedef void (*LaunchGeom)(const DrawParams&, cudaStream_t);
 typedef void (*LaunchTile)(const DrawParams&, const uint32_t*, const uint32_t*, cudaStream_t);
+typedef void (*LaunchShade)(const DrawParams&, const SurvivorStream&, cudaStream_t);
 
 struct ProgEntry
 {
@@ -38,27 +39,50 @@ struct ProgEntry
 	uint32_t slots, uniforms;
 	int ntex;
 	int texSlot[PS_MAX_BOUND_TEX];
+	bool mayDiscard, usesWrite4;
 	LaunchGeom geom;
-	LaunchTile tile;
+	LaunchTile tileImmediate, tileOrdered;
+	LaunchShade shade;
 };
 
-// PS3D_TILE_IMMEDIATE=1 selects the first tile kernel for every programme (A/B checks)
-bool tileImmediateForced() { static int on = -1; if(on < 0) { const char* e = getenv("PS3D_TILE_IMMEDIATE"); on = (e && e[0] == '1') ? 1 : 0; } return on == 1; }
+// PS3D_TILE_PATH=immediate|ordered|split forces one tile path for every draw (A/B checks); default: chosen per draw
+int tilePathForced()
+{
+	static int v = -2;
+	if(v == -2)
+	{
+		const char* e = getenv("PS3D_TILE_PATH");
+		v = !e ? -1 : (!strcmp(e, "immediate") ? 0 : (!strcmp(e, "ordered") ? 1 : (!strcmp(e, "split") ? 2 : -1)));
+	}
+	return v;
+}
 
 template<class PROG> void launchGeom(const DrawParams& P, cudaStream_t s)
 {
 	const unsigned blocks = (P.ntris + 127) / 128;
 	geom_setup_kernel<PROG><<<blocks, 128, 0, s>>>(P);
 }
-template<class PROG> void launchTile(const DrawParams& P, const uint32_t* tileStart, const uint32_t* sortedTris, cudaStream_t s)
+unsigned tileBlocks(const DrawParams& P) { return ((unsigned)(P.tilesX * P.tilesY) + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK; }
+template<class PROG> void launchTileImmediate(const DrawParams& P, const uint32_t* tileStart, const uint32_t* sortedTris, cudaStream_t s)
 {
-	const unsigned tiles = (unsigned)(P.tilesX * P.tilesY);
-	const unsigned blocks = (tiles + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK;
-	// a functor that may discard() makes the depth write wait for the shading (fragthrd.cpp:234-237): immediate kernel
-	if(PROG::F::MAY_DISCARD || tileImmediateForced())
-		tile_raster_shade_immediate_kernel<PROG><<<blocks, 32 * PS_WARPS_PER_BLOCK, 0, s>>>(P, tileStart, sortedTris);
-	else
-		tile_raster_shade_kernel<PROG><<<blocks, 32 * PS_WARPS_PER_BLOCK, 0, s>>>(P, tileStart, sortedTris);
+	tile_raster_shade_immediate_kernel<PROG><<<tileBlocks(P), 32 * PS_WARPS_PER_BLOCK, 0, s>>>(P, tileStart, sortedTris);
+}
+template<class PROG> void launchTileOrdered(const DrawParams& P, const uint32_t* tileStart, const uint32_t* sortedTris, cudaStream_t s)
+{
+	tile_raster_shade_ordered_kernel<PROG><<<tileBlocks(P), 32 * PS_WARPS_PER_BLOCK, 0, s>>>(P, tileStart, sortedTris);
+}
+template<class PROG> void launchShade(const DrawParams& P, const SurvivorStream& Q, cudaStream_t s)
+{
+	// a flat grid-stride loop over the survivor stream: exactly one resident wave
+	static int perSM = 0, sms = 0;
+	if(0 == perSM)
+	{
+		int dev = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shade_kernel<PROG>, 128, 0) != cudaSuccess || perSM <= 0) perSM = 4;
+	}
+	shade_kernel<PROG><<<sms * perSM, 128, 0, s>>>(P, Q);
 }
 template<class PROG> ProgEntry makeEntry(int fnV, int fnI, int fnF)
 {
@@ -69,8 +93,12 @@ template<class PROG> ProgEntry makeEntry(int fnV, int fnI, int fnF)
 	e.uniforms = PROG::V::UNIFORMS | PROG::F::UNIFORMS;
 	e.ntex = PROG::F::NTEX;
 	for(int i = 0; i < PS_MAX_BOUND_TEX; i++) e.texSlot[i] = i < e.ntex ? PROG::F::texSlot(i) : -1;
+	e.mayDiscard = PROG::F::MAY_DISCARD;
+	e.usesWrite4 = PROG::F::USES_WRITE4;
 	e.geom = launchGeom<PROG>;
-	e.tile = launchTile<PROG>;
+	e.tileImmediate = launchTileImmediate<PROG>;
+	e.tileOrdered = launchTileOrdered<PROG>;
+	e.shade = launchShade<PROG>;
 	return e;
 }
 
@@ -141,8 +169,12 @@ struct ps3d_pipe
 	DevBuf<TriHeader> hdr;
 	DevBuf<F4> vary;
 	DevBuf<uint32_t> triCount, triOffset, triRect, scanSums, keysA, valsA, keysB, valsB, tileCount, tileStart, sortCounts;
+	DevBuf<uint32_t> svTri, svMisc, svWinner;   // survivor stream of the draw in flight (split path)
+	DevBuf<int> svLeft, svRight;
+	DevBuf<float> svInv;
+	uint32_t* svCountDev;
 	uint32_t* totalDev;
-	uint32_t* totalHost; // pinned
+	uint32_t* totalHost; // pinned: [0] = bin pairs of the draw, [2..3] = its fragment bound
 	DeviceStats* statsDev;
 	ps3d_stats stats;
 	uint32_t* capDev;
@@ -261,6 +293,7 @@ int ps3d_create(int width, int height, int device, ps3d_pipe** out)
 	ok = ok && cudaMalloc((void**)&p->defaultDepth, dbytes + 16) == cudaSuccess;
 	ok = ok && cudaMalloc((void**)&p->totalDev, 16) == cudaSuccess && cudaMallocHost((void**)&p->totalHost, 16) == cudaSuccess;
 	ok = ok && cudaMalloc((void**)&p->statsDev, sizeof(DeviceStats)) == cudaSuccess;
+	ok = ok && cudaMalloc((void**)&p->svCountDev, 16) == cudaSuccess;
 	if(ok)
 	{
 		cudaMemsetAsync(p->display[0], 0, cbytes, p->stream);
@@ -299,7 +332,8 @@ int ps3d_destroy(ps3d_pipe* p)
 	for(Texture* t : p->textures) if(t) { for(int i = 0; i < 6; i++) if(t->layer[i]) cudaFree(t->layer[i]); delete t; }
 	for(Vbo& v : p->vbos) if(v.alive && v.data) cudaFree(v.data);
 	cudaFree(p->display[0]); cudaFree(p->display[1]); cudaFree(p->defaultDepth);
-	cudaFree(p->totalDev); cudaFreeHost(p->totalHost); cudaFree(p->statsDev);
+	cudaFree(p->totalDev); cudaFreeHost(p->totalHost); cudaFree(p->statsDev); cudaFree(p->svCountDev);
+	p->svTri.release(); p->svMisc.release(); p->svWinner.release(); p->svLeft.release(); p->svRight.release(); p->svInv.release();
 	if(p->capDev) cudaFree(p->capDev);
 	if(p->rcpDev) cudaFree(p->rcpDev);
 	if(p->rsqrtDev) cudaFree(p->rsqrtDev);
@@ -687,6 +721,7 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	CK(p, p->triRect.ensure(ntris * 2));
 	P.hdr = p->hdr.p; P.vary = p->vary.p; P.triCount = p->triCount.p; P.triRect = p->triRect.p;
 
+	CK(p, cudaMemsetAsync(&p->statsDev->fragBound, 0, sizeof(unsigned long long), p->stream));
 	{
 		ProfScope ps(p, CLS_GEOM);
 		pe->geom(P, p->stream);
@@ -701,8 +736,11 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	if(rc) return rc;
 	// the number of (tile, triangle) pairs sizes the bins: one 4-byte read-back per draw
 	CK(p, cudaMemcpyAsync(p->totalHost, p->totalDev, 4, cudaMemcpyDeviceToHost, p->stream));
+	CK(p, cudaMemcpyAsync(p->totalHost + 2, &p->statsDev->fragBound, 8, cudaMemcpyDeviceToHost, p->stream));
 	CK(p, cudaStreamSynchronize(p->stream));
 	const uint32_t total = *p->totalHost;
+	unsigned long long fragBound = 0;
+	memcpy(&fragBound, p->totalHost + 2, 8);
 	if(0 == total) return PS3D_OK;
 
 	const uint32_t ntiles = (uint32_t)(P.tilesX * P.tilesY);
@@ -740,10 +778,28 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	if(rc) return rc;
 	delete binScope; binScope = nullptr;
 
+	// which tile path (kernels.cuh): a functor that may discard() makes the depth write wait for the shading
+	// (fragthrd.cpp:234-237) -> immediate; a draw that blends needs its colours applied in submission order -> ordered;
+	// everything else -> split (raster + depth kernel, survivor stream, flat shade kernel)
+	int path = pe->mayDiscard ? 0 : (((p->behavior & PS3D_BEHAVIOR_ALPHABLEND) && pe->usesWrite4) ? 1 : 2);
+	if(tilePathForced() >= 0 && !(pe->mayDiscard)) path = tilePathForced() == 2 && 1 == path ? 1 : tilePathForced();
+	if(2 == path && (fragBound >= 0xfffffff0ull || P.vpW > 8191 || P.vpH > 8191)) path = 1;
+	if(2 == path && 0 == fragBound) return PS3D_OK;
+	ProfScope ps(p, CLS_TILE);
+	if(0 == path) { pe->tileImmediate(P, p->tileStart.p, vIn, p->stream); p->launches++; }
+	else if(1 == path) { pe->tileOrdered(P, p->tileStart.p, vIn, p->stream); p->launches++; }
+	else
 	{
-		ProfScope ps(p, CLS_TILE);
-		pe->tile(P, p->tileStart.p, vIn, p->stream);
-		p->launches++;
+		const size_t cap = (size_t)fragBound;
+		CK(p, p->svTri.ensure(cap)); CK(p, p->svLeft.ensure(cap)); CK(p, p->svRight.ensure(cap)); CK(p, p->svInv.ensure(cap)); CK(p, p->svMisc.ensure(cap));
+		CK(p, p->svWinner.ensure((size_t)P.vpW * P.vpH));
+		SurvivorStream Q;
+		Q.tri = p->svTri.p; Q.left = p->svLeft.p; Q.right = p->svRight.p; Q.inv = p->svInv.p; Q.misc = p->svMisc.p;
+		Q.count = p->svCountDev; Q.winner = p->svWinner.p; Q.capacity = (uint32_t)cap;
+		CK(p, cudaMemsetAsync(p->svCountDev, 0, 4, p->stream));
+		tile_raster_depth_kernel<<<tileBlocks(P), 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(P, Q, p->tileStart.p, vIn);
+		pe->shade(P, Q, p->stream);
+		p->launches += 2;
 	}
 	CK(p, cudaGetLastError());
 	return PS3D_OK;

@@ -245,6 +245,7 @@ struct FragmentProcessorDEF01
 {
 	static constexpr uint32_t UNIFORMS = (1u << 7) | (1u << 8) | (1u << 9);
 	static constexpr bool MAY_DISCARD = false;
+	static constexpr bool USES_WRITE4 = false;
 	static constexpr int NTEX = 1;
 	__host__ __device__ static constexpr int texSlot(int i) { return 9; }
 	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P) // :152-193
@@ -274,6 +275,7 @@ struct FragmentProcessorDEF02
 {
 	static constexpr uint32_t UNIFORMS = (1u << 7) | (1u << 8);
 	static constexpr bool MAY_DISCARD = false;
+	static constexpr bool USES_WRITE4 = false;
 	static constexpr int NTEX = 0;
 	__host__ __device__ static constexpr int texSlot(int i) { return -1; }
 	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P) // :150-190
@@ -306,6 +308,7 @@ struct FragmentProcessorDEF03
 {
 	static constexpr uint32_t UNIFORMS = (1u << 7) | (1u << 8) | (1u << 9) | (1u << 10);
 	static constexpr bool MAY_DISCARD = false;
+	static constexpr bool USES_WRITE4 = false;
 	static constexpr int NTEX = 2;
 	__host__ __device__ static constexpr int texSlot(int i) { return i == 0 ? 9 : 10; }
 	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P) // :180-239
@@ -356,6 +359,7 @@ struct FragmentProcessorDEF04
 {
 	static constexpr uint32_t UNIFORMS = (1u << 2);
 	static constexpr bool MAY_DISCARD = false;
+	static constexpr bool USES_WRITE4 = true; 
 	static constexpr int NTEX = 1;
 	__host__ __device__ static constexpr int texSlot(int i) { return 2; }
 	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P) // :127-134
@@ -389,6 +393,7 @@ struct FragmentProcessorDEF05
 {
 	static constexpr uint32_t UNIFORMS = 0;
 	static constexpr bool MAY_DISCARD = false;
+	static constexpr bool USES_WRITE4 = false;
 	static constexpr int NTEX = 0;
 	__host__ __device__ static constexpr int texSlot(int i) { return -1; }
 	PS_D static void process(const F4*, FragmentProcessorOutput&, const DrawParams&) {} // shadow.cpp:76-77
@@ -410,6 +415,7 @@ struct FragmentProcessorFLATID
 {
 	static constexpr uint32_t UNIFORMS = 0;
 	static constexpr bool MAY_DISCARD = false;
+	static constexpr bool USES_WRITE4 = true; 
 	static constexpr int NTEX = 0;
 	__host__ __device__ static constexpr int texSlot(int i) { return -1; }
 	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams&)
