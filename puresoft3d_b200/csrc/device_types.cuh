@@ -49,7 +49,10 @@ struct DeviceStats
 	unsigned long long spans;
 	unsigned long long fragments_tested;
 	unsigned long long fragments_shaded;
-	unsigned long long fragBound;   // this draw: sum of clamped span lengths = upper bound of its depth-test survivors
+	// reset at the start of every draw:
+	unsigned long long fragBound;   // sum of clamped span lengths = upper bound of the draw's depth-test survivors
+	unsigned int pairs;             // (tile, triangle) pairs = sum of the per-tile counts
+	unsigned int maxTileCount;      // longest tile list
 };
 
 // Survivors of the depth test, one record per FragmentProcessor::process call still to make (split path): structure of
@@ -82,7 +85,9 @@ struct DrawParams
 	TriHeader* hdr;
 	F4* vary;
 	uint32_t* triCount;         // bin entries per triangle (0 = culled / rejected / empty)
-	uint32_t* triRect;          // tx0 | tx1<<8... packed as 4 x uint16 in two words (see geom_setup)
+	uint32_t* triRect;          // per triangle 3 words: tx0 | tx1 << 16, ty0 | ty1 << 16, mask of touched tiles (bit = (ty-ty0)*8 + tx-tx0;
+	                            // ~0 when the rectangle exceeds 8 x 4 tiles and is used whole)
+	uint32_t* tileCount;        // per tile: triangles binned to it (atomics in geom_setup)
 	DeviceStats* stats;
 	uint32_t* cap;              // per-pixel FragmentProcessor::process counts (parity hook) or NULL
 	int capW, capH;

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 {
 	constexpr int NV = PROG::NV;
 	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
-	unsigned rasterised = 0, spans = 0, frags = 0;
+	unsigned rasterised = 0, spans = 0, frags = 0, pairs = 0;
 	if(tri < P.ntris)
 	{
 		VertexProcessorOutput<NV> vo[3];
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 		// drawvao.cpp:51-56 : the only "clipping" — drop the whole triangle
 		if(pz[0] < -1.0f || pz[0] > 1.0f || pz[1] < -1.0f || pz[1] > 1.0f || pz[2] < -1.0f || pz[2] > 1.0f) alive = false;
 
-		uint32_t count = 0, rect0 = 0, rect1 = 0;
+		uint32_t count = 0, rect0 = 0, rect1 = 0, mask = 0;
 		if(alive)
 		{
 			TriHeader h;
@@ -98,6 +98,9 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 			{
 				const int firstRow = (int)(h.rows & 0xffff), lastRow = (int)(h.rows >> 16);
 				int minX = 0x7fffffff, maxX = -1, minY = 0x7fffffff, maxY = -1;
+				// for the first four tile rows the triangle touches: the tile columns its spans reach (lo | hi << 16)
+				uint32_t tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0, trSet = 0;
+				int tyFirst = -1;
 				for(int iy = firstRow; iy <= lastRow; iy++) // drawvao.cpp:66-75
 				{
 					RowSpan r;
@@ -111,13 +114,49 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 					frags += (unsigned)(x2 - x1 + 1);
 					minX = min(minX, x1); maxX = max(maxX, x2);
 					minY = min(minY, iy); maxY = max(maxY, iy);
+					const int ty = iy / PS_TILE;
+					if(tyFirst < 0) tyFirst = ty;
+					const int k = ty - tyFirst;
+					if(k < 4)
+					{
+						uint32_t cur = 0 == k ? tr0 : (1 == k ? tr1 : (2 == k ? tr2 : tr3));
+						const uint32_t a = (uint32_t)(x1 / PS_TILE), b = (uint32_t)(x2 / PS_TILE);
+						cur = (trSet >> k) & 1 ? (min(cur & 0xffff, a) | (max(cur >> 16, b) << 16)) : (a | (b << 16));
+						trSet |= 1u << k;
+						if(0 == k) tr0 = cur; else if(1 == k) tr1 = cur; else if(2 == k) tr2 = cur; else tr3 = cur;
+					}
 				}
 				if(maxX >= 0)
 				{
 					const int tx0 = minX / PS_TILE, tx1 = maxX / PS_TILE, ty0 = minY / PS_TILE, ty1 = maxY / PS_TILE;
-					count = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
 					rect0 = (uint32_t)tx0 | ((uint32_t)tx1 << 16);
 					rect1 = (uint32_t)ty0 | ((uint32_t)ty1 << 16);
+					if(tx1 - tx0 >= 8 || ty1 - ty0 >= 4)
+					{
+						// large triangle: the whole rectangle of tiles (the tile kernels drop rows that miss a tile)
+						mask = 0xffffffffu;
+						count = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+						for(int ty = ty0; ty <= ty1; ty++)
+							for(int tx = tx0; tx <= tx1; tx++) atomicAdd(&P.tileCount[ty * P.tilesX + tx], 1u);
+					}
+					else
+					{
+						// small triangle (the common case): exactly the tiles some span of it reaches
+#pragma unroll
+						for(int k = 0; k < 4; k++)
+							if((trSet >> k) & 1)
+							{
+								const uint32_t cur = 0 == k ? tr0 : (1 == k ? tr1 : (2 == k ? tr2 : tr3));
+								const int a = (int)(cur & 0xffff) - tx0, b = (int)(cur >> 16) - tx0;   // 0 <= a <= b <= 7
+								mask |= ((2u << b) - (1u << a)) << (k * 8);
+							}
+						count = (uint32_t)__popc(mask);
+						for(uint32_t m = mask; m; m &= m - 1)
+						{
+							const int bit = __ffs(m) - 1;
+							atomicAdd(&P.tileCount[(ty0 + (bit >> 3)) * P.tilesX + tx0 + (bit & 7)], 1u);
+						}
+					}
 					h.rw0 = rw[0]; h.rw1 = rw[1]; h.rw2 = rw[2];
 					h.z0 = pz[0]; h.z1 = pz[1]; h.z2 = pz[2];
 					// 64-byte record as four 16-byte stores
@@ -137,8 +176,10 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 			}
 		}
 		P.triCount[tri] = count;
-		P.triRect[2 * tri] = rect0;
-		P.triRect[2 * tri + 1] = rect1;
+		P.triRect[3 * tri] = rect0;
+		P.triRect[3 * tri + 1] = rect1;
+		P.triRect[3 * tri + 2] = mask;
+		pairs = count;
 	}
 	const unsigned long long r = warpSumU64(rasterised), s = warpSumU64(spans);
 	unsigned long long f = frags;
@@ -150,6 +191,8 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 		if(s) atomicAdd(&P.stats->spans, s);
 		if(f) atomicAdd(&P.stats->fragBound, f);
 	}
+	const unsigned pr = (unsigned)warpSumU64(pairs);
+	if(0 == (threadIdx.x & 31) && pr) atomicAdd(&P.stats->pairs, pr);
 }
 
 // ======================================================================================================================
@@ -241,23 +284,130 @@ __global__ void __launch_bounds__(PS_SCAN_THREADS) scan_add_kernel(uint32_t* __r
 
 __global__ void __launch_bounds__(128) emit_pairs_kernel(const uint32_t* __restrict__ triCount, const uint32_t* __restrict__ triOffset,
                                                         const uint32_t* __restrict__ triRect, uint32_t* __restrict__ keys,
-                                                        uint32_t* __restrict__ vals, uint32_t* __restrict__ tileCount, uint32_t ntris, int tilesX)
+                                                        uint32_t* __restrict__ vals, uint32_t ntris, int tilesX)
 {
 	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
 	if(tri >= ntris) return;
 	if(0 == triCount[tri]) return;
 	uint32_t o = triOffset[tri];
-	const uint32_t r0 = triRect[2 * tri], r1 = triRect[2 * tri + 1];
+	const uint32_t r0 = triRect[3 * tri], r1 = triRect[3 * tri + 1], mask = triRect[3 * tri + 2];
 	const int tx0 = (int)(r0 & 0xffff), tx1 = (int)(r0 >> 16), ty0 = (int)(r1 & 0xffff), ty1 = (int)(r1 >> 16);
+	const bool whole = 0xffffffffu == mask;
 	for(int ty = ty0; ty <= ty1; ty++)
 		for(int tx = tx0; tx <= tx1; tx++)
 		{
-			const uint32_t tile = (uint32_t)(ty * tilesX + tx);
-			keys[o] = tile;
+			if(!whole && 0 == ((mask >> ((ty - ty0) * 8 + tx - tx0)) & 1)) continue;
+			keys[o] = (uint32_t)(ty * tilesX + tx);
 			vals[o] = tri;
 			o++;
-			atomicAdd(&tileCount[tile], 1u);
 		}
+}
+
+// ---- the default binning: per-tile counts came from geom_setup; scan them, fill the lists with atomics (any order), then
+// sort every tile's list by triangle id = submission order (§9.7). Lists longer than PS_SORT_LIMIT use the radix path.
+
+#define PS_SORT_LIMIT 2048
+
+// one block: tileStart = exclusive scan of tileCount (ntiles + 1 entries), the longest list -> stats->maxTileCount
+__global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileStart,
+                                                        uint32_t* __restrict__ tileFill, uint32_t ntiles, DeviceStats* stats)
+{
+	__shared__ uint32_t warpTotals[32];
+	__shared__ uint32_t carryS;
+	if(0 == threadIdx.x) carryS = 0;
+	__syncthreads();
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t longest = 0;
+	for(uint32_t base = 0; base < ntiles + 1; base += 1024)
+	{
+		const uint32_t i = base + threadIdx.x;
+		const uint32_t v = i < ntiles ? tileCount[i] : 0;
+		longest = max(longest, v);
+		uint32_t incl = v;
+#pragma unroll
+		for(int d = 1; d < 32; d <<= 1)
+		{
+			uint32_t t = __shfl_up_sync(PS_FULL, incl, d);
+			if(lane >= d) incl += t;
+		}
+		if(31 == lane) warpTotals[warp] = incl;
+		__syncthreads();
+		uint32_t warpBase = 0;
+		for(int w = 0; w < warp; w++) warpBase += warpTotals[w];
+		const uint32_t carry = carryS;
+		if(i < ntiles + 1) { tileStart[i] = carry + warpBase + incl - v; if(i < ntiles) tileFill[i] = 0; }
+		__syncthreads();
+		if(1023 == threadIdx.x) carryS = carry + warpBase + incl;
+		__syncthreads();
+	}
+	longest = __reduce_max_sync(PS_FULL, longest);
+	if(0 == lane && longest) atomicMax(&stats->maxTileCount, longest);
+}
+
+__global__ void __launch_bounds__(128) bin_fill_kernel(const uint32_t* __restrict__ triCount, const uint32_t* __restrict__ triRect,
+                                                      const uint32_t* __restrict__ tileStart, uint32_t* __restrict__ tileFill,
+                                                      uint32_t* __restrict__ lists, uint32_t ntris, int tilesX)
+{
+	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+	if(tri >= ntris) return;
+	if(0 == triCount[tri]) return;
+	const uint32_t r0 = triRect[3 * tri], r1 = triRect[3 * tri + 1], mask = triRect[3 * tri + 2];
+	const int tx0 = (int)(r0 & 0xffff), tx1 = (int)(r0 >> 16), ty0 = (int)(r1 & 0xffff), ty1 = (int)(r1 >> 16);
+	if(0xffffffffu == mask)
+	{
+		for(int ty = ty0; ty <= ty1; ty++)
+			for(int tx = tx0; tx <= tx1; tx++)
+			{
+				const uint32_t tile = (uint32_t)(ty * tilesX + tx);
+				lists[tileStart[tile] + atomicAdd(&tileFill[tile], 1u)] = tri;
+			}
+	}
+	else
+	{
+		for(uint32_t m = mask; m; m &= m - 1)
+		{
+			const int bit = __ffs(m) - 1;
+			const uint32_t tile = (uint32_t)((ty0 + (bit >> 3)) * tilesX + tx0 + (bit & 7));
+			lists[tileStart[tile] + atomicAdd(&tileFill[tile], 1u)] = tri;
+		}
+	}
+}
+
+// one warp per tile: bitonic sort of its list (<= PS_SORT_LIMIT ids) in shared memory
+__global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_list_sort_kernel(const uint32_t* __restrict__ tileStart, uint32_t* __restrict__ lists, uint32_t ntiles)
+{
+	__shared__ uint32_t buf[PS_WARPS_PER_BLOCK][PS_SORT_LIMIT];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const uint32_t tile = blockIdx.x * PS_WARPS_PER_BLOCK + w;
+	if(tile >= ntiles) return;
+	const uint32_t begin = tileStart[tile], n = tileStart[tile + 1] - begin;
+	if(n < 2 || n > PS_SORT_LIMIT) return;
+	uint32_t* a = buf[w];
+	uint32_t P2 = 2;
+	while(P2 < n) P2 <<= 1;
+	bool sorted = true;
+	for(uint32_t i = lane; i < P2; i += 32)
+	{
+		const uint32_t v = i < n ? lists[begin + i] : 0xffffffffu;
+		a[i] = v;
+		if(i > 0 && i < n && lists[begin + i - 1] > v) sorted = false;
+	}
+	__syncwarp();
+	if(__all_sync(PS_FULL, sorted)) return;
+	for(uint32_t k = 2; k <= P2; k <<= 1)
+		for(uint32_t j = k >> 1; j > 0; j >>= 1)
+		{
+			for(uint32_t t = lane; t < (P2 >> 1); t += 32)
+			{
+				// the t-th compare-exchange pair of this stage: i has bit j clear
+				const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+				const uint32_t x = a[i], y = a[i | j];
+				const bool up = 0 == (i & k);
+				if((x > y) == up) { a[i] = y; a[i | j] = x; }
+			}
+			__syncwarp();
+		}
+	for(uint32_t i = lane; i < n; i += 32) lists[begin + i] = a[i];
 }
 
 #define PS_SORT_ITEMS_PER_WARP 1024
@@ -1073,9 +1223,9 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_depth_ker
 					if(t + b < 32 && S.spanBase[t + b] <= s) t += b;
 				const int iy = S.triRow0[t] + (int)(s - S.spanBase[t]);
 				const TriHeader& h = S.hdr[t];
-				const float vx[3] = { h.vx0, h.vx1, h.vx2 }, vy[3] = { h.vy0, h.vy1, h.vy2 };
+				const float* xy = &h.vx0;
 				RowSpan r;
-				if(rowOf(h, vx, vy, iy, r) && r.left != r.right)                  // drawvao.cpp:72
+				if(rowOfXY(h, iy, r) && r.left != r.right)                        // drawvao.cpp:72
 				{
 					const int x1 = r.left < 0 ? 0 : r.left;                       // RESULT_ROW::leftClamped
 					const int x2 = r.right >= P.vpW ? P.vpW - 1 : r.right;        // RESULT_ROW::rightClamped
@@ -1085,8 +1235,8 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_depth_ker
 						const int e = r.edges;
 						// interpolateStartAndStep, interp.cpp:26-80
 						float cl[3], cr[3];
-						edgeContrib(vx, vy, e & 3, (e >> 2) & 3, (float)r.left, (float)iy, cl);
-						edgeContrib(vx, vy, (e >> 4) & 3, (e >> 6) & 3, (float)r.right, (float)iy, cr);
+						edgeContribXY(xy, e & 3, (e >> 2) & 3, (float)r.left, (float)iy, cl);
+						edgeContribXY(xy, (e >> 4) & 3, (e >> 6) & 3, (float)r.right, (float)iy, cr);
 						cl[0] = fmul(cl[0], h.rw0); cl[1] = fmul(cl[1], h.rw1); cl[2] = fmul(cl[2], h.rw2); // mulvec_3_4 (:40-41); lane 3 is 0*0
 						cr[0] = fmul(cr[0], h.rw0); cr[1] = fmul(cr[1], h.rw1); cr[2] = fmul(cr[2], h.rw2);
 						const float rcpLen = fdiv(1.0f, (float)(r.right - r.left));                          // :47
@@ -1162,6 +1312,7 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_depth_ker
 				const int rank = __popc(peers & ltMask);
 				const int maxRank = __reduce_max_sync(PS_FULL, act ? rank : 0);
 				bool pass = false;
+#pragma unroll 1
 				for(int r = 0; r <= maxRank; r++)
 				{
 					if(act && rank == r)
@@ -1261,6 +1412,7 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Draw
 			// every varying is an independent float4 (the IP's methods are per-field loops, tex1light1.cpp:60-135)
 			typedef InterpolationProcessorVec4<1> IP1;
 			typedef typename PROG::I IP;
+			const float rStep = IP1::reciprocalStepCount(stepCount);        // one divide per span, as in calcStep (tex1light1.cpp:93-107)
 #pragma unroll
 			for(int k = 0; k < NV; k++)
 			{
@@ -1269,7 +1421,7 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Draw
 				F4 vEnd;
 				IP1::interpolateByContributes(&vStart[k], &v0, &v1, &v2, cl[0], cl[1], cl[2]);
 				IP1::interpolateByContributes(&vEnd, &v0, &v1, &v2, cr[0], cr[1], cr[2]);
-				IP1::calcStep(&vStep[k], &vStart[k], &vEnd, stepCount);
+				IP1::calcStepR(&vStep[k], &vStart[k], &vEnd, rStep);
 			}
 			if(skip > 0) IP::stepForward(vStart, vStep, skip);               // interp.cpp:74-79
 #pragma unroll 1

@@ -57,6 +57,9 @@ int tilePathForced()
 	return v;
 }
 
+// PS3D_BINNING=radix forces the stable radix-sort binning (the fallback for very long tile lists) for every draw
+bool radixBinningForced() { static int on = -1; if(on < 0) { const char* e = getenv("PS3D_BINNING"); on = (e && !strcmp(e, "radix")) ? 1 : 0; } return on == 1; }
+
 template<class PROG> void launchGeom(const DrawParams& P, cudaStream_t s)
 {
 	const unsigned blocks = (P.ntris + 127) / 128;
@@ -168,7 +171,7 @@ struct ps3d_pipe
 	// per-draw scratch
 	DevBuf<TriHeader> hdr;
 	DevBuf<F4> vary;
-	DevBuf<uint32_t> triCount, triOffset, triRect, scanSums, keysA, valsA, keysB, valsB, tileCount, tileStart, sortCounts;
+	DevBuf<uint32_t> triCount, triOffset, triRect, scanSums, keysA, valsA, keysB, valsB, tileCount, tileStart, tileFill, sortCounts;
 	DevBuf<uint32_t> svTri, svMisc, svWinner;   // survivor stream of the draw in flight (split path)
 	DevBuf<int> svLeft, svRight;
 	DevBuf<float> svInv;
@@ -338,7 +341,7 @@ int ps3d_destroy(ps3d_pipe* p)
 	if(p->rcpDev) cudaFree(p->rcpDev);
 	if(p->rsqrtDev) cudaFree(p->rsqrtDev);
 	p->hdr.release(); p->vary.release(); p->triCount.release(); p->triOffset.release(); p->triRect.release(); p->scanSums.release();
-	p->keysA.release(); p->valsA.release(); p->keysB.release(); p->valsB.release(); p->tileCount.release(); p->tileStart.release(); p->sortCounts.release();
+	p->keysA.release(); p->valsA.release(); p->keysB.release(); p->valsB.release(); p->tileCount.release(); p->tileStart.release(); p->tileFill.release(); p->sortCounts.release();
 	for(auto& s : p->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
 	for(auto& e : p->eventPool) cudaEventDestroy(e);
 	cudaStreamDestroy(p->stream);
@@ -714,69 +717,83 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	P.stats = p->statsDev;
 	P.cap = p->capDev; P.capW = p->capW; P.capH = p->capH;
 
+	const uint32_t ntiles = (uint32_t)(P.tilesX * P.tilesY);
 	CK(p, p->hdr.ensure(ntris));
 	CK(p, p->vary.ensure(ntris * 3 * (size_t)(pe->nv > 0 ? pe->nv : 1)));
 	CK(p, p->triCount.ensure(ntris));
-	CK(p, p->triOffset.ensure(ntris));
-	CK(p, p->triRect.ensure(ntris * 2));
-	P.hdr = p->hdr.p; P.vary = p->vary.p; P.triCount = p->triCount.p; P.triRect = p->triRect.p;
+	CK(p, p->triRect.ensure(ntris * 3));
+	CK(p, p->tileCount.ensure(ntiles + 1)); CK(p, p->tileStart.ensure(ntiles + 1)); CK(p, p->tileFill.ensure(ntiles + 1));
+	P.hdr = p->hdr.p; P.vary = p->vary.p; P.triCount = p->triCount.p; P.triRect = p->triRect.p; P.tileCount = p->tileCount.p;
 
-	CK(p, cudaMemsetAsync(&p->statsDev->fragBound, 0, sizeof(unsigned long long), p->stream));
+	// per-draw counters (fragBound, pairs, maxTileCount are the tail of DeviceStats) and the per-tile counts
+	CK(p, cudaMemsetAsync(&p->statsDev->fragBound, 0, 16, p->stream));
+	CK(p, cudaMemsetAsync(p->tileCount.p, 0, (size_t)(ntiles + 1) * 4, p->stream));
 	{
 		ProfScope ps(p, CLS_GEOM);
 		pe->geom(P, p->stream);
 		p->launches++;
 	}
 	CK(p, cudaGetLastError());
-	int rc;
 	{
 		ProfScope ps(p, CLS_BIN);
-		rc = exclusiveScan(p, p->triCount.p, p->triOffset.p, P.ntris, p->totalDev);
-	}
-	if(rc) return rc;
-	// the number of (tile, triangle) pairs sizes the bins: one 4-byte read-back per draw
-	CK(p, cudaMemcpyAsync(p->totalHost, p->totalDev, 4, cudaMemcpyDeviceToHost, p->stream));
-	CK(p, cudaMemcpyAsync(p->totalHost + 2, &p->statsDev->fragBound, 8, cudaMemcpyDeviceToHost, p->stream));
-	CK(p, cudaStreamSynchronize(p->stream));
-	const uint32_t total = *p->totalHost;
-	unsigned long long fragBound = 0;
-	memcpy(&fragBound, p->totalHost + 2, 8);
-	if(0 == total) return PS3D_OK;
-
-	const uint32_t ntiles = (uint32_t)(P.tilesX * P.tilesY);
-	p->profPairs += p->profiling ? total : 0;
-	ProfScope* binScope = new ProfScope(p, CLS_BIN);
-	struct ScopeGuard { ProfScope*& s; ~ScopeGuard() { delete s; s = nullptr; } } binGuard{binScope};
-	CK(p, p->keysA.ensure(total)); CK(p, p->valsA.ensure(total)); CK(p, p->keysB.ensure(total)); CK(p, p->valsB.ensure(total));
-	CK(p, p->tileCount.ensure(ntiles + 1)); CK(p, p->tileStart.ensure(ntiles + 1));
-	CK(p, cudaMemsetAsync(p->tileCount.p, 0, (size_t)(ntiles + 1) * 4, p->stream));
-	emit_pairs_kernel<<<(P.ntris + 127) / 128, 128, 0, p->stream>>>(p->triCount.p, p->triOffset.p, p->triRect.p, p->keysA.p, p->valsA.p, p->tileCount.p, P.ntris, P.tilesX);
-	p->launches++;
-	CK(p, cudaGetLastError());
-
-	// stable LSD radix sort of the pairs by tile id, 8 bits per pass
-	int bits = 0;
-	while((1u << bits) < ntiles) bits++;
-	uint32_t *kIn = p->keysA.p, *vIn = p->valsA.p, *kOut = p->keysB.p, *vOut = p->valsB.p;
-	const uint32_t nwarps = (total + PS_SORT_ITEMS_PER_WARP - 1) / PS_SORT_ITEMS_PER_WARP;
-	CK(p, p->sortCounts.ensure((size_t)256 * nwarps));
-	for(int shift = 0; shift < bits; shift += 8)
-	{
-		const unsigned blocks = (nwarps + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK;
-		sort_hist_kernel<<<blocks, 128, 0, p->stream>>>(kIn, total, shift, p->sortCounts.p, nwarps);
+		tile_scan_kernel<<<1, 1024, 0, p->stream>>>(p->tileCount.p, p->tileStart.p, p->tileFill.p, ntiles, p->statsDev);
 		p->launches++;
-		rc = exclusiveScan(p, p->sortCounts.p, p->sortCounts.p, 256 * nwarps, p->totalDev);
+	}
+	// sizes of the draw's intermediates: one 16-byte read-back per draw
+	CK(p, cudaMemcpyAsync(p->totalHost, &p->statsDev->fragBound, 16, cudaMemcpyDeviceToHost, p->stream));
+	CK(p, cudaStreamSynchronize(p->stream));
+	unsigned long long fragBound = 0;
+	memcpy(&fragBound, p->totalHost, 8);
+	const uint32_t total = p->totalHost[2], longest = p->totalHost[3];
+	if(0 == total) return PS3D_OK;
+	p->profPairs += p->profiling ? total : 0;
+
+	const uint32_t* sortedTris = nullptr;
+	int rc;
+	if(longest <= PS_SORT_LIMIT && !radixBinningForced())
+	{
+		// lists filled with atomics in arrival order, then every tile's list sorted by triangle id = submission order
+		ProfScope ps(p, CLS_BIN);
+		CK(p, p->valsA.ensure(total));
+		bin_fill_kernel<<<(P.ntris + 127) / 128, 128, 0, p->stream>>>(p->triCount.p, p->triRect.p, p->tileStart.p, p->tileFill.p, p->valsA.p, P.ntris, P.tilesX);
+		tile_list_sort_kernel<<<(ntiles + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK, 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(p->tileStart.p, p->valsA.p, ntiles);
+		p->launches += 2;
+		CK(p, cudaGetLastError());
+		sortedTris = p->valsA.p;
+	}
+	else
+	{
+		// some tile list is too long for the shared-memory sort: pairs emitted in triangle order + stable LSD radix sort by tile
+		ProfScope ps(p, CLS_BIN);
+		CK(p, p->triOffset.ensure(ntris));
+		rc = exclusiveScan(p, p->triCount.p, p->triOffset.p, P.ntris, p->totalDev);
 		if(rc) return rc;
-		sort_scatter_kernel<<<blocks, 128, 0, p->stream>>>(kIn, vIn, kOut, vOut, total, shift, p->sortCounts.p, nwarps);
+		CK(p, p->keysA.ensure(total)); CK(p, p->valsA.ensure(total)); CK(p, p->keysB.ensure(total)); CK(p, p->valsB.ensure(total));
+		emit_pairs_kernel<<<(P.ntris + 127) / 128, 128, 0, p->stream>>>(p->triCount.p, p->triOffset.p, p->triRect.p, p->keysA.p, p->valsA.p, P.ntris, P.tilesX);
 		p->launches++;
 		CK(p, cudaGetLastError());
-		uint32_t* t;
-		t = kIn; kIn = kOut; kOut = t;
-		t = vIn; vIn = vOut; vOut = t;
+		int bits = 0;
+		while((1u << bits) < ntiles) bits++;
+		uint32_t *kIn = p->keysA.p, *vIn = p->valsA.p, *kOut = p->keysB.p, *vOut = p->valsB.p;
+		const uint32_t nwarps = (total + PS_SORT_ITEMS_PER_WARP - 1) / PS_SORT_ITEMS_PER_WARP;
+		CK(p, p->sortCounts.ensure((size_t)256 * nwarps));
+		for(int shift = 0; shift < bits; shift += 8)
+		{
+			const unsigned blocks = (nwarps + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK;
+			sort_hist_kernel<<<blocks, 128, 0, p->stream>>>(kIn, total, shift, p->sortCounts.p, nwarps);
+			p->launches++;
+			rc = exclusiveScan(p, p->sortCounts.p, p->sortCounts.p, 256 * nwarps, p->totalDev);
+			if(rc) return rc;
+			sort_scatter_kernel<<<blocks, 128, 0, p->stream>>>(kIn, vIn, kOut, vOut, total, shift, p->sortCounts.p, nwarps);
+			p->launches++;
+			CK(p, cudaGetLastError());
+			uint32_t* t;
+			t = kIn; kIn = kOut; kOut = t;
+			t = vIn; vIn = vOut; vOut = t;
+		}
+		sortedTris = vIn;
 	}
-	rc = exclusiveScan(p, p->tileCount.p, p->tileStart.p, ntiles + 1, p->totalDev);
-	if(rc) return rc;
-	delete binScope; binScope = nullptr;
+	const uint32_t* vIn = sortedTris;
 
 	// which tile path (kernels.cuh): a functor that may discard() makes the depth write wait for the shading
 	// (fragthrd.cpp:234-237) -> immediate; a draw that blends needs its colours applied in submission order -> ordered;

@@ -145,9 +145,51 @@ PS_D void edgeContrib(const float* vx, const float* vy, int v1, int v2, float x,
 {
 	const float x1 = sel3(vx, v1), y1 = sel3(vy, v1), x2 = sel3(vx, v2), y2 = sel3(vy, v2);
 	const float dx = fsub(x1, x2), dy = fsub(y1, y2);
-	const float c1 = fabsf(dx) > fabsf(dy) ? fdiv(fsub(x, x2), dx) : fdiv(fsub(y, y2), dy);
+	const bool alongX = fabsf(dx) > fabsf(dy);
+	const float c1 = fdiv(alongX ? fsub(x, x2) : fsub(y, y2), alongX ? dx : dy);   // one divide, the operands of the chosen branch
 	const float c2 = fsub(1.0f, c1);
 	// c[v1] = c1, c[v2] = 1 - c1, c[the third] = 0 — written with selects to stay in registers
+	c[0] = v1 == 0 ? c1 : (v2 == 0 ? c2 : 0.0f);
+	c[1] = v1 == 1 ? c1 : (v2 == 1 ? c2 : 0.0f);
+	c[2] = v1 == 2 ? c1 : (v2 == 2 ? c2 : 0.0f);
+}
+
+
+// ---- the same three routines reading the vertices by index from a TriHeader held in shared memory (vx0,vy0,vx1,vy1,vx2,vy2
+// are its first six floats): a dynamically indexed LDS instead of a chain of selects ------------------------------------
+PS_D Edge makeEdgeXY(const float* xy, int i0, int i1)
+{
+	Edge e;
+	e.x0 = xy[2 * i0]; e.y0 = xy[2 * i0 + 1];
+	e.dx = fsub(xy[2 * i1], e.x0);
+	e.dy = fsub(xy[2 * i1 + 1], e.y0);
+	if(fabsf(e.dy) < 0.000001f) e.dy = FLT_MAX;
+	return e;
+}
+PS_D bool rowOfXY(const TriHeader& h, int iy, RowSpan& r)
+{
+	int sel;
+	const int l0 = (int)(h.half1 & 0xffff), l1 = (int)(h.half1 >> 16);
+	const int u0 = (int)(h.half0 & 0xffff), u1 = (int)(h.half0 >> 16);
+	if(iy >= l0 && iy <= l1) sel = (int)((h.plan >> 8) & 0xff);
+	else if(iy >= u0 && iy <= u1) sel = (int)(h.plan & 0xff);
+	else return false;
+	const float* xy = &h.vx0;
+	const Edge L = makeEdgeXY(xy, sel & 3, (sel >> 2) & 3);
+	const Edge R = makeEdgeXY(xy, (sel >> 4) & 3, (sel >> 6) & 3);
+	const float y = (float)iy;
+	r.left = cvtt(fadd(edgeAt(L, y), 0.5f));
+	r.right = cvtt(fadd(edgeAt(R, y), 0.5f));
+	r.edges = sel;
+	return true;
+}
+PS_D void edgeContribXY(const float* xy, int v1, int v2, float x, float y, float* c)
+{
+	const float x1 = xy[2 * v1], y1 = xy[2 * v1 + 1], x2 = xy[2 * v2], y2 = xy[2 * v2 + 1];
+	const float dx = fsub(x1, x2), dy = fsub(y1, y2);
+	const bool alongX = fabsf(dx) > fabsf(dy);
+	const float c1 = fdiv(alongX ? fsub(x, x2) : fsub(y, y2), alongX ? dx : dy);
+	const float c2 = fsub(1.0f, c1);
 	c[0] = v1 == 0 ? c1 : (v2 == 0 ? c2 : 0.0f);
 	c[1] = v1 == 1 ? c1 : (v2 == 1 ? c2 : 0.0f);
 	c[2] = v1 == 2 ? c1 : (v2 == 2 ? c2 : 0.0f);

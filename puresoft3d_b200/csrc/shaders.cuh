@@ -162,12 +162,16 @@ template<int N> struct InterpolationProcessorVec4
 			out[k] = f4add(f4add(f4muls(v0[k], c0), f4muls(v1[k], c1)), f4muls(v2[k], c2));
 	}
 	// tex1light1.cpp:93-107 : (end - start) * (1.0f / stepCount), 1 when stepCount == 0
-	PS_D static void calcStep(F4* step, const F4* start, const F4* end, int stepCount)
+	PS_D static float reciprocalStepCount(int stepCount) { return 0 == stepCount ? 1.0f : fdiv(1.0f, (float)stepCount); }
+	PS_D static void calcStepR(F4* step, const F4* start, const F4* end, float reciprocalStepCount)
 	{
-		const float r = 0 == stepCount ? 1.0f : fdiv(1.0f, (float)stepCount);
 #pragma unroll
 		for(int k = 0; k < N; k++)
-			step[k] = f4muls(f4sub(end[k], start[k]), r);
+			step[k] = f4muls(f4sub(end[k], start[k]), reciprocalStepCount);
+	}
+	PS_D static void calcStep(F4* step, const F4* start, const F4* end, int stepCount)
+	{
+		calcStepR(step, start, end, reciprocalStepCount(stepCount));
 	}
 	// tex1light1.cpp:109-117
 	PS_D static void correctInterpolation(F4* out, const F4* start, float correctionFactor2)

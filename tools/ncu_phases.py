@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Per-phase instruction / lane-utilisation / stall breakdown of one kernel from an ncu report with -lineinfo.
-   python tools/ncu_phases.py REP.ncu-rep FILE.cuh 'name:first-last' ...   (line ranges in FILE; SASS is attributed to the
+   python tools/ncu_phases.py REP.ncu-rep FILE.cuh [-k=kernel-regex] 'name:first-last' ...   (line ranges in FILE; SASS is attributed to the
    most recent FILE line seen in address order, so inlined helpers count towards the phase that called them)"""
 import collections
 import csv
@@ -8,15 +8,22 @@ import subprocess
 import sys
 
 
+KERNEL = []
+
+
 def page(rep, extra):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + extra, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + KERNEL + extra, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
     return list(csv.reader(out.splitlines()))
 
 
 def main():
     rep, fname = sys.argv[1], sys.argv[2]
     ranges = []
-    for a in sys.argv[3:]:
+    args = sys.argv[3:]
+    if args and args[0].startswith("-k="):
+        KERNEL.extend(["-k", "regex:" + args[0][3:]])
+        args = args[1:]
+    for a in args:
         n, r = a.split(":")
         lo, hi = r.split("-")
         ranges.append((n, int(lo), int(hi)))
