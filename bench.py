@@ -47,49 +47,57 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md's clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clocks and throttle reasons DURING the timed regions, sampled in-process through NVML every 20 ms (the same
+    fields as B200_PROFILING.md's nvidia-smi clocks line; nvidia-smi -lms is too coarse for a 50 ms timed region)."""
 
     def __init__(self, index):
         self.index = index
         self.rows = []
-        self.proc = None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.err = None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            smax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop_flag.is_set():
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                try:
+                    power = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    power = None
+                self.rows.append((sm, smax, reasons, power))
+                time.sleep(0.02)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                smax.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err], "samples": 0}
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        seen = set()
+        for _, _, r, _ in self.rows:
+            for bit, name in names.items():
+                if r & bit:
+                    seen.add(name)
+        sm = [r[0] for r in self.rows]
+        pw = [r[3] for r in self.rows if r[3] is not None]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.rows[0][1]), "reasons": sorted(seen), "samples": len(sm),
+                "power_w_max": max(pw) if pw else None}
 
 
 def build_scene(args):
@@ -181,8 +189,8 @@ def main():
         args.steps = args.steps if args.steps is not None else 3
         args.warmup = args.warmup if args.warmup is not None else 1
         return run_reference(args, rank)
-    args.steps = args.steps if args.steps is not None else 50
-    args.warmup = args.warmup if args.warmup is not None else 5
+    args.steps = args.steps if args.steps is not None else 200
+    args.warmup = args.warmup if args.warmup is not None else 10
 
     import torch
     import torch.distributed as dist
@@ -231,7 +239,6 @@ def main():
     ev1.record(ext)
     ev1.synchronize()
     barrier()
-    clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
     prof = pipe.profileRead()
     pipe.profileEnable(False)
@@ -239,6 +246,7 @@ def main():
     stats = pipe.getStats()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     frag_t = torch.tensor([float(stats["fragments_shaded"])], dtype=torch.float64, device=dev)
+    tested_per_frame = stats["fragments_tested"] / args.steps
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(frag_t, op=dist.ReduceOp.SUM)
@@ -282,6 +290,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(frag_t, op=dist.ReduceOp.SUM)
     e2e_value = float(frag_t.item()) / (float(t.item()) / 1000.0)
+    clocks = sampler.stop()   # sampled across both timed regions
 
     # ---- roofline ------------------------------------------------------------------------------------------------
     peak, peak_src = load_peaks()
@@ -290,7 +299,8 @@ def main():
         # algorithmic bytes per launch of each kernel class (DESIGN.md "Kernels"): what an ideal implementation must move
         "geom_setup": (prof["geom_ms"], prof["geom_launches"], vertex_b),
         "binning": (prof["bin_ms"], prof["bin_launches"], 0),
-        "tile_raster_shade": (prof["tile_ms"], prof["tile_launches"], target_b + tex_b),
+        "tile_raster_depth": (prof["tile_ms"], prof["tile_launches"], target_b // 2),
+        "shade": (prof["shade_ms"], prof["shade_launches"], target_b // 2 + tex_b),
     }
     dominant = max(classes, key=lambda k: classes[k][0])
     dom_ms, dom_launches, dom_bytes = classes[dominant]
@@ -299,14 +309,19 @@ def main():
     achieved = (dom_bytes / 1e9) / (dom_ms_per_launch / 1e3) if dom_ms > 0 else 0.0
     frame_bytes = vertex_b + target_b + tex_b
     frame_achieved = (frame_bytes / 1e9) / (ms_step / 1e3)
-
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this build
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(args.workload, {}).get(dominant)
+    except Exception:
+        pass
     if rank == 0:
         line = {
             "metric": "shaded_fragments_per_s", "value": value, "unit": "fragments/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "frames_per_s": 1000.0 / ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "scene": sc.name, "triangles": sc.meta.get("triangles"), "resolution": [sc.width, sc.height],
-                       "shader": "DEF03 (Blinn-Phong + normal map)", "textures": "2 x 2048^2 BGRA nearest", "fragments_per_frame": frags_per_frame,
+                       "shader": "DEF03 (Blinn-Phong + normal map)", "textures": "2 x 2048^2 BGRA nearest", "fragments_per_frame": frags_per_frame, "fragments_tested_per_frame": tested_per_frame,
                        "parallelism": "sort-first row bands x%d, NCCL gather to rank 0" % world if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (216 MB vertex streams + 34 MB textures + 350 MB intermediates per frame vs 126 MB L2)",
                        "approx": "x86 rcpps/rsqrtss tables bits=%s" % (pipe.hostApproxInfo(),)},
@@ -315,7 +330,7 @@ def main():
                     "ms_per_step": float(t.item()) / e2e_steps, "steps": e2e_steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "ms_per_launch": dom_ms_per_launch, "algorithmic_bytes": dom_bytes},
+                         "frac": achieved / peak, "traffic": traffic, "ms_per_launch": dom_ms_per_launch, "algorithmic_bytes": dom_bytes},
             "frame_roofline": {"achieved": frame_achieved, "peak": peak, "unit": "GB/s", "frac": frame_achieved / peak,
                                "algorithmic_bytes": frame_bytes, "roofline_us": frame_bytes / (peak * 1e3)},
             "kernel_ms_per_frame": {k: v[0] / args.steps for k, v in classes.items()},

@@ -183,13 +183,14 @@ int ps3d_vbo_update_device(ps3d_pipe* p, int vbo, const void* devSrc);
 int ps3d_device_launch_count(ps3d_pipe* p, uint64_t* launches);
 
 /* Per-kernel-class device timing with CUDA events recorded on the pipe's own stream (bench.py's roofline figures).
- * While enabled every draw brackets its geometry kernel, its binning kernels and its tile kernel with event pairs;
+ * While enabled every draw brackets its geometry kernel, its binning kernels, its raster/tile kernel and its shade kernel with event pairs;
  * ps3d_profile_read() waits for the stream, sums the elapsed times since the last read and resets. */
 typedef struct ps3d_profile
 {
-	double geom_ms, bin_ms, tile_ms;
-	uint64_t geom_launches, bin_launches, tile_launches;
-	uint64_t bin_pairs;            /* (tile, triangle) pairs sorted */
+	double geom_ms, bin_ms, tile_ms, shade_ms; /* tile_ms: the raster + depth kernel (or the one-kernel tile paths); shade_ms: the shade kernel */
+	uint64_t geom_launches, bin_launches, tile_launches, shade_launches;
+	uint64_t bin_pairs;            /* (tile, triangle) pairs binned */
+	uint64_t survivors;            /* records the shade kernel consumed (split path) */
 } ps3d_profile;
 int ps3d_profile_enable(ps3d_pipe* p, int on);
 int ps3d_profile_read(ps3d_pipe* p, ps3d_profile* out);

@@ -129,6 +129,7 @@ struct ps3d_pipe
 {
 	int width, height;
 	int vpW, vpH, halfW, halfH;          /* rasterizer.cpp:26-31 */
+	int band0, band1;                    /* sort-first extension (ps3d_set_row_band): only raster rows [band0, band1) are shaded */
 	int behavior;
 	fbo_t display[2];
 	int back;
@@ -698,6 +699,7 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 			if(!row_of(p, &ts, row, &r)) continue;
 			if(r.left == r.right) continue; /* drawvao.cpp:72 */
 			p->stats.spans++;
+			if(row < p->band0 || row >= p->band1) continue; /* not in the reference: this rank does not own the row */
 
 			/* interpolateStartAndStep, interp.cpp:26-80 */
 			float cl[4], cr[4];
@@ -799,6 +801,7 @@ int ps3d_create(int width, int height, int device, ps3d_pipe** out)
 	if(!p) return PS3D_ERR_BAD_ALLOC;
 	p->width = width; p->height = height;
 	p->vpW = width; p->vpH = height; p->halfW = width / 2; p->halfH = height / 2;
+	p->band0 = 0; p->band1 = 0x7fffffff;
 	p->behavior = PS3D_BEHAVIOR_UPDATE_DEPTH | PS3D_BEHAVIOR_TEST_DEPTH | PS3D_BEHAVIOR_FACE_CULLING; /* pipeline.cpp:34 */
 	p->depthTex = -1; p->curProg = -1;
 	int depthScanline = ((int)(width / 4.0f + 0.5f) * 4) * (int)sizeof(float); /* pipeline.cpp:31 */
@@ -1118,8 +1121,10 @@ int ps3d_debug_clear_shade_counts(ps3d_pipe* p)
 
 int ps3d_set_row_band(ps3d_pipe* p, int row0, int row1)
 {
-	if(row0 == -1 && row1 == -1) return PS3D_OK;
-	return fail(p, PS3D_ERR_UNSUPPORTED, "row bands are a sort-first extension of the CUDA library");
+	if(row0 == -1 && row1 == -1) { p->band0 = 0; p->band1 = 0x7fffffff; return PS3D_OK; }
+	if(row0 < 0 || row1 < row0) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "row band");
+	p->band0 = row0; p->band1 = row1;
+	return PS3D_OK;
 }
 int ps3d_device_colour_ptr(ps3d_pipe* p, void** d, size_t* pitch) { (void)p; (void)d; (void)pitch; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_device_depth_ptr(ps3d_pipe* p, void** d, size_t* pitch) { (void)p; (void)d; (void)pitch; return PS3D_ERR_UNSUPPORTED; }

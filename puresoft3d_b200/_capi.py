@@ -46,9 +46,9 @@ class Stats(C.Structure):
 
 
 class Profile(C.Structure):
-    _fields_ = [("geom_ms", C.c_double), ("bin_ms", C.c_double), ("tile_ms", C.c_double),
+    _fields_ = [("geom_ms", C.c_double), ("bin_ms", C.c_double), ("tile_ms", C.c_double), ("shade_ms", C.c_double),
                 ("geom_launches", C.c_uint64), ("bin_launches", C.c_uint64), ("tile_launches", C.c_uint64),
-                ("bin_pairs", C.c_uint64)]
+                ("shade_launches", C.c_uint64), ("bin_pairs", C.c_uint64), ("survivors", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

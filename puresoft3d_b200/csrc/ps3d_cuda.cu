@@ -191,12 +191,12 @@ struct ps3d_pipe
 	struct Span { cudaEvent_t a, b; int cls; };
 	std::vector<Span> spans;
 	std::vector<cudaEvent_t> eventPool;
-	uint64_t profLaunches[3];
-	uint64_t profPairs;
+	uint64_t profLaunches[4];
+	uint64_t profPairs, profSurvivorBound;
 	std::string err;
 };
 
-enum { CLS_GEOM = 0, CLS_BIN = 1, CLS_TILE = 2 };
+enum { CLS_GEOM = 0, CLS_BIN = 1, CLS_TILE = 2, CLS_SHADE = 3 };
 
 static cudaEvent_t takeEvent(ps3d_pipe* p)
 {
@@ -285,7 +285,7 @@ int ps3d_create(int width, int height, int device, ps3d_pipe** out)
 	p->back = 1; p->depthTex = -1; p->curProg = -1;
 	p->capDev = nullptr; p->capW = p->capH = 0;
 	p->launches = 0;
-	p->profiling = false; p->profPairs = 0; p->profLaunches[0] = p->profLaunches[1] = p->profLaunches[2] = 0;
+	p->profiling = false; p->profPairs = 0; p->profLaunches[0] = p->profLaunches[1] = p->profLaunches[2] = p->profLaunches[3] = 0;
 	memset(&p->stats, 0, sizeof(p->stats));
 	memset(p->uniformSet, 0, sizeof(p->uniformSet));
 	p->depthScanline = ((int)(width / 4.0f + 0.5f) * 4) * (int)sizeof(float); // pipeline.cpp:31
@@ -802,9 +802,8 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	if(tilePathForced() >= 0 && !(pe->mayDiscard)) path = tilePathForced() == 2 && 1 == path ? 1 : tilePathForced();
 	if(2 == path && (fragBound >= 0xfffffff0ull || P.vpW > 8191 || P.vpH > 8191)) path = 1;
 	if(2 == path && 0 == fragBound) return PS3D_OK;
-	ProfScope ps(p, CLS_TILE);
-	if(0 == path) { pe->tileImmediate(P, p->tileStart.p, vIn, p->stream); p->launches++; }
-	else if(1 == path) { pe->tileOrdered(P, p->tileStart.p, vIn, p->stream); p->launches++; }
+	if(0 == path) { ProfScope ps(p, CLS_TILE); pe->tileImmediate(P, p->tileStart.p, vIn, p->stream); p->launches++; }
+	else if(1 == path) { ProfScope ps(p, CLS_TILE); pe->tileOrdered(P, p->tileStart.p, vIn, p->stream); p->launches++; }
 	else
 	{
 		const size_t cap = (size_t)fragBound;
@@ -814,9 +813,16 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 		Q.tri = p->svTri.p; Q.left = p->svLeft.p; Q.right = p->svRight.p; Q.inv = p->svInv.p; Q.misc = p->svMisc.p;
 		Q.count = p->svCountDev; Q.winner = p->svWinner.p; Q.capacity = (uint32_t)cap;
 		CK(p, cudaMemsetAsync(p->svCountDev, 0, 4, p->stream));
-		tile_raster_depth_kernel<<<tileBlocks(P), 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(P, Q, p->tileStart.p, vIn);
-		pe->shade(P, Q, p->stream);
-		p->launches += 2;
+		{
+			ProfScope ps(p, CLS_TILE);
+			tile_raster_depth_kernel<<<tileBlocks(P), 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(P, Q, p->tileStart.p, vIn);
+			p->launches++;
+		}
+		{
+			ProfScope ps(p, CLS_SHADE);
+			pe->shade(P, Q, p->stream);
+			p->launches++;
+		}
 	}
 	CK(p, cudaGetLastError());
 	return PS3D_OK;
@@ -946,7 +952,7 @@ int ps3d_profile_enable(ps3d_pipe* p, int on)
 	for(auto& s : p->spans) { p->eventPool.push_back(s.a); p->eventPool.push_back(s.b); }
 	p->spans.clear();
 	p->profiling = on != 0;
-	p->profPairs = 0; p->profLaunches[0] = p->profLaunches[1] = p->profLaunches[2] = 0;
+	p->profPairs = 0; p->profLaunches[0] = p->profLaunches[1] = p->profLaunches[2] = p->profLaunches[3] = 0;
 	return PS3D_OK;
 }
 int ps3d_profile_read(ps3d_pipe* p, ps3d_profile* out)
@@ -954,7 +960,7 @@ int ps3d_profile_read(ps3d_pipe* p, ps3d_profile* out)
 	TRACE();
 	cudaSetDevice(p->device);
 	CK(p, cudaStreamSynchronize(p->stream));
-	double ms[3] = { 0, 0, 0 };
+	double ms[4] = { 0, 0, 0, 0 };
 	for(auto& s : p->spans)
 	{
 		float t = 0;
@@ -963,10 +969,12 @@ int ps3d_profile_read(ps3d_pipe* p, ps3d_profile* out)
 		p->eventPool.push_back(s.a); p->eventPool.push_back(s.b);
 	}
 	p->spans.clear();
-	out->geom_ms = ms[0]; out->bin_ms = ms[1]; out->tile_ms = ms[2];
+	out->geom_ms = ms[0]; out->bin_ms = ms[1]; out->tile_ms = ms[2]; out->shade_ms = ms[3];
 	out->geom_launches = p->profLaunches[0]; out->bin_launches = p->profLaunches[1]; out->tile_launches = p->profLaunches[2];
+	out->shade_launches = p->profLaunches[3];
 	out->bin_pairs = p->profPairs;
-	p->profPairs = 0; p->profLaunches[0] = p->profLaunches[1] = p->profLaunches[2] = 0;
+	out->survivors = 0;
+	p->profPairs = 0; p->profLaunches[0] = p->profLaunches[1] = p->profLaunches[2] = p->profLaunches[3] = 0;
 	return PS3D_OK;
 }
 int ps3d_host_approx_info(int* rcpBits, int* rsqrtBits)
