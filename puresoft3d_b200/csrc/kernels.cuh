@@ -99,32 +99,52 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 				const int firstRow = (int)(h.rows & 0xffff), lastRow = (int)(h.rows >> 16);
 				int minX = 0x7fffffff, maxX = -1, minY = 0x7fffffff, maxY = -1;
 				// for the first four tile rows the triangle touches: the tile columns its spans reach (lo | hi << 16)
-				uint32_t tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0, trSet = 0;
-				int tyFirst = -1;
-				for(int iy = firstRow; iy <= lastRow; iy++) // drawvao.cpp:66-75
+				uint32_t tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0;
+				int tyFirst = -1, kCur = -1, curLo = 0, curHi = 0;
+				uint32_t trValid = 0;                                  // tile rows (relative to the first) that hold a span
+				// The rows of RESULT (drawvao.cpp:66-75), half by half so that the two edges are set up once per half instead of
+				// once per row: first the lower half (it owns the shared row, rasterizer.cpp:128-139), then what is left of the upper.
+				const int l0 = (int)(h.half1 & 0xffff), l1 = (int)(h.half1 >> 16);
+				const int u0 = (int)(h.half0 & 0xffff), u1 = (int)(h.half0 >> 16);
+#pragma unroll 1
+				for(int half = 0; half < 2; half++)
 				{
-					RowSpan r;
-					if(!rowOf(h, vx, vy, iy, r)) continue;
-					if(r.left == r.right) continue;
-					spans++;
-					if(iy < P.band0 || iy >= P.band1) continue;
-					const int x1 = r.left < 0 ? 0 : r.left;                 // RESULT_ROW::leftClamped
-					const int x2 = r.right >= P.vpW ? P.vpW - 1 : r.right;  // RESULT_ROW::rightClamped
-					if(x1 > x2) continue;
-					frags += (unsigned)(x2 - x1 + 1);
-					minX = min(minX, x1); maxX = max(maxX, x2);
-					minY = min(minY, iy); maxY = max(maxY, iy);
-					const int ty = iy / PS_TILE;
-					if(tyFirst < 0) tyFirst = ty;
-					const int k = ty - tyFirst;
-					if(k < 4)
+					const int sel = half ? (int)(h.plan & 0xff) : (int)((h.plan >> 8) & 0xff);
+					int ya = max(firstRow, half ? u0 : l0), yb = min(lastRow, half ? u1 : l1);
+					if(half && l0 <= l1) ya = max(ya, l1 + 1);   // rows of the lower half are taken (halves are stacked: u0 >= l1)
+					if(ya > yb) continue;
+					const Edge L = makeEdge(vx, vy, sel & 3, (sel >> 2) & 3);
+					const Edge R = makeEdge(vx, vy, (sel >> 4) & 3, (sel >> 6) & 3);
+#pragma unroll 1
+					for(int iy = ya; iy <= yb; iy++)
 					{
-						uint32_t cur = 0 == k ? tr0 : (1 == k ? tr1 : (2 == k ? tr2 : tr3));
-						const uint32_t a = (uint32_t)(x1 / PS_TILE), b = (uint32_t)(x2 / PS_TILE);
-						cur = (trSet >> k) & 1 ? (min(cur & 0xffff, a) | (max(cur >> 16, b) << 16)) : (a | (b << 16));
-						trSet |= 1u << k;
-						if(0 == k) tr0 = cur; else if(1 == k) tr1 = cur; else if(2 == k) tr2 = cur; else tr3 = cur;
+						const float y = (float)iy;
+						const int left = cvtt(fadd(edgeAt(L, y), 0.5f)), right = cvtt(fadd(edgeAt(R, y), 0.5f));   // rasterizer.cpp:98-117
+						if(left == right) continue;                            // drawvao.cpp:72
+						spans++;
+						if(iy < P.band0 || iy >= P.band1) continue;
+						const int x1 = left < 0 ? 0 : left;                     // RESULT_ROW::leftClamped
+						const int x2 = right >= P.vpW ? P.vpW - 1 : right;      // RESULT_ROW::rightClamped
+						if(x1 > x2) continue;
+						frags += (unsigned)(x2 - x1 + 1);
+						minX = min(minX, x1); maxX = max(maxX, x2);
+						minY = min(minY, iy); maxY = max(maxY, iy);
+						const int ty = iy / PS_TILE;
+						if(tyFirst < 0) tyFirst = ty;
+						const int k = ty - tyFirst;
+						trValid |= 1u << min(k, 31);
+						if(k != kCur)
+						{
+							const uint32_t packed = (uint32_t)curLo | ((uint32_t)curHi << 16);
+							if(0 == kCur) tr0 = packed; else if(1 == kCur) tr1 = packed; else if(2 == kCur) tr2 = packed; else if(3 == kCur) tr3 = packed;
+							kCur = k; curLo = x1 / PS_TILE; curHi = x2 / PS_TILE;
+						}
+						else { curLo = min(curLo, x1 / PS_TILE); curHi = max(curHi, x2 / PS_TILE); }
 					}
+				}
+				{
+					const uint32_t packed = (uint32_t)curLo | ((uint32_t)curHi << 16);
+					if(0 == kCur) tr0 = packed; else if(1 == kCur) tr1 = packed; else if(2 == kCur) tr2 = packed; else if(3 == kCur) tr3 = packed;
 				}
 				if(maxX >= 0)
 				{
@@ -144,12 +164,11 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 						// small triangle (the common case): exactly the tiles some span of it reaches
 #pragma unroll
 						for(int k = 0; k < 4; k++)
-							if((trSet >> k) & 1)
-							{
-								const uint32_t cur = 0 == k ? tr0 : (1 == k ? tr1 : (2 == k ? tr2 : tr3));
-								const int a = (int)(cur & 0xffff) - tx0, b = (int)(cur >> 16) - tx0;   // 0 <= a <= b <= 7
-								mask |= ((2u << b) - (1u << a)) << (k * 8);
-							}
+						{
+							const uint32_t cur = 0 == k ? tr0 : (1 == k ? tr1 : (2 == k ? tr2 : tr3));
+							const int a = (int)(cur & 0xffff) - tx0, b = (int)(cur >> 16) - tx0;
+							if((trValid >> k) & 1) mask |= ((2u << b) - (1u << a)) << (k * 8);   // 0 <= a <= b <= 7
+						}
 						count = (uint32_t)__popc(mask);
 						for(uint32_t m = mask; m; m &= m - 1)
 						{
