@@ -66,9 +66,11 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 	unsigned rasterised = 0, spans = 0, frags = 0, pairs = 0;
 	if(tri < P.ntris)
 	{
-		VertexProcessorOutput<NV> vo[3];
 		float ndcX[3], ndcY[3], rw[3], pz[3];
 		F4 pos[3];
+		// The vertex functor runs twice per vertex: here only its position is used (the compiler drops the varyings and the
+		// loads that feed nothing else), and again below — for triangles that survive culling only — for the varyings,
+		// one vertex at a time. Culled triangles never touch their normal / tangent / uv streams.
 #pragma unroll
 		for(int i = 0; i < 3; i++)
 		{
@@ -77,9 +79,10 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 #pragma unroll
 			for(int s = 0; s < 16; s++)
 				in.data[s] = (PROG::V::SLOTS >> s) & 1 ? P.slot[s] + (size_t)(tri * 3 + i) * P.stride[s] : nullptr;
-			PROG::V::process(in, vo[i], P);
-			const float reciprocalW = fdiv(1.0f, vo[i].position.w);       // vertthrd.cpp:37 (true divide)
-			pos[i] = f4muls(vo[i].position, reciprocalW);                  // :38 all four lanes
+			VertexProcessorOutput<NV> vo;
+			PROG::V::process(in, vo, P);
+			const float reciprocalW = fdiv(1.0f, vo.position.w);          // vertthrd.cpp:37 (true divide)
+			pos[i] = f4muls(vo.position, reciprocalW);                     // :38 all four lanes
 			ndcX[i] = pos[i].x; ndcY[i] = pos[i].y; pz[i] = pos[i].z; rw[i] = reciprocalW;
 		}
 		bool alive = true;
@@ -96,6 +99,33 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 			rasterised = code != 0;
 			if(1 == code)
 			{
+				// The records go out BEFORE the row walk: the 3 x NV varyings would otherwise stay live in registers across it
+				// and halve the occupancy. (A triangle that turns out to cover no pixel wrote its record for nothing.)
+				h.rw0 = rw[0]; h.rw1 = rw[1]; h.rw2 = rw[2];
+				h.z0 = pz[0]; h.z1 = pz[1]; h.z2 = pz[2];
+				{
+					// 64-byte record as four 16-byte stores
+					uint4* dst = (uint4*)(P.hdr + tri);
+					const uint4* src = (const uint4*)&h;
+					dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+					if(NV > 0)
+					{
+						float4* vd = (float4*)(P.vary + (size_t)tri * 3 * NV);
+#pragma unroll 1
+						for(int i = 0; i < 3; i++)
+						{
+							VertexProcessorInput in;
+#pragma unroll
+							for(int s = 0; s < 16; s++)
+								in.data[s] = (PROG::V::SLOTS >> s) & 1 ? P.slot[s] + (size_t)(tri * 3 + i) * P.stride[s] : nullptr;
+							VertexProcessorOutput<NV> vo;
+							PROG::V::process(in, vo, P);
+#pragma unroll
+							for(int k = 0; k < NV; k++)
+								vd[i * NV + k] = make_float4(vo.user[k].x, vo.user[k].y, vo.user[k].z, vo.user[k].w);
+						}
+					}
+				}
 				const int firstRow = (int)(h.rows & 0xffff), lastRow = (int)(h.rows >> 16);
 				int minX = 0x7fffffff, maxX = -1, minY = 0x7fffffff, maxY = -1;
 				// for the first four tile rows the triangle touches: the tile columns its spans reach (lo | hi << 16)
@@ -175,21 +205,6 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 							const int bit = __ffs(m) - 1;
 							atomicAdd(&P.tileCount[(ty0 + (bit >> 3)) * P.tilesX + tx0 + (bit & 7)], 1u);
 						}
-					}
-					h.rw0 = rw[0]; h.rw1 = rw[1]; h.rw2 = rw[2];
-					h.z0 = pz[0]; h.z1 = pz[1]; h.z2 = pz[2];
-					// 64-byte record as four 16-byte stores
-					uint4* dst = (uint4*)(P.hdr + tri);
-					const uint4* src = (const uint4*)&h;
-					dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
-					if(NV > 0)
-					{
-						float4* vd = (float4*)(P.vary + (size_t)tri * 3 * NV);
-#pragma unroll
-						for(int i = 0; i < 3; i++)
-#pragma unroll
-							for(int k = 0; k < NV; k++)
-								vd[i * NV + k] = make_float4(vo[i].user[k].x, vo[i].user[k].y, vo[i].user[k].z, vo[i].user[k].w);
 					}
 				}
 			}
