@@ -68,11 +68,16 @@ extern "C" {
 #define PS3D_FN_DEF03  3   /* tex1bump1light1.cpp + tangent-space normal map                */
 #define PS3D_FN_DEF04  4   /* skybox.cpp          cube-map skybox                           */
 #define PS3D_FN_DEF05  5   /* shadow.cpp          depth-only, 0.9 shrink                    */
-#define PS3D_FN_PLANET       16  /* src/test/testproc.cpp  VP_Planet / IP_Planet / FP_Earth      */
-#define PS3D_FN_SATELLITE    17  /*                        FP_Satellite (V/I = Planet)           */
-#define PS3D_FN_CLOUD        18  /*                        VP_Cloud / IP_Cloud / FP_Cloud        */
-#define PS3D_FN_CLOUDSHADOW  19  /*                        VP/IP/FP_CloudShadow                  */
-#define PS3D_FN_NULL         20  /*                        VP_Null? (see shaders.cuh)            */
+/* demo 1 (src/test/testproc.cpp): earth + cloud + moon with a shadow map */
+#define PS3D_FN_PLANET       16  /* VP_Planet / IP_Planet / FP_Earth (the fragment id 16 is FP_Earth)            */
+#define PS3D_FN_SATELLITE    17  /* FP_Satellite (fragment only; its V/I are PS3D_FN_PLANET)                      */
+#define PS3D_FN_CLOUD        18  /* VP_Cloud / IP_Cloud / FP_Cloud (alpha from the texture, round-to-nearest pack)  */
+#define PS3D_FN_CLOUDSHADOW  19  /* VP_CloudShadow / IP_CloudShadow / FP_CloudShadow (the one functor that discards) */
+/* demo 2 (src/test2/testproc.cpp): desk scene with a spot light and a shadow map */
+#define PS3D_FN_POSITIONONLY 32  /* VP_PositionOnly (vertex) / IP_Null (interpolation) / FP_SingleColourNoLighting   */
+#define PS3D_FN_SINGLECOLOUR 33  /* VP_SingleColour / IP_SingleColour / FP_SingleColour                              */
+#define PS3D_FN_DIFFUSEONLY  34  /* VP_DiffuseOnly / IP_DiffuseOnly / FP_DiffuseOnly                                 */
+#define PS3D_FN_SHADOW2      35  /* VP_Shadow (vertex) / FP_Null (fragment); interpolation = PS3D_FN_POSITIONONLY    */
 #define PS3D_FN_FLATID       64  /* parity-test functor (not in the reference): writes a per-triangle id */
 
 typedef struct ps3d_pipe ps3d_pipe;

@@ -25,6 +25,9 @@
 #include <math.h>
 #include <float.h>
 #include <xmmintrin.h>
+#if defined(__SSE4_1__)
+#include <smmintrin.h>
+#endif
 #include "ps3d.h"
 
 #define MAX_PROCS 256
@@ -274,14 +277,20 @@ static float samplerproj_get(const fbo_t* t, const float* proj)
 
 typedef struct
 {
-	const float* u[32];       /* uniform slots 0..31 as float pointers (NULL when unset) */
-	const fbo_t* tex[32];     /* texture named by the int in uniform slot i (NULL when not a texture id) */
+	const float* u[48];       /* uniform slots 0..47 as float pointers (NULL when unset); demo 2 reads up to slot 43 */
+	const fbo_t* tex[48];     /* texture named by the int in uniform slot i (NULL when not a texture id) */
 } shader_env;
 
-static int n_varyings(int functor) /* IP::userDataBytes() / 16 */
+static int n_varyings(int functor) /* IP::userDataBytes() / 16 — float4 fields that carry data */
 {
 	switch(functor)
 	{
+	case PS3D_FN_PLANET: case PS3D_FN_SATELLITE: return 6; /* PROCDATA_PLANET, src/test/testproc.h:7-16 */
+	case PS3D_FN_CLOUD: return 4;                          /* PROCDATA_CLOUD, :75-82 */
+	case PS3D_FN_CLOUDSHADOW: return 1;                    /* PROCDATA_CLOUDSHADOW, :122-126 */
+	case PS3D_FN_POSITIONONLY: case PS3D_FN_SHADOW2: return 0; /* IP_Null declares 16 bytes and never touches them (src/test2/testproc.cpp:26-45) */
+	case PS3D_FN_SINGLECOLOUR: return 3;                   /* PROCDATA_SINGLECOLOUR, src/test2/testproc.h:78-83 */
+	case PS3D_FN_DIFFUSEONLY: return 4;                    /* PROCDATA_DIFFUSEONLY, :129-135 */
 	case PS3D_FN_DEF01: case PS3D_FN_DEF02: return 3; /* tex1light1.h:4-9, colr1light1.h */
 	case PS3D_FN_DEF03: return 5;                      /* tex1bump1light1.h:4-11 */
 	case PS3D_FN_DEF04: return 1;                      /* skybox.h:4-7 */
@@ -360,6 +369,79 @@ static int run_vp(int functor, const shader_env* e, const unsigned char* const* 
 		m4v4(pos, pvm, adj);
 		return 1;
 	}
+	case PS3D_FN_PLANET: /* src/test/testproc.cpp:37-74 — vary: tangent, binormal, normal, worldPos, texcoord, shadowcoord */
+	{
+		if(!e->u[3] || !e->u[4] || !e->u[5] || !e->u[16] || !in[0] || !in[1] || !in[2] || !in[3] || !in[4]) return 0;
+		m4v4(vary[3].v, e->u[4], (const float*)in[0]);
+		m4v4(vary[5].v, e->u[16], vary[3].v);
+		m4v4(pos, e->u[3], vary[3].v);
+		vary[3].v[3] = 0;
+		m4v4(vary[0].v, e->u[5], (const float*)in[1]);
+		m4v4(vary[1].v, e->u[5], (const float*)in[2]);
+		m4v4(vary[2].v, e->u[5], (const float*)in[3]);
+		vary[4].v[0] = ((const float*)in[4])[0];
+		vary[4].v[1] = ((const float*)in[4])[1];
+		return 1;
+	}
+	case PS3D_FN_CLOUD: /* src/test/testproc.cpp:392-425 — vary: normal, worldPos, texcoord, shadowcoord */
+	{
+		if(!e->u[3] || !e->u[4] || !e->u[5] || !e->u[16] || !in[0] || !in[3] || !in[4]) return 0;
+		m4v4(vary[1].v, e->u[4], (const float*)in[0]);
+		m4v4(vary[3].v, e->u[16], vary[1].v);
+		m4v4(pos, e->u[3], vary[1].v);
+		vary[1].v[3] = 0;
+		m4v4(vary[0].v, e->u[5], (const float*)in[3]);
+		vary[2].v[0] = ((const float*)in[4])[0];
+		vary[2].v[1] = ((const float*)in[4])[1];
+		return 1;
+	}
+	case PS3D_FN_CLOUDSHADOW: /* src/test/testproc.cpp:595-610 — xyz *= 0.95f ; pvm = PV*M ; vary: texcoord */
+	{
+		if(!e->u[3] || !e->u[4] || !in[0] || !in[4]) return 0;
+		float adj[4], pvm[16];
+		memcpy(adj, in[0], 16);
+		adj[0] *= 0.95f; adj[1] *= 0.95f; adj[2] *= 0.95f;
+		m4m4(pvm, e->u[3], e->u[4]);
+		m4v4(pos, pvm, adj);
+		vary[0].v[0] = ((const float*)in[4])[0];
+		vary[0].v[1] = ((const float*)in[4])[1];
+		return 1;
+	}
+	case PS3D_FN_POSITIONONLY: /* src/test2/testproc.cpp:17-22 */
+		if(!e->u[5] || !in[0]) return 0;
+		m4v4(pos, e->u[5], (const float*)in[0]);
+		return 1;
+	case PS3D_FN_SHADOW2: /* src/test2/testproc.cpp:510-516 */
+	{
+		if(!e->u[5] || !in[0]) return 0;
+		float adj[4];
+		memcpy(adj, in[0], 16);
+		adj[0] *= 0.9f; adj[1] *= 0.9f; adj[2] *= 0.9f;
+		m4v4(pos, e->u[5], adj);
+		return 1;
+	}
+	case PS3D_FN_SINGLECOLOUR: /* src/test2/testproc.cpp:94-120 — vary: normal, worldPos, shadowcoord */
+	{
+		if(!e->u[0] || !e->u[1] || !e->u[5] || !e->u[6] || !in[0] || !in[3]) return 0;
+		m4v4(vary[1].v, e->u[0], (const float*)in[0]);
+		m4v4(vary[2].v, e->u[6], vary[1].v);
+		vary[1].v[3] = 0;
+		m4v4(pos, e->u[5], (const float*)in[0]);
+		m4v4(vary[0].v, e->u[1], (const float*)in[3]);
+		return 1;
+	}
+	case PS3D_FN_DIFFUSEONLY: /* src/test2/testproc.cpp:310-342 — vary: normal, worldPos, texcoord, shadowcoord */
+	{
+		if(!e->u[0] || !e->u[1] || !e->u[5] || !e->u[6] || !in[0] || !in[3] || !in[4]) return 0;
+		m4v4(vary[1].v, e->u[0], (const float*)in[0]);
+		m4v4(vary[3].v, e->u[6], vary[1].v);
+		m4v4(pos, e->u[5], (const float*)in[0]);
+		vary[1].v[3] = 0;
+		m4v4(vary[0].v, e->u[1], (const float*)in[3]);
+		vary[2].v[0] = ((const float*)in[4])[0];
+		vary[2].v[1] = ((const float*)in[4])[1];
+		return 1;
+	}
 	case PS3D_FN_FLATID: /* parity-test functor (not in the reference): pos = PV*(M*p); vary0 = slot 6 (flat id colour) */
 	{
 		if(!e->u[3] || !e->u[4] || !in[0] || !in[6]) return 0;
@@ -405,11 +487,178 @@ static uint32_t blinn_phong(const shader_env* e, float* colour, const float* wor
 	return pack_bgr_trunc(colour);
 }
 
+/* what FP_Earth and FP_Satellite share (src/test/testproc.cpp:240-262): bump normal through the TBN, L = (light-P)/len via rcpps, E, H */
+static void planet_lighting(const shader_env* e, uint32_t bumpTexel, const f4* in, float* lambert, float* specular)
+{
+	float bump[4], tbn[16], L[4], E[4], H[4];
+	bump[0] = (float)((bumpTexel >> 16) & 0xff); bump[1] = (float)((bumpTexel >> 8) & 0xff); bump[2] = (float)(bumpTexel & 0xff); bump[3] = 0;
+	div4s(bump, 255.0f);
+	mul4s(bump, 2.0f);
+	for(int i = 0; i < 4; i++) bump[i] = bump[i] - 1.0f;
+	memcpy(tbn, in[0].v, 16); memcpy(tbn + 4, in[1].v, 16); memcpy(tbn + 8, in[2].v, 16); memset(tbn + 12, 0, 16);
+	m4v4(bump, tbn, bump);
+	norm4(bump);
+	sub4(L, e->u[7], in[3].v);
+	float distance = len4(L);
+	div4s(L, distance);
+	sub4(E, e->u[8], in[3].v);
+	norm4(E);
+	add4(H, E, L);
+	norm4(H);
+	*lambert = dot4(L, bump);
+	float sp = dot4(H, bump);
+	sp = sp < 0 ? 0 : sp;
+	*specular = opt_pow(sp, 50);
+}
+
+/* cvtps2dq + packusdw + packuswb on one lane (src/test/testproc.cpp:565-571) */
+static uint32_t pack_rne_sat(float f)
+{
+#if defined(__SSE4_1__)
+	__m128i v = _mm_cvtps_epi32(_mm_set1_ps(f));
+	v = _mm_packus_epi32(v, v);
+	v = _mm_packus_epi16(v, v);
+	return (uint32_t)_mm_cvtsi128_si32(v) & 0xff;
+#else
+	int v = (f >= -2147483648.0f && f < 2147483648.0f) ? (int)lrintf(f) : (int)0x80000000u;
+	int u16 = v < 0 ? 0 : (v > 65535 ? 65535 : v);
+	int s16 = (int)(short)u16;
+	return (uint32_t)(s16 < 0 ? 0 : (s16 > 255 ? 255 : s16));
+#endif
+}
+
+/* the factors FP_SingleColour / FP_DiffuseOnly share (src/test2/testproc.cpp:230-256, 459-485) */
+static void spot_factors(const shader_env* e, const float* worldPos, const float* normal, float* lambertOut, float* specularOut)
+{
+	static const float fieldOfLight = 6.283185f * (25.0f / 360.0f);
+	float L[4], E[4], H[4];
+	sub4(L, e->u[20], worldPos);
+	norm4(L);
+	sub4(E, e->u[22], worldPos);
+	norm4(E);
+	add4(H, E, L);
+	norm4(H);
+	float factors[4] = { 0, 0, 0, 0 };
+	factors[0] = dot4(L, normal);
+	/* <math.h> in C++ resolves acos(float) / cos(float) to the float overloads, so T of opt_pow is float too */
+	float yawOfLight = acosf(dot4(L, e->u[21]));
+	float cone = 1.0f;
+	if(!(yawOfLight < fieldOfLight))
+		cone = opt_pow(cosf(yawOfLight - fieldOfLight), 150);
+	factors[0] = factors[0] * cone;
+	factors[1] = opt_pow(dot4(H, normal), (unsigned)cvtu(e->u[33][0]));
+	clamp4(factors, 0, 1.0f);
+	*lambertOut = factors[0];
+	*specularOut = factors[1];
+}
+
 static void run_fp(int functor, const shader_env* e, const f4* in, frag_out* out)
 {
 	out->discarded = 0; out->wrote = 0; out->blendable = 0; out->bgra = 0;
 	switch(functor)
 	{
+	case PS3D_FN_PLANET: /* FP_Earth, src/test/testproc.cpp:208-288 */
+	{
+		float c[4], night[4], lambert, specular;
+		unpack_bgra(c, sampler2d_get4(e->tex[9], in[4].v[0], in[4].v[1]));
+		unpack_bgra(night, sampler2d_get4(e->tex[12], in[4].v[0], in[4].v[1]));
+		uint32_t nb = sampler2d_get4(e->tex[10], in[4].v[0], in[4].v[1]);
+		float shadowFactor = samplerproj_get(e->tex[15], in[5].v);
+		uint32_t sp = sampler2d_get4(e->tex[11], in[4].v[0], in[4].v[1]);
+		float specularControl = (float)((sp >> 16) & 0xff) / 255.0f;
+		planet_lighting(e, nb, in, &lambert, &specular);
+		specular = specular * specularControl;
+		float add = 255.0f * specular;
+		for(int i = 0; i < 4; i++) c[i] = c[i] + add;
+		mul4s(c, lambert);
+		if(lambert < 0.2f) add4(c, c, night);
+		mul4s(c, shadowFactor);
+		clamp4(c, 0, 255.0f);
+		out->bgra = pack_bgr_trunc(c);
+		out->wrote = 1; out->blendable = 1;
+		return;
+	}
+	case PS3D_FN_SATELLITE: /* FP_Satellite, src/test/testproc.cpp:299-361 */
+	{
+		float c[4], lambert, specular;
+		unpack_bgra(c, sampler2d_get4(e->tex[9], in[4].v[0], in[4].v[1]));
+		uint32_t nb = sampler2d_get4(e->tex[10], in[4].v[0], in[4].v[1]);
+		float shadowFactor = samplerproj_get(e->tex[15], in[5].v);
+		planet_lighting(e, nb, in, &lambert, &specular);
+		float add = 255.0f * specular;
+		for(int i = 0; i < 4; i++) c[i] = c[i] + add;
+		mul4s(c, lambert);
+		mul4s(c, shadowFactor);
+		clamp4(c, 0, 255.0f);
+		out->bgra = pack_bgr_trunc(c);
+		out->wrote = 1; out->blendable = 1;
+		return;
+	}
+	case PS3D_FN_CLOUD: /* FP_Cloud, src/test/testproc.cpp:531-574 */
+	{
+		uint32_t tex = sampler2d_get4(e->tex[9], in[2].v[0], in[2].v[1]);
+		float cloud[4] = { 255.0f, 255.0f, 255.0f, (float)((tex >> 16) & 0xff) }, L[4];
+		float shadowFactor = samplerproj_get(e->tex[15], in[3].v);
+		sub4(L, e->u[7], in[1].v);
+		float distance = len4(L);
+		div4s(L, distance);
+		float lambert = 2.0f * dot4(L, in[0].v);
+		float k = lambert * shadowFactor;
+		cloud[0] = cloud[0] * k; cloud[1] = cloud[1] * k; cloud[2] = cloud[2] * k; /* mcemaths_mul_3 */
+		out->bgra = pack_rne_sat(cloud[0]) | (pack_rne_sat(cloud[1]) << 8) | (pack_rne_sat(cloud[2]) << 16) | (pack_rne_sat(cloud[3]) << 24);
+		out->wrote = 1; out->blendable = 1;
+		return;
+	}
+	case PS3D_FN_CLOUDSHADOW: /* FP_CloudShadow, src/test/testproc.cpp:676-685 */
+	{
+		uint32_t tex = sampler2d_get4(e->tex[9], in[0].v[0], in[0].v[1]);
+		if(((tex >> 16) & 0xff) < 150) out->discarded = 1;
+		return;
+	}
+	case PS3D_FN_POSITIONONLY: /* FP_SingleColourNoLighting, src/test2/testproc.cpp:54-67 */
+	{
+		float c[4];
+		memcpy(c, e->u[31], 16);
+		mul4s(c, 255.0f);
+		out->bgra = pack_bgr_trunc(c);
+		out->wrote = 1; out->blendable = 1;
+		return;
+	}
+	case PS3D_FN_SHADOW2: /* FP_Null, src/test2/testproc.cpp:520-524 */
+		return;
+	case PS3D_FN_SINGLECOLOUR: /* FP_SingleColour, src/test2/testproc.cpp:221-287 */
+	{
+		float lambert, specular, c[4], sc[4], ac[4];
+		float shadowFactor = samplerproj_get(e->tex[23], in[2].v);
+		spot_factors(e, in[1].v, in[0].v, &lambert, &specular);
+		memcpy(c, e->u[31], 16);
+		mul4s(c, lambert);
+		for(int i = 0; i < 4; i++) sc[i] = e->u[31][i] * e->u[32][i];
+		mul4s(sc, specular);
+		for(int i = 0; i < 4; i++) ac[i] = e->u[31][i] * e->u[30][i];
+		add4(c, c, sc);
+		mul4s(c, shadowFactor);
+		add4(c, c, ac);
+		clamp4(c, 0, 1.0f);
+		mul4s(c, 255.0f);
+		out->bgra = pack_bgr_trunc(c);
+		out->wrote = 1; out->blendable = 1;
+		return;
+	}
+	case PS3D_FN_DIFFUSEONLY: /* FP_DiffuseOnly, src/test2/testproc.cpp:448-500 */
+	{
+		float lambert, specular, c[4], ac[4];
+		float shadowFactor = samplerproj_get(e->tex[23], in[3].v);
+		unpack_bgra(c, sampler2d_get4(e->tex[40], in[2].v[0], in[2].v[1]));
+		for(int i = 0; i < 4; i++) ac[i] = c[i] * e->u[30][i];
+		spot_factors(e, in[1].v, in[0].v, &lambert, &specular);
+		mul4s(c, (lambert + specular) * shadowFactor);
+		add4(c, c, ac);
+		clamp4(c, 0, 255.0f);
+		out->bgra = pack_bgr_trunc(c);
+		out->wrote = 1; out->blendable = 1;
+		return;
+	}
 	case PS3D_FN_DEF01: /* tex1light1.cpp:152-193 — output->write(): plain store even under ALPHABLEND */
 	{
 		float c[4];
@@ -626,7 +875,7 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	/* preprocess(): latch uniform pointers (tex1light1.cpp:15-20,145-150 etc.) */
 	shader_env env;
 	memset(&env, 0, sizeof(env));
-	for(int i = 0; i < 32; i++)
+	for(int i = 0; i < 48; i++)
 	{
 		env.u[i] = (const float*)p->uniforms[i].data;
 		if(p->uniforms[i].data && p->uniforms[i].capacity >= 4)
@@ -646,6 +895,26 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 		if(fnF == PS3D_FN_DEF03 && !env.tex[10]) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "uniform 10 does not name a texture");
 		if(fnF == PS3D_FN_DEF04 && !env.tex[2]) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "uniform 2 does not name a texture");
 		if(fnV == PS3D_FN_FLATID && (!env.u[3] || !env.u[4])) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "a uniform slot the programme reads is unset");
+		{
+			/* fragment functors of the two demos: uniform slots read as vectors, then slots that must name a texture */
+			static const struct { int fn; int u[8]; int t[6]; } need[] = {
+				{ PS3D_FN_PLANET, { 7, 8, -1 }, { 9, 10, 11, 12, 15, -1 } },
+				{ PS3D_FN_SATELLITE, { 7, 8, -1 }, { 9, 10, 15, -1 } },
+				{ PS3D_FN_CLOUD, { 7, 8, -1 }, { 9, 15, -1 } },
+				{ PS3D_FN_CLOUDSHADOW, { -1 }, { 9, -1 } },
+				{ PS3D_FN_POSITIONONLY, { 31, -1 }, { -1 } },
+				{ PS3D_FN_SINGLECOLOUR, { 20, 21, 22, 30, 31, 32, 33, -1 }, { 23, -1 } },
+				{ PS3D_FN_DIFFUSEONLY, { 20, 21, 22, 30, 33, -1 }, { 23, 40, -1 } },
+			};
+			for(size_t k = 0; k < sizeof(need) / sizeof(need[0]); k++)
+				if(need[k].fn == fnF)
+				{
+					for(int j = 0; need[k].u[j] >= 0; j++)
+						if(!env.u[need[k].u[j]]) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "a uniform slot the programme reads is unset");
+					for(int j = 0; need[k].t[j] >= 0; j++)
+						if(!env.tex[need[k].t[j]]) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "a texture uniform does not name a live texture");
+				}
+		}
 	}
 
 	/* vbo cursors: all attached slots advance in lock-step, the draw ends when any runs out (vertthrd.cpp:21-31) */
@@ -664,6 +933,8 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	fbo_t* colour = &p->display[p->back];
 	fbo_t* depth = depth_target(p);
 	const int behavior = p->behavior;
+	/* IP_Planet::stepForward advances tangent and binormal by the NORMAL's step (src/test/testproc.cpp:178-188): replicated */
+	const int planetQuirk = PS3D_FN_PLANET == fnI;
 
 	for(size_t tri = 0; tri < ntris; tri++)
 	{
@@ -734,8 +1005,9 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 				for(int k = 0; k < nv; k++)
 					for(int l = 0; l < 4; l++)
 					{
-						if(1 == skip) start[k].v[l] = start[k].v[l] + step[k].v[l];                 /* add_3_4_ip */
-						else start[k].v[l] = start[k].v[l] + step[k].v[l] * (float)skip;            /* step_3_4_ip */
+						const float st = step[planetQuirk && k < 2 ? 2 : k].v[l];
+						if(1 == skip) start[k].v[l] = start[k].v[l] + st;                           /* add_3_4_ip */
+						else start[k].v[l] = start[k].v[l] + st * (float)skip;                      /* step_3_4_ip */
 					}
 			}
 
@@ -757,7 +1029,7 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 					for(int l = 0; l < 4; l++)
 					{
 						frag[k].v[l] = start[k].v[l] * inv;
-						start[k].v[l] = start[k].v[l] + step[k].v[l];
+						start[k].v[l] = start[k].v[l] + step[planetQuirk && k < 2 ? 2 : k].v[l];
 					}
 				float z = zStart * inv;
 				zStart += zStep;

@@ -30,7 +30,7 @@ REPO = os.path.dirname(os.path.dirname(HERE))
 REF = os.environ.get("PS3D_REFERENCE_ROOT", "/root/reference")
 OUT_DIR = os.path.join(REPO, "oracle", "_ref")
 OUT_SO = os.path.join(OUT_DIR, "libps3d_ref.so")
-DEMOS = os.environ.get("PS3D_REF_DEMOS", "0") == "1"
+DEMOS = os.environ.get("PS3D_REF_DEMOS", "1") == "1"   # the demos' own shader triples (src/test, src/test2)
 
 PIPE_SOURCES = [
     "drawvao.cpp", "vertthrd.cpp", "rasterizer.cpp", "interp.cpp", "fragthrd.cpp", "fbo.cpp",
@@ -112,7 +112,7 @@ def patch_demo_shader(which, text):
     for b in blocks:
         out.append(translate_simple_asm(b, which))
     it = iter(out)
-    return ASM_BLOCK.sub(lambda m: next(it), text)
+    return "#include <smmintrin.h>\n" + ASM_BLOCK.sub(lambda m: next(it), text)
 
 
 def translate_simple_asm(block, what):
@@ -123,7 +123,8 @@ def translate_simple_asm(block, what):
          cvtps2dq / packusdw / packuswb / movd / movss / mulps / shufps ... (FP_Cloud pack)
        Anything unknown aborts the build (never guess)."""
     lines = []
-    for raw in block.split("\n")[1:-1]:
+    inner = block[block.index("{") + 1:block.rindex("}")]
+    for raw in inner.split("\n"):
         code = raw.split(";")[0].strip()
         if code:
             lines.append(code)
@@ -133,11 +134,16 @@ def translate_simple_asm(block, what):
     def addr(expr):
         expr = expr.strip()[1:-1].strip()
         m = re.match(r"(\w+)\s*(?:\+\s*(\w+))?$", expr)
-        if not m or m.group(1) not in regs:
+        if not m:
             raise SystemExit("%s: cannot translate address %r" % (what, expr))
         off = m.group(2)
         offv = int(off, 0) if off else 0
-        return "((const char*)(%s) + %d)" % (regs[m.group(1)], offv)
+        base = regs.get(m.group(1))
+        if base is None:
+            if re.match(r"e[a-ds][xi]$", m.group(1)):
+                raise SystemExit("%s: register %s used before it was loaded" % (what, m.group(1)))
+            base = m.group(1)  # [variable]: a C array in scope
+        return "((const char*)(%s) + %d)" % (base, offv)
 
     for code in lines:
         m = re.match(r"(\w+)\s+(.*)$", code)
@@ -208,7 +214,8 @@ def main():
         objs = []
         jobs = [(os.path.join(scratch, "p", s), "p_" + s) for s in PIPE_SOURCES]
         jobs += [] if not DEMOS else [(os.path.join(scratch, "t1", "testproc.cpp"), "t1_testproc.cpp"),
-                 (os.path.join(scratch, "t2", "testproc.cpp"), "t2_testproc.cpp")]
+                 (os.path.join(scratch, "t2", "testproc.cpp"), "t2_testproc.cpp"),
+                 (os.path.join(HERE, "demo_procs1.cpp"), "t1_demo_procs1.cpp"), (os.path.join(HERE, "demo_procs2.cpp"), "t2_demo_procs2.cpp")]
         jobs += [(os.path.join(HERE, s), "s_" + s) for s in ("win32_shim.cpp", "mcemath_sse.cpp", "ref_capi.cpp")]
         for path, tag in jobs:
             obj = os.path.join(scratch, tag + ".o")
@@ -217,8 +224,8 @@ def main():
                 extra = ["-I", os.path.join(scratch, "t1"), "-DPS3D_DEMO=1"]
             if tag.startswith("t2_"):
                 extra = ["-I", os.path.join(scratch, "t2"), "-DPS3D_DEMO=2"]
-            if tag == "s_ref_capi.cpp":
-                extra = ["-DPS3D_T1_DIR=\"%s\"" % os.path.join(scratch, "t1"), "-DPS3D_T2_DIR=\"%s\"" % os.path.join(scratch, "t2")]
+            if tag == "s_ref_capi.cpp" and DEMOS:
+                extra = ["-DPS3D_WITH_DEMO_SHADERS=1"]
             run(["g++"] + CXXFLAGS + inc + extra + ["-c", path, "-o", obj])
             objs.append(obj)
         os.makedirs(OUT_DIR, exist_ok=True)

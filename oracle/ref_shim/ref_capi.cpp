@@ -25,7 +25,8 @@
 #include "ps3d.h"
 
 #ifdef PS3D_WITH_DEMO_SHADERS
-PuresoftProcessor* ps3d_demo_make_processor(int kind, int functor); // demo_procs.cpp
+PuresoftProcessor* ps3d_demo1_make_processor(int kind, int functor); // demo_procs1.cpp (src/test/testproc.cpp)
+PuresoftProcessor* ps3d_demo2_make_processor(int kind, int functor); // demo_procs2.cpp (src/test2/testproc.cpp)
 #endif
 
 namespace
@@ -359,7 +360,7 @@ static PuresoftProcessor* makeProcessor(int kind, int functor)
 		return kind == PS3D_PROC_VERTEX ? (PuresoftProcessor*)new VertexProcesserDEF05 : kind == PS3D_PROC_INTERPOLATION ? (PuresoftProcessor*)new InterpolationProcessorDEF05 : (PuresoftProcessor*)new FragmentProcessorDEF05;
 	default:
 #ifdef PS3D_WITH_DEMO_SHADERS
-		return ps3d_demo_make_processor(kind, functor);
+		return functor < 32 ? ps3d_demo1_make_processor(kind, functor) : ps3d_demo2_make_processor(kind, functor);
 #else
 		return NULL;
 #endif

@@ -27,7 +27,8 @@ WRAP_CLAMP, WRAP_WRAP = 0, 1
 PROC_VERTEX, PROC_INTERPOLATION, PROC_FRAGMENT = 0, 1, 2
 
 FN_DEF01, FN_DEF02, FN_DEF03, FN_DEF04, FN_DEF05 = 1, 2, 3, 4, 5
-FN_PLANET, FN_SATELLITE, FN_CLOUD, FN_CLOUDSHADOW, FN_NULL = 16, 17, 18, 19, 20
+FN_PLANET, FN_SATELLITE, FN_CLOUD, FN_CLOUDSHADOW = 16, 17, 18, 19
+FN_POSITIONONLY, FN_SINGLECOLOUR, FN_DIFFUSEONLY, FN_SHADOW2 = 32, 33, 34, 35
 FN_FLATID = 64
 
 

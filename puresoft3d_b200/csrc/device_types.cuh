@@ -13,7 +13,7 @@
 #define PS_TILE 16            // screen tile edge in pixels; one warp owns one tile
 #define PS_SEG 8              // a lane owns one row segment of PS_SEG pixels: 16 rows x 2 segments = 32 lanes
 #define PS_MAX_VARY 6         // float4 varyings per vertex (PROCDATA_PLANET, src/test/testproc.h:7-16, has 6)
-#define PS_UNIFORM_SLOTS 32   // slots latched per draw, first 64 bytes each (a mat4)
+#define PS_UNIFORM_SLOTS 48   // slots latched per draw, first 64 bytes each (a mat4); demo 2 uses slots up to 43 (src/test2/testproc.h:4-37)
 #define PS_MAX_BOUND_TEX 6
 
 #define PS_BEHAVIOR_UPDATE_DEPTH 0x1

@@ -36,7 +36,8 @@ struct ProgEntry
 {
 	int fnV, fnI, fnF;
 	int nv;
-	uint32_t slots, uniforms;
+	uint32_t slots;
+	uint64_t uniforms;
 	int ntex;
 	int texSlot[PS_MAX_BOUND_TEX];
 	bool mayDiscard, usesWrite4;
@@ -116,6 +117,15 @@ const std::vector<ProgEntry>& programmeTable()
 		t.push_back(makeEntry<ProgDEF04>(PS3D_FN_DEF04, PS3D_FN_DEF04, PS3D_FN_DEF04));
 		t.push_back(makeEntry<ProgDEF05>(PS3D_FN_DEF05, PS3D_FN_DEF05, PS3D_FN_DEF05));
 		t.push_back(makeEntry<ProgFLATID>(PS3D_FN_FLATID, PS3D_FN_FLATID, PS3D_FN_FLATID));
+		// demo 1 (src/test/testproc.cpp) and demo 2 (src/test2/testproc.cpp): the triples their scene objects create
+		t.push_back(makeEntry<ProgEarth>(PS3D_FN_PLANET, PS3D_FN_PLANET, PS3D_FN_PLANET));
+		t.push_back(makeEntry<ProgSatellite>(PS3D_FN_PLANET, PS3D_FN_PLANET, PS3D_FN_SATELLITE));
+		t.push_back(makeEntry<ProgCloud>(PS3D_FN_CLOUD, PS3D_FN_CLOUD, PS3D_FN_CLOUD));
+		t.push_back(makeEntry<ProgCloudShadow>(PS3D_FN_CLOUDSHADOW, PS3D_FN_CLOUDSHADOW, PS3D_FN_CLOUDSHADOW));
+		t.push_back(makeEntry<ProgPositionOnly>(PS3D_FN_POSITIONONLY, PS3D_FN_POSITIONONLY, PS3D_FN_POSITIONONLY));
+		t.push_back(makeEntry<ProgSingleColour>(PS3D_FN_SINGLECOLOUR, PS3D_FN_SINGLECOLOUR, PS3D_FN_SINGLECOLOUR));
+		t.push_back(makeEntry<ProgDiffuseOnly>(PS3D_FN_DIFFUSEONLY, PS3D_FN_DIFFUSEONLY, PS3D_FN_DIFFUSEONLY));
+		t.push_back(makeEntry<ProgShadow2>(PS3D_FN_SHADOW2, PS3D_FN_POSITIONONLY, PS3D_FN_SHADOW2));
 	}
 	return t;
 }

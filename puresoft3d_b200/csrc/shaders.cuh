@@ -232,7 +232,7 @@ PS_D uint32_t blinnPhong(const DrawParams& P, F4 colour, F4 worldPos, F4 normal)
 struct VertexProcesserDEF01
 {
 	static constexpr uint32_t SLOTS = (1u << 0) | (1u << 3) | (1u << 4);
-	static constexpr uint32_t UNIFORMS = (1u << 3) | (1u << 4) | (1u << 5);
+	static constexpr uint64_t UNIFORMS = (1u << 3) | (1u << 4) | (1u << 5);
 	PS_D static void process(const VertexProcessorInput& in, VertexProcessorOutput<3>& out, const DrawParams& P) // :22-41
 	{
 		F4 worldPos = m4v4(P.u[4], ldF4(in.data[0]));
@@ -247,7 +247,7 @@ struct VertexProcesserDEF01
 };
 struct FragmentProcessorDEF01
 {
-	static constexpr uint32_t UNIFORMS = (1u << 7) | (1u << 8) | (1u << 9);
+	static constexpr uint64_t UNIFORMS = (1u << 7) | (1u << 8) | (1u << 9);
 	static constexpr bool MAY_DISCARD = false;
 	static constexpr bool USES_WRITE4 = false;
 	static constexpr int NTEX = 1;
@@ -264,7 +264,7 @@ struct FragmentProcessorDEF01
 struct VertexProcesserDEF02
 {
 	static constexpr uint32_t SLOTS = (1u << 0) | (1u << 1) | (1u << 2);
-	static constexpr uint32_t UNIFORMS = (1u << 3) | (1u << 4) | (1u << 5);
+	static constexpr uint64_t UNIFORMS = (1u << 3) | (1u << 4) | (1u << 5);
 	PS_D static void process(const VertexProcessorInput& in, VertexProcessorOutput<3>& out, const DrawParams& P) // :21-39
 	{
 		F4 worldPos = m4v4(P.u[4], ldF4(in.data[0]));
@@ -277,7 +277,7 @@ struct VertexProcesserDEF02
 };
 struct FragmentProcessorDEF02
 {
-	static constexpr uint32_t UNIFORMS = (1u << 7) | (1u << 8);
+	static constexpr uint64_t UNIFORMS = (1u << 7) | (1u << 8);
 	static constexpr bool MAY_DISCARD = false;
 	static constexpr bool USES_WRITE4 = false;
 	static constexpr int NTEX = 0;
@@ -293,7 +293,7 @@ struct FragmentProcessorDEF02
 struct VertexProcesserDEF03
 {
 	static constexpr uint32_t SLOTS = (1u << 0) | (1u << 1) | (1u << 2) | (1u << 3) | (1u << 4);
-	static constexpr uint32_t UNIFORMS = (1u << 3) | (1u << 4) | (1u << 5);
+	static constexpr uint64_t UNIFORMS = (1u << 3) | (1u << 4) | (1u << 5);
 	PS_D static void process(const VertexProcessorInput& in, VertexProcessorOutput<5>& out, const DrawParams& P) // :22-45
 	{
 		F4 worldPos = m4v4(P.u[4], ldF4(in.data[0]));
@@ -310,7 +310,7 @@ struct VertexProcesserDEF03
 };
 struct FragmentProcessorDEF03
 {
-	static constexpr uint32_t UNIFORMS = (1u << 7) | (1u << 8) | (1u << 9) | (1u << 10);
+	static constexpr uint64_t UNIFORMS = (1u << 7) | (1u << 8) | (1u << 9) | (1u << 10);
 	static constexpr bool MAY_DISCARD = false;
 	static constexpr bool USES_WRITE4 = false;
 	static constexpr int NTEX = 2;
@@ -340,7 +340,7 @@ struct FragmentProcessorDEF03
 struct VertexProcesserDEF04
 {
 	static constexpr uint32_t SLOTS = (1u << 0);
-	static constexpr uint32_t UNIFORMS = (1u << 1);
+	static constexpr uint64_t UNIFORMS = (1u << 1);
 	PS_D static void process(const VertexProcessorInput& in, VertexProcessorOutput<1>& out, const DrawParams& P) // :23-44
 	{
 		const F4 position = ldF4(in.data[0]);
@@ -361,7 +361,7 @@ struct VertexProcesserDEF04
 };
 struct FragmentProcessorDEF04
 {
-	static constexpr uint32_t UNIFORMS = (1u << 2);
+	static constexpr uint64_t UNIFORMS = (1u << 2);
 	static constexpr bool MAY_DISCARD = false;
 	static constexpr bool USES_WRITE4 = true; 
 	static constexpr int NTEX = 1;
@@ -377,7 +377,7 @@ struct FragmentProcessorDEF04
 struct VertexProcesserDEF05
 {
 	static constexpr uint32_t SLOTS = (1u << 0);
-	static constexpr uint32_t UNIFORMS = (1u << 3) | (1u << 4);
+	static constexpr uint64_t UNIFORMS = (1u << 3) | (1u << 4);
 	PS_D static void process(const VertexProcessorInput& in, VertexProcessorOutput<0>& out, const DrawParams& P) // :21-29
 	{
 		F4 p = ldF4(in.data[0]);
@@ -395,7 +395,7 @@ struct VertexProcesserDEF05
 };
 struct FragmentProcessorDEF05
 {
-	static constexpr uint32_t UNIFORMS = 0;
+	static constexpr uint64_t UNIFORMS = 0;
 	static constexpr bool MAY_DISCARD = false;
 	static constexpr bool USES_WRITE4 = false;
 	static constexpr int NTEX = 0;
@@ -403,12 +403,366 @@ struct FragmentProcessorDEF05
 	PS_D static void process(const F4*, FragmentProcessorOutput&, const DrawParams&) {} // shadow.cpp:76-77
 };
 
+// =====================================================================================================================
+// demo 1 — src/test/testproc.cpp (earth + moon + cloud layer, one shadow map). Uniform slots: 3 PV, 4 M, 5 Mrot, 7 light,
+// 8 camera, 9 diffuse, 10 bump, 11 specular map, 12 night map, 15 shadow map, 16 shadow PV (src/test/testproc.cpp:29-35,198-206)
+// =====================================================================================================================
+
+PS_D F4 uvec(const DrawParams& P, int slot) { return f4(P.u[slot][0], P.u[slot][1], P.u[slot][2], P.u[slot][3]); }
+
+// the part FP_Earth / FP_Satellite share with DEF03 (testproc.cpp:240-262): bump normal through the TBN, L by length + rcp, E, H
+PS_D void planetLighting(const DrawParams& P, uint32_t bumpTexel, F4 T, F4 B, F4 N, F4 worldPos, float& lambert, float& specular)
+{
+	F4 bump = f4((float)((bumpTexel >> 16) & 0xff), (float)((bumpTexel >> 8) & 0xff), (float)(bumpTexel & 0xff), 0);
+	bump = f4divs(bump, 255.0f, P.approx);
+	bump = f4muls(bump, 2.0f);
+	bump = f4subs(bump, 1.0f);
+	F4 r; // mcemaths_make_tbn + transform_m4v4_ip: columns T, B, N, 0
+	r.x = fadd(fadd(fadd(fmul(bump.x, T.x), fmul(bump.y, B.x)), fmul(bump.z, N.x)), fmul(bump.w, 0.0f));
+	r.y = fadd(fadd(fadd(fmul(bump.x, T.y), fmul(bump.y, B.y)), fmul(bump.z, N.y)), fmul(bump.w, 0.0f));
+	r.z = fadd(fadd(fadd(fmul(bump.x, T.z), fmul(bump.y, B.z)), fmul(bump.z, N.z)), fmul(bump.w, 0.0f));
+	r.w = fadd(fadd(fadd(fmul(bump.x, T.w), fmul(bump.y, B.w)), fmul(bump.z, N.w)), fmul(bump.w, 0.0f));
+	bump = f4norm(r, P.approx);
+	F4 L = f4sub(uvec(P, 7), worldPos);
+	const float distance = f4len(L);
+	L = f4divs(L, distance, P.approx);
+	const F4 E = f4norm(f4sub(uvec(P, 8), worldPos), P.approx);
+	const F4 H = f4norm(f4add(E, L), P.approx);
+	lambert = f4dot(L, bump);
+	specular = f4dot(H, bump);
+	specular = specular < 0 ? 0 : specular;
+	specular = opt_pow(specular, 50);
+}
+
+struct VP_Planet // testproc.cpp:37-74 — varyings: tangent, binormal, normal, worldPos, texcoord, shadowcoord
+{
+	static constexpr uint32_t SLOTS = (1u << 0) | (1u << 1) | (1u << 2) | (1u << 3) | (1u << 4);
+	static constexpr uint64_t UNIFORMS = (1ull << 3) | (1ull << 4) | (1ull << 5) | (1ull << 16);
+	PS_D static void process(const VertexProcessorInput& in, VertexProcessorOutput<6>& out, const DrawParams& P)
+	{
+		F4 worldPos = m4v4(P.u[4], ldF4(in.data[0]));
+		out.user[5] = m4v4(P.u[16], worldPos);
+		out.position = m4v4(P.u[3], worldPos);
+		worldPos.w = 0;
+		out.user[3] = worldPos;
+		out.user[0] = m4v4(P.u[5], ldF4(in.data[1]));
+		out.user[1] = m4v4(P.u[5], ldF4(in.data[2]));
+		out.user[2] = m4v4(P.u[5], ldF4(in.data[3]));
+		float tu, tv;
+		ldF2(in.data[4], tu, tv);
+		out.user[4] = f4(tu, tv, 0, 0);   // [2],[3] are never written by the reference (stale buffer contents), never read either
+	}
+};
+// IP_Planet::stepForward advances tangent AND binormal by the NORMAL's step (testproc.cpp:178-188) — replicated
+struct IP_Planet : InterpolationProcessorVec4<6>
+{
+	PS_D static void stepForward(F4* start, const F4* step, int stepCount)
+	{
+		if(1 == stepCount)
+		{
+			start[0] = f4add(start[0], step[2]); start[1] = f4add(start[1], step[2]); start[2] = f4add(start[2], step[2]);
+			start[3] = f4add(start[3], step[3]); start[4] = f4add(start[4], step[4]); start[5] = f4add(start[5], step[5]);
+		}
+		else
+		{
+			const float n = (float)stepCount;
+			start[0] = f4add(start[0], f4muls(step[2], n)); start[1] = f4add(start[1], f4muls(step[2], n)); start[2] = f4add(start[2], f4muls(step[2], n));
+			start[3] = f4add(start[3], f4muls(step[3], n)); start[4] = f4add(start[4], f4muls(step[4], n)); start[5] = f4add(start[5], f4muls(step[5], n));
+		}
+	}
+};
+struct FP_Earth // testproc.cpp:198-288
+{
+	static constexpr uint64_t UNIFORMS = (1ull << 7) | (1ull << 8) | (1ull << 9) | (1ull << 10) | (1ull << 11) | (1ull << 12) | (1ull << 15);
+	static constexpr bool MAY_DISCARD = false;
+	static constexpr bool USES_WRITE4 = true;
+	static constexpr int NTEX = 5;
+	__host__ __device__ static constexpr int texSlot(int i) { return i == 0 ? 9 : (i == 1 ? 10 : (i == 2 ? 11 : (i == 3 ? 12 : 15))); }
+	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P)
+	{
+		F4 colour = unpackBGRA(PuresoftSampler2D::get4(P.tex[0], in[4].x, in[4].y));
+		const F4 night = unpackBGRA(PuresoftSampler2D::get4(P.tex[3], in[4].x, in[4].y));
+		const uint32_t nb = PuresoftSampler2D::get4(P.tex[1], in[4].x, in[4].y);
+		const float shadowFactor = PuresoftSamplerProjection::get(P.tex[4], in[5], P.approx);
+		const uint32_t sp = PuresoftSampler2D::get4(P.tex[2], in[4].x, in[4].y);
+		const float specularControl = fdiv((float)((sp >> 16) & 0xff), 255.0f);
+		float lambert, specular;
+		planetLighting(P, nb, in[0], in[1], in[2], in[3], lambert, specular);
+		specular = fmul(specular, specularControl);
+		colour = f4adds(colour, fmul(255.0f, specular));
+		colour = f4muls(colour, lambert);
+		if(lambert < 0.2f) colour = f4add(colour, night);
+		colour = f4muls(colour, shadowFactor);
+		colour = f4clamp(colour, 0, 255.0f);
+		out.write4(packBGRtrunc(colour));
+	}
+};
+struct FP_Satellite // testproc.cpp:290-361
+{
+	static constexpr uint64_t UNIFORMS = (1ull << 7) | (1ull << 8) | (1ull << 9) | (1ull << 10) | (1ull << 15);
+	static constexpr bool MAY_DISCARD = false;
+	static constexpr bool USES_WRITE4 = true;
+	static constexpr int NTEX = 3;
+	__host__ __device__ static constexpr int texSlot(int i) { return i == 0 ? 9 : (i == 1 ? 10 : 15); }
+	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P)
+	{
+		F4 colour = unpackBGRA(PuresoftSampler2D::get4(P.tex[0], in[4].x, in[4].y));
+		const uint32_t nb = PuresoftSampler2D::get4(P.tex[1], in[4].x, in[4].y);
+		const float shadowFactor = PuresoftSamplerProjection::get(P.tex[2], in[5], P.approx);
+		float lambert, specular;
+		planetLighting(P, nb, in[0], in[1], in[2], in[3], lambert, specular);
+		colour = f4adds(colour, fmul(255.0f, specular));
+		colour = f4muls(colour, lambert);
+		colour = f4muls(colour, shadowFactor);
+		colour = f4clamp(colour, 0, 255.0f);
+		out.write4(packBGRtrunc(colour));
+	}
+};
+
+// cvtps2dq + packusdw + packuswb on one lane (testproc.cpp:565-571): round to nearest even (INT_MIN when out of range), saturate
+// the SIGNED 32-bit value to 0..65535, then the SIGNED 16-bit reading of that to 0..255 — so 32768..65535 become 0
+PS_D uint32_t packRneSat(float f)
+{
+	int v;
+	if(!(f >= -2147483648.0f && f < 2147483648.0f)) v = (int)0x80000000u; else v = __float2int_rn(f);
+	const int u16 = v < 0 ? 0 : (v > 65535 ? 65535 : v);
+	const int s16 = (int)(short)u16;
+	return (uint32_t)(s16 < 0 ? 0 : (s16 > 255 ? 255 : s16));
+}
+
+struct VP_Cloud // testproc.cpp:392-425 — varyings: normal, worldPos, texcoord, shadowcoord
+{
+	static constexpr uint32_t SLOTS = (1u << 0) | (1u << 3) | (1u << 4);
+	static constexpr uint64_t UNIFORMS = (1ull << 3) | (1ull << 4) | (1ull << 5) | (1ull << 16);
+	PS_D static void process(const VertexProcessorInput& in, VertexProcessorOutput<4>& out, const DrawParams& P)
+	{
+		F4 worldPos = m4v4(P.u[4], ldF4(in.data[0]));
+		out.user[3] = m4v4(P.u[16], worldPos);
+		out.position = m4v4(P.u[3], worldPos);
+		worldPos.w = 0;
+		out.user[1] = worldPos;
+		out.user[0] = m4v4(P.u[5], ldF4(in.data[3]));
+		float tu, tv;
+		ldF2(in.data[4], tu, tv);
+		out.user[2] = f4(tu, tv, 0, 0);
+	}
+};
+struct FP_Cloud // testproc.cpp:531-574 — alpha = the texture's red channel; blended by the caller's ALPHABLEND (write4)
+{
+	static constexpr uint64_t UNIFORMS = (1ull << 7) | (1ull << 8) | (1ull << 9) | (1ull << 15);
+	static constexpr bool MAY_DISCARD = false;
+	static constexpr bool USES_WRITE4 = true;
+	static constexpr int NTEX = 2;
+	__host__ __device__ static constexpr int texSlot(int i) { return i == 0 ? 9 : 15; }
+	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P)
+	{
+		const uint32_t tex = PuresoftSampler2D::get4(P.tex[0], in[2].x, in[2].y);
+		F4 cloud = f4(255.0f, 255.0f, 255.0f, (float)((tex >> 16) & 0xff));
+		const float shadowFactor = PuresoftSamplerProjection::get(P.tex[1], in[3], P.approx);
+		F4 L = f4sub(uvec(P, 7), in[1]);
+		const float distance = f4len(L);
+		L = f4divs(L, distance, P.approx);
+		// E and H are computed by the reference and never used (:551-556)
+		const float lambert = fmul(2.0f, f4dot(L, in[0]));
+		const float k = fmul(lambert, shadowFactor);
+		cloud.x = fmul(cloud.x, k); cloud.y = fmul(cloud.y, k); cloud.z = fmul(cloud.z, k);   // mcemaths_mul_3: xyz only
+		out.write4(packRneSat(cloud.x) | (packRneSat(cloud.y) << 8) | (packRneSat(cloud.z) << 16) | (packRneSat(cloud.w) << 24));
+	}
+};
+
+struct VP_CloudShadow // testproc.cpp:595-610 — 0.95 shrink, pvm = PV * M per vertex; varying: texcoord
+{
+	static constexpr uint32_t SLOTS = (1u << 0) | (1u << 4);
+	static constexpr uint64_t UNIFORMS = (1ull << 3) | (1ull << 4);
+	PS_D static void process(const VertexProcessorInput& in, VertexProcessorOutput<1>& out, const DrawParams& P)
+	{
+		F4 p = ldF4(in.data[0]);
+		p.x = fmul(p.x, 0.95f); p.y = fmul(p.y, 0.95f); p.z = fmul(p.z, 0.95f);
+		float pvm[16];
+#pragma unroll
+		for(int c = 0; c < 4; c++)
+		{
+			F4 col = m4v4(P.u[3], f4(P.u[4][c * 4], P.u[4][c * 4 + 1], P.u[4][c * 4 + 2], P.u[4][c * 4 + 3]));
+			pvm[c * 4] = col.x; pvm[c * 4 + 1] = col.y; pvm[c * 4 + 2] = col.z; pvm[c * 4 + 3] = col.w;
+		}
+		out.position = m4v4(pvm, p);
+		float tu, tv;
+		ldF2(in.data[4], tu, tv);
+		out.user[0] = f4(tu, tv, 0, 0);
+	}
+};
+struct FP_CloudShadow // testproc.cpp:671-685 — the only functor of the reference that discards: thin cloud casts no shadow
+{
+	static constexpr uint64_t UNIFORMS = (1ull << 9);
+	static constexpr bool MAY_DISCARD = true;
+	static constexpr bool USES_WRITE4 = false;
+	static constexpr int NTEX = 1;
+	__host__ __device__ static constexpr int texSlot(int i) { return 9; }
+	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P)
+	{
+		const uint32_t tex = PuresoftSampler2D::get4(P.tex[0], in[0].x, in[0].y);
+		if(((tex >> 16) & 0xff) < 150) out.discard();
+	}
+};
+
+// =====================================================================================================================
+// demo 2 — src/test2/testproc.cpp (desk scene, spot light, shadow map). Uniform slots (src/test2/testproc.h:4-37): 0 M, 1 Mrot,
+// 4 PV, 5 PVM, 6 shadow PV, 20 light position, 21 light direction, 22 camera, 23 shadow map, 30 ambient, 31 diffuse colour,
+// 32 specular colour, 33 specular exponent, 40 diffuse texture
+// =====================================================================================================================
+
+struct VP_PositionOnly // testproc.cpp:17-22
+{
+	static constexpr uint32_t SLOTS = (1u << 0);
+	static constexpr uint64_t UNIFORMS = (1ull << 5);
+	PS_D static void process(const VertexProcessorInput& in, VertexProcessorOutput<0>& out, const DrawParams& P)
+	{
+		out.position = m4v4(P.u[5], ldF4(in.data[0]));
+	}
+};
+struct VP_Shadow // testproc.cpp:510-516 — 0.9 shrink (xyz), then PVM
+{
+	static constexpr uint32_t SLOTS = (1u << 0);
+	static constexpr uint64_t UNIFORMS = (1ull << 5);
+	PS_D static void process(const VertexProcessorInput& in, VertexProcessorOutput<0>& out, const DrawParams& P)
+	{
+		F4 p = ldF4(in.data[0]);
+		p.x = fmul(p.x, 0.9f); p.y = fmul(p.y, 0.9f); p.z = fmul(p.z, 0.9f);
+		out.position = m4v4(P.u[5], p);
+	}
+};
+// IP_Null (testproc.cpp:26-45) declares 16 bytes of user data and never touches them: no varying reaches the fragment functor
+struct FP_Null // testproc.cpp:520-524
+{
+	static constexpr uint64_t UNIFORMS = 0;
+	static constexpr bool MAY_DISCARD = false;
+	static constexpr bool USES_WRITE4 = false;
+	static constexpr int NTEX = 0;
+	__host__ __device__ static constexpr int texSlot(int i) { return -1; }
+	PS_D static void process(const F4*, FragmentProcessorOutput&, const DrawParams&) {}
+};
+struct FP_SingleColourNoLighting // testproc.cpp:49-67
+{
+	static constexpr uint64_t UNIFORMS = (1ull << 31);
+	static constexpr bool MAY_DISCARD = false;
+	static constexpr bool USES_WRITE4 = true;
+	static constexpr int NTEX = 0;
+	__host__ __device__ static constexpr int texSlot(int i) { return -1; }
+	PS_D static void process(const F4*, FragmentProcessorOutput& out, const DrawParams& P)
+	{
+		out.write4(packBGRtrunc(f4muls(uvec(P, 31), 255.0f)));
+	}
+};
+
+static constexpr float kFieldOfLight = 6.283185f * (25.0f / 360.0f);   // testproc.cpp:9
+
+// the lighting factors FP_SingleColour and FP_DiffuseOnly share (testproc.cpp:230-256 / 459-485): L, E, H by rsqrt, a spot
+// cone through acosf / cosf / opt_pow(.,150), specular by opt_pow, both clamped to [0,1]
+PS_D void spotFactors(const DrawParams& P, F4 worldPos, F4 normal, float& lambertOut, float& specularOut)
+{
+	const F4 L = f4norm(f4sub(uvec(P, 20), worldPos), P.approx);
+	const F4 E = f4norm(f4sub(uvec(P, 22), worldPos), P.approx);
+	const F4 H = f4norm(f4add(E, L), P.approx);
+	float lambert = f4dot(L, normal);
+	// <math.h> in C++ resolves acos(float) / cos(float) to the float overloads (acosf / cosf of the host's libm, correctly
+	// rounded in all but rare cases): evaluated here in double and rounded once, which gives the same float except in those cases
+	const float yawOfLight = (float)acos((double)f4dot(L, uvec(P, 21)));
+	float cone = 1.0f;
+	if(!(yawOfLight < kFieldOfLight))
+		cone = opt_pow((float)cos((double)fsub(yawOfLight, kFieldOfLight)), 150);
+	lambert = fmul(lambert, cone);
+	float specular = opt_pow(f4dot(H, normal), (unsigned)cvtu(P.u[33][0]));
+	lambertOut = clamp1(lambert, 0, 1.0f);
+	specularOut = clamp1(specular, 0, 1.0f);
+}
+
+struct VP_SingleColour // testproc.cpp:94-120 — varyings: normal, worldPos, shadowcoord
+{
+	static constexpr uint32_t SLOTS = (1u << 0) | (1u << 3);
+	static constexpr uint64_t UNIFORMS = (1ull << 0) | (1ull << 1) | (1ull << 5) | (1ull << 6);
+	PS_D static void process(const VertexProcessorInput& in, VertexProcessorOutput<3>& out, const DrawParams& P)
+	{
+		const F4 position = ldF4(in.data[0]);
+		F4 worldPos = m4v4(P.u[0], position);
+		out.user[2] = m4v4(P.u[6], worldPos);
+		worldPos.w = 0;
+		out.user[1] = worldPos;
+		out.position = m4v4(P.u[5], position);
+		out.user[0] = m4v4(P.u[1], ldF4(in.data[3]));
+	}
+};
+struct FP_SingleColour // testproc.cpp:209-287
+{
+	static constexpr uint64_t UNIFORMS = (1ull << 20) | (1ull << 21) | (1ull << 22) | (1ull << 23) | (1ull << 30) | (1ull << 31) | (1ull << 32) | (1ull << 33);
+	static constexpr bool MAY_DISCARD = false;
+	static constexpr bool USES_WRITE4 = true;
+	static constexpr int NTEX = 1;
+	__host__ __device__ static constexpr int texSlot(int i) { return 23; }
+	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P)
+	{
+		const float shadowFactor = PuresoftSamplerProjection::get(P.tex[0], in[2], P.approx);
+		float lambert, specular;
+		spotFactors(P, in[1], in[0], lambert, specular);
+		const F4 diffuse = uvec(P, 31), specCol = uvec(P, 32), ambient = uvec(P, 30);
+		F4 colour = f4muls(diffuse, lambert);
+		F4 specularColour = f4(fmul(diffuse.x, specCol.x), fmul(diffuse.y, specCol.y), fmul(diffuse.z, specCol.z), fmul(diffuse.w, specCol.w));
+		specularColour = f4muls(specularColour, specular);
+		const F4 ambientColour = f4(fmul(diffuse.x, ambient.x), fmul(diffuse.y, ambient.y), fmul(diffuse.z, ambient.z), fmul(diffuse.w, ambient.w));
+		colour = f4add(colour, specularColour);
+		colour = f4muls(colour, shadowFactor);
+		colour = f4add(colour, ambientColour);
+		colour = f4clamp(colour, 0, 1.0f);
+		colour = f4muls(colour, 255.0f);
+		out.write4(packBGRtrunc(colour));
+	}
+};
+
+struct VP_DiffuseOnly // testproc.cpp:310-342 — varyings: normal, worldPos, texcoord, shadowcoord
+{
+	static constexpr uint32_t SLOTS = (1u << 0) | (1u << 3) | (1u << 4);
+	static constexpr uint64_t UNIFORMS = (1ull << 0) | (1ull << 1) | (1ull << 5) | (1ull << 6);
+	PS_D static void process(const VertexProcessorInput& in, VertexProcessorOutput<4>& out, const DrawParams& P)
+	{
+		const F4 position = ldF4(in.data[0]);
+		F4 worldPos = m4v4(P.u[0], position);
+		out.user[3] = m4v4(P.u[6], worldPos);
+		out.position = m4v4(P.u[5], position);
+		worldPos.w = 0;
+		out.user[1] = worldPos;
+		out.user[0] = m4v4(P.u[1], ldF4(in.data[3]));
+		float tu, tv;
+		ldF2(in.data[4], tu, tv);
+		out.user[2] = f4(tu, tv, 0, 0);
+	}
+};
+struct FP_DiffuseOnly // testproc.cpp:437-500
+{
+	static constexpr uint64_t UNIFORMS = (1ull << 20) | (1ull << 21) | (1ull << 22) | (1ull << 23) | (1ull << 30) | (1ull << 33) | (1ull << 40);
+	static constexpr bool MAY_DISCARD = false;
+	static constexpr bool USES_WRITE4 = true;
+	static constexpr int NTEX = 2;
+	__host__ __device__ static constexpr int texSlot(int i) { return i == 0 ? 23 : 40; }
+	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P)
+	{
+		const float shadowFactor = PuresoftSamplerProjection::get(P.tex[0], in[3], P.approx);
+		F4 colour = unpackBGRA(PuresoftSampler2D::get4(P.tex[1], in[2].x, in[2].y));
+		const F4 ambient = uvec(P, 30);
+		const F4 ambientColour = f4(fmul(colour.x, ambient.x), fmul(colour.y, ambient.y), fmul(colour.z, ambient.z), fmul(colour.w, ambient.w));
+		float lambert, specular;
+		spotFactors(P, in[1], in[0], lambert, specular);
+		colour = f4muls(colour, fmul(fadd(lambert, specular), shadowFactor));
+		colour = f4add(colour, ambientColour);
+		colour = f4clamp(colour, 0, 255.0f);
+		out.write4(packBGRtrunc(colour));
+	}
+};
+
 // ---- FLATID: parity-test functor, not in the reference: carries a per-triangle id colour to the pixel --------------
 
 struct VertexProcesserFLATID
 {
 	static constexpr uint32_t SLOTS = (1u << 0) | (1u << 6);
-	static constexpr uint32_t UNIFORMS = (1u << 3) | (1u << 4);
+	static constexpr uint64_t UNIFORMS = (1u << 3) | (1u << 4);
 	PS_D static void process(const VertexProcessorInput& in, VertexProcessorOutput<1>& out, const DrawParams& P)
 	{
 		out.position = m4v4(P.u[3], m4v4(P.u[4], ldF4(in.data[0])));
@@ -417,7 +771,7 @@ struct VertexProcesserFLATID
 };
 struct FragmentProcessorFLATID
 {
-	static constexpr uint32_t UNIFORMS = 0;
+	static constexpr uint64_t UNIFORMS = 0;
 	static constexpr bool MAY_DISCARD = false;
 	static constexpr bool USES_WRITE4 = true; 
 	static constexpr int NTEX = 0;
@@ -446,3 +800,11 @@ typedef Programme<VertexProcesserDEF03, InterpolationProcessorVec4<5>, FragmentP
 typedef Programme<VertexProcesserDEF04, InterpolationProcessorVec4<1>, FragmentProcessorDEF04> ProgDEF04;
 typedef Programme<VertexProcesserDEF05, InterpolationProcessorVec4<0>, FragmentProcessorDEF05> ProgDEF05;
 typedef Programme<VertexProcesserFLATID, InterpolationProcessorVec4<1>, FragmentProcessorFLATID> ProgFLATID;
+typedef Programme<VP_Planet, IP_Planet, FP_Earth> ProgEarth;
+typedef Programme<VP_Planet, IP_Planet, FP_Satellite> ProgSatellite;
+typedef Programme<VP_Cloud, InterpolationProcessorVec4<4>, FP_Cloud> ProgCloud;
+typedef Programme<VP_CloudShadow, InterpolationProcessorVec4<1>, FP_CloudShadow> ProgCloudShadow;
+typedef Programme<VP_PositionOnly, InterpolationProcessorVec4<0>, FP_SingleColourNoLighting> ProgPositionOnly;
+typedef Programme<VP_SingleColour, InterpolationProcessorVec4<3>, FP_SingleColour> ProgSingleColour;
+typedef Programme<VP_DiffuseOnly, InterpolationProcessorVec4<4>, FP_DiffuseOnly> ProgDiffuseOnly;
+typedef Programme<VP_Shadow, InterpolationProcessorVec4<0>, FP_Null> ProgShadow2;

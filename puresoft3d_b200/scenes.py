@@ -119,7 +119,9 @@ class Scene:
     def vertex_bytes_read(self):
         """Σ over draws of the bytes the bound vertex functor reads."""
         slots_read = {K.FN_DEF01: (0, 3, 4), K.FN_DEF02: (0, 1, 2), K.FN_DEF03: (0, 1, 2, 3, 4), K.FN_DEF04: (0,),
-                      K.FN_DEF05: (0,), K.FN_FLATID: (0, 6)}
+                      K.FN_DEF05: (0,), K.FN_FLATID: (0, 6), K.FN_PLANET: (0, 1, 2, 3, 4), K.FN_CLOUD: (0, 3, 4),
+                      K.FN_CLOUDSHADOW: (0, 4), K.FN_POSITIONONLY: (0,), K.FN_SHADOW2: (0,), K.FN_SINGLECOLOUR: (0, 3),
+                      K.FN_DIFFUSEONLY: (0, 3, 4)}
         total, prog = 0, None
         for c in self.commands:
             if c[0] == "use":
@@ -483,4 +485,218 @@ def scene_soup(width=320, height=240, seed=7, count=400, functor=K.FN_DEF02, cul
     sc.cmd("draw", vao)
     if not cull:
         sc.cmd("enable", K.BEHAVIOR_FACE_CULLING)
+    return sc
+
+
+# ---- the two demos of the reference as headless scenes (BASELINE.json configs[2]) ----------------
+
+BIAS = np.array([[0.5, 0, 0, 0.5], [0, 0.5, 0, 0.5], [0, 0, 1.0, 0], [0, 0, 0, 1.0]], dtype=F32)   # src/test/puresoft.cpp:38-44
+
+
+def sphere_mesh(stacks=16, slices=32, radius=1.0):
+    """UV sphere, un-indexed triangles, with tangent (d/du), binormal (d/dv), normal and uv like sphere.objx carries them."""
+    def vert(i, j):
+        v, u = i / stacks, j / slices
+        th, ph = math.pi * v, 2 * math.pi * u
+        n = np.array([math.sin(th) * math.cos(ph), math.cos(th), math.sin(th) * math.sin(ph)])
+        t = np.array([-math.sin(ph), 0.0, math.cos(ph)])
+        b = np.cross(n, t)
+        return n * radius, t, b, n, (u, 1.0 - v)
+    pos, tan, bin_, nrm, uv = [], [], [], [], []
+    for i in range(stacks):
+        for j in range(slices):
+            a, b, c, d = vert(i, j), vert(i + 1, j), vert(i + 1, j + 1), vert(i, j + 1)
+            for tri in ((a, c, b), (a, d, c)):
+                for (p, t, bb, n, q) in tri:
+                    pos.append(list(p) + [1.0]); tan.append(list(t) + [0.0]); bin_.append(list(bb) + [0.0]); nrm.append(list(n) + [0.0]); uv.append(q)
+    return (np.array(pos, F32), np.array(tan, F32), np.array(bin_, F32), np.array(nrm, F32), np.array(uv, F32))
+
+
+def tex_cloud(rng, w, h):
+    """Cloud layer: alpha lives in the red channel (FP_Cloud reads .r, FP_CloudShadow discards below 150)."""
+    t = tex_smooth_bgra(rng, w, h, octaves=5)
+    g = t[..., 0].astype(np.float64)
+    g = (g - g.min()) / max(1.0, g.max() - g.min())
+    out = np.zeros((h, w, 4), dtype=np.uint8)
+    out[..., 2] = np.clip(g * 330.0 - 40.0, 0, 255)
+    out[..., 3] = 255
+    return out
+
+
+def scene_planets(width=800, height=500, shadow=480, seed=3, stacks=16, slices=32, tex_size=256):
+    """Demo 1 (src/test/puresoft.cpp:113-206): shadow pass into a float texture (earth + moon with DEF05, cloud layer with the
+    discarding CloudShadow triple), then skybox (DEF04, depth off), earth (VP/IP_Planet + FP_Earth), moon (FP_Satellite) and the
+    alpha-blended cloud layer (VP/IP/FP_Cloud). Uniform slots as src/test/testobjs.cpp:45-145."""
+    rng = np.random.default_rng(seed)
+    sc = Scene("demo1-planets-%dx%d" % (width, height), width, height)
+    diffuse = sc.add_texture(tex_size, tex_size, 4, tex_smooth_bgra(rng, tex_size, tex_size))
+    bump = sc.add_texture(tex_size, tex_size, 4, tex_smooth_bgra(rng, tex_size, tex_size, normal_map=True))
+    spec = sc.add_texture(tex_size, tex_size, 4, tex_smooth_bgra(rng, tex_size, tex_size))
+    night = sc.add_texture(tex_size, tex_size, 4, (tex_smooth_bgra(rng, tex_size, tex_size) // 3).astype(np.uint8))
+    cloud = sc.add_texture(tex_size, tex_size, 4, tex_cloud(rng, tex_size, tex_size))
+    moon_d = sc.add_texture(tex_size // 2, tex_size // 2, 4, tex_smooth_bgra(rng, tex_size // 2, tex_size // 2))
+    moon_b = sc.add_texture(tex_size // 2, tex_size // 2, 4, tex_smooth_bgra(rng, tex_size // 2, tex_size // 2, normal_map=True))
+    sky = sc.add_texture(64, 64, 4, layers=[tex_smooth_bgra(rng, 64, 64) for _ in range(6)])
+    shadow_tex = sc.add_texture(shadow, shadow, 4, None)   # float depth, created empty (puresoft.cpp:141-147)
+    sphere = sc.add_vao(_std_slots(sphere_mesh(stacks, slices, radius=0.5)))
+    quad = sc.add_vao({0: (16, np.array([(-1, 1, 0, 1), (-1, -1, 0, 1), (1, -1, 0, 1), (1, -1, 0, 1), (1, 1, 0, 1), (-1, 1, 0, 1)], F32))})
+    p_shadow = sc.add_programme(K.FN_DEF05)
+    p_cloudshadow = sc.add_programme(K.FN_CLOUDSHADOW)
+    p_sky = sc.add_programme(K.FN_DEF04)
+    p_earth = sc.add_programme(K.FN_PLANET)
+    p_moon = sc.add_programme(K.FN_PLANET, K.FN_PLANET, K.FN_SATELLITE)
+    p_cloud = sc.add_programme(K.FN_CLOUD)
+
+    light, camera = (-2.0, 0.6, 2.4), (0.0, 0.0, 2.2)
+    proj = mat_perspective(0.1, 10.0, width / height, 2 * math.pi * (30.0 / 360.0))
+    view = mat_translation(-camera[0], -camera[1], -camera[2])
+    pv = (proj.astype(np.float64) @ view.astype(np.float64)).astype(F32)
+    lproj = mat_perspective(0.1, 10.0, 1.0, 2 * math.pi * (30.0 / 360.0))
+    lview = mat_look_at(light, (0, 0, 0))
+    lpv = (lproj.astype(np.float64) @ lview.astype(np.float64)).astype(F32)
+    lpvb = (BIAS.astype(np.float64) @ lpv.astype(np.float64)).astype(F32)
+    rot_e = mat_rotation((0, 1, 0), 0.7)
+    model_e = rot_e
+    rot_c = mat_rotation((0, 1, 0), 1.9)
+    model_c = (rot_c.astype(np.float64) @ mat_scaling(1.1, 1.1, 1.1).astype(np.float64)).astype(F32)
+    rot_m = mat_rotation((0, 1, 0), 2.6)
+    model_m = (rot_m.astype(np.float64) @ mat_translation(0.95, 0, 0).astype(np.float64) @ mat_scaling(0.2, 0.2, 0.2).astype(np.float64)).astype(F32)
+
+    def obj_uniforms(model, rot):
+        sc.cmd("uniform", 4, colmajor(model))
+        sc.cmd("uniform", 5, colmajor(rot))
+
+    sc.cmd("uniform", 7, vec4(*light))
+    sc.cmd("uniform", 8, vec4(*camera))
+    sc.cmd("clearColour", 0xFF000000)
+    # ---- shadow map
+    sc.cmd("uniform", 0, colmajor(lproj)); sc.cmd("uniform", 1, colmajor(lview)); sc.cmd("uniform", 3, colmajor(lpv))
+    sc.cmd("depth", shadow_tex)
+    sc.cmd("clearDepth", 1.0)
+    sc.cmd("viewport", shadow, shadow)
+    sc.cmd("use", p_shadow)
+    obj_uniforms(model_e, rot_e); sc.cmd("draw", sphere)
+    obj_uniforms(model_m, rot_m); sc.cmd("draw", sphere)
+    obj_uniforms(model_c, rot_c); sc.cmd("tex_uniform", 9, cloud)
+    sc.cmd("use", p_cloudshadow); sc.cmd("enable", K.BEHAVIOR_ALPHABLEND); sc.cmd("draw", sphere); sc.cmd("disable", K.BEHAVIOR_ALPHABLEND)
+    # ---- the scene
+    sc.cmd("uniform", 0, colmajor(proj)); sc.cmd("uniform", 1, colmajor(view)); sc.cmd("uniform", 3, colmajor(pv))
+    sc.cmd("depth", -1)
+    sc.cmd("clearDepth", 1.0)
+    sc.cmd("viewport", width, height)
+    sc.cmd("tex_uniform", 15, shadow_tex)
+    sc.cmd("uniform", 16, colmajor(lpvb))
+    sc.cmd("tex_uniform", 2, sky)
+    sc.cmd("disable", K.BEHAVIOR_UPDATE_DEPTH | K.BEHAVIOR_TEST_DEPTH)
+    sc.cmd("use", p_sky); sc.cmd("draw", quad, True)
+    sc.cmd("enable", K.BEHAVIOR_UPDATE_DEPTH | K.BEHAVIOR_TEST_DEPTH)
+    obj_uniforms(model_e, rot_e)
+    sc.cmd("tex_uniform", 9, diffuse); sc.cmd("tex_uniform", 10, bump); sc.cmd("tex_uniform", 11, spec); sc.cmd("tex_uniform", 12, night)
+    sc.cmd("use", p_earth); sc.cmd("draw", sphere)
+    obj_uniforms(model_m, rot_m)
+    sc.cmd("tex_uniform", 9, moon_d); sc.cmd("tex_uniform", 10, moon_b)
+    sc.cmd("use", p_moon); sc.cmd("draw", sphere)
+    obj_uniforms(model_c, rot_c)
+    sc.cmd("tex_uniform", 9, cloud)
+    sc.cmd("use", p_cloud); sc.cmd("enable", K.BEHAVIOR_ALPHABLEND); sc.cmd("draw", sphere); sc.cmd("disable", K.BEHAVIOR_ALPHABLEND)
+    sc.meta["triangles"] = 3 * stacks * slices * 2 * 2 + 2
+    return sc
+
+
+def box_mesh(sx, sy, sz):
+    pos, tan, bin_, nrm, uv = cube_mesh()
+    pos = pos.copy()
+    pos[:, 0] *= sx; pos[:, 1] *= sy; pos[:, 2] *= sz
+    return pos, tan, bin_, nrm, uv
+
+
+def scene_desk(width=1024, height=640, shadow=1024, seed=5, clutter=24, tex_size=256, skybox=True):
+    """Demo 2 / BASELINE.json configs[2] (src/test2/puresoft.cpp:185-248): a depth-only pass into a float texture through
+    VP_Shadow / IP_Null / FP_Null, then the lit pass: a textured desk top and boxes (DiffuseOnly triple: spot light through
+    double-precision acos/cos, 4-tap projective shadow lookup), single-colour objects (SingleColour triple), an unlit marker
+    at the light (PositionOnly + FP_SingleColourNoLighting), in front of a cube-map skybox (DEF04, depth off)."""
+    rng = np.random.default_rng(seed)
+    sc = Scene("demo2-desk-%dx%d-s%d" % (width, height, shadow), width, height)
+    wood = sc.add_texture(tex_size, tex_size, 4, tex_smooth_bgra(rng, tex_size, tex_size))
+    sky = sc.add_texture(64, 64, 4, layers=[tex_smooth_bgra(rng, 64, 64) for _ in range(6)])
+    shadow_tex = sc.add_texture(shadow, shadow, 4, None)
+    p_shadow = sc.add_programme(K.FN_SHADOW2, K.FN_POSITIONONLY, K.FN_SHADOW2)
+    p_tex = sc.add_programme(K.FN_DIFFUSEONLY)
+    p_col = sc.add_programme(K.FN_SINGLECOLOUR)
+    p_unlit = sc.add_programme(K.FN_POSITIONONLY)
+    p_sky = sc.add_programme(K.FN_DEF04)
+    quad = sc.add_vao({0: (16, np.array([(-1, 1, 0, 1), (-1, -1, 0, 1), (1, -1, 0, 1), (1, -1, 0, 1), (1, 1, 0, 1), (-1, 1, 0, 1)], F32))})
+
+    light, camera = (1.2, 2.4, 1.6), (0.0, 1.6, 3.2)
+    proj = mat_perspective(0.1, 10.0, width / height, math.radians(50.0))
+    view = mat_look_at(camera, (0, 0.2, 0))
+    pv = (proj.astype(np.float64) @ view.astype(np.float64)).astype(F32)
+    lproj = mat_perspective(0.1, 10.0, 1.0, math.radians(60.0))
+    lview = mat_look_at(light, (0, 0, 0))
+    lpv = (lproj.astype(np.float64) @ lview.astype(np.float64)).astype(F32)
+    lpvb = (BIAS.astype(np.float64) @ lpv.astype(np.float64)).astype(F32)
+    ldir = np.array(light, dtype=np.float64)
+    ldir = ldir / np.linalg.norm(ldir)   # points from the scene to the light, like L in the fragment functor
+
+    objects = []   # (vao, model, rot, programme, colour or None, casts_shadow)
+    desk = sc.add_vao(_std_slots(box_mesh(4.0, 0.1, 3.0)))
+    objects.append((desk, mat_translation(0, -0.05, 0), mat_identity(), p_tex, None, True))
+    for i in range(clutter):
+        w, h, d = rng.uniform(0.1, 0.45, size=3)
+        vao = sc.add_vao(_std_slots(box_mesh(w, h, d)))
+        ang = rng.uniform(0, 2 * math.pi)
+        rot = mat_rotation((0, 1, 0), ang)
+        x, z = rng.uniform(-1.6, 1.6), rng.uniform(-1.1, 1.1)
+        model = (mat_translation(x, h / 2, z).astype(np.float64) @ rot.astype(np.float64)).astype(F32)
+        if i % 2:
+            objects.append((vao, model, rot, p_col, tuple(rng.uniform(0.2, 0.95, size=3)), True))
+        else:
+            objects.append((vao, model, rot, p_tex, None, True))
+    ball = sc.add_vao(_std_slots(sphere_mesh(12, 24, 0.3)))
+    objects.append((ball, mat_translation(-0.4, 0.3, 0.5), mat_identity(), p_col, (0.9, 0.3, 0.2), True))
+    marker = sc.add_vao(_std_slots(box_mesh(0.08, 0.08, 0.08)))
+    objects.append((marker, mat_translation(*light), mat_identity(), p_unlit, (1.0, 1.0, 0.8), False))
+
+    def place(model, rot, pvm_base):
+        sc.cmd("uniform", 0, colmajor(model))
+        sc.cmd("uniform", 1, colmajor(rot))
+        sc.cmd("uniform", 5, colmajor((pvm_base.astype(np.float64) @ model.astype(np.float64)).astype(F32)))
+
+    sc.cmd("clearColour", 0xFF000000)
+    # ---- shadow map
+    sc.cmd("uniform", 2, colmajor(lview)); sc.cmd("uniform", 3, colmajor(lproj)); sc.cmd("uniform", 4, colmajor(lpv))
+    sc.cmd("depth", shadow_tex)
+    sc.cmd("clearDepth", 1.0)
+    sc.cmd("viewport", shadow, shadow)
+    sc.cmd("use", p_shadow)
+    for (vao, model, rot, _prog, _col, casts) in objects:
+        if casts:
+            place(model, rot, lpv)
+            sc.cmd("draw", vao)
+    # ---- the scene
+    sc.cmd("uniform", 2, colmajor(view)); sc.cmd("uniform", 3, colmajor(proj)); sc.cmd("uniform", 4, colmajor(pv))
+    sc.cmd("uniform", 6, colmajor(lpvb))
+    sc.cmd("uniform", 20, vec4(*light)); sc.cmd("uniform", 21, vec4(*ldir)); sc.cmd("uniform", 22, vec4(*camera))
+    sc.cmd("tex_uniform", 23, shadow_tex)
+    sc.cmd("depth", -1)
+    sc.cmd("clearDepth", 1.0)
+    sc.cmd("viewport", width, height)
+    if skybox:
+        sc.cmd("uniform", 1, colmajor(view))     # DEF04 reads the view matrix from slot 1 (skybox.cpp:17-21)
+        sc.cmd("tex_uniform", 2, sky)
+        sc.cmd("disable", K.BEHAVIOR_UPDATE_DEPTH | K.BEHAVIOR_TEST_DEPTH)
+        sc.cmd("use", p_sky); sc.cmd("draw", quad, True)
+        sc.cmd("enable", K.BEHAVIOR_UPDATE_DEPTH | K.BEHAVIOR_TEST_DEPTH)
+        sc.cmd("uniform", 2, colmajor(view))     # slot 2 is the view matrix again for the demo-2 functors' callers
+    sc.cmd("uniform", 30, vec4(0.15, 0.15, 0.15, 0)); sc.cmd("uniform", 32, vec4(1.0, 1.0, 1.0, 0)); sc.cmd("uniform", 33, np.array([30.0], F32))
+    sc.cmd("tex_uniform", 40, wood)
+    ntri = 0
+    for (vao, model, rot, prog, col, _casts) in objects:
+        place(model, rot, pv)
+        if col is not None:
+            sc.cmd("uniform", 31, vec4(col[2], col[1], col[0], 0))   # BGR order, the functors output b,g,r from [0],[1],[2]
+        sc.cmd("use", prog)
+        sc.cmd("draw", vao)
+        ntri += sc.vaos[vao][0][1].shape[0] // 3
+    sc.meta["triangles"] = 2 * ntri + 2
     return sc

@@ -14,4 +14,7 @@ SMALL = {
     "c2_heightfield_small": lambda: scenes.scene_heightfield(480, 270, grid=40, layers=2, tex_size=256),
     "c2_heightfield_tiny_tris": lambda: scenes.scene_heightfield(256, 144, grid=96, layers=3, tex_size=128),
     "c4_blend_overdraw": lambda: scenes.scene_blend_overdraw(480, 270, randoms=200),
+    # the reference's two demos as headless scenes: shadow pass + projective shadow lookup + cube skybox + blending + discard
+    "demo1_planets": lambda: scenes.scene_planets(400, 250, shadow=240, stacks=12, slices=24, tex_size=128),
+    "c3_demo2_desk": lambda: scenes.scene_desk(384, 240, shadow=256, clutter=10, tex_size=128),
 }
