@@ -65,7 +65,7 @@ struct SurvivorStream
 	float* inv;           // 1 / correctionFactor2 at the pixel (interp.cpp:85)
 	uint32_t* misc;       // x | y << 13 | edge code << 26 (two 3-bit ordered vertex pairs)
 	uint32_t* count;      // records appended so far
-	uint32_t* winner;     // vpW x vpH: index of the LAST record of each pixel (only that one's colour lands)
+	uint32_t* winner;     // vpW x vpH: 1 + index of the LAST record of each pixel (only that one's colour lands); 0 = none
 	uint32_t capacity;
 };
 

@@ -1127,21 +1127,26 @@ PS_D uint32_t edgeCode3(int v0, int v1) { return (uint32_t)(v0 * 2 + (v1 > v0 ? 
 PS_D void edgeDecode3(uint32_t c, int& v0, int& v1) { v0 = (int)(c >> 1); const int t = (int)(c & 1); v1 = t + (t >= v0 ? 1 : 0); }
 
 #define PS_RQCAP 64   // raster kernel's staging queue: < 32 left by a flush + at most 32 pushed by one pixel batch
+#define PS_HIZ_MARGIN 0.00002f   // slack of the conservative span reject (chain estimate + approximate reciprocal err << this)
 
 struct RasterSmem
 {
 	float depth[PS_TILE * PS_TILE];
 	uint32_t lastIdx[PS_TILE * PS_TILE];   // stream index of the last survivor of each pixel
+	float segMax[32];                      // upper bound of the depth of every 8-pixel row segment (index = row * 2 + segment)
 	TriHeader hdr[32];                     // the chunk's triangles, submission order
 	uint32_t triId[32];
 	uint32_t spanBase[33];
 	int triRow0[32];
-	// spans of the current pass (slot = lane of phase A2; slot order = submission order on every row)
+	// spans that reach this tile, waiting for their set-up (ring of 64; order = submission order on every row)
+	uint32_t lInfo[64];                    // chunk lane of the triangle | row << 5 | RowSpan::edges << 9
+	int lLeft[64], lRight[64];
+	// slots of the current pass: the non-empty spans, compacted, in list order
 	float rCf2[32], rCf2Step[32], rZ[32], rZStep[32];
 	int rLeft[32], rRight[32];
 	uint32_t rMisc[32];                    // xs | row << 4 | edge code << 8 (xs, row tile-relative)
 	uint32_t rTri[32];
-	uint32_t pixBase[33];                  // exclusive scan of span lengths inside the tile
+	uint32_t pixBase[32];                  // first pixel index of each slot in the pass
 	// staging queue of survivors
 	uint32_t qTri[PS_RQCAP];
 	int qLeft[PS_RQCAP], qRight[PS_RQCAP];
@@ -1155,22 +1160,200 @@ PS_D void flushSurvivors(const SurvivorStream& Q, RasterSmem& S, int lane, uint3
 	uint32_t base = 0;
 	if(0 == lane) base = atomicAdd(Q.count, n);
 	base = __shfl_sync(PS_FULL, base, 0);
-	const bool act = (uint32_t)lane < n;
-	uint32_t pix = 0x1000u + lane;
-	if(act)
+	if((uint32_t)lane < n)
 	{
 		const uint32_t i = base + lane;
 		const uint32_t m = S.qMisc[lane];
-		pix = m & 0xff;
 		if(i < Q.capacity)
 		{
 			Q.tri[i] = S.qTri[lane]; Q.left[i] = S.qLeft[lane]; Q.right[i] = S.qRight[lane]; Q.inv[i] = S.qInv[lane];
 			Q.misc[i] = (uint32_t)(tx0 + (int)(m & 15)) | ((uint32_t)(ty0 + (int)((m >> 4) & 15)) << 13) | ((m >> 8) << 26);
 		}
+		// queue order = submission order inside a pixel and bases grow with time: the latest record has the highest index
+		atomicMax(&S.lastIdx[m & 0xff], i + 1);
 	}
-	const uint32_t peers = __match_any_sync(PS_FULL, pix);
-	if(act && 0 == (peers >> lane >> 1)) S.lastIdx[pix] = base + lane;   // the highest lane of a pixel = the latest in submission order
 	__syncwarp();
+}
+
+struct RasterCtx
+{
+	int lane, tx0, ty0, tileX1, depthLimitX, vpW;
+	bool testDepth, updateDepth;
+	uint32_t ltMask;
+	// warp-uniform running state
+	uint32_t qCount;
+	unsigned survived;
+	// per lane
+	unsigned tested;
+	bool depthWrote;
+};
+
+// One pass over n <= 32 waiting spans (ring positions head .. head + n - 1):
+//   Y  lane = span: the depth half of interpolateStartAndStep (interp.cpp:26-80), chains advanced to the tile's edge,
+//      then a conservative whole-span depth reject against the segment bounds
+//   B  lane = pixel of a surviving span, dense: interpolateNextStep (interp.cpp:82-92) + the depth rule (fragthrd.cpp:217-237)
+PS_D void rasterPass(const DrawParams& P, const SurvivorStream& Q, RasterSmem& S, RasterCtx& C, uint32_t head, uint32_t n)
+{
+	const int lane = C.lane;
+	int len = 0;
+	float cf2 = 0, cf2Step = 0, z0 = 0, zStep = 0;
+	int left = 0, right = 0;
+	uint32_t misc = 0, triId = 0;
+	if((uint32_t)lane < n)
+	{
+		const uint32_t pos = (head + lane) & 63;
+		const uint32_t info = S.lInfo[pos];
+		left = S.lLeft[pos]; right = S.lRight[pos];
+		const int t = (int)(info & 31), row = (int)((info >> 5) & 15), e = (int)(info >> 9);
+		const int iy = C.ty0 + row;
+		const TriHeader& h = S.hdr[t];
+		const float* xy = &h.vx0;
+		const int x1 = left < 0 ? 0 : left;                           // RESULT_ROW::leftClamped
+		const int x2 = right >= C.vpW ? C.vpW - 1 : right;            // RESULT_ROW::rightClamped
+		const int xsA = max(x1, C.tx0), xeA = min(min(x2, C.tileX1), C.depthLimitX);
+		// interpolateStartAndStep, interp.cpp:26-80
+		float cl[3], cr[3];
+		edgeContribXY(xy, e & 3, (e >> 2) & 3, (float)left, (float)iy, cl);
+		edgeContribXY(xy, (e >> 4) & 3, (e >> 6) & 3, (float)right, (float)iy, cr);
+		cl[0] = fmul(cl[0], h.rw0); cl[1] = fmul(cl[1], h.rw1); cl[2] = fmul(cl[2], h.rw2); // mulvec_3_4 (:40-41); lane 3 is 0*0
+		cr[0] = fmul(cr[0], h.rw0); cr[1] = fmul(cr[1], h.rw1); cr[2] = fmul(cr[2], h.rw2);
+		const float rcpLen = fdiv(1.0f, (float)(right - left));                               // :47
+		z0 = hsum4(fmul(cl[0], h.z0), fmul(cl[1], h.z1), fmul(cl[2], h.z2), 0.0f);            // :49 dot_3_4
+		zStep = hsum4(fmul(cr[0], h.z0), fmul(cr[1], h.z1), fmul(cr[2], h.z2), 0.0f);         // :50
+		zStep = fmul(fsub(zStep, z0), rcpLen);                                                // :51
+		cf2 = hsum4(cl[0], cl[1], cl[2], 0.0f);                                               // :55-68
+		cf2Step = hsum4(cr[0], cr[1], cr[2], 0.0f);
+		cf2Step = fmul(fsub(cf2Step, cf2), rcpLen);                                           // :72
+		const int skip = x1 - left;                                                           // drawvao.cpp:90
+		if(skip > 0)                                                                          // interp.cpp:74-79
+		{
+			cf2 = fadd(cf2, fmul(cf2Step, (float)skip));
+			z0 = fadd(z0, fmul(zStep, (float)skip));
+		}
+		// the k-th pixel's value is k rounded additions from the span start (§9.6): replay them up to the tile
+#pragma unroll 1
+		for(int x = x1; x < xsA; x++)
+		{
+			cf2 = fadd(cf2, cf2Step);
+			z0 = fadd(z0, zStep);
+		}
+		len = xeA - xsA + 1;
+		misc = (uint32_t)(xsA - C.tx0) | ((uint32_t)row << 4)
+		     | ((edgeCode3(e & 3, (e >> 2) & 3) | (edgeCode3((e >> 4) & 3, (e >> 6) & 3) << 3)) << 8);
+		triId = S.triId[t];
+		if(C.testDepth)
+		{
+			// Conservative whole-span reject. A fragment fails when z - cur >= -0.0001 (fragthrd.cpp:227), certainly when
+			// z >= cur. Along the span z = z0_k / cf2_k is a ratio of two linear functions of k, monotone while cf2 keeps its
+			// sign, so its minimum over the tile's pixels is at one of the two ends; both ends are ESTIMATED here (approximate
+			// reciprocal, end of the chain in closed form; error ~1e-6) and compared with a margin against an upper bound of
+			// the depths the span could meet. Rejected spans still count as tested; everything else takes the exact path.
+			const float nf = (float)(len - 1);
+			const float cf2e = cf2 + nf * cf2Step, z0e = z0 + nf * zStep;
+			const float zs = __fdividef(z0, cf2), ze = __fdividef(z0e, cf2e);
+			const int sA = (xsA - C.tx0) >> 3, sB = (xeA - C.tx0) >> 3;
+			const float bound = fmaxf(S.segMax[row * 2 + sA], S.segMax[row * 2 + sB]);
+			if(cf2 > 0.0f && cf2e > 0.0f && zs - PS_HIZ_MARGIN >= bound && ze - PS_HIZ_MARGIN >= bound)
+			{
+				C.tested += (unsigned)len;
+				len = 0;
+			}
+		}
+	}
+	// compact the non-empty spans into slots; pixel index space of the pass
+	const uint32_t nz = __ballot_sync(PS_FULL, len > 0);
+	uint32_t pincl = (uint32_t)len;
+#pragma unroll
+	for(int d = 1; d < 32; d <<= 1)
+	{
+		const uint32_t t = __shfl_up_sync(PS_FULL, pincl, d);
+		if(lane >= d) pincl += t;
+	}
+	const int myBase = (int)(pincl - (uint32_t)len);
+	const uint32_t totalPix = __shfl_sync(PS_FULL, pincl, 31);
+	if(0 == totalPix) return;
+	if(len > 0)
+	{
+		const int slot = __popc(nz & C.ltMask);
+		S.rCf2[slot] = cf2; S.rCf2Step[slot] = cf2Step; S.rZ[slot] = z0; S.rZStep[slot] = zStep;
+		S.rLeft[slot] = left; S.rRight[slot] = right; S.rTri[slot] = triId; S.rMisc[slot] = misc;
+		S.pixBase[slot] = (uint32_t)myBase;
+	}
+	__syncwarp();
+
+	// ---- B: lane = pixel of a span, dense; spans in slot order, pixels left to right. ----
+	int startedBefore = 0;                             // slots whose first pixel lies before this batch (warp-uniform)
+	for(uint32_t p0 = 0; p0 < totalPix; p0 += 32)
+	{
+		// slot of pixel p = (number of slots starting at or before p) - 1 : one bit per slot start inside the batch
+		const int dStart = myBase - (int)p0;
+		const uint32_t starts = __reduce_or_sync(PS_FULL, (len > 0 && dStart >= 0 && dStart < 32) ? 1u << dStart : 0u);
+		const uint32_t p = p0 + lane;
+		const bool act = p < totalPix;
+		const int slot = startedBefore + __popc(starts & (C.ltMask | (1u << lane))) - 1;
+		startedBefore += __popc(starts);
+		uint32_t pix = 0x1000u + lane, smisc = 0;
+		float z = 0, inv = 0;
+		if(act)
+		{
+			const int k = (int)(p - S.pixBase[slot]);
+			smisc = S.rMisc[slot];
+			float c2 = S.rCf2[slot], zz = S.rZ[slot];
+			const float c2Step = S.rCf2Step[slot], zzStep = S.rZStep[slot];
+#pragma unroll 1
+			for(int j = 0; j < k; j++)
+			{
+				c2 = fadd(c2, c2Step);
+				zz = fadd(zz, zzStep);
+			}
+			// interpolateNextStep, interp.cpp:82-92
+			inv = fdiv(1.0f, c2);
+			z = fmul(zz, inv);
+			pix = (((smisc >> 4) & 15) << 4) | ((smisc & 15) + (uint32_t)k);
+			C.tested++;
+		}
+		// fragments of one pixel are tested in lane order = submission order (§9.7)
+		const uint32_t peers = __match_any_sync(PS_FULL, pix);
+		const int rank = __popc(peers & C.ltMask);
+		const int maxRank = __reduce_max_sync(PS_FULL, act ? rank : 0);
+		bool pass = false;
+#pragma unroll 1
+		for(int r = 0; r <= maxRank; r++)
+		{
+			if(act && rank == r)
+			{
+				const float cur = C.testDepth ? S.depth[pix] : 1.0f;             // fragthrd.cpp:217-225
+				if(-1.0f < z && fsub(z, cur) < -0.0001f)                         // fragthrd.cpp:227
+				{
+					pass = true;
+					// no functor on this path discards, so the depth write does not wait for the shading (fragthrd.cpp:234-237)
+					if(C.updateDepth) { S.depth[pix] = z; C.depthWrote = true; }
+				}
+			}
+			__syncwarp();
+		}
+		const uint32_t b = __ballot_sync(PS_FULL, pass);
+		if(pass)
+		{
+			const uint32_t q = C.qCount + __popc(b & C.ltMask);
+			S.qTri[q] = S.rTri[slot]; S.qLeft[q] = S.rLeft[slot]; S.qRight[q] = S.rRight[slot]; S.qInv[q] = inv;
+			S.qMisc[q] = pix | ((smisc >> 8) << 8);
+		}
+		C.qCount += __popc(b);
+		__syncwarp();
+		if(C.qCount >= 32)
+		{
+			flushSurvivors(Q, S, lane, 32, C.tx0, C.ty0);
+			C.survived += 32;
+			const uint32_t rem = C.qCount - 32;
+			uint32_t a = 0, d = 0; int bb = 0, c = 0; float f = 0;
+			if((uint32_t)lane < rem) { a = S.qTri[32 + lane]; bb = S.qLeft[32 + lane]; c = S.qRight[32 + lane]; f = S.qInv[32 + lane]; d = S.qMisc[32 + lane]; }
+			__syncwarp();
+			if((uint32_t)lane < rem) { S.qTri[lane] = a; S.qLeft[lane] = bb; S.qRight[lane] = c; S.qInv[lane] = f; S.qMisc[lane] = d; }
+			C.qCount = rem;
+			__syncwarp();
+		}
+	}
 }
 
 __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_depth_kernel(const __grid_constant__ DrawParams P, const SurvivorStream Q,
@@ -1201,19 +1384,20 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_depth_ker
 		float d = 1.0f;
 		if(useDepth && depthRowOk && x < P.depth.width) d = *(const float*)(depthRow + (size_t)x * 4);
 		S.depth[rr * PS_TILE + seg * PS_SEG + i] = d;
-		S.lastIdx[rr * PS_TILE + seg * PS_SEG + i] = 0xffffffffu;
+		S.lastIdx[rr * PS_TILE + seg * PS_SEG + i] = 0;
 	}
 	__syncwarp();
 
-	unsigned tested = 0, survived = 0;
-	bool depthWrote = false;
-	uint32_t qCount = 0;                               // warp-uniform
+	RasterCtx C;
+	C.lane = lane; C.tx0 = tx0; C.ty0 = ty0; C.tileX1 = tx0 + PS_TILE - 1; C.vpW = P.vpW;
 	// the reference reads a clamped column/row when the viewport exceeds the depth target (fbo.cpp:101,150); that
 	// behaviour is not reproducible tile-locally, such fragments are dropped (DESIGN.md "divergences")
-	const int depthLimitX = useDepth ? P.depth.width - 1 : 0x7fffffff;
+	C.depthLimitX = useDepth ? P.depth.width - 1 : 0x7fffffff;
 	const int depthLimitY = useDepth ? P.depth.height - 1 : 0x7fffffff;
-	const int tileX1 = tx0 + PS_TILE - 1;
-	const uint32_t ltMask = (1u << lane) - 1;
+	C.testDepth = testDepth; C.updateDepth = updateDepth;
+	C.ltMask = (1u << lane) - 1;
+	C.qCount = 0; C.survived = 0; C.tested = 0; C.depthWrote = false;
+	uint32_t lHead = 0, lCount = 0;                    // ring of waiting spans (warp-uniform)
 
 	for(uint32_t chunk = listBegin; chunk < listEnd; chunk += 32)
 	{
@@ -1242,171 +1426,86 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_depth_ker
 		S.spanBase[lane] = incl - (uint32_t)nrows;
 		S.triRow0[lane] = r0;
 		const uint32_t total = __shfl_sync(PS_FULL, incl, 31);
+		// depths only decrease while a draw runs, so a bound refreshed once per chunk stays an upper bound
+		if(testDepth)
+		{
+			float m = S.depth[lane * PS_SEG];
+#pragma unroll
+			for(int i = 1; i < PS_SEG; i++) m = fmaxf(m, S.depth[lane * PS_SEG + i]);
+			S.segMax[lane] = m;
+		}
 		__syncwarp();
 
 		for(uint32_t s0 = 0; s0 < total; s0 += 32)
 		{
-			// ---- A2: lane = span (triangle, row), dense. RESULT_ROW + interpolateStartAndStep's depth half. ----
+			// ---- X: lane = candidate (triangle, row), dense. RESULT_ROW; only the spans that reach the tile go on. ----
 			const uint32_t s = s0 + lane;
-			int len = 0;
+			bool ok = false;
+			uint32_t info = 0;
+			RowSpan r;
+			r.left = r.right = r.edges = 0;
 			if(s < total)
 			{
 				int t = 0; // the last triangle whose base <= s
 #pragma unroll
 				for(int b = 16; b > 0; b >>= 1)
-					if(t + b < 32 && S.spanBase[t + b] <= s) t += b;
+					if(S.spanBase[t + b] <= s) t += b;
 				const int iy = S.triRow0[t] + (int)(s - S.spanBase[t]);
-				const TriHeader& h = S.hdr[t];
-				const float* xy = &h.vx0;
-				RowSpan r;
-				if(rowOfXY(h, iy, r) && r.left != r.right)                        // drawvao.cpp:72
+				if(rowOfXY(S.hdr[t], iy, r) && r.left != r.right)                 // drawvao.cpp:72
 				{
-					const int x1 = r.left < 0 ? 0 : r.left;                       // RESULT_ROW::leftClamped
-					const int x2 = r.right >= P.vpW ? P.vpW - 1 : r.right;        // RESULT_ROW::rightClamped
-					const int xsA = max(x1, tx0), xeA = min(min(x2, tileX1), depthLimitX);
-					if(x1 <= x2 && xsA <= xeA)
-					{
-						const int e = r.edges;
-						// interpolateStartAndStep, interp.cpp:26-80
-						float cl[3], cr[3];
-						edgeContribXY(xy, e & 3, (e >> 2) & 3, (float)r.left, (float)iy, cl);
-						edgeContribXY(xy, (e >> 4) & 3, (e >> 6) & 3, (float)r.right, (float)iy, cr);
-						cl[0] = fmul(cl[0], h.rw0); cl[1] = fmul(cl[1], h.rw1); cl[2] = fmul(cl[2], h.rw2); // mulvec_3_4 (:40-41); lane 3 is 0*0
-						cr[0] = fmul(cr[0], h.rw0); cr[1] = fmul(cr[1], h.rw1); cr[2] = fmul(cr[2], h.rw2);
-						const float rcpLen = fdiv(1.0f, (float)(r.right - r.left));                          // :47
-						float z0 = hsum4(fmul(cl[0], h.z0), fmul(cl[1], h.z1), fmul(cl[2], h.z2), 0.0f);      // :49 dot_3_4
-						float zStep = hsum4(fmul(cr[0], h.z0), fmul(cr[1], h.z1), fmul(cr[2], h.z2), 0.0f);   // :50
-						zStep = fmul(fsub(zStep, z0), rcpLen);                                               // :51
-						float cf2 = hsum4(cl[0], cl[1], cl[2], 0.0f);                                        // :55-68
-						float cf2Step = hsum4(cr[0], cr[1], cr[2], 0.0f);
-						cf2Step = fmul(fsub(cf2Step, cf2), rcpLen);                                          // :72
-						const int skip = x1 - r.left;                                                        // drawvao.cpp:90
-						if(skip > 0)                                                                         // interp.cpp:74-79
-						{
-							cf2 = fadd(cf2, fmul(cf2Step, (float)skip));
-							z0 = fadd(z0, fmul(zStep, (float)skip));
-						}
-						// the k-th pixel's value is k rounded additions from the span start (§9.6): replay them up to the tile
-#pragma unroll 1
-						for(int x = x1; x < xsA; x++)
-						{
-							cf2 = fadd(cf2, cf2Step);
-							z0 = fadd(z0, zStep);
-						}
-						len = xeA - xsA + 1;
-						S.rCf2[lane] = cf2; S.rCf2Step[lane] = cf2Step; S.rZ[lane] = z0; S.rZStep[lane] = zStep;
-						S.rLeft[lane] = r.left; S.rRight[lane] = r.right; S.rTri[lane] = S.triId[t];
-						S.rMisc[lane] = (uint32_t)(xsA - tx0) | ((uint32_t)(iy - ty0) << 4)
-						              | ((edgeCode3(e & 3, (e >> 2) & 3) | (edgeCode3((e >> 4) & 3, (e >> 6) & 3) << 3)) << 8);
-					}
+					const int x1 = r.left < 0 ? 0 : r.left;
+					const int x2 = r.right >= P.vpW ? P.vpW - 1 : r.right;
+					const int xsA = max(x1, tx0), xeA = min(min(x2, C.tileX1), C.depthLimitX);
+					ok = x1 <= x2 && xsA <= xeA;
+					info = (uint32_t)t | ((uint32_t)(iy - ty0) << 5) | ((uint32_t)r.edges << 9);
 				}
 			}
-			uint32_t pincl = (uint32_t)len;
-#pragma unroll
-			for(int d = 1; d < 32; d <<= 1)
+			const uint32_t okb = __ballot_sync(PS_FULL, ok);
+			if(ok)
 			{
-				const uint32_t t = __shfl_up_sync(PS_FULL, pincl, d);
-				if(lane >= d) pincl += t;
+				const uint32_t pos = (lHead + lCount + __popc(okb & C.ltMask)) & 63;
+				S.lInfo[pos] = info; S.lLeft[pos] = r.left; S.lRight[pos] = r.right;
 			}
-			S.pixBase[lane] = pincl - (uint32_t)len;
-			const uint32_t totalPix = __shfl_sync(PS_FULL, pincl, 31);
+			lCount += __popc(okb);
 			__syncwarp();
-
-			// ---- B: lane = pixel of a span, dense; spans in slot order, pixels left to right. ----
-			for(uint32_t p0 = 0; p0 < totalPix; p0 += 32)
+			if(lCount >= 32)
 			{
-				const uint32_t p = p0 + lane;
-				const bool act = p < totalPix;
-				uint32_t pix = 0x1000u + lane, misc = 0;
-				int slot = 0;
-				float z = 0, inv = 0;
-				if(act)
-				{
-#pragma unroll
-					for(int b = 16; b > 0; b >>= 1)
-						if(slot + b < 32 && S.pixBase[slot + b] <= p) slot += b;
-					const int k = (int)(p - S.pixBase[slot]);
-					misc = S.rMisc[slot];
-					float cf2 = S.rCf2[slot], z0 = S.rZ[slot];
-					const float cf2Step = S.rCf2Step[slot], zStep = S.rZStep[slot];
-#pragma unroll 1
-					for(int j = 0; j < k; j++)
-					{
-						cf2 = fadd(cf2, cf2Step);
-						z0 = fadd(z0, zStep);
-					}
-					// interpolateNextStep, interp.cpp:82-92
-					inv = fdiv(1.0f, cf2);
-					z = fmul(z0, inv);
-					pix = (((misc >> 4) & 15) << 4) | ((misc & 15) + (uint32_t)k);
-					tested++;
-				}
-				// fragments of one pixel are tested in lane order = submission order (§9.7)
-				const uint32_t peers = __match_any_sync(PS_FULL, pix);
-				const int rank = __popc(peers & ltMask);
-				const int maxRank = __reduce_max_sync(PS_FULL, act ? rank : 0);
-				bool pass = false;
-#pragma unroll 1
-				for(int r = 0; r <= maxRank; r++)
-				{
-					if(act && rank == r)
-					{
-						const float cur = testDepth ? S.depth[pix] : 1.0f;               // fragthrd.cpp:217-225
-						if(-1.0f < z && fsub(z, cur) < -0.0001f)                         // fragthrd.cpp:227
-						{
-							pass = true;
-							// no functor on this path discards, so the depth write does not wait for the shading (fragthrd.cpp:234-237)
-							if(updateDepth) { S.depth[pix] = z; depthWrote = true; }
-						}
-					}
-					__syncwarp();
-				}
-				const uint32_t b = __ballot_sync(PS_FULL, pass);
-				if(pass)
-				{
-					const uint32_t q = qCount + __popc(b & ltMask);
-					S.qTri[q] = S.rTri[slot]; S.qLeft[q] = S.rLeft[slot]; S.qRight[q] = S.rRight[slot]; S.qInv[q] = inv;
-					S.qMisc[q] = pix | ((misc >> 8) << 8);
-				}
-				qCount += __popc(b);
-				__syncwarp();
-				if(qCount >= 32)
-				{
-					flushSurvivors(Q, S, lane, 32, tx0, ty0);
-					survived += 32;
-					const uint32_t rem = qCount - 32;
-					uint32_t a = 0, d = 0; int bb = 0, c = 0; float f = 0;
-					if((uint32_t)lane < rem) { a = S.qTri[32 + lane]; bb = S.qLeft[32 + lane]; c = S.qRight[32 + lane]; f = S.qInv[32 + lane]; d = S.qMisc[32 + lane]; }
-					__syncwarp();
-					if((uint32_t)lane < rem) { S.qTri[lane] = a; S.qLeft[lane] = bb; S.qRight[lane] = c; S.qInv[lane] = f; S.qMisc[lane] = d; }
-					qCount = rem;
-					__syncwarp();
-				}
+				rasterPass(P, Q, S, C, lHead, 32);
+				lHead = (lHead + 32) & 63;
+				lCount -= 32;
 			}
 		}
+		// the waiting spans refer to this chunk's headers: drain before the next chunk overwrites them
+		if(lCount)
+		{
+			rasterPass(P, Q, S, C, lHead, lCount);
+			lHead = 0; lCount = 0;
+		}
+		__syncwarp();
 	}
-	if(qCount) { flushSurvivors(Q, S, lane, qCount, tx0, ty0); survived += qCount; }
+	if(C.qCount) { flushSurvivors(Q, S, lane, C.qCount, tx0, ty0); C.survived += C.qCount; }
 
 	// ---- write back: depth tile, and which record won each pixel
-	if(__any_sync(PS_FULL, depthWrote) && depthRowOk)
+	if(__any_sync(PS_FULL, C.depthWrote) && depthRowOk)
 	{
 #pragma unroll
 		for(int i = 0; i < PS_SEG; i++)
 			if(sx0 + i < P.depth.width) *(float*)(depthRow + (size_t)(sx0 + i) * 4) = S.depth[rr * PS_TILE + seg * PS_SEG + i];
 	}
-	if(survived && y < P.vpH)
+	if(C.survived && y < P.vpH)
 	{
 #pragma unroll
 		for(int i = 0; i < PS_SEG; i++)
 			if(sx0 + i < P.vpW) Q.winner[(size_t)y * P.vpW + sx0 + i] = S.lastIdx[rr * PS_TILE + seg * PS_SEG + i];
 	}
-	const unsigned long long t = warpSumU64(tested);
+	const unsigned long long t = warpSumU64(C.tested);
 	if(0 == lane)
 	{
 		if(t) atomicAdd(&P.stats->fragments_tested, t);
-		if(survived) atomicAdd(&P.stats->fragments_shaded, (unsigned long long)survived);   // every survivor is shaded exactly once by shade_kernel
+		if(C.survived) atomicAdd(&P.stats->fragments_shaded, (unsigned long long)C.survived);   // every survivor is shaded exactly once by shade_kernel
 	}
 }
+
 
 // lane = survivor record, any order: varyings (interp.cpp:26-92), fragment functor (fragthrd.cpp:231), winner stores its colour
 template<class PROG>
@@ -1466,7 +1565,7 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Draw
 		out.discarded = false; out.wrote = false; out.blendable = false; out.bgra = 0;
 		PROG::F::process(frag, out, P);                                      // fragthrd.cpp:231
 		if(P.cap && x < P.capW && y < P.capH) atomicAdd(&P.cap[(size_t)y * P.capW + x], 1u);
-		if(out.wrote && y < P.colour.height && x < P.colour.width && Q.winner[(size_t)y * P.vpW + x] == i)
+		if(out.wrote && y < P.colour.height && x < P.colour.width && Q.winner[(size_t)y * P.vpW + x] == i + 1)
 		{
 			// FBOBridge::write / write4 without ALPHABLEND: a plain store (fragthrd.cpp:54-82); later survivors of the pixel overwrite
 			uint8_t* row = P.colour.ptr + (size_t)(P.colour.topDown ? P.colour.height - 1 - y : y) * P.colour.scanline;
