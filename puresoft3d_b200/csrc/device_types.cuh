@@ -43,16 +43,29 @@ struct alignas(16) TriHeader
 	uint32_t plan;              // 2-bit vertex ids: eL0.i0,eL0.i1,eR0.i0,eR0.i1,eL1.i0,eL1.i1,eR1.i0,eR1.i1 ; bit 16: two halves
 };
 
-struct DeviceStats
+// Counters live in PS_STATS_COPIES replicas, one 128-byte line each: a block adds to replica (blockIdx.x mod copies), so
+// no single address takes the whole grid's atomics (one shared line cost geom_setup 34 us of 170 on C2). The host sums
+// the replicas; tile_scan_kernel folds and resets the per-draw part.
+#define PS_STATS_COPIES 32
+struct alignas(128) DeviceStats
 {
 	unsigned long long triangles_rasterised;
 	unsigned long long spans;
 	unsigned long long fragments_tested;
 	unsigned long long fragments_shaded;
-	// reset at the start of every draw:
+	// per draw (reset by tile_scan_kernel):
 	unsigned long long fragBound;   // sum of clamped span lengths = upper bound of the draw's depth-test survivors
+};
+
+// What the host learns about a draw after its geometry + tile scan, written by tile_scan_kernel into mapped pinned host
+// memory (read after the event recorded behind that kernel; no copy is enqueued).
+struct DrawReport
+{
+	unsigned int bad;               // a speculated capacity was too small (or a list too long): the guarded tail did nothing
 	unsigned int pairs;             // (tile, triangle) pairs = sum of the per-tile counts
-	unsigned int maxTileCount;      // longest tile list
+	unsigned int longest;           // longest tile list
+	unsigned int pad;
+	unsigned long long fragBound;
 };
 
 // Survivors of the depth test, one record per FragmentProcessor::process call still to make (split path): structure of
@@ -88,7 +101,8 @@ struct DrawParams
 	uint32_t* triRect;          // per triangle 3 words: tx0 | tx1 << 16, ty0 | ty1 << 16, mask of touched tiles (bit = (ty-ty0)*8 + tx-tx0;
 	                            // ~0 when the rectangle exceeds 8 x 4 tiles and is used whole)
 	uint32_t* tileCount;        // per tile: triangles binned to it (atomics in geom_setup)
-	DeviceStats* stats;
+	DeviceStats* stats;         // PS_STATS_COPIES replicas
+	const uint32_t* poison;     // != 0: a speculated capacity of this draw was too small, every kernel behind the tile scan returns at once
 	uint32_t* cap;              // per-pixel FragmentProcessor::process counts (parity hook) or NULL
 	int capW, capH;
 };

@@ -58,11 +58,70 @@ PS_D bool isBackFace(F4 v0, F4 v1, F4 v2, const ApproxTables& ap)
 	return f4dot(f4(0, 0, 1.0f, 0), c) < 0;
 }
 
-template<class PROG>
-__global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__ DrawParams P)
+// ---- bulk asynchronous copy global -> shared (TMA, 1-D) completing on an mbarrier -----------------------------------
+PS_D uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+PS_D void mbarInit(uint64_t* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smemAddr(bar)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+PS_D void mbarExpectTx(uint64_t* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+PS_D void bulkCopyG2S(void* dstSmem, const void* srcGlobal, uint32_t bytes, uint64_t* bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(smemAddr(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+}
+PS_D void mbarWait(uint64_t* bar, uint32_t parity)
+{
+	uint32_t done = 0;
+	while(!done)
+		asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+		             : "=r"(done) : "r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+
+#define PS_GEOM_THREADS 128
+
+// STAGED: the block's vertex range of every slot the functor reads (PS_GEOM_THREADS x 3 consecutive elements, contiguous in
+// the un-indexed stream) is brought into shared memory by one bulk copy per slot; the functor then reads shared memory.
+// All of a block's HBM reads are in flight at once and no load latency is left on the arithmetic path.
+template<class PROG, bool STAGED>
+__global__ void __launch_bounds__(PS_GEOM_THREADS) geom_setup_kernel(const __grid_constant__ DrawParams P)
 {
 	constexpr int NV = PROG::NV;
 	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+	extern __shared__ __align__(128) uint8_t stage[];
+	__shared__ uint64_t stageBar;
+	uint32_t stageOff[16];
+	if(STAGED)
+	{
+		const uint32_t tri0 = blockIdx.x * PS_GEOM_THREADS;
+		const uint32_t nt = min((uint32_t)PS_GEOM_THREADS, P.ntris - tri0);
+		uint32_t off = 0;
+#pragma unroll
+		for(int s = 0; s < 16; s++)
+		{
+			stageOff[s] = off;
+			if((PROG::V::SLOTS >> s) & 1) off += (PS_GEOM_THREADS * 3 * P.stride[s] + 127u) & ~127u;
+		}
+		if(0 == threadIdx.x) mbarInit(&stageBar, 1);
+		__syncthreads();
+		if(0 == threadIdx.x)
+		{
+			uint32_t total = 0;
+#pragma unroll
+			for(int s = 0; s < 16; s++)
+				if((PROG::V::SLOTS >> s) & 1) total += (nt * 3 * P.stride[s] + 15u) & ~15u;
+			mbarExpectTx(&stageBar, total);
+#pragma unroll
+			for(int s = 0; s < 16; s++)
+				if((PROG::V::SLOTS >> s) & 1)
+					bulkCopyG2S(stage + stageOff[s], P.slot[s] + (size_t)tri0 * 3 * P.stride[s], (nt * 3 * P.stride[s] + 15u) & ~15u, &stageBar);
+		}
+		mbarWait(&stageBar, 0);
+	}
 	unsigned rasterised = 0, spans = 0, frags = 0, pairs = 0;
 	if(tri < P.ntris)
 	{
@@ -78,7 +137,8 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 			VertexProcessorInput in;
 #pragma unroll
 			for(int s = 0; s < 16; s++)
-				in.data[s] = (PROG::V::SLOTS >> s) & 1 ? P.slot[s] + (size_t)(tri * 3 + i) * P.stride[s] : nullptr;
+				in.data[s] = (PROG::V::SLOTS >> s) & 1 ? (STAGED ? stage + stageOff[s] + (size_t)(threadIdx.x * 3 + i) * P.stride[s]
+				                                                  : P.slot[s] + (size_t)(tri * 3 + i) * P.stride[s]) : nullptr;
 			VertexProcessorOutput<NV> vo;
 			PROG::V::process(in, vo, P);
 			const float reciprocalW = fdiv(1.0f, vo.position.w);          // vertthrd.cpp:37 (true divide)
@@ -97,7 +157,10 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 			float vx[3], vy[3];
 			const int code = setupTriangle(P.vpW, P.vpH, P.halfW, P.halfH, ndcX, ndcY, h, vx, vy);
 			rasterised = code != 0;
-			if(1 == code)
+			// sort-first: a triangle whose rows all lie outside this rank's band leaves nothing behind here (no header, no
+			// varyings, no row walk; its spans are counted by the rank that owns them)
+			if(1 == code && ((int)(h.rows >> 16) < P.band0 || (int)(h.rows & 0xffff) >= P.band1)) alive = false;
+			if(1 == code && alive)
 			{
 				// The records go out BEFORE the row walk: the 3 x NV varyings would otherwise stay live in registers across it
 				// and halve the occupancy. (A triangle that turns out to cover no pixel wrote its record for nothing.)
@@ -117,7 +180,8 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 							VertexProcessorInput in;
 #pragma unroll
 							for(int s = 0; s < 16; s++)
-								in.data[s] = (PROG::V::SLOTS >> s) & 1 ? P.slot[s] + (size_t)(tri * 3 + i) * P.stride[s] : nullptr;
+								in.data[s] = (PROG::V::SLOTS >> s) & 1 ? (STAGED ? stage + stageOff[s] + (size_t)(threadIdx.x * 3 + i) * P.stride[s]
+								                                                  : P.slot[s] + (size_t)(tri * 3 + i) * P.stride[s]) : nullptr;
 							VertexProcessorOutput<NV> vo;
 							PROG::V::process(in, vo, P);
 #pragma unroll
@@ -132,45 +196,45 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 				uint32_t tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0;
 				int tyFirst = -1, kCur = -1, curLo = 0, curHi = 0;
 				uint32_t trValid = 0;                                  // tile rows (relative to the first) that hold a span
-				// The rows of RESULT (drawvao.cpp:66-75), half by half so that the two edges are set up once per half instead of
-				// once per row: first the lower half (it owns the shared row, rasterizer.cpp:128-139), then what is left of the upper.
+				// The rows of RESULT (drawvao.cpp:66-75) in one flat loop (a lane's trip count is its row count, whichever half the
+				// rows belong to). The edges of both halves are set up once; the lower half owns the shared row
+				// (rasterizer.cpp:128-139), rows outside both halves were never written by the reference and are skipped.
 				const int l0 = (int)(h.half1 & 0xffff), l1 = (int)(h.half1 >> 16);
 				const int u0 = (int)(h.half0 & 0xffff), u1 = (int)(h.half0 >> 16);
+				const int selL = (int)((h.plan >> 8) & 0xff), selU = (int)(h.plan & 0xff);
+				const Edge LU = makeEdge(vx, vy, selU & 3, (selU >> 2) & 3), RU = makeEdge(vx, vy, (selU >> 4) & 3, (selU >> 6) & 3);
+				Edge LL = LU, RL = RU;
+				if(l0 <= l1) { LL = makeEdge(vx, vy, selL & 3, (selL >> 2) & 3); RL = makeEdge(vx, vy, (selL >> 4) & 3, (selL >> 6) & 3); }
 #pragma unroll 1
-				for(int half = 0; half < 2; half++)
+				for(int iy = firstRow; iy <= lastRow; iy++)
 				{
-					const int sel = half ? (int)(h.plan & 0xff) : (int)((h.plan >> 8) & 0xff);
-					int ya = max(firstRow, half ? u0 : l0), yb = min(lastRow, half ? u1 : l1);
-					if(half && l0 <= l1) ya = max(ya, l1 + 1);   // rows of the lower half are taken (halves are stacked: u0 >= l1)
-					if(ya > yb) continue;
-					const Edge L = makeEdge(vx, vy, sel & 3, (sel >> 2) & 3);
-					const Edge R = makeEdge(vx, vy, (sel >> 4) & 3, (sel >> 6) & 3);
-#pragma unroll 1
-					for(int iy = ya; iy <= yb; iy++)
+					const bool lower = iy >= l0 && iy <= l1;
+					if(!lower && !(iy >= u0 && iy <= u1)) continue;
+					const float y = (float)iy;
+					Edge L, R;
+					L.dx = lower ? LL.dx : LU.dx; L.dy = lower ? LL.dy : LU.dy; L.x0 = lower ? LL.x0 : LU.x0; L.y0 = lower ? LL.y0 : LU.y0;
+					R.dx = lower ? RL.dx : RU.dx; R.dy = lower ? RL.dy : RU.dy; R.x0 = lower ? RL.x0 : RU.x0; R.y0 = lower ? RL.y0 : RU.y0;
+					const int left = cvtt(fadd(edgeAt(L, y), 0.5f)), right = cvtt(fadd(edgeAt(R, y), 0.5f));   // rasterizer.cpp:98-117
+					if(left == right) continue;                            // drawvao.cpp:72
+					spans++;
+					if(iy < P.band0 || iy >= P.band1) continue;
+					const int x1 = left < 0 ? 0 : left;                     // RESULT_ROW::leftClamped
+					const int x2 = right >= P.vpW ? P.vpW - 1 : right;      // RESULT_ROW::rightClamped
+					if(x1 > x2) continue;
+					frags += (unsigned)(x2 - x1 + 1);
+					minX = min(minX, x1); maxX = max(maxX, x2);
+					minY = min(minY, iy); maxY = max(maxY, iy);
+					const int ty = iy / PS_TILE;
+					if(tyFirst < 0) tyFirst = ty;
+					const int k = ty - tyFirst;
+					trValid |= 1u << min(k, 31);
+					if(k != kCur)
 					{
-						const float y = (float)iy;
-						const int left = cvtt(fadd(edgeAt(L, y), 0.5f)), right = cvtt(fadd(edgeAt(R, y), 0.5f));   // rasterizer.cpp:98-117
-						if(left == right) continue;                            // drawvao.cpp:72
-						spans++;
-						if(iy < P.band0 || iy >= P.band1) continue;
-						const int x1 = left < 0 ? 0 : left;                     // RESULT_ROW::leftClamped
-						const int x2 = right >= P.vpW ? P.vpW - 1 : right;      // RESULT_ROW::rightClamped
-						if(x1 > x2) continue;
-						frags += (unsigned)(x2 - x1 + 1);
-						minX = min(minX, x1); maxX = max(maxX, x2);
-						minY = min(minY, iy); maxY = max(maxY, iy);
-						const int ty = iy / PS_TILE;
-						if(tyFirst < 0) tyFirst = ty;
-						const int k = ty - tyFirst;
-						trValid |= 1u << min(k, 31);
-						if(k != kCur)
-						{
-							const uint32_t packed = (uint32_t)curLo | ((uint32_t)curHi << 16);
-							if(0 == kCur) tr0 = packed; else if(1 == kCur) tr1 = packed; else if(2 == kCur) tr2 = packed; else if(3 == kCur) tr3 = packed;
-							kCur = k; curLo = x1 / PS_TILE; curHi = x2 / PS_TILE;
-						}
-						else { curLo = min(curLo, x1 / PS_TILE); curHi = max(curHi, x2 / PS_TILE); }
+						const uint32_t packed = (uint32_t)curLo | ((uint32_t)curHi << 16);
+						if(0 == kCur) tr0 = packed; else if(1 == kCur) tr1 = packed; else if(2 == kCur) tr2 = packed; else if(3 == kCur) tr3 = packed;
+						kCur = k; curLo = x1 / PS_TILE; curHi = x2 / PS_TILE;
 					}
+					else { curLo = min(curLo, x1 / PS_TILE); curHi = max(curHi, x2 / PS_TILE); }
 				}
 				{
 					const uint32_t packed = (uint32_t)curLo | ((uint32_t)curHi << 16);
@@ -215,18 +279,23 @@ __global__ void __launch_bounds__(128) geom_setup_kernel(const __grid_constant__
 		P.triRect[3 * tri + 2] = mask;
 		pairs = count;
 	}
+	// counters: one set of atomics per block, on the block's replica
+	__shared__ unsigned long long blockSums[PS_GEOM_THREADS / 32][3];
 	const unsigned long long r = warpSumU64(rasterised), s = warpSumU64(spans);
 	unsigned long long f = frags;
 #pragma unroll
 	for(int d = 16; d > 0; d >>= 1) f += __shfl_xor_sync(PS_FULL, f, d);
-	if(0 == (threadIdx.x & 31))
+	if(0 == (threadIdx.x & 31)) { blockSums[threadIdx.x >> 5][0] = r; blockSums[threadIdx.x >> 5][1] = s; blockSums[threadIdx.x >> 5][2] = f; }
+	__syncthreads();
+	if(threadIdx.x < 3)
 	{
-		if(r) atomicAdd(&P.stats->triangles_rasterised, r);
-		if(s) atomicAdd(&P.stats->spans, s);
-		if(f) atomicAdd(&P.stats->fragBound, f);
+		unsigned long long v = 0;
+#pragma unroll
+		for(int w = 0; w < PS_GEOM_THREADS / 32; w++) v += blockSums[w][threadIdx.x];
+		DeviceStats* st = P.stats + (blockIdx.x & (PS_STATS_COPIES - 1));
+		if(v) atomicAdd(0 == threadIdx.x ? &st->triangles_rasterised : (1 == threadIdx.x ? &st->spans : &st->fragBound), v);
 	}
-	const unsigned pr = (unsigned)warpSumU64(pairs);
-	if(0 == (threadIdx.x & 31) && pr) atomicAdd(&P.stats->pairs, pr);
+	(void)pairs;
 }
 
 // ======================================================================================================================
@@ -342,15 +411,29 @@ __global__ void __launch_bounds__(128) emit_pairs_kernel(const uint32_t* __restr
 
 #define PS_SORT_LIMIT 2048
 
-// one block: tileStart = exclusive scan of tileCount (ntiles + 1 entries), the longest list -> stats->maxTileCount
-__global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileStart,
-                                                        uint32_t* __restrict__ tileFill, uint32_t ntiles, DeviceStats* stats)
+// one block: tileStart = exclusive scan of tileCount (ntiles + 1 entries); tileCount and tileFill are left zeroed for the
+// next draw; the draw's fragment bound is folded out of the counter replicas. Then the verdict on the capacities the
+// host speculated with: if the pairs, the survivor bound or the longest list do not fit, *poison is raised and every
+// kernel enqueued behind this one returns at once, leaving the targets untouched for the host's exact retry.
+__global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileStart,
+                                                        uint32_t* __restrict__ tileFill, uint32_t ntiles, DeviceStats* stats,
+                                                        uint32_t pairCap, unsigned long long survivorCap, uint32_t listLimit,
+                                                        uint32_t* poison, DrawReport* report)
 {
 	__shared__ uint32_t warpTotals[32];
-	__shared__ uint32_t carryS;
-	if(0 == threadIdx.x) carryS = 0;
-	__syncthreads();
+	__shared__ uint32_t carryS, longestS;
+	__shared__ unsigned long long boundS;
+	if(0 == threadIdx.x) { carryS = 0; longestS = 0; }
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if(0 == warp)
+	{
+		unsigned long long b = lane < PS_STATS_COPIES ? stats[lane].fragBound : 0ull;
+		if(lane < PS_STATS_COPIES) stats[lane].fragBound = 0;
+#pragma unroll
+		for(int d = 16; d > 0; d >>= 1) b += __shfl_xor_sync(PS_FULL, b, d);
+		if(0 == lane) boundS = b;
+	}
+	__syncthreads();
 	uint32_t longest = 0;
 	for(uint32_t base = 0; base < ntiles + 1; base += 1024)
 	{
@@ -369,19 +452,30 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restr
 		uint32_t warpBase = 0;
 		for(int w = 0; w < warp; w++) warpBase += warpTotals[w];
 		const uint32_t carry = carryS;
-		if(i < ntiles + 1) { tileStart[i] = carry + warpBase + incl - v; if(i < ntiles) tileFill[i] = 0; }
+		if(i < ntiles + 1) { tileStart[i] = carry + warpBase + incl - v; if(i < ntiles) { tileFill[i] = 0; tileCount[i] = 0; } }
 		__syncthreads();
 		if(1023 == threadIdx.x) carryS = carry + warpBase + incl;
 		__syncthreads();
 	}
 	longest = __reduce_max_sync(PS_FULL, longest);
-	if(0 == lane && longest) atomicMax(&stats->maxTileCount, longest);
+	if(0 == lane && longest) atomicMax(&longestS, longest);
+	__syncthreads();
+	if(0 == threadIdx.x)
+	{
+		const uint32_t total = carryS, lng = longestS;
+		const unsigned long long bound = boundS;
+		const uint32_t bad = (total > pairCap || bound > survivorCap || lng > listLimit) ? 1u : 0u;
+		report->pairs = total; report->longest = lng; report->fragBound = bound; report->bad = bad;
+		__threadfence_system();
+		*poison = bad;
+	}
 }
 
 __global__ void __launch_bounds__(128) bin_fill_kernel(const uint32_t* __restrict__ triCount, const uint32_t* __restrict__ triRect,
                                                       const uint32_t* __restrict__ tileStart, uint32_t* __restrict__ tileFill,
-                                                      uint32_t* __restrict__ lists, uint32_t ntris, int tilesX)
+                                                      uint32_t* __restrict__ lists, uint32_t ntris, int tilesX, const uint32_t* __restrict__ poison)
 {
+	if(*poison) return;
 	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
 	if(tri >= ntris) return;
 	if(0 == triCount[tri]) return;
@@ -408,9 +502,11 @@ __global__ void __launch_bounds__(128) bin_fill_kernel(const uint32_t* __restric
 }
 
 // one warp per tile: bitonic sort of its list (<= PS_SORT_LIMIT ids) in shared memory
-__global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_list_sort_kernel(const uint32_t* __restrict__ tileStart, uint32_t* __restrict__ lists, uint32_t ntiles)
+__global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_list_sort_kernel(const uint32_t* __restrict__ tileStart, uint32_t* __restrict__ lists, uint32_t ntiles,
+                                                                                const uint32_t* __restrict__ poison)
 {
 	__shared__ uint32_t buf[PS_WARPS_PER_BLOCK][PS_SORT_LIMIT];
+	if(*poison) return;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const uint32_t tile = blockIdx.x * PS_WARPS_PER_BLOCK + w;
 	if(tile >= ntiles) return;
@@ -561,6 +657,7 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_imm
 	constexpr int NV = PROG::NV;
 	typedef typename PROG::I IP;
 	__shared__ TileSmem smem[PS_WARPS_PER_BLOCK];
+	if(*P.poison) return;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const int tile = blockIdx.x * PS_WARPS_PER_BLOCK + w;
 	if(tile >= P.tilesX * P.tilesY) return;
@@ -752,8 +849,8 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_imm
 	const unsigned long long t = warpSumU64(tested), s = warpSumU64(shaded);
 	if(0 == lane)
 	{
-		if(t) atomicAdd(&P.stats->fragments_tested, t);
-		if(s) atomicAdd(&P.stats->fragments_shaded, s);
+		if(t) atomicAdd(&P.stats[blockIdx.x & (PS_STATS_COPIES - 1)].fragments_tested, t);
+		if(s) atomicAdd(&P.stats[blockIdx.x & (PS_STATS_COPIES - 1)].fragments_shaded, s);
 	}
 }
 
@@ -896,6 +993,7 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_ord
                                                                                   const uint32_t* __restrict__ sortedTris)
 {
 	__shared__ TileSmem2 smem[PS_WARPS_PER_BLOCK];
+	if(*P.poison) return;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const int tile = blockIdx.x * PS_WARPS_PER_BLOCK + w;
 	if(tile >= P.tilesX * P.tilesY) return;
@@ -1106,8 +1204,8 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_ord
 	const unsigned long long t = warpSumU64(tested), sh = warpSumU64(shaded);
 	if(0 == lane)
 	{
-		if(t) atomicAdd(&P.stats->fragments_tested, t);
-		if(sh) atomicAdd(&P.stats->fragments_shaded, sh);
+		if(t) atomicAdd(&P.stats[blockIdx.x & (PS_STATS_COPIES - 1)].fragments_tested, t);
+		if(sh) atomicAdd(&P.stats[blockIdx.x & (PS_STATS_COPIES - 1)].fragments_shaded, sh);
 	}
 }
 
@@ -1361,6 +1459,7 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_depth_ker
                                                                                   const uint32_t* __restrict__ sortedTris)
 {
 	__shared__ RasterSmem smem[PS_WARPS_PER_BLOCK];
+	if(*P.poison) return;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const int tile = blockIdx.x * PS_WARPS_PER_BLOCK + w;
 	if(tile >= P.tilesX * P.tilesY) return;
@@ -1501,8 +1600,8 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_depth_ker
 	const unsigned long long t = warpSumU64(C.tested);
 	if(0 == lane)
 	{
-		if(t) atomicAdd(&P.stats->fragments_tested, t);
-		if(C.survived) atomicAdd(&P.stats->fragments_shaded, (unsigned long long)C.survived);   // every survivor is shaded exactly once by shade_kernel
+		if(t) atomicAdd(&P.stats[blockIdx.x & (PS_STATS_COPIES - 1)].fragments_tested, t);
+		if(C.survived) atomicAdd(&P.stats[blockIdx.x & (PS_STATS_COPIES - 1)].fragments_shaded, (unsigned long long)C.survived);   // every survivor is shaded exactly once by shade_kernel
 	}
 }
 
@@ -1512,6 +1611,7 @@ template<class PROG>
 __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ DrawParams P, const SurvivorStream Q)
 {
 	constexpr int NV = PROG::NV;
+	if(*P.poison) return;
 	const uint32_t n = min(*Q.count, Q.capacity);
 	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
 	{

@@ -10,6 +10,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include <mutex>
 #include "ps3d.h"
 #include "kernels.cuh"
@@ -61,10 +62,34 @@ int tilePathForced()
 // PS3D_BINNING=radix forces the stable radix-sort binning (the fallback for very long tile lists) for every draw
 bool radixBinningForced() { static int on = -1; if(on < 0) { const char* e = getenv("PS3D_BINNING"); on = (e && !strcmp(e, "radix")) ? 1 : 0; } return on == 1; }
 
+// PS3D_GEOM_STAGE=0 turns the shared-memory staging of the vertex streams off (A/B checks)
+bool geomStagingOn() { static int on = -1; if(on < 0) { const char* e = getenv("PS3D_GEOM_STAGE"); on = (e && e[0] == '0') ? 0 : 1; } return on == 1; }
+
 template<class PROG> void launchGeom(const DrawParams& P, cudaStream_t s)
 {
-	const unsigned blocks = (P.ntris + 127) / 128;
-	geom_setup_kernel<PROG><<<blocks, 128, 0, s>>>(P);
+	const unsigned blocks = (P.ntris + PS_GEOM_THREADS - 1) / PS_GEOM_THREADS;
+	// bytes of the block's vertex range, every slot the functor reads (bulk copies need 16-byte aligned sources: the
+	// block's first element sits at a multiple of 384 * stride bytes from the 256-byte aligned VBO base)
+	size_t bytes = 0;
+	bool aligned = true;
+	for(int i = 0; i < 16; i++)
+		if((PROG::V::SLOTS >> i) & 1)
+		{
+			bytes += ((size_t)PS_GEOM_THREADS * 3 * P.stride[i] + 127) & ~(size_t)127;
+			aligned = aligned && 0 == ((uintptr_t)P.slot[i] & 15);
+		}
+	if(geomStagingOn() && aligned && bytes > 0 && bytes <= 96 * 1024)
+	{
+		static size_t attr = 0;
+		if(bytes > attr)
+		{
+			cudaFuncSetAttribute(geom_setup_kernel<PROG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024));
+			attr = 96 * 1024;
+		}
+		geom_setup_kernel<PROG, true><<<blocks, PS_GEOM_THREADS, bytes, s>>>(P);
+	}
+	else
+		geom_setup_kernel<PROG, false><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
 }
 unsigned tileBlocks(const DrawParams& P) { return ((unsigned)(P.tilesX * P.tilesY) + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK; }
 template<class PROG> void launchTileImmediate(const DrawParams& P, const uint32_t* tileStart, const uint32_t* sortedTris, cudaStream_t s)
@@ -187,8 +212,16 @@ struct ps3d_pipe
 	DevBuf<float> svInv;
 	uint32_t* svCountDev;
 	uint32_t* totalDev;
-	uint32_t* totalHost; // pinned: [0] = bin pairs of the draw, [2..3] = its fragment bound
-	DeviceStats* statsDev;
+	DeviceStats* statsDev;      // PS_STATS_COPIES replicas
+	// asynchronous draws: the tail of a draw (binning, raster, shade) is enqueued behind the tile scan with SPECULATED
+	// buffer sizes and guarded by *poisonDev; the scan's report is read at the next API call (settle)
+	uint32_t* poisonDev;
+	DrawReport* report;         // mapped pinned host memory, written by tile_scan_kernel
+	DrawReport* reportDev;      // the device's alias of it
+	cudaEvent_t scanEvent;
+	bool speculate;
+	size_t pairHigh, survivorHigh;   // high-water marks of earlier draws: the next speculation
+	struct Pending { bool valid; DrawParams P; const ProgEntry* pe; int path; bool radix; } pending;
 	ps3d_stats stats;
 	uint32_t* capDev;
 	int capW, capH;
@@ -234,6 +267,9 @@ struct ProfScope
 
 #define CK(p, call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { (p)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return PS3D_ERR_DEVICE; } } while(0)
 
+static int settle(ps3d_pipe* p);
+#define SETTLE(p) do { int rc_ = settle(p); if(rc_) return rc_; } while(0)
+
 static int fail(ps3d_pipe* p, int code, const char* msg) { p->err = msg; return code; }
 
 // PS3D_TRACE=1 prints every C-ABI entry to stderr (debug aid)
@@ -275,6 +311,113 @@ static TargetDesc depthTarget(ps3d_pipe* p)
 	return d;
 }
 
+static int ensureSurvivors(ps3d_pipe* p, size_t cap, const DrawParams& P)
+{
+	CK(p, p->svTri.ensure(cap)); CK(p, p->svLeft.ensure(cap)); CK(p, p->svRight.ensure(cap)); CK(p, p->svInv.ensure(cap)); CK(p, p->svMisc.ensure(cap));
+	CK(p, p->svWinner.ensure((size_t)P.vpW * P.vpH));
+	return PS3D_OK;
+}
+
+// The draw behind its tile scan: binning by atomics + per-tile sort (or, radix == true, the stable radix sort for
+// lists too long for shared memory), then the tile kernels of the chosen path. Every kernel here returns at once when
+// the scan raised *poison. Buffers must already be large enough (speculated, or sized exactly by settle()).
+static int launchTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe, int path, bool radix)
+{
+	const uint32_t ntiles = (uint32_t)(P.tilesX * P.tilesY);
+	const uint32_t* sortedTris = nullptr;
+	if(!radix)
+	{
+		// lists filled with atomics in arrival order, then every tile's list sorted by triangle id = submission order
+		ProfScope ps(p, CLS_BIN);
+		bin_fill_kernel<<<(P.ntris + 127) / 128, 128, 0, p->stream>>>(p->triCount.p, p->triRect.p, p->tileStart.p, p->tileFill.p, p->valsA.p, P.ntris, P.tilesX, p->poisonDev);
+		tile_list_sort_kernel<<<(ntiles + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK, 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(p->tileStart.p, p->valsA.p, ntiles, p->poisonDev);
+		p->launches += 2;
+		CK(p, cudaGetLastError());
+		sortedTris = p->valsA.p;
+	}
+	else
+	{
+		// some tile list is too long for the shared-memory sort: pairs emitted in triangle order + stable LSD radix sort by tile
+		ProfScope ps(p, CLS_BIN);
+		const uint32_t total = p->report->pairs;
+		CK(p, p->triOffset.ensure(P.ntris));
+		int rc = exclusiveScan(p, p->triCount.p, p->triOffset.p, P.ntris, p->totalDev);
+		if(rc) return rc;
+		CK(p, p->keysA.ensure(total)); CK(p, p->valsA.ensure(total)); CK(p, p->keysB.ensure(total)); CK(p, p->valsB.ensure(total));
+		emit_pairs_kernel<<<(P.ntris + 127) / 128, 128, 0, p->stream>>>(p->triCount.p, p->triOffset.p, p->triRect.p, p->keysA.p, p->valsA.p, P.ntris, P.tilesX);
+		p->launches++;
+		CK(p, cudaGetLastError());
+		int bits = 0;
+		while((1u << bits) < ntiles) bits++;
+		uint32_t *kIn = p->keysA.p, *vIn = p->valsA.p, *kOut = p->keysB.p, *vOut = p->valsB.p;
+		const uint32_t nwarps = (total + PS_SORT_ITEMS_PER_WARP - 1) / PS_SORT_ITEMS_PER_WARP;
+		CK(p, p->sortCounts.ensure((size_t)256 * nwarps));
+		for(int shift = 0; shift < bits; shift += 8)
+		{
+			const unsigned blocks = (nwarps + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK;
+			sort_hist_kernel<<<blocks, 128, 0, p->stream>>>(kIn, total, shift, p->sortCounts.p, nwarps);
+			p->launches++;
+			rc = exclusiveScan(p, p->sortCounts.p, p->sortCounts.p, 256 * nwarps, p->totalDev);
+			if(rc) return rc;
+			sort_scatter_kernel<<<blocks, 128, 0, p->stream>>>(kIn, vIn, kOut, vOut, total, shift, p->sortCounts.p, nwarps);
+			p->launches++;
+			CK(p, cudaGetLastError());
+			uint32_t* t;
+			t = kIn; kIn = kOut; kOut = t;
+			t = vIn; vIn = vOut; vOut = t;
+		}
+		sortedTris = vIn;
+	}
+	if(0 == path) { ProfScope ps(p, CLS_TILE); pe->tileImmediate(P, p->tileStart.p, sortedTris, p->stream); p->launches++; }
+	else if(1 == path) { ProfScope ps(p, CLS_TILE); pe->tileOrdered(P, p->tileStart.p, sortedTris, p->stream); p->launches++; }
+	else
+	{
+		SurvivorStream Q;
+		Q.tri = p->svTri.p; Q.left = p->svLeft.p; Q.right = p->svRight.p; Q.inv = p->svInv.p; Q.misc = p->svMisc.p;
+		Q.count = p->svCountDev; Q.winner = p->svWinner.p; Q.capacity = (uint32_t)std::min<size_t>(p->svTri.cap, 0xfffffff0u);
+		CK(p, cudaMemsetAsync(p->svCountDev, 0, 4, p->stream));
+		{
+			ProfScope ps(p, CLS_TILE);
+			tile_raster_depth_kernel<<<tileBlocks(P), 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(P, Q, p->tileStart.p, sortedTris);
+			p->launches++;
+		}
+		{
+			ProfScope ps(p, CLS_SHADE);
+			pe->shade(P, Q, p->stream);
+			p->launches++;
+		}
+	}
+	CK(p, cudaGetLastError());
+	return PS3D_OK;
+}
+
+// Reads the verdict of the last draw's tile scan (waits for that kernel only — by the next API call it is long done).
+// A draw whose speculated sizes were too small did nothing behind its scan: size the buffers exactly and enqueue its
+// tail again, before anything else reaches the stream. Every entry point that touches the stream or device memory
+// settles first.
+static int settle(ps3d_pipe* p)
+{
+	if(!p->pending.valid) return PS3D_OK;
+	p->pending.valid = false;
+	CK(p, cudaEventSynchronize(p->scanEvent));
+	const DrawReport r = *p->report;
+	const DrawParams& P = p->pending.P;
+	const ProgEntry* pe = p->pending.pe;
+	int path = p->pending.path;
+	p->profPairs += p->profiling ? r.pairs : 0;
+	if(r.pairs > p->pairHigh) p->pairHigh = r.pairs;
+	if(2 == path && r.fragBound > p->survivorHigh) p->survivorHigh = (size_t)r.fragBound;
+	if(p->speculate && !radixBinningForced() && !r.bad) return PS3D_OK;   // the guarded tail ran
+	CK(p, cudaMemsetAsync(p->poisonDev, 0, 4, p->stream));
+	if(0 == r.pairs) return PS3D_OK;
+	if(2 == path && r.fragBound >= 0xfffffff0ull) path = 1;
+	if(2 == path && 0 == r.fragBound) return PS3D_OK;
+	const bool radix = r.longest > PS_SORT_LIMIT || radixBinningForced();
+	CK(p, p->valsA.ensure(r.pairs));
+	if(2 == path) { int rc = ensureSurvivors(p, (size_t)r.fragBound, P); if(rc) return rc; }
+	return launchTail(p, P, pe, path, radix);
+}
+
 extern "C" {
 
 const char* ps3d_backend_name(void) { return "cuda-sm100a"; }
@@ -304,15 +447,26 @@ int ps3d_create(int width, int height, int device, ps3d_pipe** out)
 	const size_t cbytes = (size_t)width * 4 * height, dbytes = (size_t)p->depthScanline * height;
 	ok = ok && cudaMalloc((void**)&p->display[0], cbytes) == cudaSuccess && cudaMalloc((void**)&p->display[1], cbytes) == cudaSuccess;
 	ok = ok && cudaMalloc((void**)&p->defaultDepth, dbytes + 16) == cudaSuccess;
-	ok = ok && cudaMalloc((void**)&p->totalDev, 16) == cudaSuccess && cudaMallocHost((void**)&p->totalHost, 16) == cudaSuccess;
-	ok = ok && cudaMalloc((void**)&p->statsDev, sizeof(DeviceStats)) == cudaSuccess;
+	ok = ok && cudaMalloc((void**)&p->totalDev, 16) == cudaSuccess;
+	ok = ok && cudaMalloc((void**)&p->statsDev, sizeof(DeviceStats) * PS_STATS_COPIES) == cudaSuccess;
+	ok = ok && cudaMalloc((void**)&p->poisonDev, 16) == cudaSuccess;
+	ok = ok && cudaHostAlloc((void**)&p->report, sizeof(DrawReport), cudaHostAllocMapped) == cudaSuccess;
+	ok = ok && cudaHostGetDevicePointer((void**)&p->reportDev, p->report, 0) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&p->scanEvent, cudaEventDisableTiming) == cudaSuccess;
+	p->pending.valid = false; p->pairHigh = p->survivorHigh = 0;
+	{
+		const char* e = getenv("PS3D_SPECULATE");   // PS3D_SPECULATE=0: size every draw exactly after a mid-draw host sync (A/B checks)
+		p->speculate = !(e && e[0] == '0');
+	}
 	ok = ok && cudaMalloc((void**)&p->svCountDev, 16) == cudaSuccess;
 	if(ok)
 	{
 		cudaMemsetAsync(p->display[0], 0, cbytes, p->stream);
 		cudaMemsetAsync(p->display[1], 0, cbytes, p->stream);
 		cudaMemsetAsync(p->defaultDepth, 0, dbytes, p->stream);
-		cudaMemsetAsync(p->statsDev, 0, sizeof(DeviceStats), p->stream);
+		cudaMemsetAsync(p->statsDev, 0, sizeof(DeviceStats) * PS_STATS_COPIES, p->stream);
+		cudaMemsetAsync(p->poisonDev, 0, 16, p->stream);
+		memset(p->report, 0, sizeof(DrawReport));
 	}
 	p->rcpDev = p->rsqrtDev = nullptr;
 	p->approx.rcp = p->approx.rsqrt = nullptr; p->approx.rcpBits = p->approx.rsqrtBits = 0;
@@ -341,11 +495,12 @@ int ps3d_destroy(ps3d_pipe* p)
 	TRACE();
 	if(!p) return PS3D_ERR_INVALID_ARGUMENT;
 	cudaSetDevice(p->device);
+	settle(p);
 	cudaStreamSynchronize(p->stream);
 	for(Texture* t : p->textures) if(t) { for(int i = 0; i < 6; i++) if(t->layer[i]) cudaFree(t->layer[i]); delete t; }
 	for(Vbo& v : p->vbos) if(v.alive && v.data) cudaFree(v.data);
 	cudaFree(p->display[0]); cudaFree(p->display[1]); cudaFree(p->defaultDepth);
-	cudaFree(p->totalDev); cudaFreeHost(p->totalHost); cudaFree(p->statsDev); cudaFree(p->svCountDev);
+	cudaFree(p->totalDev); cudaFree(p->statsDev); cudaFree(p->svCountDev); cudaFree(p->poisonDev); cudaFreeHost(p->report); cudaEventDestroy(p->scanEvent);
 	p->svTri.release(); p->svMisc.release(); p->svWinner.release(); p->svLeft.release(); p->svRight.release(); p->svInv.release();
 	if(p->capDev) cudaFree(p->capDev);
 	if(p->rcpDev) cudaFree(p->rcpDev);
@@ -366,6 +521,7 @@ int ps3d_texture_create(ps3d_pipe* p, unsigned width, unsigned scanline, unsigne
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	if(1 != elemLen && 4 != elemLen) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "PuresoftFBO: elemLen must be 1 or 4"); // fbo.cpp:21-24
 	if(extraLayers < 0 || extraLayers > 5) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftFBO: extraLayers");
 	if(!width || !height || scanline < width * elemLen) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "texture geometry");
@@ -403,6 +559,7 @@ int ps3d_texture_upload(ps3d_pipe* p, int idx, int layer, const void* pixels)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	Texture* t = texLayer(p, idx, layer);
 	if(!t) return fail(p, PS3D_ERR_OUT_OF_RANGE, "getTexture: index/layer out of range");
 	CK(p, cudaMemcpyAsync(t->layer[layer], pixels, (size_t)t->scanline * t->height, cudaMemcpyHostToDevice, p->stream));
@@ -413,6 +570,7 @@ int ps3d_texture_download(ps3d_pipe* p, int idx, int layer, void* pixels)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	Texture* t = texLayer(p, idx, layer);
 	if(!t) return fail(p, PS3D_ERR_OUT_OF_RANGE, "getTexture: index/layer out of range");
 	CK(p, cudaMemcpyAsync(pixels, t->layer[layer], (size_t)t->scanline * t->height, cudaMemcpyDeviceToHost, p->stream));
@@ -423,6 +581,7 @@ int ps3d_texture_destroy(ps3d_pipe* p, int idx)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	if(idx < 0 || idx >= (int)p->textures.size()) return fail(p, PS3D_ERR_OUT_OF_RANGE, "destroyTexture: index out of range"); // tex.cpp:48-51
 	if(p->textures[idx])
 	{
@@ -441,6 +600,7 @@ int ps3d_vbo_create(ps3d_pipe* p, size_t unitBytes, size_t unitCount, int* vbo)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	size_t slot = 0;
 	for(; slot < p->vbos.size(); slot++) if(!p->vbos[slot].alive) break;
 	Vbo v;
@@ -456,6 +616,7 @@ int ps3d_vbo_update(ps3d_pipe* p, int vbo, const void* src)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
 	// vbo.cpp:28-31 copies synchronously: the caller may free `src` on return
 	CK(p, cudaMemcpyAsync(p->vbos[vbo].data, src, p->vbos[vbo].unitBytes * p->vbos[vbo].unitCount, cudaMemcpyHostToDevice, p->stream));
@@ -466,6 +627,7 @@ int ps3d_vbo_update_device(ps3d_pipe* p, int vbo, const void* devSrc)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
 	CK(p, cudaMemcpyAsync(p->vbos[vbo].data, devSrc, p->vbos[vbo].unitBytes * p->vbos[vbo].unitCount, cudaMemcpyDeviceToDevice, p->stream));
 	return PS3D_OK;
@@ -474,6 +636,7 @@ int ps3d_vbo_destroy(ps3d_pipe* p, int vbo)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
 	cudaStreamSynchronize(p->stream);
 	cudaFree(p->vbos[vbo].data);
@@ -528,6 +691,7 @@ int ps3d_vao_destroy(ps3d_pipe* p, int vao)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	if(vao < 0 || vao >= (int)p->vaos.size()) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::attachVBO vao"); // pipeline.cpp:185-188
 	if(!p->vaos[vao].alive) return PS3D_OK;
 	cudaStreamSynchronize(p->stream);
@@ -640,6 +804,7 @@ int ps3d_clear_depth(ps3d_pipe* p, float furthest) // pipeline.cpp:334-338 -> cl
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	TargetDesc d = depthTarget(p);
 	const size_t quads = ((size_t)d.scanline * d.height) >> 4;
 	const int blocks = (int)((quads + 255) / 256 < 148 * 16 ? (quads + 255) / 256 : 148 * 16);
@@ -652,6 +817,7 @@ int ps3d_clear_colour(ps3d_pipe* p, uint32_t bgra) // pipeline.cpp:340-343 -> cl
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	if(p->height < 2) return PS3D_OK;
 	clear_colour_kernel<<<148 * 8, 256, 0, p->stream>>>(p->display[p->back], p->width, p->height - 1, p->width * 4, bgra);
 	p->launches++;
@@ -666,6 +832,7 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	TRACE();
 	(void)callerThread;
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	if(p->curProg < 0 || vao < 0 || vao >= (int)p->vaos.size() || !p->vaos[vao].alive) return PS3D_OK; // drawvao.cpp:12-15
 	const Prog pg = p->progs[p->curProg];
 	if(pg.vp < 0) return PS3D_OK;
@@ -732,12 +899,40 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	CK(p, p->vary.ensure(ntris * 3 * (size_t)(pe->nv > 0 ? pe->nv : 1)));
 	CK(p, p->triCount.ensure(ntris));
 	CK(p, p->triRect.ensure(ntris * 3));
-	CK(p, p->tileCount.ensure(ntiles + 1)); CK(p, p->tileStart.ensure(ntiles + 1)); CK(p, p->tileFill.ensure(ntiles + 1));
+	{
+		// tile_scan_kernel leaves the per-tile counts zeroed behind every draw; a fresh allocation starts zeroed
+		const uint32_t* before = p->tileCount.p;
+		CK(p, p->tileCount.ensure(ntiles + 1)); CK(p, p->tileStart.ensure(ntiles + 1)); CK(p, p->tileFill.ensure(ntiles + 1));
+		if(p->tileCount.p != before) CK(p, cudaMemsetAsync(p->tileCount.p, 0, p->tileCount.cap * 4, p->stream));
+	}
 	P.hdr = p->hdr.p; P.vary = p->vary.p; P.triCount = p->triCount.p; P.triRect = p->triRect.p; P.tileCount = p->tileCount.p;
+	P.poison = p->poisonDev;
 
-	// per-draw counters (fragBound, pairs, maxTileCount are the tail of DeviceStats) and the per-tile counts
-	CK(p, cudaMemsetAsync(&p->statsDev->fragBound, 0, 16, p->stream));
-	CK(p, cudaMemsetAsync(p->tileCount.p, 0, (size_t)(ntiles + 1) * 4, p->stream));
+	// which tile path (kernels.cuh): a functor that may discard() makes the depth write wait for the shading
+	// (fragthrd.cpp:234-237) -> immediate; a draw that blends needs its colours applied in submission order -> ordered;
+	// everything else -> split (raster + depth kernel, survivor stream, flat shade kernel)
+	int path = pe->mayDiscard ? 0 : (((p->behavior & PS3D_BEHAVIOR_ALPHABLEND) && pe->usesWrite4) ? 1 : 2);
+	if(tilePathForced() >= 0 && !(pe->mayDiscard)) path = tilePathForced() == 2 && 1 == path ? 1 : tilePathForced();
+	if(2 == path && (P.vpW > 8191 || P.vpH > 8191)) path = 1;      // the survivor record packs x and y in 13 bits each
+
+	// Speculation: the draw's tail is enqueued right behind the tile scan, sized by the high-water marks of earlier draws;
+	// the scan checks the sizes on the device and the host reads its verdict at the next API call (settle()).
+	const bool speculate = p->speculate && !radixBinningForced();
+	uint32_t pairCap = 0xffffffffu, listLimit = 0xffffffffu;
+	unsigned long long survivorCap = ~0ull;
+	if(speculate)
+	{
+		const size_t pairGuess = std::max(p->pairHigh + p->pairHigh / 4, ntris + ntris / 2 + 1024);
+		CK(p, p->valsA.ensure(pairGuess));
+		pairCap = (uint32_t)std::min<size_t>(p->valsA.cap, 0xffffffffu);
+		listLimit = PS_SORT_LIMIT;
+		if(2 == path)
+		{
+			const size_t svGuess = std::max(p->survivorHigh + p->survivorHigh / 4, (size_t)P.vpW * P.vpH * 2);
+			{ const int rc = ensureSurvivors(p, svGuess, P); if(rc) return rc; }
+			survivorCap = std::min<size_t>(p->svTri.cap, 0xfffffff0u);
+		}
+	}
 	{
 		ProfScope ps(p, CLS_GEOM);
 		pe->geom(P, p->stream);
@@ -746,94 +941,15 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	CK(p, cudaGetLastError());
 	{
 		ProfScope ps(p, CLS_BIN);
-		tile_scan_kernel<<<1, 1024, 0, p->stream>>>(p->tileCount.p, p->tileStart.p, p->tileFill.p, ntiles, p->statsDev);
+		tile_scan_kernel<<<1, 1024, 0, p->stream>>>(p->tileCount.p, p->tileStart.p, p->tileFill.p, ntiles, p->statsDev,
+		                                          pairCap, survivorCap, listLimit, p->poisonDev, p->reportDev);
 		p->launches++;
 	}
-	// sizes of the draw's intermediates: one 16-byte read-back per draw
-	CK(p, cudaMemcpyAsync(p->totalHost, &p->statsDev->fragBound, 16, cudaMemcpyDeviceToHost, p->stream));
-	CK(p, cudaStreamSynchronize(p->stream));
-	unsigned long long fragBound = 0;
-	memcpy(&fragBound, p->totalHost, 8);
-	const uint32_t total = p->totalHost[2], longest = p->totalHost[3];
-	if(0 == total) return PS3D_OK;
-	p->profPairs += p->profiling ? total : 0;
-
-	const uint32_t* sortedTris = nullptr;
-	int rc;
-	if(longest <= PS_SORT_LIMIT && !radixBinningForced())
-	{
-		// lists filled with atomics in arrival order, then every tile's list sorted by triangle id = submission order
-		ProfScope ps(p, CLS_BIN);
-		CK(p, p->valsA.ensure(total));
-		bin_fill_kernel<<<(P.ntris + 127) / 128, 128, 0, p->stream>>>(p->triCount.p, p->triRect.p, p->tileStart.p, p->tileFill.p, p->valsA.p, P.ntris, P.tilesX);
-		tile_list_sort_kernel<<<(ntiles + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK, 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(p->tileStart.p, p->valsA.p, ntiles);
-		p->launches += 2;
-		CK(p, cudaGetLastError());
-		sortedTris = p->valsA.p;
-	}
-	else
-	{
-		// some tile list is too long for the shared-memory sort: pairs emitted in triangle order + stable LSD radix sort by tile
-		ProfScope ps(p, CLS_BIN);
-		CK(p, p->triOffset.ensure(ntris));
-		rc = exclusiveScan(p, p->triCount.p, p->triOffset.p, P.ntris, p->totalDev);
-		if(rc) return rc;
-		CK(p, p->keysA.ensure(total)); CK(p, p->valsA.ensure(total)); CK(p, p->keysB.ensure(total)); CK(p, p->valsB.ensure(total));
-		emit_pairs_kernel<<<(P.ntris + 127) / 128, 128, 0, p->stream>>>(p->triCount.p, p->triOffset.p, p->triRect.p, p->keysA.p, p->valsA.p, P.ntris, P.tilesX);
-		p->launches++;
-		CK(p, cudaGetLastError());
-		int bits = 0;
-		while((1u << bits) < ntiles) bits++;
-		uint32_t *kIn = p->keysA.p, *vIn = p->valsA.p, *kOut = p->keysB.p, *vOut = p->valsB.p;
-		const uint32_t nwarps = (total + PS_SORT_ITEMS_PER_WARP - 1) / PS_SORT_ITEMS_PER_WARP;
-		CK(p, p->sortCounts.ensure((size_t)256 * nwarps));
-		for(int shift = 0; shift < bits; shift += 8)
-		{
-			const unsigned blocks = (nwarps + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK;
-			sort_hist_kernel<<<blocks, 128, 0, p->stream>>>(kIn, total, shift, p->sortCounts.p, nwarps);
-			p->launches++;
-			rc = exclusiveScan(p, p->sortCounts.p, p->sortCounts.p, 256 * nwarps, p->totalDev);
-			if(rc) return rc;
-			sort_scatter_kernel<<<blocks, 128, 0, p->stream>>>(kIn, vIn, kOut, vOut, total, shift, p->sortCounts.p, nwarps);
-			p->launches++;
-			CK(p, cudaGetLastError());
-			uint32_t* t;
-			t = kIn; kIn = kOut; kOut = t;
-			t = vIn; vIn = vOut; vOut = t;
-		}
-		sortedTris = vIn;
-	}
-	const uint32_t* vIn = sortedTris;
-
-	// which tile path (kernels.cuh): a functor that may discard() makes the depth write wait for the shading
-	// (fragthrd.cpp:234-237) -> immediate; a draw that blends needs its colours applied in submission order -> ordered;
-	// everything else -> split (raster + depth kernel, survivor stream, flat shade kernel)
-	int path = pe->mayDiscard ? 0 : (((p->behavior & PS3D_BEHAVIOR_ALPHABLEND) && pe->usesWrite4) ? 1 : 2);
-	if(tilePathForced() >= 0 && !(pe->mayDiscard)) path = tilePathForced() == 2 && 1 == path ? 1 : tilePathForced();
-	if(2 == path && (fragBound >= 0xfffffff0ull || P.vpW > 8191 || P.vpH > 8191)) path = 1;
-	if(2 == path && 0 == fragBound) return PS3D_OK;
-	if(0 == path) { ProfScope ps(p, CLS_TILE); pe->tileImmediate(P, p->tileStart.p, vIn, p->stream); p->launches++; }
-	else if(1 == path) { ProfScope ps(p, CLS_TILE); pe->tileOrdered(P, p->tileStart.p, vIn, p->stream); p->launches++; }
-	else
-	{
-		const size_t cap = (size_t)fragBound;
-		CK(p, p->svTri.ensure(cap)); CK(p, p->svLeft.ensure(cap)); CK(p, p->svRight.ensure(cap)); CK(p, p->svInv.ensure(cap)); CK(p, p->svMisc.ensure(cap));
-		CK(p, p->svWinner.ensure((size_t)P.vpW * P.vpH));
-		SurvivorStream Q;
-		Q.tri = p->svTri.p; Q.left = p->svLeft.p; Q.right = p->svRight.p; Q.inv = p->svInv.p; Q.misc = p->svMisc.p;
-		Q.count = p->svCountDev; Q.winner = p->svWinner.p; Q.capacity = (uint32_t)cap;
-		CK(p, cudaMemsetAsync(p->svCountDev, 0, 4, p->stream));
-		{
-			ProfScope ps(p, CLS_TILE);
-			tile_raster_depth_kernel<<<tileBlocks(P), 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(P, Q, p->tileStart.p, vIn);
-			p->launches++;
-		}
-		{
-			ProfScope ps(p, CLS_SHADE);
-			pe->shade(P, Q, p->stream);
-			p->launches++;
-		}
-	}
+	CK(p, cudaEventRecord(p->scanEvent, p->stream));
+	p->pending.valid = true; p->pending.P = P; p->pending.pe = pe; p->pending.path = path;
+	if(!speculate) return settle(p);          // exact sizes after a host sync in the middle of the draw
+	int rc = launchTail(p, P, pe, path, false);
+	if(rc) { p->pending.valid = false; return rc; }
 	CK(p, cudaGetLastError());
 	return PS3D_OK;
 }
@@ -842,6 +958,7 @@ int ps3d_finish(ps3d_pipe* p)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	CK(p, cudaStreamSynchronize(p->stream));
 	return PS3D_OK;
 }
@@ -851,6 +968,7 @@ int ps3d_read_colour(ps3d_pipe* p, void* bgra, size_t pitch)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	if(pitch < (size_t)p->width * 4) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "pitch");
 	CK(p, cudaMemcpy2DAsync(bgra, pitch, p->display[p->back], (size_t)p->width * 4, (size_t)p->width * 4, p->height, cudaMemcpyDeviceToHost, p->stream));
 	CK(p, cudaStreamSynchronize(p->stream));
@@ -860,6 +978,7 @@ int ps3d_read_depth(ps3d_pipe* p, float* depth, size_t pitch)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	if(pitch < (size_t)p->width * 4) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "pitch");
 	CK(p, cudaMemcpy2DAsync(depth, pitch, p->defaultDepth, p->depthScanline, (size_t)p->width * 4, p->height, cudaMemcpyDeviceToHost, p->stream));
 	CK(p, cudaStreamSynchronize(p->stream));
@@ -869,6 +988,7 @@ int ps3d_write_colour(ps3d_pipe* p, const void* bgra, size_t pitch)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	if(pitch < (size_t)p->width * 4) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "pitch");
 	CK(p, cudaMemcpy2DAsync(p->display[p->back], (size_t)p->width * 4, bgra, pitch, (size_t)p->width * 4, p->height, cudaMemcpyHostToDevice, p->stream));
 	CK(p, cudaStreamSynchronize(p->stream));
@@ -878,6 +998,7 @@ int ps3d_write_depth(ps3d_pipe* p, const float* depth, size_t pitch)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	if(pitch < (size_t)p->width * 4) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "pitch");
 	CK(p, cudaMemcpy2DAsync(p->defaultDepth, p->depthScanline, depth, pitch, (size_t)p->width * 4, p->height, cudaMemcpyHostToDevice, p->stream));
 	CK(p, cudaStreamSynchronize(p->stream));
@@ -888,22 +1009,28 @@ int ps3d_get_stats(ps3d_pipe* p, ps3d_stats* out)
 {
 	TRACE();
 	cudaSetDevice(p->device);
-	DeviceStats d;
-	CK(p, cudaMemcpyAsync(&d, p->statsDev, sizeof(d), cudaMemcpyDeviceToHost, p->stream));
+	SETTLE(p);
+	static DeviceStats d[PS_STATS_COPIES];
+	CK(p, cudaMemcpyAsync(d, p->statsDev, sizeof(d), cudaMemcpyDeviceToHost, p->stream));
 	CK(p, cudaStreamSynchronize(p->stream));
 	*out = p->stats;
-	out->triangles_rasterised = d.triangles_rasterised;
-	out->spans = d.spans;
-	out->fragments_tested = d.fragments_tested;
-	out->fragments_shaded = d.fragments_shaded;
+	out->triangles_rasterised = out->spans = out->fragments_tested = out->fragments_shaded = 0;
+	for(int i = 0; i < PS_STATS_COPIES; i++)
+	{
+		out->triangles_rasterised += d[i].triangles_rasterised;
+		out->spans += d[i].spans;
+		out->fragments_tested += d[i].fragments_tested;
+		out->fragments_shaded += d[i].fragments_shaded;
+	}
 	return PS3D_OK;
 }
 int ps3d_reset_stats(ps3d_pipe* p)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	memset(&p->stats, 0, sizeof(p->stats));
-	CK(p, cudaMemsetAsync(p->statsDev, 0, sizeof(DeviceStats), p->stream));
+	CK(p, cudaMemsetAsync(p->statsDev, 0, sizeof(DeviceStats) * PS_STATS_COPIES, p->stream));
 	return PS3D_OK;
 }
 
@@ -911,6 +1038,7 @@ int ps3d_debug_capture(ps3d_pipe* p, int width, int height)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	if(width < 0 || height < 0) return PS3D_ERR_INVALID_ARGUMENT;
 	CK(p, cudaStreamSynchronize(p->stream));
 	if(p->capDev) cudaFree(p->capDev);
@@ -927,6 +1055,7 @@ int ps3d_debug_read_shade_counts(ps3d_pipe* p, uint32_t* counts)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	if(!p->capDev) return PS3D_ERR_INVALID_ARGUMENT;
 	CK(p, cudaMemcpyAsync(counts, p->capDev, (size_t)p->capW * p->capH * 4, cudaMemcpyDeviceToHost, p->stream));
 	CK(p, cudaStreamSynchronize(p->stream));
@@ -936,6 +1065,7 @@ int ps3d_debug_clear_shade_counts(ps3d_pipe* p)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	if(p->capDev) CK(p, cudaMemsetAsync(p->capDev, 0, (size_t)p->capW * p->capH * 4, p->stream));
 	return PS3D_OK;
 }
@@ -949,15 +1079,16 @@ int ps3d_set_row_band(ps3d_pipe* p, int row0, int row1)
 	return PS3D_OK;
 }
 
-int ps3d_device_colour_ptr(ps3d_pipe* p, void** devPtr, size_t* pitch) { *devPtr = p->display[p->back]; *pitch = (size_t)p->width * 4; return PS3D_OK; }
-int ps3d_device_depth_ptr(ps3d_pipe* p, void** devPtr, size_t* pitch) { *devPtr = p->defaultDepth; *pitch = (size_t)p->depthScanline; return PS3D_OK; }
-int ps3d_device_stream(ps3d_pipe* p, void** s) { *s = (void*)p->stream; return PS3D_OK; }
+int ps3d_device_colour_ptr(ps3d_pipe* p, void** devPtr, size_t* pitch) { SETTLE(p); *devPtr = p->display[p->back]; *pitch = (size_t)p->width * 4; return PS3D_OK; }
+int ps3d_device_depth_ptr(ps3d_pipe* p, void** devPtr, size_t* pitch) { SETTLE(p); *devPtr = p->defaultDepth; *pitch = (size_t)p->depthScanline; return PS3D_OK; }
+int ps3d_device_stream(ps3d_pipe* p, void** s) { SETTLE(p); *s = (void*)p->stream; return PS3D_OK; }
 int ps3d_device_launch_count(ps3d_pipe* p, uint64_t* n) { *n = p->launches; return PS3D_OK; }
 
 int ps3d_profile_enable(ps3d_pipe* p, int on)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	CK(p, cudaStreamSynchronize(p->stream));
 	for(auto& s : p->spans) { p->eventPool.push_back(s.a); p->eventPool.push_back(s.b); }
 	p->spans.clear();
@@ -969,6 +1100,7 @@ int ps3d_profile_read(ps3d_pipe* p, ps3d_profile* out)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	CK(p, cudaStreamSynchronize(p->stream));
 	double ms[4] = { 0, 0, 0, 0 };
 	for(auto& s : p->spans)

@@ -25,25 +25,27 @@ struct FragmentProcessorOutput                                     // proc.h:51-
 	PS_D void write4(uint32_t c) { wrote = true; blendable = true; bgra = c; }   // FBOBridge::write4: blend4 under ALPHABLEND
 };
 
+// Attribute fetch. Plain (generic) loads: in.data[] points either into the VBO in global memory or into the copy of the
+// block's vertex range that geom_setup staged in shared memory with one bulk copy per slot.
 PS_D F4 ldF4(const uint8_t* p)
 {
 	if(0 == ((uintptr_t)p & 15))
 	{
-		float4 v = __ldg((const float4*)p);
+		const float4 v = *(const float4*)p;
 		return f4(v.x, v.y, v.z, v.w);
 	}
 	const float* q = (const float*)p;
-	return f4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+	return f4(q[0], q[1], q[2], q[3]);
 }
 PS_D void ldF2(const uint8_t* p, float& a, float& b)
 {
 	if(0 == ((uintptr_t)p & 7))
 	{
-		float2 v = __ldg((const float2*)p);
+		const float2 v = *(const float2*)p;
 		a = v.x; b = v.y;
 		return;
 	}
-	a = __ldg((const float*)p); b = __ldg((const float*)p + 1);
+	a = ((const float*)p)[0]; b = ((const float*)p)[1];
 }
 
 // ---- PuresoftFBO random access + the three samplers ---------------------------------------------------------------
