@@ -309,10 +309,20 @@ def main():
     achieved = (dom_bytes / 1e9) / (dom_ms_per_launch / 1e3) if dom_ms > 0 else 0.0
     frame_bytes = vertex_b + target_b + tex_b
     frame_achieved = (frame_bytes / 1e9) / (ms_step / 1e3)
-    traffic = None
-    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this build
+    traffic, issue_frac, kernel_issue = None, None, {}
+    try:  # per launch, from the committed `ncu --set full` capture of this build: DRAM bytes and warp instructions
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(args.workload, {}).get(dominant)
+            tj = json.load(f).get(args.workload, {})
+        traffic = tj.get(dominant, {}).get("bytes") if world == 1 else None
+        # The path is instruction-issue bound (exact IEEE operation order: no FMA, true divides), so next to the HBM
+        # roofline: warp instructions per launch (ncu) / live launch time / (SMs x 4 schedulers x SM clock).
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        issue_peak = torch.cuda.get_device_properties(dev).multi_processor_count * 4 * sm_hz
+        for k, (ms, _, _) in classes.items():
+            wi = tj.get(k, {}).get("warp_inst")
+            if wi and ms > 0 and world == 1:
+                kernel_issue[k] = (wi / (ms / draws / 1e3)) / issue_peak
+        issue_frac = kernel_issue.get(dominant)
     except Exception:
         pass
     if rank == 0:
@@ -330,10 +340,12 @@ def main():
                     "ms_per_step": float(t.item()) / e2e_steps, "steps": e2e_steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "ms_per_launch": dom_ms_per_launch, "algorithmic_bytes": dom_bytes},
+                         "frac": achieved / peak, "traffic": traffic, "ms_per_launch": dom_ms_per_launch, "algorithmic_bytes": dom_bytes,
+                         "issue_frac": issue_frac, "note": "issue-bound, not HBM-bound: issue_frac = warp instructions (ncu, profiles/traffic.json) / launch time / (SMs x 4 x SM clock)"},
             "frame_roofline": {"achieved": frame_achieved, "peak": peak, "unit": "GB/s", "frac": frame_achieved / peak,
                                "algorithmic_bytes": frame_bytes, "roofline_us": frame_bytes / (peak * 1e3)},
             "kernel_ms_per_frame": {k: v[0] / args.steps for k, v in classes.items()},
+            "kernel_issue_frac": kernel_issue,
             "bin_pairs_per_frame": prof["bin_pairs"] / args.steps,
         }
         if world == 1 and not args.no_cpu_baseline:
