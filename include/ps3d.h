@@ -48,6 +48,10 @@ extern "C" {
 /* PuresoftFBO::WRAPMODE, PuresoftFBO::LAYER: src/puresoft3d/fbo.h:18-19 */
 #define PS3D_WRAP_CLAMP 0
 #define PS3D_WRAP_WRAP  1
+
+/* Sampler filter of a texture (extension: PuresoftSampler2D is nearest-only, samplr2d.cpp:19-25). */
+#define PS3D_FILTER_NEAREST  0
+#define PS3D_FILTER_BILINEAR 1
 #define PS3D_LAYER_XPOS 0
 #define PS3D_LAYER_XNEG 1
 #define PS3D_LAYER_YPOS 2
@@ -79,6 +83,8 @@ extern "C" {
 #define PS3D_FN_DIFFUSEONLY  34  /* VP_DiffuseOnly / IP_DiffuseOnly / FP_DiffuseOnly                                 */
 #define PS3D_FN_SHADOW2      35  /* VP_Shadow (vertex) / FP_Null (fragment); interpolation = PS3D_FN_POSITIONONLY    */
 #define PS3D_FN_FLATID       64  /* parity-test functor (not in the reference): writes a per-triangle id */
+#define PS3D_FN_TEXPROBE     65  /* parity-test functor (not in the reference): clip-space position from slot 0, uv from slot 4,
+                                    writes PuresoftSampler2D::get4(texture of uniform 9, u, v) unlit */
 
 typedef struct ps3d_pipe ps3d_pipe;
 
@@ -102,6 +108,14 @@ int ps3d_texture_create(ps3d_pipe* p, unsigned width, unsigned scanline, unsigne
 int ps3d_texture_upload(ps3d_pipe* p, int idx, int layer, const void* pixels);
 int ps3d_texture_download(ps3d_pipe* p, int idx, int layer, void* pixels);
 int ps3d_texture_destroy(ps3d_pipe* p, int idx);
+/* EXTENSION (no reference counterpart; BASELINE.json's configs ask for bilinear sampling): how
+ * PuresoftSampler2D::get4 reads this texture. NEAREST (the default) is the reference's sampler, bit for bit. BILINEAR:
+ * texel i sits at u = i / width as in the reference's nearest rule; x = width*u, y = height*v; the four texels around
+ * (floor(x), floor(y)) are fetched through clampCoord (so CLAMP / WRAP behave as for nearest) and every 8-bit channel is
+ * lerp(lerp(c00, c10, fx), lerp(c01, c11, fx), fy) in fp32 with lerp(a, b, t) = a + (b - a) * t (separate mul and add),
+ * then (int)(value + 0.5f). The CPU restatement in oracle/ implements the same definition ("parity unpinned": the
+ * reference has nothing to compare with); the reference build (oracle/_ref) returns PS3D_ERR_UNSUPPORTED. */
+int ps3d_texture_set_filter(ps3d_pipe* p, int idx, int filter);
 
 /* new PuresoftVBO(unitBytes, unitCount) / updateContent / delete — vbo.h:16-18, vbo.cpp:8-31 */
 int ps3d_vbo_create(ps3d_pipe* p, size_t unitBytes, size_t unitCount, int* vbo);

@@ -149,6 +149,8 @@ public:
 		return idx;
 	}
 	void destroyTexture(int idx) { check(ps3d_texture_destroy(m_pipe, idx)); }
+	// extension: bilinear filtering for PuresoftSampler2D reads of this texture (the reference is nearest-only)
+	void setTextureFilter(int idx, bool bilinear) { check(ps3d_texture_set_filter(m_pipe, idx, bilinear ? PS3D_FILTER_BILINEAR : PS3D_FILTER_NEAREST)); }
 	void uploadTexture(int idx, const void* pixels, PuresoftFBO::LAYER layer = PuresoftFBO::LAYER_DEFAULT) { check(ps3d_texture_upload(m_pipe, idx, (int)layer, pixels)); }
 	void downloadTexture(int idx, void* pixels, PuresoftFBO::LAYER layer = PuresoftFBO::LAYER_DEFAULT) { check(ps3d_texture_download(m_pipe, idx, (int)layer, pixels)); }
 

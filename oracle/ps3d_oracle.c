@@ -118,6 +118,7 @@ static int cvtu(float f)
 typedef struct
 {
 	int width, height, scanline, elemLen, wrap, topDown;
+	int filter;                          /* PS3D_FILTER_* (extension; 0 = the reference's nearest sampler) */
 	int nLayers;
 	unsigned char* layer[6];
 } fbo_t;
@@ -206,8 +207,31 @@ static uint32_t fbo_read4(const fbo_t* f, int layer, int row, int col)
 /* ---- samplers ------------------------------------------------------------------------------------------- */
 
 /* samplr2d.cpp:19-25 : nearest, +0.5f, (unsigned) casts, row from v / col from u */
+/* EXTENSION (include/ps3d.h, ps3d_texture_set_filter): bilinear. No reference counterpart — "parity unpinned". */
+static float lerp1(float a, float b, float t) { float d = b - a; float m = d * t; return a + m; }
+static uint32_t sampler2d_bilinear4(const fbo_t* t, float u, float v)
+{
+	float x = (float)t->width * u, y = (float)t->height * v;
+	float x0 = floorf(x), y0 = floorf(y);
+	float fx = x - x0, fy = y - y0;
+	int col = cvtt(x0), row = cvtt(y0);
+	uint32_t c00 = fbo_read4(t, 0, row, col), c10 = fbo_read4(t, 0, row, col + 1);
+	uint32_t c01 = fbo_read4(t, 0, row + 1, col), c11 = fbo_read4(t, 0, row + 1, col + 1);
+	uint32_t out = 0;
+	for(int ch = 0; ch < 4; ch++)
+	{
+		float a = (float)((c00 >> (8 * ch)) & 0xff), b = (float)((c10 >> (8 * ch)) & 0xff);
+		float c = (float)((c01 >> (8 * ch)) & 0xff), d = (float)((c11 >> (8 * ch)) & 0xff);
+		float r = lerp1(lerp1(a, b, fx), lerp1(c, d, fx), fy);
+		int q = cvtt(r + 0.5f);
+		q = q < 0 ? 0 : (q > 255 ? 255 : q);
+		out |= (uint32_t)q << (8 * ch);
+	}
+	return out;
+}
 static uint32_t sampler2d_get4(const fbo_t* t, float u, float v)
 {
+	if(t->filter) return sampler2d_bilinear4(t, u, v);
 	int row = cvtu((float)t->height * v + 0.5f);
 	int col = cvtu((float)t->width * u + 0.5f);
 	return fbo_read4(t, 0, row, col);
@@ -296,6 +320,7 @@ static int n_varyings(int functor) /* IP::userDataBytes() / 16 — float4 fields
 	case PS3D_FN_DEF04: return 1;                      /* skybox.h:4-7 */
 	case PS3D_FN_DEF05: return 0;                      /* shadow.h:4-6 */
 	case PS3D_FN_FLATID: return 1;
+	case PS3D_FN_TEXPROBE: return 1;
 	default: return -1;
 	}
 }
@@ -440,6 +465,15 @@ static int run_vp(int functor, const shader_env* e, const unsigned char* const* 
 		m4v4(vary[0].v, e->u[1], (const float*)in[3]);
 		vary[2].v[0] = ((const float*)in[4])[0];
 		vary[2].v[1] = ((const float*)in[4])[1];
+		return 1;
+	}
+	case PS3D_FN_TEXPROBE: /* parity-test functor (not in the reference): clip-space position as given; vary0 = (u, v, 0, 0) */
+	{
+		if(!in[0] || !in[4]) return 0;
+		memcpy(pos, in[0], 16);
+		vary[0].v[0] = ((const float*)in[4])[0];
+		vary[0].v[1] = ((const float*)in[4])[1];
+		vary[0].v[2] = vary[0].v[3] = 0.0f;
 		return 1;
 	}
 	case PS3D_FN_FLATID: /* parity-test functor (not in the reference): pos = PV*(M*p); vary0 = slot 6 (flat id colour) */
@@ -697,6 +731,11 @@ static void run_fp(int functor, const shader_env* e, const f4* in, frag_out* out
 		return;
 	case PS3D_FN_DEF05: /* shadow.cpp:76-77 — writes nothing */
 		return;
+	case PS3D_FN_TEXPROBE: /* parity-test functor: the 2-D sampler's output, unlit */
+		out->bgra = sampler2d_get4(e->tex[9], in[0].v[0], in[0].v[1]);
+		out->wrote = 1;
+		out->blendable = 0;
+		return;
 	case PS3D_FN_FLATID: /* parity-test functor: id colour rounded to bytes, write4 */
 	{
 		uint32_t b = (uint32_t)(cvtt(in[0].v[0] + 0.5f) & 0xff), g = (uint32_t)(cvtt(in[0].v[1] + 0.5f) & 0xff);
@@ -895,6 +934,7 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 		if(fnF == PS3D_FN_DEF03 && !env.tex[10]) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "uniform 10 does not name a texture");
 		if(fnF == PS3D_FN_DEF04 && !env.tex[2]) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "uniform 2 does not name a texture");
 		if(fnV == PS3D_FN_FLATID && (!env.u[3] || !env.u[4])) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "a uniform slot the programme reads is unset");
+		if(fnF == PS3D_FN_TEXPROBE && !env.tex[9]) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "uniform 9 does not name a texture");
 		{
 			/* fragment functors of the two demos: uniform slots read as vectors, then slots that must name a texture */
 			static const struct { int fn; int u[8]; int t[6]; } need[] = {
@@ -1119,6 +1159,14 @@ int ps3d_texture_create(ps3d_pipe* p, unsigned width, unsigned scanline, unsigne
 	p->textures[slot] = f;
 	if(slot == p->nTextures) p->nTextures++;
 	*idx = slot;
+	return PS3D_OK;
+}
+
+int ps3d_texture_set_filter(ps3d_pipe* p, int idx, int filter)
+{
+	if(idx < 0 || idx >= p->nTextures || !p->textures[idx]) return fail(p, PS3D_ERR_OUT_OF_RANGE, "getTexture: index out of range");
+	if(PS3D_FILTER_NEAREST != filter && PS3D_FILTER_BILINEAR != filter) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "filter");
+	p->textures[idx]->filter = filter;
 	return PS3D_OK;
 }
 

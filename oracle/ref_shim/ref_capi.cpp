@@ -258,6 +258,15 @@ int ps3d_texture_download(ps3d_pipe* p, int idx, int layer, void* pixels)
 	PS3D_CATCH(p)
 }
 
+int ps3d_texture_set_filter(ps3d_pipe* p, int idx, int filter)
+{
+	// the reference's PuresoftSampler2D is nearest-only (samplr2d.cpp:19-25): nothing to switch
+	(void)idx;
+	if(PS3D_FILTER_NEAREST == filter) return PS3D_OK;
+	p->err = "the reference has no bilinear sampler";
+	return PS3D_ERR_UNSUPPORTED;
+}
+
 int ps3d_texture_destroy(ps3d_pipe* p, int idx)
 {
 	PS3D_TRY(p)

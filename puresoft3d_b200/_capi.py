@@ -30,6 +30,7 @@ FN_DEF01, FN_DEF02, FN_DEF03, FN_DEF04, FN_DEF05 = 1, 2, 3, 4, 5
 FN_PLANET, FN_SATELLITE, FN_CLOUD, FN_CLOUDSHADOW = 16, 17, 18, 19
 FN_POSITIONONLY, FN_SINGLECOLOUR, FN_DIFFUSEONLY, FN_SHADOW2 = 32, 33, 34, 35
 FN_FLATID = 64
+FN_TEXPROBE = 65
 
 
 class Stats(C.Structure):
@@ -68,6 +69,7 @@ PROTOTYPES = {
     "ps3d_texture_upload": (C.c_int, [_P, C.c_int, C.c_int, C.c_void_p]),
     "ps3d_texture_download": (C.c_int, [_P, C.c_int, C.c_int, C.c_void_p]),
     "ps3d_texture_destroy": (C.c_int, [_P, C.c_int]),
+    "ps3d_texture_set_filter": (C.c_int, [_P, C.c_int, C.c_int]),
     "ps3d_vbo_create": (C.c_int, [_P, C.c_size_t, C.c_size_t, _INT_P]),
     "ps3d_vbo_update": (C.c_int, [_P, C.c_int, C.c_void_p]),
     "ps3d_vbo_destroy": (C.c_int, [_P, C.c_int]),

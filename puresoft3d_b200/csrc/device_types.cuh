@@ -25,6 +25,7 @@ struct TexDesc
 {
 	const uint8_t* layer[6];
 	int width, height, scanline, wrap, nLayers, elemLen;
+	int filter;                 // PS3D_FILTER_*: 0 = nearest (the reference's sampler), 1 = bilinear (extension)
 };
 
 struct TargetDesc

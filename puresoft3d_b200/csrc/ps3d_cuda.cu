@@ -21,7 +21,7 @@ namespace
 
 struct Texture
 {
-	int width, height, scanline, elemLen, wrap, nLayers;
+	int width, height, scanline, elemLen, wrap, nLayers, filter;
 	uint8_t* layer[6];
 };
 struct Vbo { size_t unitBytes, unitCount; uint8_t* data; bool alive; };
@@ -142,6 +142,7 @@ const std::vector<ProgEntry>& programmeTable()
 		t.push_back(makeEntry<ProgDEF04>(PS3D_FN_DEF04, PS3D_FN_DEF04, PS3D_FN_DEF04));
 		t.push_back(makeEntry<ProgDEF05>(PS3D_FN_DEF05, PS3D_FN_DEF05, PS3D_FN_DEF05));
 		t.push_back(makeEntry<ProgFLATID>(PS3D_FN_FLATID, PS3D_FN_FLATID, PS3D_FN_FLATID));
+		t.push_back(makeEntry<ProgTEXPROBE>(PS3D_FN_TEXPROBE, PS3D_FN_TEXPROBE, PS3D_FN_TEXPROBE));
 		// demo 1 (src/test/testproc.cpp) and demo 2 (src/test2/testproc.cpp): the triples their scene objects create
 		t.push_back(makeEntry<ProgEarth>(PS3D_FN_PLANET, PS3D_FN_PLANET, PS3D_FN_PLANET));
 		t.push_back(makeEntry<ProgSatellite>(PS3D_FN_PLANET, PS3D_FN_PLANET, PS3D_FN_SATELLITE));
@@ -529,7 +530,7 @@ int ps3d_texture_create(ps3d_pipe* p, unsigned width, unsigned scanline, unsigne
 	for(; slot < p->textures.size(); slot++) if(!p->textures[slot]) break; // tex.cpp:6-16 first free slot
 	Texture* t = new Texture();
 	memset(t, 0, sizeof(*t));
-	t->width = (int)width; t->height = (int)height; t->scanline = (int)scanline; t->elemLen = (int)elemLen; t->wrap = wrapMode; t->nLayers = 1 + extraLayers;
+	t->width = (int)width; t->height = (int)height; t->scanline = (int)scanline; t->elemLen = (int)elemLen; t->wrap = wrapMode; t->nLayers = 1 + extraLayers; t->filter = PS3D_FILTER_NEAREST;
 	const size_t bytes = (size_t)scanline * height;
 	for(int i = 0; i < t->nLayers; i++)
 	{
@@ -591,6 +592,15 @@ int ps3d_texture_destroy(ps3d_pipe* p, int idx)
 		p->textures[idx] = nullptr;
 		if(p->depthTex == idx) p->depthTex = -1;
 	}
+	return PS3D_OK;
+}
+
+int ps3d_texture_set_filter(ps3d_pipe* p, int idx, int filter) // extension, include/ps3d.h
+{
+	TRACE();
+	if(idx < 0 || idx >= (int)p->textures.size() || !p->textures[idx]) return fail(p, PS3D_ERR_OUT_OF_RANGE, "getTexture: index out of range");
+	if(PS3D_FILTER_NEAREST != filter && PS3D_FILTER_BILINEAR != filter) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "filter");
+	p->textures[idx]->filter = filter;   // latched per draw like every other texture property
 	return PS3D_OK;
 }
 
@@ -875,7 +885,7 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 		if(4 != t->elemLen) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "sampler needs a 4-byte texture");
 		for(int l = 0; l < 6; l++) P.tex[k].layer[l] = t->layer[l];
 		P.tex[k].width = t->width; P.tex[k].height = t->height; P.tex[k].scanline = t->scanline; P.tex[k].wrap = t->wrap;
-		P.tex[k].nLayers = t->nLayers; P.tex[k].elemLen = t->elemLen;
+		P.tex[k].nLayers = t->nLayers; P.tex[k].elemLen = t->elemLen; P.tex[k].filter = t->filter;
 	}
 	p->stats.draws++;
 	p->stats.triangles_submitted += ntris;

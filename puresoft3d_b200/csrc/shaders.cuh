@@ -77,9 +77,34 @@ struct PuresoftSampler2D
 	// samplr2d.cpp:19-25 — nearest; row from v, column from u; +0.5f then (unsigned int)
 	PS_D static uint32_t get4(const TexDesc& t, float u, float v)
 	{
+		if(t.filter) return bilinear4(t, u, v);
 		int row = cvtu(fadd(fmul((float)t.height, v), 0.5f));
 		int col = cvtu(fadd(fmul((float)t.width, u), 0.5f));
 		return directRead4(t, 0, row, col);
+	}
+	// EXTENSION (include/ps3d.h, ps3d_texture_set_filter): texel i at u = i / width, four taps through clampCoord,
+	// per channel lerp(lerp(c00, c10, fx), lerp(c01, c11, fx), fy), lerp(a, b, t) = a + (b - a) * t, (int)(x + 0.5f)
+	PS_D static float lerp1(float a, float b, float t) { return fadd(a, fmul(fsub(b, a), t)); }
+	PS_D static uint32_t bilinear4(const TexDesc& t, float u, float v)
+	{
+		const float x = fmul((float)t.width, u), y = fmul((float)t.height, v);
+		const float x0 = floorf(x), y0 = floorf(y);
+		const float fx = fsub(x, x0), fy = fsub(y, y0);
+		const int col = cvtt(x0), row = cvtt(y0);
+		const uint32_t c00 = directRead4(t, 0, row, col), c10 = directRead4(t, 0, row, col + 1);
+		const uint32_t c01 = directRead4(t, 0, row + 1, col), c11 = directRead4(t, 0, row + 1, col + 1);
+		uint32_t out = 0;
+#pragma unroll
+		for(int ch = 0; ch < 4; ch++)
+		{
+			const float a = (float)((c00 >> (8 * ch)) & 0xff), b = (float)((c10 >> (8 * ch)) & 0xff);
+			const float c = (float)((c01 >> (8 * ch)) & 0xff), d = (float)((c11 >> (8 * ch)) & 0xff);
+			const float r = lerp1(lerp1(a, b, fx), lerp1(c, d, fx), fy);
+			int q = cvtt(fadd(r, 0.5f));
+			q = q < 0 ? 0 : (q > 255 ? 255 : q);
+			out |= (uint32_t)q << (8 * ch);
+		}
+		return out;
 	}
 };
 
@@ -786,6 +811,32 @@ struct FragmentProcessorFLATID
 	}
 };
 
+// ---- TEXPROBE: parity-test functor, not in the reference: the 2-D sampler's output, unlit, straight to the target ----
+struct VertexProcesserTEXPROBE
+{
+	static constexpr uint32_t SLOTS = (1u << 0) | (1u << 4);
+	static constexpr uint64_t UNIFORMS = 0;
+	PS_D static void process(const VertexProcessorInput& in, VertexProcessorOutput<1>& out, const DrawParams&)
+	{
+		out.position = ldF4(in.data[0]);
+		float tu, tv;
+		ldF2(in.data[4], tu, tv);
+		out.user[0] = f4(tu, tv, 0.0f, 0.0f);
+	}
+};
+struct FragmentProcessorTEXPROBE
+{
+	static constexpr uint64_t UNIFORMS = 1u << 9;
+	static constexpr bool MAY_DISCARD = false;
+	static constexpr bool USES_WRITE4 = false;
+	static constexpr int NTEX = 1;
+	__host__ __device__ static constexpr int texSlot(int i) { return 9; }
+	PS_D static void process(const F4* in, FragmentProcessorOutput& out, const DrawParams& P)
+	{
+		out.write(PuresoftSampler2D::get4(P.tex[0], in[0].x, in[0].y));
+	}
+};
+
 // ---- programme = (V, I, F) ------------------------------------------------------------------------------------------
 
 template<class VP, class IP, class FP> struct Programme
@@ -802,6 +853,7 @@ typedef Programme<VertexProcesserDEF03, InterpolationProcessorVec4<5>, FragmentP
 typedef Programme<VertexProcesserDEF04, InterpolationProcessorVec4<1>, FragmentProcessorDEF04> ProgDEF04;
 typedef Programme<VertexProcesserDEF05, InterpolationProcessorVec4<0>, FragmentProcessorDEF05> ProgDEF05;
 typedef Programme<VertexProcesserFLATID, InterpolationProcessorVec4<1>, FragmentProcessorFLATID> ProgFLATID;
+typedef Programme<VertexProcesserTEXPROBE, InterpolationProcessorVec4<1>, FragmentProcessorTEXPROBE> ProgTEXPROBE;
 typedef Programme<VP_Planet, IP_Planet, FP_Earth> ProgEarth;
 typedef Programme<VP_Planet, IP_Planet, FP_Satellite> ProgSatellite;
 typedef Programme<VP_Cloud, InterpolationProcessorVec4<4>, FP_Cloud> ProgCloud;

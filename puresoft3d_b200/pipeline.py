@@ -155,6 +155,11 @@ class PuresoftPipeline:
     def destroyTexture(self, idx):
         self._check(self._lib.ps3d_texture_destroy(self._h, int(idx)))
 
+    def setTextureFilter(self, idx, bilinear):
+        """Extension (include/ps3d.h): PuresoftSampler2D reads texture `idx` with bilinear filtering instead of the
+        reference's nearest rule. The reference build refuses (PS3D_ERR_UNSUPPORTED)."""
+        self._check(self._lib.ps3d_texture_set_filter(self._h, int(idx), 1 if bilinear else 0))
+
     # ---- processor api (pipeline.h:36-40) ------------------------------------------------------------------
     def addProcessor(self, proc):
         idx = C.c_int(-1)

@@ -100,9 +100,9 @@ class Scene:
         self.commands = []    # tuples, see replay()
         self.meta = {}
 
-    def add_texture(self, width, height, elemLen=4, pixels=None, layers=None, wrap=K.WRAP_CLAMP):
+    def add_texture(self, width, height, elemLen=4, pixels=None, layers=None, wrap=K.WRAP_CLAMP, bilinear=False):
         lay = layers if layers is not None else [pixels]
-        self.textures.append(dict(width=width, height=height, elemLen=elemLen, layers=lay, wrap=wrap))
+        self.textures.append(dict(width=width, height=height, elemLen=elemLen, layers=lay, wrap=wrap, bilinear=bilinear))
         return len(self.textures) - 1
 
     def add_vao(self, slots):
@@ -119,7 +119,7 @@ class Scene:
     def vertex_bytes_read(self):
         """Σ over draws of the bytes the bound vertex functor reads."""
         slots_read = {K.FN_DEF01: (0, 3, 4), K.FN_DEF02: (0, 1, 2), K.FN_DEF03: (0, 1, 2, 3, 4), K.FN_DEF04: (0,),
-                      K.FN_DEF05: (0,), K.FN_FLATID: (0, 6), K.FN_PLANET: (0, 1, 2, 3, 4), K.FN_CLOUD: (0, 3, 4),
+                      K.FN_DEF05: (0,), K.FN_FLATID: (0, 6), K.FN_TEXPROBE: (0, 4), K.FN_PLANET: (0, 1, 2, 3, 4), K.FN_CLOUD: (0, 3, 4),
                       K.FN_CLOUDSHADOW: (0, 4), K.FN_POSITIONONLY: (0,), K.FN_SHADOW2: (0,), K.FN_SINGLECOLOUR: (0, 3),
                       K.FN_DIFFUSEONLY: (0, 3, 4)}
         total, prog = 0, None
@@ -148,6 +148,8 @@ def upload(pipe, scene):
                                  extraLayers=len(t["layers"]) - 1, mode=t["wrap"])
         for li in range(1, len(t["layers"])):
             pipe.uploadTexture(idx, t["layers"][li], layer=li)
+        if t.get("bilinear"):
+            pipe.setTextureFilter(idx, True)   # extension: the reference build refuses
         up.textures.append(idx)
     for slots in scene.vaos:
         vao = pipe.createVAO()
@@ -335,11 +337,12 @@ def _camera_uniforms(sc, width, height, eye, model, mrot, light):
 
 # ---- the BASELINE.json configs --------------------------------------------------------------------------------
 
-def scene_cube(width=640, height=480, seed=1, functor=K.FN_DEF01):
-    """C1: textured cube, 12 triangles, DEF01 (per-pixel Blinn-Phong), 256² BGRA texture, depth test on."""
+def scene_cube(width=640, height=480, seed=1, functor=K.FN_DEF01, bilinear=False, wrap=K.WRAP_CLAMP, tex_size=256):
+    """C1: textured cube, 12 triangles, DEF01 (per-pixel Blinn-Phong), 256² BGRA texture, depth test on.
+    bilinear=True is BASELINE.json's literal C1 (bilinear filtering) — an extension the reference cannot render."""
     rng = np.random.default_rng(seed)
-    sc = Scene("C1-cube", width, height)
-    tex = sc.add_texture(256, 256, 4, tex_random_bgra(rng, 256, 256))
+    sc = Scene("C1-cube" + ("-bilinear" if bilinear else ""), width, height)
+    tex = sc.add_texture(tex_size, tex_size, 4, tex_random_bgra(rng, tex_size, tex_size), wrap=wrap, bilinear=bilinear)
     vao = sc.add_vao(_std_slots(cube_mesh()))
     prog = sc.add_programme(functor)
     rot = (mat_rotation((0, 1, 0), math.radians(30.0)).astype(np.float64) @ mat_rotation((1, 0, 0), math.radians(20.0)).astype(np.float64)).astype(F32)
@@ -350,8 +353,29 @@ def scene_cube(width=640, height=480, seed=1, functor=K.FN_DEF01):
     _camera_uniforms(sc, width, height, (0.0, 0.0, 3.0), rot, rot, (-3.0, 2.0, 3.0))
     sc.cmd("tex_uniform", 9, tex)
     if functor == K.FN_DEF03:
-        bump = sc.add_texture(256, 256, 4, tex_smooth_bgra(rng, 256, 256, normal_map=True))
+        bump = sc.add_texture(256, 256, 4, tex_smooth_bgra(rng, 256, 256, normal_map=True), bilinear=bilinear)
         sc.cmd("tex_uniform", 10, bump)
+    sc.cmd("use", prog)
+    sc.cmd("draw", vao)
+    return sc
+
+
+def scene_texprobe(width=64, height=48, tex=None, bilinear=True, wrap=K.WRAP_CLAMP, uv_scale=1.0, uv_offset=0.0):
+    """Sampler probe (parity-test functor TEXPROBE, not in the reference): one screen-filling quad given directly in clip
+    space, uv = (x / width, y / height) * uv_scale + uv_offset at pixel (x, y), the 2-D sampler's output written unlit."""
+    sc = Scene("texprobe", width, height)
+    t = sc.add_texture(tex.shape[1], tex.shape[0], 4, tex, wrap=wrap, bilinear=bilinear)
+    lo, hi = uv_offset, uv_offset + uv_scale
+    pos = np.array([[-1, -1, 0, 1], [1, -1, 0, 1], [1, 1, 0, 1], [-1, -1, 0, 1], [1, 1, 0, 1], [-1, 1, 0, 1]], dtype=F32)
+    uv = np.array([[lo, lo], [hi, lo], [hi, hi], [lo, lo], [hi, hi], [lo, hi]], dtype=F32)
+    vao = sc.add_vao({0: (16, pos), 4: (8, uv)})
+    prog = sc.add_programme(K.FN_TEXPROBE)
+    sc.cmd("viewport", width, height)
+    sc.cmd("depth", -1)
+    sc.cmd("clearDepth", 1.0)
+    sc.cmd("clearColour", 0)
+    sc.cmd("disable", K.BEHAVIOR_FACE_CULLING)
+    sc.cmd("tex_uniform", 9, t)
     sc.cmd("use", prog)
     sc.cmd("draw", vao)
     return sc

@@ -18,3 +18,11 @@ SMALL = {
     "demo1_planets": lambda: scenes.scene_planets(400, 250, shadow=240, stacks=12, slices=24, tex_size=128),
     "c3_demo2_desk": lambda: scenes.scene_desk(384, 240, shadow=256, clutter=10, tex_size=128),
 }
+
+# Extensions with no reference counterpart: checked CUDA-vs-oracle only, "parity unpinned".
+EXTENSION = {
+    "c1_cube_bilinear": lambda: scenes.scene_cube(320, 240, bilinear=True),
+    "c1_cube_bilinear_def03": lambda: scenes.scene_cube(320, 240, functor=K.FN_DEF03, bilinear=True),
+    # a 16x16 texture magnified ~10x so that every pixel is a real blend, WRAP addressing (modulo size-1, fbo.cpp:582-590)
+    "c1_cube_bilinear_wrap_magnified": lambda: scenes.scene_cube(320, 240, bilinear=True, wrap=K.WRAP_WRAP, tex_size=16),
+}
