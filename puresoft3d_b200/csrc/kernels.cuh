@@ -84,9 +84,12 @@ PS_D void mbarWait(uint64_t* bar, uint32_t parity)
 
 #define PS_GEOM_THREADS 128
 
-// STAGED: the block's vertex range of every slot the functor reads (PS_GEOM_THREADS x 3 consecutive elements, contiguous in
-// the un-indexed stream) is brought into shared memory by one bulk copy per slot; the functor then reads shared memory.
-// All of a block's HBM reads are in flight at once and no load latency is left on the arithmetic path.
+// STAGED: the block's vertex range (PS_GEOM_THREADS x 3 consecutive elements, contiguous in the un-indexed stream) of the
+// POSITION slot — slot 0 in every vertex functor of the reference — is brought into shared memory by one bulk copy; the
+// position pass, which every triangle runs, then reads shared memory with no load latency on its arithmetic path. The
+// other slots are read straight from global memory by the varyings pass, i.e. only for triangles that survive culling
+// and (sort-first) lie in this rank's band: at N ranks most triangles never touch them.
+#define PS_GEOM_STAGE_SLOTS 1u
 template<class PROG, bool STAGED>
 __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_setup_kernel(const __grid_constant__ DrawParams P)
 {
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_setup_kernel(const __gri
 		for(int s = 0; s < 16; s++)
 		{
 			stageOff[s] = off;
-			if((PROG::V::SLOTS >> s) & 1) off += (PS_GEOM_THREADS * 3 * P.stride[s] + 127u) & ~127u;
+			if(((PROG::V::SLOTS & PS_GEOM_STAGE_SLOTS) >> s) & 1) off += (PS_GEOM_THREADS * 3 * P.stride[s] + 127u) & ~127u;
 		}
 		if(0 == threadIdx.x) mbarInit(&stageBar, 1);
 		__syncthreads();
@@ -113,11 +116,11 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_setup_kernel(const __gri
 			uint32_t total = 0;
 #pragma unroll
 			for(int s = 0; s < 16; s++)
-				if((PROG::V::SLOTS >> s) & 1) total += (nt * 3 * P.stride[s] + 15u) & ~15u;
+				if(((PROG::V::SLOTS & PS_GEOM_STAGE_SLOTS) >> s) & 1) total += (nt * 3 * P.stride[s] + 15u) & ~15u;
 			mbarExpectTx(&stageBar, total);
 #pragma unroll
 			for(int s = 0; s < 16; s++)
-				if((PROG::V::SLOTS >> s) & 1)
+				if(((PROG::V::SLOTS & PS_GEOM_STAGE_SLOTS) >> s) & 1)
 					bulkCopyG2S(stage + stageOff[s], P.slot[s] + (size_t)tri0 * 3 * P.stride[s], (nt * 3 * P.stride[s] + 15u) & ~15u, &stageBar);
 		}
 		mbarWait(&stageBar, 0);
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_setup_kernel(const __gri
 			VertexProcessorInput in;
 #pragma unroll
 			for(int s = 0; s < 16; s++)
-				in.data[s] = (PROG::V::SLOTS >> s) & 1 ? (STAGED ? stage + stageOff[s] + (size_t)(threadIdx.x * 3 + i) * P.stride[s]
+				in.data[s] = (PROG::V::SLOTS >> s) & 1 ? ((STAGED && ((PS_GEOM_STAGE_SLOTS >> s) & 1)) ? stage + stageOff[s] + (size_t)(threadIdx.x * 3 + i) * P.stride[s]
 				                                                  : P.slot[s] + (size_t)(tri * 3 + i) * P.stride[s]) : nullptr;
 			VertexProcessorOutput<NV> vo;
 			PROG::V::process(in, vo, P);
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_setup_kernel(const __gri
 							VertexProcessorInput in;
 #pragma unroll
 							for(int s = 0; s < 16; s++)
-								in.data[s] = (PROG::V::SLOTS >> s) & 1 ? (STAGED ? stage + stageOff[s] + (size_t)(threadIdx.x * 3 + i) * P.stride[s]
+								in.data[s] = (PROG::V::SLOTS >> s) & 1 ? ((STAGED && ((PS_GEOM_STAGE_SLOTS >> s) & 1)) ? stage + stageOff[s] + (size_t)(threadIdx.x * 3 + i) * P.stride[s]
 								                                                  : P.slot[s] + (size_t)(tri * 3 + i) * P.stride[s]) : nullptr;
 							VertexProcessorOutput<NV> vo;
 							PROG::V::process(in, vo, P);

@@ -68,12 +68,12 @@ bool geomStagingOn() { static int on = -1; if(on < 0) { const char* e = getenv("
 template<class PROG> void launchGeom(const DrawParams& P, cudaStream_t s)
 {
 	const unsigned blocks = (P.ntris + PS_GEOM_THREADS - 1) / PS_GEOM_THREADS;
-	// bytes of the block's vertex range, every slot the functor reads (bulk copies need 16-byte aligned sources: the
+	// bytes of the block's vertex range of the staged (position) slot (bulk copies need 16-byte aligned sources: the
 	// block's first element sits at a multiple of 384 * stride bytes from the 256-byte aligned VBO base)
 	size_t bytes = 0;
 	bool aligned = true;
 	for(int i = 0; i < 16; i++)
-		if((PROG::V::SLOTS >> i) & 1)
+		if(((PROG::V::SLOTS & PS_GEOM_STAGE_SLOTS) >> i) & 1)
 		{
 			bytes += ((size_t)PS_GEOM_THREADS * 3 * P.stride[i] + 127) & ~(size_t)127;
 			aligned = aligned && 0 == ((uintptr_t)P.slot[i] & 15);

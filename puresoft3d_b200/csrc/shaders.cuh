@@ -85,7 +85,7 @@ struct PuresoftSampler2D
 	// EXTENSION (include/ps3d.h, ps3d_texture_set_filter): texel i at u = i / width, four taps through clampCoord,
 	// per channel lerp(lerp(c00, c10, fx), lerp(c01, c11, fx), fy), lerp(a, b, t) = a + (b - a) * t, (int)(x + 0.5f)
 	PS_D static float lerp1(float a, float b, float t) { return fadd(a, fmul(fsub(b, a), t)); }
-	PS_D static uint32_t bilinear4(const TexDesc& t, float u, float v)
+	static __device__ __noinline__ uint32_t bilinear4(const TexDesc& t, float u, float v)
 	{
 		const float x = fmul((float)t.width, u), y = fmul((float)t.height, v);
 		const float x0 = floorf(x), y0 = floorf(y);
