@@ -263,31 +263,52 @@ def main():
     frags_per_frame = frags_total / args.steps
 
     # ---- end to end: host buffers in, colour image out, every step ----------------------------------------------
-    host_streams = []
-    for (vbo, arr) in up.vbos:
-        tsr = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
-        host_streams.append((vbo, tsr))
-    host_colour = torch.empty((sc.height, sc.width), dtype=torch.int32).pin_memory()
-    h2d = sum(tsr.numel() * tsr.element_size() for _, tsr in host_streams)
-    d2h = host_colour.numel() * 4
+    # Through the public API with the transfers PIPELINED (include/ps3d.h "Pipelined transfers"): two sets of VBOs, so
+    # that step i+1's vertex streams cross PCIe (copy stream) while step i renders (pipe stream) and step i's image goes
+    # back (read-back stream, double-buffered display targets via swapBuffers). At N > 1 every rank uploads only its 1/N
+    # of each stream from its own pinned buffer and the shards are all-gathered in place over NVLink
+    # (sortfirst.ShardedUpload): the step's inputs cross PCIe once in total, not once per rank.
+    ups = [up, scenes.upload(pipe, sc)]
+    uploaders, host_colour = [], []
+    host_streams = {}
+    for u in ups:
+        items = []
+        for (vbo, arr) in u.vbos:
+            key = arr.ctypes.data
+            if key not in host_streams:
+                host_streams[key] = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).pin_memory()
+            items.append((vbo, host_streams[key]))
+        uploaders.append(sortfirst.ShardedUpload(pipe, items, rank, world, dev))
+        host_colour.append(torch.empty((sc.height, sc.width), dtype=torch.int32).pin_memory())
+    h2d_t = torch.tensor([float(uploaders[0].h2d_bytes)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(h2d_t, op=dist.ReduceOp.SUM)
+    h2d = int(h2d_t.item())          # all ranks together
+    d2h = host_colour[0].numel() * 4
 
-    def frame_e2e():
-        for vbo, tsr in host_streams:
-            pipe._check(pipe._lib.ps3d_vbo_update(pipe._h, vbo.handle, tsr.data_ptr()))
-        frame()
+    def frame_e2e(i):
+        s = i & 1
+        uploaders[s].step()
+        scenes.replay(pipe, sc, ups[s], finish=False)
+        if comp:
+            comp.gather_to_rank0()
         if rank == 0:
-            pipe._check(pipe._lib.ps3d_read_colour(pipe._h, host_colour.data_ptr(), sc.width * 4))
+            pipe.readColourAsync(host_colour[s].data_ptr(), sc.width * 4)
+        pipe.swapBuffers()
 
-    e2e_steps = max(3, min(args.steps, 20))
-    for _ in range(2):
-        frame_e2e()
+    e2e_steps = max(4, min(args.steps, 40))
+    for i in range(4):
+        frame_e2e(i)
+    pipe.finish()
     pipe.resetStats()
     barrier()
     ev0.record(ext)
-    for _ in range(e2e_steps):
-        frame_e2e()
+    for i in range(e2e_steps):
+        frame_e2e(i)
+    pipe.deviceJoin()                # the last read-back belongs to the timed region
     ev1.record(ext)
     ev1.synchronize()
+    pipe.finish()
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
@@ -296,6 +317,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(frag_t, op=dist.ReduceOp.SUM)
     e2e_value = float(frag_t.item()) / (float(t.item()) / 1000.0)
+    # the images the pipelined steps read back must be the frame the kernel-only leg renders (rank 0 holds the composite)
+    frame()
+    e2e_check = None
+    if rank == 0:
+        want = pipe.readColour().view(np.uint32)
+        e2e_check = bool(np.array_equal(want, host_colour[0].numpy().view(np.uint32)) and np.array_equal(want, host_colour[1].numpy().view(np.uint32)))
     clocks = sampler.stop()   # sampled across both timed regions
 
     # ---- roofline ------------------------------------------------------------------------------------------------
@@ -343,7 +370,9 @@ def main():
                        "approx": "x86 rcpps/rsqrtss tables bits=%s" % (pipe.hostApproxInfo(),)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": float(t.item()) / e2e_steps, "steps": e2e_steps},
+                    "ms_per_step": float(t.item()) / e2e_steps, "steps": e2e_steps,
+                    "transfers": "pipelined: double-buffered VBO sets + display targets, uploads on a copy stream" + (", 1/%d of every stream per rank + in-place NCCL all-gather" % world if world > 1 else ""),
+                    "image_matches_kernel_only_leg": e2e_check},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "ms_per_launch": dom_ms_per_launch, "algorithmic_bytes": dom_bytes,

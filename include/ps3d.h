@@ -198,6 +198,25 @@ int ps3d_device_depth_ptr(ps3d_pipe* p, void** devPtr, size_t* pitchBytes);
 int ps3d_device_stream(ps3d_pipe* p, void** cudaStream);
 /* Same as ps3d_vbo_update / ps3d_texture_upload but the source is a device pointer (HBM-resident inputs). */
 int ps3d_vbo_update_device(ps3d_pipe* p, int vbo, const void* devSrc);
+/* Pipelined transfers (CUDA library only; the reference's updateContent / getBuffer are synchronous, vbo.cpp:28-31 —
+ * these are the asynchronous forms the double-buffered presenter of SURVEY.md §8(f) and the sharded upload use).
+ *  ps3d_vbo_update_async   units [firstUnit, firstUnit + unitCount) from PINNED host memory on the pipe's copy stream;
+ *                          returns at once. The copy waits for the last draw that read the VBO, later draws that read
+ *                          it wait for the copy. The source must stay valid until ps3d_finish (or any synchronous call).
+ *  ps3d_vbo_device_ptr     the VBO's storage in HBM (e.g. as the buffer of an all-gather between ranks).
+ *  ps3d_vbo_device_written somebody else wrote that storage on `cudaStream` (a collective, a peer copy): later draws
+ *                          wait for what is enqueued on that stream now.
+ *  ps3d_device_copy_stream the copy stream (a cudaStream_t), so that such writers can be ordered behind the uploads.
+ *  ps3d_read_colour_async  the colour target into PINNED host memory on a read-back stream, behind everything enqueued
+ *                          on the pipe's stream so far; returns at once; complete after ps3d_finish. Later writes to the
+ *                          same target wait for the read-back (use ps3d_swap_buffers to overlap them). */
+int ps3d_vbo_update_async(ps3d_pipe* p, int vbo, size_t firstUnit, size_t unitCount, const void* pinnedSrc);
+int ps3d_vbo_device_ptr(ps3d_pipe* p, int vbo, void** devPtr, size_t* bytes);
+int ps3d_vbo_device_written(ps3d_pipe* p, int vbo, void* cudaStream);
+int ps3d_device_copy_stream(ps3d_pipe* p, void** cudaStream);
+int ps3d_read_colour_async(ps3d_pipe* p, void* pinnedBgra, size_t pitchBytes);
+/* the pipe's stream waits for everything enqueued so far on the copy and read-back streams */
+int ps3d_device_join(ps3d_pipe* p);
 /* number of kernels this pipe has launched since creation (bench.py's gpu_launches) */
 int ps3d_device_launch_count(ps3d_pipe* p, uint64_t* launches);
 

@@ -1450,6 +1450,12 @@ int ps3d_device_colour_ptr(ps3d_pipe* p, void** d, size_t* pitch) { (void)p; (vo
 int ps3d_device_depth_ptr(ps3d_pipe* p, void** d, size_t* pitch) { (void)p; (void)d; (void)pitch; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_device_stream(ps3d_pipe* p, void** s) { (void)p; (void)s; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_vbo_update_device(ps3d_pipe* p, int vbo, const void* src) { (void)p; (void)vbo; (void)src; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_vbo_update_async(ps3d_pipe* p, int vbo, size_t first, size_t count, const void* src) { (void)p; (void)vbo; (void)first; (void)count; (void)src; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_vbo_device_ptr(ps3d_pipe* p, int vbo, void** d, size_t* b) { (void)p; (void)vbo; (void)d; (void)b; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_vbo_device_written(ps3d_pipe* p, int vbo, void* s) { (void)p; (void)vbo; (void)s; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_device_copy_stream(ps3d_pipe* p, void** s) { (void)p; (void)s; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_read_colour_async(ps3d_pipe* p, void* dst, size_t pitch) { (void)p; (void)dst; (void)pitch; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_device_join(ps3d_pipe* p) { (void)p; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_device_launch_count(ps3d_pipe* p, uint64_t* n) { (void)p; if(n) *n = 0; return PS3D_OK; }
 int ps3d_profile_enable(ps3d_pipe* p, int on) { (void)p; (void)on; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_profile_read(ps3d_pipe* p, ps3d_profile* out) { (void)p; (void)out; return PS3D_ERR_UNSUPPORTED; }

@@ -582,6 +582,12 @@ int ps3d_device_colour_ptr(ps3d_pipe*, void**, size_t*) { return PS3D_ERR_UNSUPP
 int ps3d_device_depth_ptr(ps3d_pipe*, void**, size_t*) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_device_stream(ps3d_pipe*, void**) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_vbo_update_device(ps3d_pipe*, int, const void*) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_vbo_update_async(ps3d_pipe*, int, size_t, size_t, const void*) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_vbo_device_ptr(ps3d_pipe*, int, void**, size_t*) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_vbo_device_written(ps3d_pipe*, int, void*) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_device_copy_stream(ps3d_pipe*, void**) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_read_colour_async(ps3d_pipe*, void*, size_t) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_device_join(ps3d_pipe*) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_device_launch_count(ps3d_pipe*, uint64_t* n) { if(n) *n = 0; return PS3D_OK; }
 int ps3d_profile_enable(ps3d_pipe*, int) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_profile_read(ps3d_pipe*, ps3d_profile*) { return PS3D_ERR_UNSUPPORTED; }

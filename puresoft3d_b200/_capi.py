@@ -107,6 +107,12 @@ PROTOTYPES = {
     "ps3d_device_depth_ptr": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "ps3d_device_stream": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
     "ps3d_vbo_update_device": (C.c_int, [_P, C.c_int, C.c_void_p]),
+    "ps3d_vbo_update_async": (C.c_int, [_P, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p]),
+    "ps3d_vbo_device_ptr": (C.c_int, [_P, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "ps3d_vbo_device_written": (C.c_int, [_P, C.c_int, C.c_void_p]),
+    "ps3d_device_copy_stream": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
+    "ps3d_read_colour_async": (C.c_int, [_P, C.c_void_p, C.c_size_t]),
+    "ps3d_device_join": (C.c_int, [_P]),
     "ps3d_device_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "ps3d_profile_enable": (C.c_int, [_P, C.c_int]),
     "ps3d_profile_read": (C.c_int, [_P, C.POINTER(Profile)]),

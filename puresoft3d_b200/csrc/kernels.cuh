@@ -421,12 +421,14 @@ __global__ void __launch_bounds__(128) emit_pairs_kernel(const uint32_t* __restr
 __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileStart,
                                                         uint32_t* __restrict__ tileFill, uint32_t ntiles, DeviceStats* stats,
                                                         uint32_t pairCap, unsigned long long survivorCap, uint32_t listLimit,
-                                                        uint32_t* poison, DrawReport* report)
+                                                        uint32_t* poison, DrawReport* report, uint32_t* __restrict__ tileOrder)
 {
 	__shared__ uint32_t warpTotals[32];
 	__shared__ uint32_t carryS, longestS;
 	__shared__ unsigned long long boundS;
+	__shared__ uint32_t hist[256];                     // tiles per length class, longest lists first
 	if(0 == threadIdx.x) { carryS = 0; longestS = 0; }
+	if(threadIdx.x < 256) hist[threadIdx.x] = 0;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	if(0 == warp)
 	{
@@ -443,6 +445,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ 
 		const uint32_t i = base + threadIdx.x;
 		const uint32_t v = i < ntiles ? tileCount[i] : 0;
 		longest = max(longest, v);
+		if(i < ntiles) atomicAdd(&hist[255u - min(v >> 2, 255u)], 1u);
 		uint32_t incl = v;
 #pragma unroll
 		for(int d = 1; d < 32; d <<= 1)
@@ -463,6 +466,31 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ 
 	longest = __reduce_max_sync(PS_FULL, longest);
 	if(0 == lane && longest) atomicMax(&longestS, longest);
 	__syncthreads();
+	// tileOrder: the tiles by descending list length (counting sort over 256 length classes; any order inside a class).
+	// The tile kernels take their tiles in this order, so the longest lists start first and the grid's tail is made of
+	// short ones; the four warps of a block get lists of similar length.
+	if(0 == warp)
+	{
+		uint32_t h[8], sum = 0;
+#pragma unroll
+		for(int k = 0; k < 8; k++) { h[k] = hist[lane * 8 + k]; sum += h[k]; }
+		uint32_t incl = sum;
+#pragma unroll
+		for(int d = 1; d < 32; d <<= 1)
+		{
+			const uint32_t t = __shfl_up_sync(PS_FULL, incl, d);
+			if(lane >= d) incl += t;
+		}
+		uint32_t run = incl - sum;
+#pragma unroll
+		for(int k = 0; k < 8; k++) { hist[lane * 8 + k] = run; run += h[k]; }
+	}
+	__syncthreads();
+	for(uint32_t i = threadIdx.x; i < ntiles; i += 1024)
+	{
+		const uint32_t v = tileStart[i + 1] - tileStart[i];
+		tileOrder[atomicAdd(&hist[255u - min(v >> 2, 255u)], 1u)] = i;
+	}
 	if(0 == threadIdx.x)
 	{
 		const uint32_t total = carryS, lng = longestS;
@@ -662,8 +690,9 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_imm
 	__shared__ TileSmem smem[PS_WARPS_PER_BLOCK];
 	if(*P.poison) return;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	const int tile = blockIdx.x * PS_WARPS_PER_BLOCK + w;
-	if(tile >= P.tilesX * P.tilesY) return;
+	const int tileSlot = blockIdx.x * PS_WARPS_PER_BLOCK + w;
+	if(tileSlot >= P.tilesX * P.tilesY) return;
+	const int tile = (int)P.tileOrder[tileSlot];         // longest lists first (tile_scan_kernel)
 	const uint32_t listBegin = tileStart[tile], listEnd = tileStart[tile + 1];
 	if(listBegin == listEnd) return;
 	TileSmem& S = smem[w];
@@ -998,8 +1027,9 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_ord
 	__shared__ TileSmem2 smem[PS_WARPS_PER_BLOCK];
 	if(*P.poison) return;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	const int tile = blockIdx.x * PS_WARPS_PER_BLOCK + w;
-	if(tile >= P.tilesX * P.tilesY) return;
+	const int tileSlot = blockIdx.x * PS_WARPS_PER_BLOCK + w;
+	if(tileSlot >= P.tilesX * P.tilesY) return;
+	const int tile = (int)P.tileOrder[tileSlot];         // longest lists first (tile_scan_kernel)
 	const uint32_t listBegin = tileStart[tile], listEnd = tileStart[tile + 1];
 	if(listBegin == listEnd) return;
 	TileSmem2& S = smem[w];
@@ -1464,8 +1494,9 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_depth_ker
 	__shared__ RasterSmem smem[PS_WARPS_PER_BLOCK];
 	if(*P.poison) return;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	const int tile = blockIdx.x * PS_WARPS_PER_BLOCK + w;
-	if(tile >= P.tilesX * P.tilesY) return;
+	const int tileSlot = blockIdx.x * PS_WARPS_PER_BLOCK + w;
+	if(tileSlot >= P.tilesX * P.tilesY) return;
+	const int tile = (int)P.tileOrder[tileSlot];         // longest lists first (tile_scan_kernel)
 	const uint32_t listBegin = tileStart[tile], listEnd = tileStart[tile + 1];
 	if(listBegin == listEnd) return;
 	RasterSmem& S = smem[w];

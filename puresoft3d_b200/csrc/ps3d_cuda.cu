@@ -24,7 +24,10 @@ struct Texture
 	int width, height, scanline, elemLen, wrap, nLayers, filter;
 	uint8_t* layer[6];
 };
-struct Vbo { size_t unitBytes, unitCount; uint8_t* data; bool alive; };
+// ready    : recorded on the copy stream behind the last asynchronous write (ps3d_vbo_update_async / ps3d_vbo_device_written);
+//            every draw that reads the VBO makes the pipe's stream wait for it
+// lastRead : recorded on the pipe's stream behind the last geometry kernel that read the VBO; an asynchronous write waits for it
+struct Vbo { size_t unitBytes, unitCount; uint8_t* data; bool alive; cudaEvent_t ready, lastRead; bool readyValid, readValid; };
 struct Vao { bool alive; int vbo[PS3D_MAX_VBOS]; };
 struct Proc { bool alive; int kind, functor; };
 struct Prog { int vp, ip, fp; };
@@ -187,6 +190,10 @@ struct ps3d_pipe
 {
 	int device;
 	cudaStream_t stream;
+	cudaStream_t copyStream;    // asynchronous uploads (ps3d_vbo_update_async)
+	cudaStream_t readStream;    // asynchronous read-backs (ps3d_read_colour_async): its own stream, so that a read-back waiting for its frame does not hold up the next frame's uploads
+	cudaEvent_t frameDone, readDone[2];
+	bool readValid[2];
 	int width, height;
 	int vpW, vpH;
 	int behavior;
@@ -207,7 +214,7 @@ struct ps3d_pipe
 	// per-draw scratch
 	DevBuf<TriHeader> hdr;
 	DevBuf<F4> vary;
-	DevBuf<uint32_t> triCount, triOffset, triRect, scanSums, keysA, valsA, keysB, valsB, tileCount, tileStart, tileFill, sortCounts;
+	DevBuf<uint32_t> triCount, triOffset, triRect, scanSums, keysA, valsA, keysB, valsB, tileCount, tileStart, tileFill, tileOrder, sortCounts;
 	DevBuf<uint32_t> svTri, svMisc, svWinner;   // survivor stream of the draw in flight (split path)
 	DevBuf<int> svLeft, svRight;
 	DevBuf<float> svInv;
@@ -272,6 +279,19 @@ static int settle(ps3d_pipe* p);
 #define SETTLE(p) do { int rc_ = settle(p); if(rc_) return rc_; } while(0)
 
 static int fail(ps3d_pipe* p, int code, const char* msg) { p->err = msg; return code; }
+static void freeVbo(Vbo& v)
+{
+	if(v.data) cudaFree(v.data);
+	if(v.ready) cudaEventDestroy(v.ready);
+	if(v.lastRead) cudaEventDestroy(v.lastRead);
+	v.data = nullptr; v.ready = v.lastRead = nullptr; v.readyValid = v.readValid = false; v.alive = false;
+}
+static int vboEvents(ps3d_pipe* p, Vbo& v)
+{
+	if(!v.ready) CK(p, cudaEventCreateWithFlags(&v.ready, cudaEventDisableTiming));
+	if(!v.lastRead) CK(p, cudaEventCreateWithFlags(&v.lastRead, cudaEventDisableTiming));
+	return PS3D_OK;
+}
 
 // PS3D_TRACE=1 prints every C-ABI entry to stderr (debug aid)
 static bool traceOn() { static int on = -1; if(on < 0) { const char* e = getenv("PS3D_TRACE"); on = (e && e[0] == '1') ? 1 : 0; } return on == 1; }
@@ -445,6 +465,12 @@ int ps3d_create(int width, int height, int device, ps3d_pipe** out)
 	p->depthScanline = ((int)(width / 4.0f + 0.5f) * 4) * (int)sizeof(float); // pipeline.cpp:31
 	if(p->depthScanline < width * 4) p->depthScanline = width * 4;           // the reference under-allocates when W%4==1
 	bool ok = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && cudaStreamCreateWithFlags(&p->copyStream, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && cudaStreamCreateWithFlags(&p->readStream, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&p->frameDone, cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&p->readDone[0], cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&p->readDone[1], cudaEventDisableTiming) == cudaSuccess;
+	p->readValid[0] = p->readValid[1] = false;
 	const size_t cbytes = (size_t)width * 4 * height, dbytes = (size_t)p->depthScanline * height;
 	ok = ok && cudaMalloc((void**)&p->display[0], cbytes) == cudaSuccess && cudaMalloc((void**)&p->display[1], cbytes) == cudaSuccess;
 	ok = ok && cudaMalloc((void**)&p->defaultDepth, dbytes + 16) == cudaSuccess;
@@ -499,7 +525,8 @@ int ps3d_destroy(ps3d_pipe* p)
 	settle(p);
 	cudaStreamSynchronize(p->stream);
 	for(Texture* t : p->textures) if(t) { for(int i = 0; i < 6; i++) if(t->layer[i]) cudaFree(t->layer[i]); delete t; }
-	for(Vbo& v : p->vbos) if(v.alive && v.data) cudaFree(v.data);
+	cudaStreamSynchronize(p->copyStream); cudaStreamSynchronize(p->readStream);
+	for(Vbo& v : p->vbos) if(v.alive) freeVbo(v);
 	cudaFree(p->display[0]); cudaFree(p->display[1]); cudaFree(p->defaultDepth);
 	cudaFree(p->totalDev); cudaFree(p->statsDev); cudaFree(p->svCountDev); cudaFree(p->poisonDev); cudaFreeHost(p->report); cudaEventDestroy(p->scanEvent);
 	p->svTri.release(); p->svMisc.release(); p->svWinner.release(); p->svLeft.release(); p->svRight.release(); p->svInv.release();
@@ -507,10 +534,11 @@ int ps3d_destroy(ps3d_pipe* p)
 	if(p->rcpDev) cudaFree(p->rcpDev);
 	if(p->rsqrtDev) cudaFree(p->rsqrtDev);
 	p->hdr.release(); p->vary.release(); p->triCount.release(); p->triOffset.release(); p->triRect.release(); p->scanSums.release();
-	p->keysA.release(); p->valsA.release(); p->keysB.release(); p->valsB.release(); p->tileCount.release(); p->tileStart.release(); p->tileFill.release(); p->sortCounts.release();
+	p->keysA.release(); p->valsA.release(); p->keysB.release(); p->valsB.release(); p->tileCount.release(); p->tileStart.release(); p->tileFill.release(); p->tileOrder.release(); p->sortCounts.release();
 	for(auto& s : p->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
 	for(auto& e : p->eventPool) cudaEventDestroy(e);
-	cudaStreamDestroy(p->stream);
+	cudaStreamDestroy(p->stream); cudaStreamDestroy(p->copyStream); cudaStreamDestroy(p->readStream);
+	cudaEventDestroy(p->frameDone); cudaEventDestroy(p->readDone[0]); cudaEventDestroy(p->readDone[1]);
 	delete p;
 	return PS3D_OK;
 }
@@ -615,8 +643,12 @@ int ps3d_vbo_create(ps3d_pipe* p, size_t unitBytes, size_t unitCount, int* vbo)
 	for(; slot < p->vbos.size(); slot++) if(!p->vbos[slot].alive) break;
 	Vbo v;
 	v.unitBytes = unitBytes; v.unitCount = unitCount; v.alive = true; v.data = nullptr;
+	v.ready = v.lastRead = nullptr; v.readyValid = v.readValid = false;
 	if(cudaMalloc((void**)&v.data, unitBytes * unitCount + 64) != cudaSuccess) return fail(p, PS3D_ERR_BAD_ALLOC, "vbo"); // vbo.cpp:14
 	cudaMemsetAsync(v.data, 0, unitBytes * unitCount + 64, p->stream);
+	// the fill runs on the pipe's stream: an asynchronous upload (copy stream) must not overtake it
+	{ const int rc = vboEvents(p, v); if(rc) { freeVbo(v); return rc; } }
+	cudaEventRecord(v.lastRead, p->stream); v.readValid = true;
 	if(slot == p->vbos.size()) p->vbos.push_back(v); else p->vbos[slot] = v;
 	*vbo = (int)slot;
 	return PS3D_OK;
@@ -640,6 +672,57 @@ int ps3d_vbo_update_device(ps3d_pipe* p, int vbo, const void* devSrc)
 	SETTLE(p);
 	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
 	CK(p, cudaMemcpyAsync(p->vbos[vbo].data, devSrc, p->vbos[vbo].unitBytes * p->vbos[vbo].unitCount, cudaMemcpyDeviceToDevice, p->stream));
+	if(p->vbos[vbo].lastRead) { CK(p, cudaEventRecord(p->vbos[vbo].lastRead, p->stream)); p->vbos[vbo].readValid = true; }
+	return PS3D_OK;
+}
+// Units [firstUnit, firstUnit + unitCount) from PINNED host memory, on the copy stream; returns at once. The copy waits for
+// the last draw that read the VBO; every later draw that reads it waits for the copy. `pinnedSrc` must stay valid until
+// the copy has run (ps3d_finish, or any synchronous call).
+int ps3d_vbo_update_async(ps3d_pipe* p, int vbo, size_t firstUnit, size_t unitCount, const void* pinnedSrc)
+{
+	TRACE();
+	cudaSetDevice(p->device);
+	// no settle(): nothing here touches the pipe's stream, and a draw waiting for its retry re-runs only its tail, which
+	// does not read vertex streams — so the host can queue the next frame's upload while the last frame is in flight
+	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
+	Vbo& v = p->vbos[vbo];
+	if(firstUnit > v.unitCount || unitCount > v.unitCount - firstUnit) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo range");
+	{ const int rc = vboEvents(p, v); if(rc) return rc; }
+	if(v.readValid) CK(p, cudaStreamWaitEvent(p->copyStream, v.lastRead, 0));
+	if(unitCount) CK(p, cudaMemcpyAsync(v.data + firstUnit * v.unitBytes, pinnedSrc, unitCount * v.unitBytes, cudaMemcpyHostToDevice, p->copyStream));
+	CK(p, cudaEventRecord(v.ready, p->copyStream));
+	v.readyValid = true;
+	return PS3D_OK;
+}
+// Somebody else (a collective, a peer copy) wrote the VBO's device memory on `cudaStream`: draws wait for what is enqueued there now.
+int ps3d_vbo_device_written(ps3d_pipe* p, int vbo, void* cudaStream)
+{
+	TRACE();
+	cudaSetDevice(p->device);
+	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
+	Vbo& v = p->vbos[vbo];
+	{ const int rc = vboEvents(p, v); if(rc) return rc; }
+	CK(p, cudaEventRecord(v.ready, (cudaStream_t)cudaStream));
+	v.readyValid = true;
+	return PS3D_OK;
+}
+int ps3d_vbo_device_ptr(ps3d_pipe* p, int vbo, void** devPtr, size_t* bytes)
+{
+	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
+	*devPtr = p->vbos[vbo].data; *bytes = p->vbos[vbo].unitBytes * p->vbos[vbo].unitCount;
+	return PS3D_OK;
+}
+int ps3d_device_copy_stream(ps3d_pipe* p, void** s) { *s = (void*)p->copyStream; return PS3D_OK; }
+// the pipe's stream waits for everything enqueued so far on the copy and read-back streams (e.g. before an event that closes a timed region)
+int ps3d_device_join(ps3d_pipe* p)
+{
+	TRACE();
+	cudaSetDevice(p->device);
+	SETTLE(p);
+	cudaEvent_t e = takeEvent(p);
+	CK(p, cudaEventRecord(e, p->copyStream)); CK(p, cudaStreamWaitEvent(p->stream, e, 0));
+	CK(p, cudaEventRecord(e, p->readStream)); CK(p, cudaStreamWaitEvent(p->stream, e, 0));
+	p->eventPool.push_back(e);
 	return PS3D_OK;
 }
 int ps3d_vbo_destroy(ps3d_pipe* p, int vbo)
@@ -649,8 +732,8 @@ int ps3d_vbo_destroy(ps3d_pipe* p, int vbo)
 	SETTLE(p);
 	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
 	cudaStreamSynchronize(p->stream);
-	cudaFree(p->vbos[vbo].data);
-	p->vbos[vbo].data = nullptr; p->vbos[vbo].alive = false;
+	cudaStreamSynchronize(p->copyStream);
+	freeVbo(p->vbos[vbo]);
 	for(Vao& a : p->vaos) if(a.alive) for(int s = 0; s < PS3D_MAX_VBOS; s++) if(a.vbo[s] == vbo) a.vbo[s] = -1;
 	return PS3D_OK;
 }
@@ -708,7 +791,7 @@ int ps3d_vao_destroy(ps3d_pipe* p, int vao)
 	for(int s = 0; s < PS3D_MAX_VBOS; s++) // pipeline.cpp:194-201: the pipeline owns attached VBOs
 	{
 		const int v = p->vaos[vao].vbo[s];
-		if(v >= 0 && p->vbos[v].alive) { cudaFree(p->vbos[v].data); p->vbos[v].data = nullptr; p->vbos[v].alive = false; }
+		if(v >= 0 && p->vbos[v].alive) freeVbo(p->vbos[v]);
 	}
 	p->vaos[vao].alive = false;
 	return PS3D_OK;
@@ -829,6 +912,7 @@ int ps3d_clear_colour(ps3d_pipe* p, uint32_t bgra) // pipeline.cpp:340-343 -> cl
 	cudaSetDevice(p->device);
 	SETTLE(p);
 	if(p->height < 2) return PS3D_OK;
+	if(p->readValid[p->back]) { CK(p, cudaStreamWaitEvent(p->stream, p->readDone[p->back], 0)); p->readValid[p->back] = false; }
 	clear_colour_kernel<<<148 * 8, 256, 0, p->stream>>>(p->display[p->back], p->width, p->height - 1, p->width * 4, bgra);
 	p->launches++;
 	CK(p, cudaGetLastError());
@@ -867,6 +951,11 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	if(!any) return PS3D_OK;
 	for(int s = 0; s < PS3D_MAX_VBOS; s++)
 		if(((pe->slots >> s) & 1) && !P.slot[s]) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "vertex functor reads a VBO slot that is not attached");
+	// asynchronous uploads (ps3d_vbo_update_async / ps3d_vbo_device_written) of the streams this draw reads must have landed
+	for(int s = 0; s < PS3D_MAX_VBOS; s++)
+		if(va.vbo[s] >= 0 && p->vbos[va.vbo[s]].readyValid) CK(p, cudaStreamWaitEvent(p->stream, p->vbos[va.vbo[s]].ready, 0));
+	// ... and an asynchronous read-back of the target this draw writes must have left it
+	if(p->readValid[p->back]) { CK(p, cudaStreamWaitEvent(p->stream, p->readDone[p->back], 0)); p->readValid[p->back] = false; }
 	const size_t ntris = nverts / 3;
 	if(ntris > 0x7fffffffu / 3) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "too many triangles in one draw");
 	// uniforms are latched now (the reference latches pointers in preprocess(), drawvao.cpp:18-20)
@@ -912,10 +1001,10 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	{
 		// tile_scan_kernel leaves the per-tile counts zeroed behind every draw; a fresh allocation starts zeroed
 		const uint32_t* before = p->tileCount.p;
-		CK(p, p->tileCount.ensure(ntiles + 1)); CK(p, p->tileStart.ensure(ntiles + 1)); CK(p, p->tileFill.ensure(ntiles + 1));
+		CK(p, p->tileCount.ensure(ntiles + 1)); CK(p, p->tileStart.ensure(ntiles + 1)); CK(p, p->tileFill.ensure(ntiles + 1)); CK(p, p->tileOrder.ensure(ntiles + 1));
 		if(p->tileCount.p != before) CK(p, cudaMemsetAsync(p->tileCount.p, 0, p->tileCount.cap * 4, p->stream));
 	}
-	P.hdr = p->hdr.p; P.vary = p->vary.p; P.triCount = p->triCount.p; P.triRect = p->triRect.p; P.tileCount = p->tileCount.p;
+	P.hdr = p->hdr.p; P.vary = p->vary.p; P.triCount = p->triCount.p; P.triRect = p->triRect.p; P.tileCount = p->tileCount.p; P.tileOrder = p->tileOrder.p;
 	P.poison = p->poisonDev;
 
 	// which tile path (kernels.cuh): a functor that may discard() makes the depth write wait for the shading
@@ -949,10 +1038,18 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 		p->launches++;
 	}
 	CK(p, cudaGetLastError());
+	// the geometry kernel is the only reader of the vertex streams: asynchronous uploads may overwrite them behind it
+	for(int s = 0; s < PS3D_MAX_VBOS; s++)
+		if(va.vbo[s] >= 0 && p->vbos[va.vbo[s]].readyValid)
+		{
+			Vbo& v = p->vbos[va.vbo[s]];
+			CK(p, cudaEventRecord(v.lastRead, p->stream));
+			v.readValid = true;
+		}
 	{
 		ProfScope ps(p, CLS_BIN);
 		tile_scan_kernel<<<1, 1024, 0, p->stream>>>(p->tileCount.p, p->tileStart.p, p->tileFill.p, ntiles, p->statsDev,
-		                                          pairCap, survivorCap, listLimit, p->poisonDev, p->reportDev);
+		                                          pairCap, survivorCap, listLimit, p->poisonDev, p->reportDev, p->tileOrder.p);
 		p->launches++;
 	}
 	CK(p, cudaEventRecord(p->scanEvent, p->stream));
@@ -970,6 +1067,8 @@ int ps3d_finish(ps3d_pipe* p)
 	cudaSetDevice(p->device);
 	SETTLE(p);
 	CK(p, cudaStreamSynchronize(p->stream));
+	CK(p, cudaStreamSynchronize(p->copyStream));
+	CK(p, cudaStreamSynchronize(p->readStream));
 	return PS3D_OK;
 }
 int ps3d_swap_buffers(ps3d_pipe* p) { p->back ^= 1; return PS3D_OK; } // pipeline.cpp:314-322
@@ -982,6 +1081,21 @@ int ps3d_read_colour(ps3d_pipe* p, void* bgra, size_t pitch)
 	if(pitch < (size_t)p->width * 4) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "pitch");
 	CK(p, cudaMemcpy2DAsync(bgra, pitch, p->display[p->back], (size_t)p->width * 4, (size_t)p->width * 4, p->height, cudaMemcpyDeviceToHost, p->stream));
 	CK(p, cudaStreamSynchronize(p->stream));
+	return PS3D_OK;
+}
+// The colour target into PINNED host memory on the read-back stream, behind everything enqueued on the pipe's stream so far;
+// returns at once. The image is complete after ps3d_finish. Later writes to the same target wait for the read-back.
+int ps3d_read_colour_async(ps3d_pipe* p, void* pinnedBgra, size_t pitch)
+{
+	TRACE();
+	cudaSetDevice(p->device);
+	SETTLE(p);
+	if(pitch < (size_t)p->width * 4) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "pitch");
+	CK(p, cudaEventRecord(p->frameDone, p->stream));
+	CK(p, cudaStreamWaitEvent(p->readStream, p->frameDone, 0));
+	CK(p, cudaMemcpy2DAsync(pinnedBgra, pitch, p->display[p->back], (size_t)p->width * 4, (size_t)p->width * 4, p->height, cudaMemcpyDeviceToHost, p->readStream));
+	CK(p, cudaEventRecord(p->readDone[p->back], p->readStream));
+	p->readValid[p->back] = true;
 	return PS3D_OK;
 }
 int ps3d_read_depth(ps3d_pipe* p, float* depth, size_t pitch)

@@ -90,6 +90,20 @@ class PuresoftVBO:
         """Source already resident in HBM (a CUDA device pointer)."""
         self._pipe._check(self._pipe._lib.ps3d_vbo_update_device(self._pipe._h, self.handle, C.c_void_p(dev_ptr)))
 
+    # ---- pipelined transfers (CUDA library only; include/ps3d.h "Pipelined transfers") -----------------------
+    def updateContentAsync(self, pinned_ptr, firstUnit=0, unitCount=None):
+        """Units [firstUnit, firstUnit + unitCount) from PINNED host memory (an address) on the pipe's copy stream."""
+        n = self.unitCount - int(firstUnit) if unitCount is None else int(unitCount)
+        self._pipe._check(self._pipe._lib.ps3d_vbo_update_async(self._pipe._h, self.handle, int(firstUnit), n, C.c_void_p(pinned_ptr)))
+
+    def devicePtr(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._pipe._check(self._pipe._lib.ps3d_vbo_device_ptr(self._pipe._h, self.handle, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def deviceWritten(self, cuda_stream):
+        self._pipe._check(self._pipe._lib.ps3d_vbo_device_written(self._pipe._h, self.handle, C.c_void_p(cuda_stream)))
+
 
 class PuresoftPipeline:
     def __init__(self, deviceWidth, deviceHeight, device=0, lib=None):
@@ -303,6 +317,19 @@ class PuresoftPipeline:
         s = C.c_void_p()
         self._check(self._lib.ps3d_device_stream(self._h, C.byref(s)))
         return s.value or 0
+
+    def deviceCopyStream(self):
+        s = C.c_void_p()
+        self._check(self._lib.ps3d_device_copy_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def readColourAsync(self, pinned_ptr, pitchBytes=None):
+        """Colour target into PINNED host memory behind the work enqueued so far; complete after finish()."""
+        self._check(self._lib.ps3d_read_colour_async(self._h, C.c_void_p(pinned_ptr), int(pitchBytes or self.width * 4)))
+
+    def deviceJoin(self):
+        """The pipe's stream waits for everything enqueued so far on the copy and read-back streams."""
+        self._check(self._lib.ps3d_device_join(self._h))
 
     def profileEnable(self, on=True):
         self._check(self._lib.ps3d_profile_enable(self._h, 1 if on else 0))

@@ -74,3 +74,51 @@ class Compositor:
     def gather_to_rank0(self):
         with torch.cuda.stream(self.ext):
             gather_bands(self._colour(), self.bands, self.rank, self.world, self.pipe.height)
+
+
+def shard_units(units, world):
+    """Equal shards of a vertex stream: rank r owns units [r*per, (r+1)*per); the `rem` units behind world*per (fewer
+    than `world`) are uploaded by every rank itself, so the exchange is one in-place all-gather of equal pieces."""
+    per = units // world
+    return per, units - per * world
+
+
+def all_gather_shards(flat, per_bytes, rank, world):
+    """In place: flat[r*per_bytes:(r+1)*per_bytes] holds rank r's shard on rank r; afterwards on every rank."""
+    if world == 1 or per_bytes == 0:
+        return
+    dist.all_gather_into_tensor(flat[:world * per_bytes], flat[rank * per_bytes:(rank + 1) * per_bytes])
+
+
+class ShardedUpload:
+    """A step's vertex streams cross PCIe once in total instead of once per rank: rank r copies only its 1/N of every
+    stream from its pinned host buffer (ps3d_vbo_update_async, on the pipe's copy stream) and the shards are
+    all-gathered in place in the VBOs' own device storage over NVLink — the upload's one exchange step. Draws wait for
+    the gathered streams through the VBOs' ready events (ps3d_vbo_device_written); nothing blocks the host."""
+
+    def __init__(self, pipe, vbos, rank, world, device):
+        """vbos: [(PuresoftVBO, pinned uint8 torch tensor holding the WHOLE stream's bytes)]"""
+        self.pipe, self.rank, self.world = pipe, rank, world
+        self.copy_stream = pipe.deviceCopyStream()
+        self.ext = torch.cuda.ExternalStream(self.copy_stream, device=device)
+        self.items = []
+        for vbo, host in vbos:
+            ptr, nbytes = vbo.devicePtr()
+            per, rem = shard_units(vbo.unitCount, world)
+            flat = torch.as_tensor(_DevicePtr(ptr, (nbytes,), "|u1"), device=device) if world > 1 else None
+            self.items.append((vbo, host, per, rem, flat))
+        self.h2d_bytes = sum((per + rem) * vbo.unitBytes for vbo, _, per, rem, _ in self.items)
+
+    def step(self):
+        r, w = self.rank, self.world
+        for vbo, host, per, rem, _ in self.items:
+            base = host.data_ptr()
+            vbo.updateContentAsync(base + r * per * vbo.unitBytes, r * per, per)
+            if rem:
+                vbo.updateContentAsync(base + w * per * vbo.unitBytes, w * per, rem)
+        if w > 1:
+            with torch.cuda.stream(self.ext):
+                for vbo, _, per, _, flat in self.items:
+                    all_gather_shards(flat, per * vbo.unitBytes, r, w)
+            for vbo, _, _, _, _ in self.items:
+                vbo.deviceWritten(self.copy_stream)

@@ -32,6 +32,22 @@ def main():
     shaded = torch.tensor([p.getStats()["fragments_shaded"]], dtype=torch.int64)
     p.close()
     sortfirst.gather_bands(frame, bands, rank, world, sc.height)
+    # the sharded upload's exchange (sortfirst.ShardedUpload): every rank fills only its shard (+ the tail every rank
+    # uploads itself) of each vertex stream, the in-place all-gather must rebuild the whole stream on every rank
+    shards_ok = True
+    for slots in sc.vaos:
+        for _, (unit, arr) in sorted(slots.items()):
+            whole_bytes = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1).copy())
+            units = whole_bytes.numel() // unit
+            per, rem = sortfirst.shard_units(units, world)
+            mine = torch.full_like(whole_bytes, 0xEE)
+            mine[rank * per * unit:(rank + 1) * per * unit] = whole_bytes[rank * per * unit:(rank + 1) * per * unit]
+            if rem:
+                mine[world * per * unit:] = whole_bytes[world * per * unit:]
+            sortfirst.all_gather_shards(mine, per * unit, rank, world)
+            shards_ok = shards_ok and bool(torch.equal(mine, whole_bytes))
+    flag = torch.tensor([1 if shards_ok else 0], dtype=torch.int64)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.all_reduce(shaded)
     if rank == 0:
         q = PuresoftPipeline(sc.width, sc.height, lib=lib)
@@ -39,7 +55,7 @@ def main():
         whole = q.readColour().view(np.int32)
         whole_shaded = q.getStats()["fragments_shaded"]
         q.close()
-        ok = np.array_equal(frame.numpy(), whole) and int(shaded.item()) == whole_shaded
+        ok = np.array_equal(frame.numpy(), whole) and int(shaded.item()) == whole_shaded and int(flag.item()) == 1
         with open(out_path, "w") as f:
             f.write("ok" if ok else "mismatch: %d differing pixels, shaded %d vs %d" % (int((frame.numpy() != whole).sum()), int(shaded.item()), whole_shaded))
     dist.barrier()

@@ -26,6 +26,13 @@ def test_row_bands_partition_the_frame(height, world):
         assert m1 - m0 == r1 - r0 and 0 <= m0 <= m1 <= height
 
 
+@pytest.mark.parametrize("units", [0, 1, 7, 36, 3007584])
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_shard_units_cover_the_stream(units, world):
+    per, rem = sortfirst.shard_units(units, world)
+    assert per * world + rem == units and 0 <= rem < world
+
+
 def free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
