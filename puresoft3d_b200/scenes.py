@@ -10,6 +10,7 @@ Vertex layout follows the demos (src/test/scenobj.cpp:135-158): slot 0 position 
 2 binormal float4, 3 normal float4, 4 uv float2. Matrices are column-major like mcemath (m[col*4+row]).
 """
 import math
+import os
 
 import numpy as np
 
@@ -723,4 +724,157 @@ def scene_desk(width=1024, height=640, shadow=1024, seed=5, clutter=24, tex_size
         sc.cmd("draw", vao)
         ntri += sc.vaos[vao][0][1].shape[0] // 3
     sc.meta["triangles"] = 2 * ntri + 2
+    return sc
+
+
+# ---- demo 2 from an OBJX file -----------------------------------------------------------
+
+OBJX_PROGRAMMES = {   # mesh_header::programme -> functor triple (src/test2/loadscene.cpp findOrCreateProgramme, procreator.cpp)
+    "VP_SingleColour:IP_SingleColour:FP_SingleColour": (K.FN_SINGLECOLOUR, K.FN_SINGLECOLOUR, K.FN_SINGLECOLOUR),
+    "VP_DiffuseOnly:IP_DiffuseOnly:FP_DiffuseOnly": (K.FN_DIFFUSEONLY, K.FN_DIFFUSEONLY, K.FN_DIFFUSEONLY),
+    "VP_PositionOnly:IP_Null:FP_SingleColourNoLighting": (K.FN_POSITIONONLY, K.FN_POSITIONONLY, K.FN_POSITIONONLY),
+}
+
+
+def mat_view_ypr(eye, ypr):
+    """View matrix of a camera at `eye` looking along yaw/pitch (mat4::view(from, ypr), mcemaths.hpp:133; sight vector as in
+    src/mcemath/matrxgl.cpp:163-166: (cos p sin y, -sin p, -cos p cos y)). Built once; every backend gets the same bytes."""
+    y, p = float(ypr[0]), float(ypr[1])
+    sight = np.array([math.cos(p) * math.sin(y), -math.sin(p), -math.cos(p) * math.cos(y)])
+    e = np.asarray(eye[:3], dtype=np.float64)
+    return mat_look_at(tuple(e), tuple(e + sight))
+
+
+def write_demo_objx(path, seed=11, clutter=6):
+    """A small desk scene in OBJX form — the shape of src/test2/plane.objx (world-space positions, 'object/mesh' names,
+    programme strings, '@noshadow' tags, the light1/from and light1/to marker meshes, camera position + yaw/pitch in the
+    file header) — so that the OBJX path can be exercised where the reference's own assets are not present."""
+    from . import objx
+    rng = np.random.default_rng(seed)
+
+    def placed(mesh, at):
+        pos, tan, _bin, nrm, uv = mesh
+        p = pos.copy()
+        p[:, :3] += np.asarray(at, F32)
+        p[:, 3] = 0.0       # the loader sets w = 1 (loadscene.cpp:231)
+        return {"vertices": p, "normals": nrm, "tangents": tan, "texcoords": uv}
+
+    meshes = []
+
+    def add(name, mesh, at, programme, diffuse=(0.8, 0.8, 0.8, 0), spec_exp=30.0, diffuse_file=""):
+        m = placed(mesh, at)
+        m.update(name=name, programme=programme, ambient=(0.15, 0.15, 0.15, 0), diffuse=diffuse, specular=(1, 1, 1, 0),
+                 specular_exponent=spec_exp, diffuse_file=diffuse_file)
+        meshes.append(m)
+
+    single, diffuse_only, unlit = list(OBJX_PROGRAMMES)
+    add("plane/top@noshadow", box_mesh(3.0, 0.06, 2.4), (0, -0.03, 0), diffuse_only, diffuse_file="top.jpg")
+    for i in range(clutter):
+        w, h, d = rng.uniform(0.12, 0.4, size=3)
+        x, z = rng.uniform(-1.1, 1.1), rng.uniform(-0.8, 0.8)
+        if i % 2:
+            add("box%d/body" % i, box_mesh(w, h, d), (x, h / 2, z), single, diffuse=tuple(rng.uniform(0.2, 0.95, size=3)) + (0,))
+            add("box%d/lid" % i, box_mesh(w * 0.8, 0.03, d * 0.8), (x, h + 0.015, z), single, diffuse=(0.9, 0.9, 0.2, 0))
+        else:
+            add("crate%d/body" % i, box_mesh(w, h, d), (x, h / 2, z), diffuse_only, diffuse_file="marmite.jpg")
+    add("ball/skin", sphere_mesh(10, 20, 0.22), (-0.35, 0.22, 0.45), single, diffuse=(0.9, 0.3, 0.2, 0))
+    add("lamp/lamp@noshadow", box_mesh(0.07, 0.07, 0.07), (0.9, 1.7, 1.1), unlit, diffuse=(1.0, 1.0, 0.8, 0))
+    add("light1/from", box_mesh(0.02, 0.02, 0.02), (0.9, 1.7, 1.1), diffuse_only, diffuse_file="top.jpg")
+    add("light1/to", box_mesh(0.02, 0.02, 0.02), (0.0, 0.0, 0.0), single)
+    scene = {"camera_pos": (-1.6, 1.3, 2.2, 0), "camera_ypr": (0.62, 0.42, 0, 0)}
+    objx.write_objx(path, scene, meshes)
+    return path
+
+
+def scene_desk_objx(path, width=1024, height=640, shadow=1024, picture_dir=None, seed=5, tex_size=256):
+    """Demo 2's frame (src/test2/puresoft.cpp:115-248) replayed headless from an OBJX file: loadScene (loadscene.cpp:137-345)
+    through puresoft3d_b200.objx, the shadow pass over everything not tagged '@noshadow' with VP_Shadow/IP_Null/FP_Null into a
+    float texture, then every component with its own programme, material uniforms 30-33 and texture ids 40-43
+    (SceneObject::draw, loadscene.cpp:112-135), in the reference's std::map order. Pictures named by the file are loaded
+    from `picture_dir` (load_picture); a name that is not found there gets a seeded synthetic texture instead (the
+    reference would be left with texture id -2)."""
+    from . import objx
+    rng = np.random.default_rng(seed)
+    desc, comps = objx.load_scene_meshes(path)
+    sc = Scene("demo2-objx-%s-%dx%d-s%d" % (os.path.basename(str(path)), width, height, shadow), width, height)
+    shadow_tex = sc.add_texture(shadow, shadow, 4, None)
+    p_shadow = sc.add_programme(K.FN_SHADOW2, K.FN_POSITIONONLY, K.FN_SHADOW2)
+    progs, texs = {}, {}
+
+    def programme(name):
+        if name not in progs:
+            progs[name] = sc.add_programme(*OBJX_PROGRAMMES[name])
+        return progs[name]
+
+    def texture(name):
+        if name not in texs:
+            pix = None
+            if picture_dir and name and os.path.exists(os.path.join(picture_dir, name)):
+                pix = objx.load_picture(os.path.join(picture_dir, name))
+            if pix is None:
+                pix = tex_smooth_bgra(rng, tex_size, tex_size)
+            texs[name] = sc.add_texture(pix.shape[1], pix.shape[0], 4, np.ascontiguousarray(pix))
+        return texs[name]
+
+    by_name = {c["component"]: c for c in comps}
+    light_from = by_name["light1/from"]["world_translation"].astype(np.float64)
+    light_to = by_name["light1/to"]["world_translation"].astype(np.float64)
+    rdir = light_from - light_to
+    rdir = rdir / np.linalg.norm(rdir)                                           # light1RDir, puresoft.cpp:133-135
+    camera = desc["camera_pos"].astype(np.float64)[:3]
+    proj = mat_perspective(0.1, 5.0, width / height, 2 * math.pi * (45.0 / 360.0))   # puresoft.cpp:119
+    view = mat_view_ypr(camera, desc["camera_ypr"])
+    pv = (proj.astype(np.float64) @ view.astype(np.float64)).astype(F32)
+    lproj = mat_perspective(0.1, 5.0, 1.0, 2 * math.pi * (90.0 / 360.0))           # puresoft.cpp:146
+    lview = mat_look_at(tuple(light_from), tuple(light_to))
+    lpv = (lproj.astype(np.float64) @ lview.astype(np.float64)).astype(F32)
+    lpvb = (BIAS.astype(np.float64) @ lpv.astype(np.float64)).astype(F32)
+
+    drawn = []
+    for c in comps:                      # light1/from and light1/to are marker meshes, erased from the scene (loadscene.cpp:437-439)
+        if c["component"] in ("light1/from", "light1/to"):
+            continue
+        vao = sc.add_vao(objx.mesh_slots(c))
+        model = mat_translation(*[float(x) for x in c["world_translation"]])
+        tex = texture(c["diffuse_file"]) if OBJX_PROGRAMMES[c["programme"]][0] == K.FN_DIFFUSEONLY else None
+        drawn.append((c, vao, model, programme(c["programme"]), tex))
+
+    def place(c, model, pvm_base):
+        sc.cmd("uniform", 0, colmajor(model))
+        sc.cmd("uniform", 1, colmajor(mat_identity()))
+        sc.cmd("uniform", 5, colmajor((pvm_base.astype(np.float64) @ model.astype(np.float64)).astype(F32)))
+        sc.cmd("uniform", 30, vec4(*c["ambient"][:3])); sc.cmd("uniform", 31, vec4(*c["diffuse"][:3]))
+        sc.cmd("uniform", 32, vec4(*c["specular"][:3])); sc.cmd("uniform", 33, np.array([c["specular_exponent"]], F32))
+
+    # ---- shadow map (puresoft.cpp:185-205)
+    sc.cmd("uniform", 2, colmajor(lview)); sc.cmd("uniform", 3, colmajor(lproj)); sc.cmd("uniform", 4, colmajor(lpv))
+    sc.cmd("depth", shadow_tex)
+    sc.cmd("clearDepth", 1.0)
+    sc.cmd("viewport", shadow, shadow)
+    sc.cmd("use", p_shadow)
+    ntri = 0
+    for (c, vao, model, _prog, _tex) in drawn:
+        if "@noshadow" in c["component"]:
+            continue
+        place(c, model, lpv)
+        sc.cmd("draw", vao)
+        ntri += c["vertices"].shape[0] // 3
+    # ---- the scene (puresoft.cpp:211-240)
+    sc.cmd("uniform", 2, colmajor(view)); sc.cmd("uniform", 3, colmajor(proj)); sc.cmd("uniform", 4, colmajor(pv))
+    sc.cmd("uniform", 6, colmajor(lpvb))
+    sc.cmd("uniform", 20, vec4(*light_from)); sc.cmd("uniform", 21, vec4(*rdir)); sc.cmd("uniform", 22, vec4(*camera))
+    sc.cmd("tex_uniform", 23, shadow_tex)
+    sc.cmd("depth", -1)
+    sc.cmd("clearDepth", 1.0)
+    sc.cmd("clearColour", 0)
+    sc.cmd("viewport", width, height)
+    for (c, vao, model, prog, tex) in drawn:
+        place(c, model, pv)
+        if tex is not None:
+            sc.cmd("tex_uniform", 40, tex)
+        sc.cmd("use", prog)
+        sc.cmd("draw", vao)
+        ntri += c["vertices"].shape[0] // 3
+    sc.meta["triangles"] = ntri
+    sc.meta["components"] = [c["component"] for (c, _, _, _, _) in drawn]
     return sc

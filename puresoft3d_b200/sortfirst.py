@@ -93,32 +93,37 @@ def all_gather_shards(flat, per_bytes, rank, world):
 class ShardedUpload:
     """A step's vertex streams cross PCIe once in total instead of once per rank: rank r copies only its 1/N of every
     stream from its pinned host buffer (ps3d_vbo_update_async, on the pipe's copy stream) and the shards are
-    all-gathered in place in the VBOs' own device storage over NVLink — the upload's one exchange step. Draws wait for
-    the gathered streams through the VBOs' ready events (ps3d_vbo_device_written); nothing blocks the host."""
+    all-gathered in place in the VBOs' own device storage over NVLink — the upload's one exchange step, on a stream of
+    its own behind a per-stream event, so that stream k is gathered while stream k+1 is still crossing PCIe and the
+    next step's uploads never wait for a collective. Draws wait for the gathered streams through the VBOs' ready events
+    (ps3d_vbo_device_written); nothing blocks the host."""
 
     def __init__(self, pipe, vbos, rank, world, device):
         """vbos: [(PuresoftVBO, pinned uint8 torch tensor holding the WHOLE stream's bytes)]"""
         self.pipe, self.rank, self.world = pipe, rank, world
         self.copy_stream = pipe.deviceCopyStream()
         self.ext = torch.cuda.ExternalStream(self.copy_stream, device=device)
+        self.gather = torch.cuda.Stream(device=device) if world > 1 else None
         self.items = []
         for vbo, host in vbos:
             ptr, nbytes = vbo.devicePtr()
             per, rem = shard_units(vbo.unitCount, world)
             flat = torch.as_tensor(_DevicePtr(ptr, (nbytes,), "|u1"), device=device) if world > 1 else None
-            self.items.append((vbo, host, per, rem, flat))
-        self.h2d_bytes = sum((per + rem) * vbo.unitBytes for vbo, _, per, rem, _ in self.items)
+            self.items.append((vbo, host, per, rem, flat, torch.cuda.Event() if world > 1 else None))
+        self.h2d_bytes = sum((per + rem) * vbo.unitBytes for vbo, _, per, rem, _, _ in self.items)
 
     def step(self):
         r, w = self.rank, self.world
-        for vbo, host, per, rem, _ in self.items:
+        for vbo, host, per, rem, flat, ev in self.items:
             base = host.data_ptr()
             vbo.updateContentAsync(base + r * per * vbo.unitBytes, r * per, per)
             if rem:
                 vbo.updateContentAsync(base + w * per * vbo.unitBytes, w * per, rem)
-        if w > 1:
-            with torch.cuda.stream(self.ext):
-                for vbo, _, per, _, flat in self.items:
+            if w > 1:
+                # the copy stream has also waited for the last draw that read this VBO (ps3d_vbo_update_async), so the
+                # gather behind this event cannot overwrite a stream a geometry kernel is still reading
+                ev.record(self.ext)
+                self.gather.wait_event(ev)
+                with torch.cuda.stream(self.gather):
                     all_gather_shards(flat, per * vbo.unitBytes, r, w)
-            for vbo, _, _, _, _ in self.items:
-                vbo.deviceWritten(self.copy_stream)
+                vbo.deviceWritten(self.gather.cuda_stream)

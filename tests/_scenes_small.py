@@ -1,7 +1,22 @@
 """The seeded scene set shared by the oracle pin, the golden fixtures and the GPU parity tests (sizes the CPU
 checkers finish in well under a second each)."""
+import os
+import tempfile
+
 from puresoft3d_b200 import _capi as K
 from puresoft3d_b200 import scenes
+
+
+def _demo2_from_objx():
+    """Demo 2's frame driven by an OBJX FILE (native reader, loadScene's re-centring, programme strings, material
+    uniforms): the file is written by the native writer first, in the shape of the reference's plane.objx."""
+    path = os.path.join(tempfile.gettempdir(), "ps3d_demo2_%d.objx" % os.getpid())
+    scenes.write_demo_objx(path, seed=11, clutter=6)
+    try:
+        return scenes.scene_desk_objx(path, 384, 240, shadow=256, tex_size=128)
+    finally:
+        os.unlink(path)
+
 
 SMALL = {
     "c1_cube_def01": lambda: scenes.scene_cube(320, 240),
@@ -17,6 +32,7 @@ SMALL = {
     # the reference's two demos as headless scenes: shadow pass + projective shadow lookup + cube skybox + blending + discard
     "demo1_planets": lambda: scenes.scene_planets(400, 250, shadow=240, stacks=12, slices=24, tex_size=128),
     "c3_demo2_desk": lambda: scenes.scene_desk(384, 240, shadow=256, clutter=10, tex_size=128),
+    "demo2_objx_file": _demo2_from_objx,
 }
 
 # Extensions with no reference counterpart: checked CUDA-vs-oracle only, "parity unpinned".
