@@ -1543,14 +1543,18 @@ PS_D void rasterPass(const DrawParams& P, const SurvivorStream& Q, RasterSmem& S
 
 __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_depth_kernel(const __grid_constant__ DrawParams P, const SurvivorStream Q,
                                                                                   const uint32_t* __restrict__ tileStart,
-                                                                                  const uint32_t* __restrict__ sortedTris)
+                                                                                  const uint32_t* __restrict__ sortedTris, int parts)
 {
 	__shared__ RasterSmem smem[PS_WARPS_PER_BLOCK];
 	if(*P.poison) return;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	const int tileSlot = blockIdx.x * PS_WARPS_PER_BLOCK + w;
-	if(tileSlot >= P.tilesX * P.tilesY) return;
-	const int tile = (int)P.tileOrder[tileSlot];         // longest lists first (tile_scan_kernel)
+	// A warp walks its tile's list as one dependent chain (~100 us on C2 whatever the load): rows are independent in this
+	// rasteriser, so when there are fewer tiles than the GPU has warp slots (a sort-first band, a small target) a tile is
+	// cut into `parts` (1, 2 or 4) groups of PS_TILE / parts rows, one warp each, all reading the same list.
+	const int warpSlot = blockIdx.x * PS_WARPS_PER_BLOCK + w;
+	if(warpSlot >= P.tilesX * P.tilesY * parts) return;
+	const int tile = (int)P.tileOrder[warpSlot / parts];   // longest lists first (tile_scan_kernel)
+	const int rowsPer = PS_TILE / parts, partRow0 = (warpSlot % parts) * rowsPer;
 	const uint32_t listBegin = tileStart[tile], listEnd = tileStart[tile + 1];
 	if(listBegin == listEnd) return;
 	RasterSmem& S = smem[w];
@@ -1562,6 +1566,7 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_depth_ker
 	const bool updateDepth = 0 != (P.behavior & PS_BEHAVIOR_UPDATE_DEPTH);
 	const bool useDepth = testDepth || updateDepth;
 
+	const bool mine = rr >= partRow0 && rr < partRow0 + rowsPer;   // rows of the tile this warp owns (staging, write-back)
 	const bool depthRowOk = y < P.depth.height;
 	uint8_t* depthRow = P.depth.ptr + (size_t)(P.depth.topDown ? P.depth.height - 1 - y : y) * P.depth.scanline;
 #pragma unroll
@@ -1569,7 +1574,7 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_depth_ker
 	{
 		const int x = sx0 + i;
 		float d = 1.0f;
-		if(useDepth && depthRowOk && x < P.depth.width) d = *(const float*)(depthRow + (size_t)x * 4);
+		if(mine && useDepth && depthRowOk && x < P.depth.width) d = *(const float*)(depthRow + (size_t)x * 4);
 		S.depth[rr * PS_TILE + seg * PS_SEG + i] = d;
 		S.lastIdx[rr * PS_TILE + seg * PS_SEG + i] = 0;
 	}
@@ -1599,8 +1604,8 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_depth_ker
 			const uint4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
 			uint4* dst = (uint4*)&S.hdr[lane];
 			dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3;
-			r0 = max(max((int)(q3.x & 0xffff), ty0), P.band0);
-			const int r1 = min(min(min((int)(q3.x >> 16), ty0 + PS_TILE - 1), P.band1 - 1), depthLimitY);
+			r0 = max(max((int)(q3.x & 0xffff), ty0 + partRow0), P.band0);
+			const int r1 = min(min(min((int)(q3.x >> 16), ty0 + partRow0 + rowsPer - 1), P.band1 - 1), depthLimitY);
 			nrows = r1 >= r0 ? r1 - r0 + 1 : 0;
 		}
 		uint32_t incl = (uint32_t)nrows;
@@ -1673,13 +1678,13 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_depth_ker
 	if(C.qCount) { flushSurvivors(Q, S, lane, C.qCount, tx0, ty0); C.survived += C.qCount; }
 
 	// ---- write back: depth tile, and which record won each pixel
-	if(__any_sync(PS_FULL, C.depthWrote) && depthRowOk)
+	if(__any_sync(PS_FULL, C.depthWrote) && depthRowOk && mine)
 	{
 #pragma unroll
 		for(int i = 0; i < PS_SEG; i++)
 			if(sx0 + i < P.depth.width) *(float*)(depthRow + (size_t)(sx0 + i) * 4) = S.depth[rr * PS_TILE + seg * PS_SEG + i];
 	}
-	if(C.survived && y < P.vpH)
+	if(C.survived && y < P.vpH && mine)
 	{
 #pragma unroll
 		for(int i = 0; i < PS_SEG; i++)

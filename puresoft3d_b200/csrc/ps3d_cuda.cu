@@ -94,6 +94,8 @@ template<class PROG> void launchGeom(const DrawParams& P, cudaStream_t s)
 	else
 		geom_setup_kernel<PROG, false><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
 }
+// PS3D_RASTER_PARTS=1|2|4 forces the number of row groups a tile is cut into (A/B checks, tests)
+int rasterPartsForced() { static int v = -2; if(-2 == v) { const char* e = getenv("PS3D_RASTER_PARTS"); v = e ? atoi(e) : 0; if(v != 1 && v != 2 && v != 4) v = 0; } return v; }
 unsigned tileBlocks(const DrawParams& P) { return ((unsigned)(P.tilesX * P.tilesY) + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK; }
 template<class PROG> void launchTileImmediate(const DrawParams& P, const uint32_t* tileStart, const uint32_t* sortedTris, cudaStream_t s)
 {
@@ -189,6 +191,7 @@ template<typename T> struct DevBuf
 struct ps3d_pipe
 {
 	int device;
+	int smCount;
 	cudaStream_t stream;
 	cudaStream_t copyStream;    // asynchronous uploads (ps3d_vbo_update_async)
 	cudaStream_t readStream;    // asynchronous read-backs (ps3d_read_colour_async): its own stream, so that a read-back waiting for its frame does not hold up the next frame's uploads
@@ -399,7 +402,14 @@ static int launchTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe, in
 		CK(p, cudaMemsetAsync(p->svCountDev, 0, 4, p->stream));
 		{
 			ProfScope ps(p, CLS_TILE);
-			tile_raster_depth_kernel<<<tileBlocks(P), 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(P, Q, p->tileStart.p, sortedTris);
+			// fewer tiles in play than warp slots on the GPU: cut every tile into 2 or 4 row groups, one warp each
+			const int bandRows = std::max(0, std::min(P.band1, P.vpH) - std::max(P.band0, 0));
+			const long long tilesInPlay = (long long)P.tilesX * ((bandRows + PS_TILE - 1) / PS_TILE);
+			const long long warpSlots = (long long)p->smCount * 28;      // resident warps of this kernel (shared memory / registers)
+			int parts = rasterPartsForced();
+			if(parts <= 0) parts = tilesInPlay * 4 * 4 <= warpSlots * 5 ? 4 : (tilesInPlay * 2 * 4 <= warpSlots * 5 ? 2 : 1);
+			const unsigned blocks = ((unsigned)(P.tilesX * P.tilesY) * (unsigned)parts + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK;
+			tile_raster_depth_kernel<<<blocks, 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(P, Q, p->tileStart.p, sortedTris, parts);
 			p->launches++;
 		}
 		{
@@ -453,6 +463,7 @@ int ps3d_create(int width, int height, int device, ps3d_pipe** out)
 	if(cudaSetDevice(device) != cudaSuccess) return PS3D_ERR_DEVICE;
 	ps3d_pipe* p = new ps3d_pipe();
 	p->device = device;
+	{ cudaDeviceProp prop; p->smCount = (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ? prop.multiProcessorCount : 148; }
 	p->width = width; p->height = height; p->vpW = width; p->vpH = height;
 	p->behavior = PS3D_BEHAVIOR_UPDATE_DEPTH | PS3D_BEHAVIOR_TEST_DEPTH | PS3D_BEHAVIOR_FACE_CULLING; // pipeline.cpp:34
 	p->band0 = 0; p->band1 = 0x7fffffff;
