@@ -155,6 +155,17 @@ int ps3d_clear_colour(ps3d_pipe* p, uint32_t bgra);
 int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread);
 int ps3d_finish(ps3d_pipe* p);
 
+/* postProcess(PuresoftPostProcessor*) — pipeline.h:56, post.cpp:3-19. The reference hands (colour target, depth target)
+ * to the processor once per worker thread with a row interleave (threadIndex, threadCount; proc.h:89-94); here the
+ * processor is a device functor run over the whole current colour target by one tile-parallel kernel, after every draw
+ * enqueued so far. Functors:
+ *   PS3D_POST_DEPTHOFFIELD  PP_DepthofField, the reference's only (unfinished) post-processor, src/test2/testpost.cpp:9-43:
+ *                           adds 50 to every BYTE of every pixel, wrapping (paddb), two pixels per step — with an odd
+ *                           width each row's last step also touches the pixel behind the row's end (the next row's first
+ *                           pixel; past the buffer on the last row, where it is dropped here). */
+#define PS3D_POST_DEPTHOFFIELD 1
+int ps3d_post_process(ps3d_pipe* p, int functor);
+
 /* swapBuffers — pipeline.cpp:314-322 (headless: flips the two display buffers). */
 int ps3d_swap_buffers(ps3d_pipe* p);
 

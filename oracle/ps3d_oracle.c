@@ -1383,6 +1383,31 @@ int ps3d_clear_colour(ps3d_pipe* p, uint32_t bgra) /* pipeline.cpp:340-343 -> cl
 int ps3d_finish(ps3d_pipe* p) { (void)p; return PS3D_OK; }
 int ps3d_swap_buffers(ps3d_pipe* p) { p->back ^= 1; return PS3D_OK; } /* pipeline.cpp:314-322 */
 
+/* postProcess, post.cpp:3-19, with PP_DepthofField::process, src/test2/testpost.cpp:9-43: every worker takes the rows
+ * threadIndex, threadIndex + threadCount, ... of the colour target and, two pixels (8 bytes) per step for x = 0, 2, ... < width,
+ * adds 50 to each byte with wrap-around (paddb). Rows are disjoint between workers, so the row order is free; with an odd
+ * width the last step of a row also covers the first pixel of the next row in memory (scanline = width * 4) — two workers
+ * then read-modify-write the same 8 bytes unsynchronised in the reference; the sequential result (both additions land)
+ * is what is restated, and the step that would run past the buffer's end on the last row is clipped. */
+int ps3d_post_process(ps3d_pipe* p, int functor)
+{
+	if(functor != PS3D_POST_DEPTHOFFIELD) return fail(p, PS3D_ERR_UNSUPPORTED, "post-processor");
+	fbo_t* c = &p->display[p->back];
+	unsigned char* base = c->layer[0];
+	const size_t bytes = (size_t)c->scanline * (size_t)p->height;
+	for(int y = 0; y < p->height; y++)
+	{
+		unsigned char* row = base + (size_t)y * c->scanline;
+		for(int x = 0; x < p->width; x += 2)
+			for(int b = 0; b < 8; b++)
+			{
+				unsigned char* q = row + (size_t)x * 4 + b;
+				if((size_t)(q - base) < bytes) *q = (unsigned char)(*q + 50);
+			}
+	}
+	return PS3D_OK;
+}
+
 int ps3d_read_colour(ps3d_pipe* p, void* bgra, size_t pitch)
 {
 	if(pitch < (size_t)p->width * 4) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "pitch");

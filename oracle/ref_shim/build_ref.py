@@ -175,6 +175,23 @@ def translate_simple_asm(block, what):
     return "\n".join(body)
 
 
+# src/test2/testpost.cpp (PP_DepthofField): two MMX asm blocks — load the constant, then movq / paddb / movntq per two pixels
+# (the dead `mov eax,1 / movd mm1,eax` pair has no effect on the result).
+TESTPOST_ASM = [
+    "__m64 mm2_ = *(const __m64*)f; /* shim: lea eax,f / movq mm2,[eax] */",
+    "{ /* shim: movq mm0,[row] / paddb mm0,mm2 / movntq [row],mm0 */\n\t\t\t\t__m64 mm0_ = *(const __m64*)row;\n\t\t\t\tmm0_ = _mm_add_pi8(mm0_, mm2_);\n\t\t\t\t_mm_stream_pi((__m64*)row, mm0_);\n\t\t\t}",
+]
+
+
+def patch_testpost(text):
+    text = text.replace("\r\n", "\n")
+    blocks = ASM_BLOCK.findall(text)
+    if len(blocks) != 2:
+        raise SystemExit("testpost.cpp: expected 2 asm blocks, found %d" % len(blocks))
+    it = iter(TESTPOST_ASM)
+    return "#include <xmmintrin.h>\n#include <mmintrin.h>\n" + ASM_BLOCK.sub(lambda m: next(it), text)
+
+
 def run(cmd):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
@@ -208,13 +225,19 @@ def main():
                     text = patch_demo_shader("src/%s/%s" % (sub, fn), text)
                 with open(os.path.join(scratch, dst, fn), "w", encoding="latin-1") as f:
                     f.write(text)
+        if DEMOS:
+            for fn in ("testpost.cpp", "testpost.h"):
+                with open(os.path.join(REF, "src", "test2", fn), "r", encoding="latin-1") as f:
+                    text = f.read()
+                with open(os.path.join(scratch, "t2", fn), "w", encoding="latin-1") as f:
+                    f.write(patch_testpost(text) if fn.endswith(".cpp") else text)
         inc = ["-I", os.path.join(HERE, "include"), "-I", os.path.join(scratch, "p"),
                "-I", os.path.join(REF, "src", "mcemath"), "-I", os.path.join(REPO, "include"),
                "-include", os.path.join(HERE, "prelude.h")]
         objs = []
         jobs = [(os.path.join(scratch, "p", s), "p_" + s) for s in PIPE_SOURCES]
         jobs += [] if not DEMOS else [(os.path.join(scratch, "t1", "testproc.cpp"), "t1_testproc.cpp"),
-                 (os.path.join(scratch, "t2", "testproc.cpp"), "t2_testproc.cpp"),
+                 (os.path.join(scratch, "t2", "testproc.cpp"), "t2_testproc.cpp"), (os.path.join(scratch, "t2", "testpost.cpp"), "t2_testpost.cpp"),
                  (os.path.join(HERE, "demo_procs1.cpp"), "t1_demo_procs1.cpp"), (os.path.join(HERE, "demo_procs2.cpp"), "t2_demo_procs2.cpp")]
         jobs += [(os.path.join(HERE, s), "s_" + s) for s in ("win32_shim.cpp", "mcemath_sse.cpp", "ref_capi.cpp")]
         for path, tag in jobs:

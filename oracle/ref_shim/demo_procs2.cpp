@@ -3,6 +3,7 @@
 #include "windows.h"
 #include "pipeline.h"
 #include "testproc.h"
+#include "testpost.h"
 #include "ps3d.h"
 
 PuresoftProcessor* ps3d_demo2_make_processor(int kind, int functor)
@@ -19,4 +20,9 @@ PuresoftProcessor* ps3d_demo2_make_processor(int kind, int functor)
 		return kind == PS3D_PROC_VERTEX ? (PuresoftProcessor*)new VP_Shadow : kind == PS3D_PROC_FRAGMENT ? (PuresoftProcessor*)new FP_Null : NULL;
 	}
 	return NULL;
+}
+
+PuresoftPostProcessor* ps3d_demo2_make_post_processor(int functor)
+{
+	return functor == PS3D_POST_DEPTHOFFIELD ? new PP_DepthofField : NULL;
 }

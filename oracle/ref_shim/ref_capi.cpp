@@ -27,6 +27,7 @@
 #ifdef PS3D_WITH_DEMO_SHADERS
 PuresoftProcessor* ps3d_demo1_make_processor(int kind, int functor); // demo_procs1.cpp (src/test/testproc.cpp)
 PuresoftProcessor* ps3d_demo2_make_processor(int kind, int functor); // demo_procs2.cpp (src/test2/testproc.cpp)
+PuresoftPostProcessor* ps3d_demo2_make_post_processor(int functor); // demo_procs2.cpp (src/test2/testpost.cpp)
 #endif
 
 namespace
@@ -489,6 +490,21 @@ int ps3d_swap_buffers(ps3d_pipe* p)
 	p->pipe->swapBuffers();
 	PS3D_CATCH(p)
 }
+
+// the reference's own PP_DepthofField (src/test2/testpost.cpp, asm -> intrinsics by build_ref.py) through its own postProcess (post.cpp)
+#ifdef PS3D_WITH_DEMO_SHADERS
+int ps3d_post_process(ps3d_pipe* p, int functor)
+{
+	PS3D_TRY(p)
+	PuresoftPostProcessor* pp = ps3d_demo2_make_post_processor(functor);
+	if(!pp) throw std::invalid_argument("post-processor");
+	p->pipe->postProcess(pp);
+	delete pp;
+	PS3D_CATCH(p)
+}
+#else
+int ps3d_post_process(ps3d_pipe*, int) { return PS3D_ERR_UNSUPPORTED; }
+#endif
 
 int ps3d_read_colour(ps3d_pipe* p, void* bgra, size_t pitchBytes)
 {

@@ -29,6 +29,7 @@ PROC_VERTEX, PROC_INTERPOLATION, PROC_FRAGMENT = 0, 1, 2
 FN_DEF01, FN_DEF02, FN_DEF03, FN_DEF04, FN_DEF05 = 1, 2, 3, 4, 5
 FN_PLANET, FN_SATELLITE, FN_CLOUD, FN_CLOUDSHADOW = 16, 17, 18, 19
 FN_POSITIONONLY, FN_SINGLECOLOUR, FN_DIFFUSEONLY, FN_SHADOW2 = 32, 33, 34, 35
+POST_DEPTHOFFIELD = 1
 FN_FLATID = 64
 FN_TEXPROBE = 65
 
@@ -92,6 +93,7 @@ PROTOTYPES = {
     "ps3d_clear_colour": (C.c_int, [_P, C.c_uint32]),
     "ps3d_draw_vao": (C.c_int, [_P, C.c_int, C.c_int]),
     "ps3d_finish": (C.c_int, [_P]),
+    "ps3d_post_process": (C.c_int, [_P, C.c_int]),
     "ps3d_swap_buffers": (C.c_int, [_P]),
     "ps3d_read_colour": (C.c_int, [_P, C.c_void_p, C.c_size_t]),
     "ps3d_read_depth": (C.c_int, [_P, C.c_void_p, C.c_size_t]),

@@ -700,6 +700,41 @@ __global__ void clear_colour_kernel(uint8_t* __restrict__ buf, int width, int ro
 }
 
 // ======================================================================================================================
+// post-processing (post.cpp:3-19): device functors over the finished colour target
+// ======================================================================================================================
+
+// PP_DepthofField (src/test2/testpost.cpp:9-43), the reference's stub: paddb 50 on 8 bytes = two pixels per step, x += 2.
+// A pixel is touched once by its own row, and — odd widths only — pixel 0 of a row once more by the last step of the row
+// before it in memory (scanline = width * 4, so "the pixel behind the end" is the next row's first).
+struct PostDepthofField
+{
+	PS_D static uint32_t apply(uint32_t bgra, float /*depth*/, int x, int y, int width, int /*height*/)
+	{
+		const int times = 1 + ((width & 1) && 0 == x && y > 0 ? 1 : 0);
+		const uint32_t add = 50u * (uint32_t)times;
+		uint32_t out = 0;
+#pragma unroll
+		for(int ch = 0; ch < 4; ch++) out |= ((((bgra >> (8 * ch)) & 0xff) + add) & 0xff) << (8 * ch);
+		return out;
+	}
+};
+
+// y = memory row of the colour target (top-down, fbo.cpp:104-105); depth is bottom-up
+template<class POST>
+__global__ void __launch_bounds__(256) post_process_kernel(TargetDesc colour, TargetDesc depth)
+{
+	const size_t total = (size_t)colour.width * colour.height;
+	for(size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+	{
+		const int y = (int)(i / colour.width), x = (int)(i - (size_t)y * colour.width);
+		uint32_t* px = (uint32_t*)(colour.ptr + (size_t)y * colour.scanline) + x;
+		const int dy = colour.height - 1 - y;
+		const float d = (depth.ptr && dy >= 0 && dy < depth.height && x < depth.width) ? *((const float*)(depth.ptr + (size_t)dy * depth.scanline) + x) : 1.0f;
+		*px = POST::apply(*px, d, x, y, colour.width, colour.height);
+	}
+}
+
+// ======================================================================================================================
 // tile raster + shade
 // ======================================================================================================================
 

@@ -1084,6 +1084,22 @@ int ps3d_finish(ps3d_pipe* p)
 }
 int ps3d_swap_buffers(ps3d_pipe* p) { p->back ^= 1; return PS3D_OK; } // pipeline.cpp:314-322
 
+int ps3d_post_process(ps3d_pipe* p, int functor)   // post.cpp:3-19
+{
+	TRACE();
+	cudaSetDevice(p->device);
+	SETTLE(p);
+	if(functor != PS3D_POST_DEPTHOFFIELD) return fail(p, PS3D_ERR_UNSUPPORTED, "no device functor for this post-processor");
+	if(p->readValid[p->back]) { CK(p, cudaStreamWaitEvent(p->stream, p->readDone[p->back], 0)); p->readValid[p->back] = false; }
+	TargetDesc c;
+	c.ptr = p->display[p->back]; c.width = p->width; c.height = p->height; c.scanline = p->width * 4; c.topDown = 1;
+	const TargetDesc d = depthTarget(p);
+	post_process_kernel<PostDepthofField><<<p->smCount * 8, 256, 0, p->stream>>>(c, d);
+	p->launches++;
+	CK(p, cudaGetLastError());
+	return PS3D_OK;
+}
+
 int ps3d_read_colour(ps3d_pipe* p, void* bgra, size_t pitch)
 {
 	TRACE();

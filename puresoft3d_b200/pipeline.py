@@ -46,6 +46,17 @@ class PuresoftProcessor:
             self.functor = functor
 
 
+class PuresoftPostProcessor:
+    """proc.h:89-94. The reference calls process(threadIndex, threadCount, frame, depth) on every worker; here the object
+    names a device functor run over the whole colour target by one kernel (include/ps3d.h, ps3d_post_process)."""
+    functor = None
+
+
+class PP_DepthofField(PuresoftPostProcessor):
+    """src/test2/testpost.cpp:9-43 — the reference's only post-processor, an unfinished stub: +50 on every byte, wrapping."""
+    functor = _capi.POST_DEPTHOFFIELD
+
+
 def _proc(name, kind, functor):
     return type(name, (PuresoftProcessor,), {"kind": kind, "functor": functor})
 
@@ -242,6 +253,10 @@ class PuresoftPipeline:
 
     def finish(self):
         self._check(self._lib.ps3d_finish(self._h))
+
+    def postProcess(self, processor):
+        """pipeline.h:56 / post.cpp:3-19"""
+        self._check(self._lib.ps3d_post_process(self._h, int(processor.functor)))
 
     def swapBuffers(self):
         self._check(self._lib.ps3d_swap_buffers(self._h))

@@ -202,6 +202,11 @@ def replay(pipe, scene, up, finish=True):
             pipe.useProgramme(up.programmes[c[1]])
         elif op == "draw":
             pipe.drawVAO(up.vaos[c[1]], bool(c[2]) if len(c) > 2 else False)
+        elif op == "post":
+            from .pipeline import PuresoftPostProcessor
+            pp = PuresoftPostProcessor()
+            pp.functor = c[1]
+            pipe.postProcess(pp)
         else:
             raise ValueError("unknown scene command %r" % (op,))
     if finish:
@@ -786,7 +791,7 @@ def write_demo_objx(path, seed=11, clutter=6):
     return path
 
 
-def scene_desk_objx(path, width=1024, height=640, shadow=1024, picture_dir=None, seed=5, tex_size=256):
+def scene_desk_objx(path, width=1024, height=640, shadow=1024, picture_dir=None, seed=5, tex_size=256, post=False):
     """Demo 2's frame (src/test2/puresoft.cpp:115-248) replayed headless from an OBJX file: loadScene (loadscene.cpp:137-345)
     through puresoft3d_b200.objx, the shadow pass over everything not tagged '@noshadow' with VP_Shadow/IP_Null/FP_Null into a
     float texture, then every component with its own programme, material uniforms 30-33 and texture ids 40-43
@@ -875,6 +880,8 @@ def scene_desk_objx(path, width=1024, height=640, shadow=1024, picture_dir=None,
         sc.cmd("use", prog)
         sc.cmd("draw", vao)
         ntri += c["vertices"].shape[0] // 3
+    if post:
+        sc.cmd("post", K.POST_DEPTHOFFIELD)      # pipeline.postProcess(&depthofField), puresoft.cpp:243 (commented out there)
     sc.meta["triangles"] = ntri
     sc.meta["components"] = [c["component"] for (c, _, _, _, _) in drawn]
     return sc

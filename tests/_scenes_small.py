@@ -7,13 +7,13 @@ from puresoft3d_b200 import _capi as K
 from puresoft3d_b200 import scenes
 
 
-def _demo2_from_objx():
+def _demo2_from_objx(post=False, size=(384, 240)):
     """Demo 2's frame driven by an OBJX FILE (native reader, loadScene's re-centring, programme strings, material
     uniforms): the file is written by the native writer first, in the shape of the reference's plane.objx."""
     path = os.path.join(tempfile.gettempdir(), "ps3d_demo2_%d.objx" % os.getpid())
     scenes.write_demo_objx(path, seed=11, clutter=6)
     try:
-        return scenes.scene_desk_objx(path, 384, 240, shadow=256, tex_size=128)
+        return scenes.scene_desk_objx(path, size[0], size[1], shadow=256, tex_size=128, post=post)
     finally:
         os.unlink(path)
 
@@ -33,6 +33,8 @@ SMALL = {
     "demo1_planets": lambda: scenes.scene_planets(400, 250, shadow=240, stacks=12, slices=24, tex_size=128),
     "c3_demo2_desk": lambda: scenes.scene_desk(384, 240, shadow=256, clutter=10, tex_size=128),
     "demo2_objx_file": _demo2_from_objx,
+    # + the post-processing hook (PP_DepthofField through the reference's own postProcess)
+    "demo2_post": lambda: _demo2_from_objx(post=True),
 }
 
 # Extensions with no reference counterpart: checked CUDA-vs-oracle only, "parity unpinned".
@@ -41,4 +43,12 @@ EXTENSION = {
     "c1_cube_bilinear_def03": lambda: scenes.scene_cube(320, 240, functor=K.FN_DEF03, bilinear=True),
     # a 16x16 texture magnified ~10x so that every pixel is a real blend, WRAP addressing (modulo size-1, fbo.cpp:582-590)
     "c1_cube_bilinear_wrap_magnified": lambda: scenes.scene_cube(320, 240, bilinear=True, wrap=K.WRAP_WRAP, tex_size=16),
+}
+
+# PP_DepthofField on an ODD width: each row's last 8-byte step runs into the next row's first pixel, which another worker
+# read-modify-writes at the same time in the reference (src/test2/testpost.cpp:27-40) — a data race there, so column 0 is
+# +50 or +100 from run to run. The restatement and the CUDA functor implement the sequential result (+100); everything
+# but column 0 is still pinned against the reference (tests/test_post_process.py).
+RACY_IN_REFERENCE = {
+    "demo2_post_odd_width": lambda: _demo2_from_objx(post=True, size=(251, 160)),
 }
