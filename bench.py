@@ -214,7 +214,8 @@ def main():
     pipe = PuresoftPipeline(sc.width, sc.height, device=local_rank)
     up = scenes.upload(pipe, sc)
     ext = torch.cuda.ExternalStream(pipe.deviceStream(), device=dev)
-    comp = sortfirst.Compositor(pipe, rank, world, dev, ext) if world > 1 else None
+    native = sortfirst.init_native_comm(pipe, rank, world, dev) if world > 1 else False
+    comp = sortfirst.Compositor(pipe, rank, world, dev, ext, native=native) if world > 1 else None
     if comp:
         pipe.setRowBand(*comp.band)
 
@@ -278,7 +279,7 @@ def main():
             if key not in host_streams:
                 host_streams[key] = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).pin_memory()
             items.append((vbo, host_streams[key]))
-        uploaders.append(sortfirst.ShardedUpload(pipe, items, rank, world, dev))
+        uploaders.append(sortfirst.ShardedUpload(pipe, items, rank, world, dev, native=native))
         host_colour.append(torch.empty((sc.height, sc.width), dtype=torch.int32).pin_memory())
     h2d_t = torch.tensor([float(uploaders[0].h2d_bytes)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -365,7 +366,7 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "scene": sc.name, "triangles": sc.meta.get("triangles"), "resolution": [sc.width, sc.height],
                        "shader": "DEF03 (Blinn-Phong + normal map)", "textures": "2 x %d^2 BGRA nearest" % sc.textures[0]["width"], "fragments_per_frame": frags_per_frame, "fragments_tested_per_frame": tested_per_frame,
-                       "parallelism": "sort-first row bands x%d, NCCL gather to rank 0" % world if world > 1 else "single GPU",
+                       "parallelism": ("sort-first row bands x%d, NCCL send/recv to rank 0 (%s)" % (world, "issued by the library on the pipe's stream" if native else "torch.distributed")) if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (%d MB vertex streams + %d MB textures + header/varying/survivor intermediates of the same order per frame vs 126 MB L2)" % (vertex_b // 1000000, sum(a.nbytes for t in sc.textures for a in t["layers"]) // 1000000),
                        "approx": "x86 rcpps/rsqrtss tables bits=%s" % (pipe.hostApproxInfo(),)},
             "clocks": clocks,

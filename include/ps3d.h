@@ -202,6 +202,23 @@ int ps3d_debug_clear_shade_counts(ps3d_pipe* p);
  * before binning. (-1,-1) = whole viewport. */
 int ps3d_set_row_band(ps3d_pipe* p, int row0, int row1);
 
+/* The exchange steps of sort-first rendering issued from inside the library (NCCL over NVLink on the pipe's own streams;
+ * no host synchronisation, no per-frame work in the host language). libnccl.so.2 is bound at run time (the copy the
+ * process already has, or can load); without it these return PS3D_ERR_UNSUPPORTED.
+ *  ps3d_comm_unique_id   rank 0: 256 bytes (two NCCL unique ids) to hand to every rank by any host transport.
+ *  ps3d_comm_init        collective over all ranks: one communicator for the frame composite (pipe stream) and one for the
+ *                        upload all-gathers (a gather stream), so that frame i's composite and frame i+1's uploads overlap.
+ *  ps3d_composite_bands  bands = 2 * world ints, the raster rows [row0, row1) each rank rendered (ps3d_set_row_band):
+ *                        every rank's band lands in rank 0's colour target, one grouped send/recv behind the frame.
+ *  ps3d_vbo_all_gather   sharded upload: rank r has uploaded units [r * per, (r + 1) * per), per = unitCount / world,
+ *                        with ps3d_vbo_update_async; one in-place all-gather behind it completes the VBO on every rank
+ *                        (units behind world * per are uploaded by every rank itself). Draws wait through the VBO's event. */
+int ps3d_comm_unique_id(void* id256);
+int ps3d_comm_init(ps3d_pipe* p, int rank, int world, const void* id256);
+int ps3d_comm_destroy(ps3d_pipe* p);
+int ps3d_composite_bands(ps3d_pipe* p, const int* bands);
+int ps3d_vbo_all_gather(ps3d_pipe* p, int vbo);
+
 /* Device-resident access for the benchmark and the multi-GPU composite (CUDA library only; the CPU
  * libraries return PS3D_ERR_UNSUPPORTED). Pointers are CUDA device pointers owned by the pipe. */
 int ps3d_device_colour_ptr(ps3d_pipe* p, void** devPtr, size_t* pitchBytes);

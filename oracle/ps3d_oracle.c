@@ -1481,6 +1481,11 @@ int ps3d_vbo_device_written(ps3d_pipe* p, int vbo, void* s) { (void)p; (void)vbo
 int ps3d_device_copy_stream(ps3d_pipe* p, void** s) { (void)p; (void)s; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_read_colour_async(ps3d_pipe* p, void* dst, size_t pitch) { (void)p; (void)dst; (void)pitch; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_device_join(ps3d_pipe* p) { (void)p; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_comm_unique_id(void* id) { (void)id; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_comm_init(ps3d_pipe* p, int r, int w, const void* id) { (void)p; (void)r; (void)w; (void)id; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_comm_destroy(ps3d_pipe* p) { (void)p; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_composite_bands(ps3d_pipe* p, const int* b) { (void)p; (void)b; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_vbo_all_gather(ps3d_pipe* p, int vbo) { (void)p; (void)vbo; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_device_launch_count(ps3d_pipe* p, uint64_t* n) { (void)p; if(n) *n = 0; return PS3D_OK; }
 int ps3d_profile_enable(ps3d_pipe* p, int on) { (void)p; (void)on; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_profile_read(ps3d_pipe* p, ps3d_profile* out) { (void)p; (void)out; return PS3D_ERR_UNSUPPORTED; }

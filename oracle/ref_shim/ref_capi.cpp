@@ -604,6 +604,11 @@ int ps3d_vbo_device_written(ps3d_pipe*, int, void*) { return PS3D_ERR_UNSUPPORTE
 int ps3d_device_copy_stream(ps3d_pipe*, void**) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_read_colour_async(ps3d_pipe*, void*, size_t) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_device_join(ps3d_pipe*) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_comm_unique_id(void*) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_comm_init(ps3d_pipe*, int, int, const void*) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_comm_destroy(ps3d_pipe*) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_composite_bands(ps3d_pipe*, const int*) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_vbo_all_gather(ps3d_pipe*, int) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_device_launch_count(ps3d_pipe*, uint64_t* n) { if(n) *n = 0; return PS3D_OK; }
 int ps3d_profile_enable(ps3d_pipe*, int) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_profile_read(ps3d_pipe*, ps3d_profile*) { return PS3D_ERR_UNSUPPORTED; }

@@ -115,6 +115,11 @@ PROTOTYPES = {
     "ps3d_device_copy_stream": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
     "ps3d_read_colour_async": (C.c_int, [_P, C.c_void_p, C.c_size_t]),
     "ps3d_device_join": (C.c_int, [_P]),
+    "ps3d_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "ps3d_comm_init": (C.c_int, [_P, C.c_int, C.c_int, C.c_void_p]),
+    "ps3d_comm_destroy": (C.c_int, [_P]),
+    "ps3d_composite_bands": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "ps3d_vbo_all_gather": (C.c_int, [_P, C.c_int]),
     "ps3d_device_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "ps3d_profile_enable": (C.c_int, [_P, C.c_int]),
     "ps3d_profile_read": (C.c_int, [_P, C.POINTER(Profile)]),

@@ -12,9 +12,14 @@
 #include <vector>
 #include <algorithm>
 #include <mutex>
+#include <dlfcn.h>
 #include "ps3d.h"
 #include "kernels.cuh"
 #include "x86_approx.h"
+
+// the few NCCL types the run-time binding below needs (stable NCCL 2 ABI: a 128-byte unique id by value, an opaque communicator)
+typedef struct { char internal[128]; } Ps3dNcclUniqueId;
+typedef struct ncclComm* Ps3dNcclComm;
 
 namespace
 {
@@ -196,6 +201,11 @@ struct ps3d_pipe
 	cudaStream_t copyStream;    // asynchronous uploads (ps3d_vbo_update_async)
 	cudaStream_t readStream;    // asynchronous read-backs (ps3d_read_colour_async): its own stream, so that a read-back waiting for its frame does not hold up the next frame's uploads
 	cudaEvent_t frameDone, readDone[2];
+	// sort-first exchange (ps3d_comm_*): one communicator per stream that carries collectives, so that the composite of
+	// frame i (pipe stream) and the upload all-gathers of frame i + 1 (gather stream) do not serialise on each other
+	Ps3dNcclComm commFrame, commUpload;
+	cudaStream_t gatherStream;
+	int commRank, commWorld;
 	bool readValid[2];
 	int width, height;
 	int vpW, vpH;
@@ -279,6 +289,50 @@ struct ProfScope
 #define CK(p, call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { (p)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return PS3D_ERR_DEVICE; } } while(0)
 
 static int settle(ps3d_pipe* p);
+
+// ---- NCCL, bound at run time ------------------------------------------------------------------------------------------
+// The sort-first exchange steps (band composite to rank 0, all-gather of the sharded vertex upload) are issued from inside
+// the library on the pipe's own streams. libnccl is not a link-time dependency: the entry points are looked up in the
+// libnccl.so.2 the process already has (torch.distributed's, when the host side is Python) or can load; the few types
+// are declared here (stable NCCL 2 ABI: a 128-byte unique id by value, opaque communicator, int enums).
+struct NcclApi
+{
+	void* lib;
+	int (*GetUniqueId)(Ps3dNcclUniqueId*);
+	int (*CommInitRank)(Ps3dNcclComm*, int, Ps3dNcclUniqueId, int);
+	int (*CommDestroy)(Ps3dNcclComm);
+	int (*GroupStart)();
+	int (*GroupEnd)();
+	int (*Send)(const void*, size_t, int, int, Ps3dNcclComm, cudaStream_t);
+	int (*Recv)(void*, size_t, int, int, Ps3dNcclComm, cudaStream_t);
+	int (*AllGather)(const void*, void*, size_t, int, Ps3dNcclComm, cudaStream_t);
+	const char* (*GetErrorString)(int);
+};
+enum { PS_NCCL_UINT8 = 1 };   // ncclUint8 / ncclChar's unsigned sibling in nccl.h's ncclDataType_t
+static const NcclApi* ncclApi()
+{
+	static NcclApi api;
+	static std::once_flag once;
+	std::call_once(once, [] {
+		memset(&api, 0, sizeof(api));
+		void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+		if(!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+		if(!h) h = dlopen("libnccl.so", RTLD_NOW);
+		if(!h) return;
+		api.GetUniqueId = (int (*)(Ps3dNcclUniqueId*))dlsym(h, "ncclGetUniqueId");
+		api.CommInitRank = (int (*)(Ps3dNcclComm*, int, Ps3dNcclUniqueId, int))dlsym(h, "ncclCommInitRank");
+		api.CommDestroy = (int (*)(Ps3dNcclComm))dlsym(h, "ncclCommDestroy");
+		api.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+		api.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+		api.Send = (int (*)(const void*, size_t, int, int, Ps3dNcclComm, cudaStream_t))dlsym(h, "ncclSend");
+		api.Recv = (int (*)(void*, size_t, int, int, Ps3dNcclComm, cudaStream_t))dlsym(h, "ncclRecv");
+		api.AllGather = (int (*)(const void*, void*, size_t, int, Ps3dNcclComm, cudaStream_t))dlsym(h, "ncclAllGather");
+		api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+		if(api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Send && api.Recv && api.AllGather) api.lib = h;
+	});
+	return api.lib ? &api : nullptr;
+}
+#define NK(p, call) do { int r_ = (call); if(r_ != 0) { const NcclApi* a_ = ncclApi(); (p)->err = std::string(#call) + ": " + ((a_ && a_->GetErrorString) ? a_->GetErrorString(r_) : "nccl error"); return PS3D_ERR_DEVICE; } } while(0)
 #define SETTLE(p) do { int rc_ = settle(p); if(rc_) return rc_; } while(0)
 
 static int fail(ps3d_pipe* p, int code, const char* msg) { p->err = msg; return code; }
@@ -482,6 +536,7 @@ int ps3d_create(int width, int height, int device, ps3d_pipe** out)
 	ok = ok && cudaEventCreateWithFlags(&p->readDone[0], cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&p->readDone[1], cudaEventDisableTiming) == cudaSuccess;
 	p->readValid[0] = p->readValid[1] = false;
+	p->commFrame = p->commUpload = nullptr; p->gatherStream = nullptr; p->commRank = 0; p->commWorld = 1;
 	const size_t cbytes = (size_t)width * 4 * height, dbytes = (size_t)p->depthScanline * height;
 	ok = ok && cudaMalloc((void**)&p->display[0], cbytes) == cudaSuccess && cudaMalloc((void**)&p->display[1], cbytes) == cudaSuccess;
 	ok = ok && cudaMalloc((void**)&p->defaultDepth, dbytes + 16) == cudaSuccess;
@@ -537,6 +592,7 @@ int ps3d_destroy(ps3d_pipe* p)
 	cudaStreamSynchronize(p->stream);
 	for(Texture* t : p->textures) if(t) { for(int i = 0; i < 6; i++) if(t->layer[i]) cudaFree(t->layer[i]); delete t; }
 	cudaStreamSynchronize(p->copyStream); cudaStreamSynchronize(p->readStream);
+	ps3d_comm_destroy(p);
 	for(Vbo& v : p->vbos) if(v.alive) freeVbo(v);
 	cudaFree(p->display[0]); cudaFree(p->display[1]); cudaFree(p->defaultDepth);
 	cudaFree(p->totalDev); cudaFree(p->statsDev); cudaFree(p->svCountDev); cudaFree(p->poisonDev); cudaFreeHost(p->report); cudaEventDestroy(p->scanEvent);
@@ -1080,6 +1136,7 @@ int ps3d_finish(ps3d_pipe* p)
 	CK(p, cudaStreamSynchronize(p->stream));
 	CK(p, cudaStreamSynchronize(p->copyStream));
 	CK(p, cudaStreamSynchronize(p->readStream));
+	if(p->gatherStream) CK(p, cudaStreamSynchronize(p->gatherStream));
 	return PS3D_OK;
 }
 int ps3d_swap_buffers(ps3d_pipe* p) { p->back ^= 1; return PS3D_OK; } // pipeline.cpp:314-322
@@ -1218,6 +1275,96 @@ int ps3d_debug_clear_shade_counts(ps3d_pipe* p)
 	cudaSetDevice(p->device);
 	SETTLE(p);
 	if(p->capDev) CK(p, cudaMemsetAsync(p->capDev, 0, (size_t)p->capW * p->capH * 4, p->stream));
+	return PS3D_OK;
+}
+
+// ---- sort-first exchange steps, issued natively on the pipe's streams ------------------------------------
+
+int ps3d_comm_unique_id(void* id256)
+{
+	const NcclApi* a = ncclApi();
+	if(!a || !id256) return PS3D_ERR_UNSUPPORTED;
+	Ps3dNcclUniqueId ids[2];
+	if(a->GetUniqueId(&ids[0]) != 0 || a->GetUniqueId(&ids[1]) != 0) return PS3D_ERR_DEVICE;
+	memcpy(id256, ids, sizeof(ids));
+	return PS3D_OK;
+}
+int ps3d_comm_init(ps3d_pipe* p, int rank, int world, const void* id256)
+{
+	TRACE();
+	const NcclApi* a = ncclApi();
+	if(!a) return fail(p, PS3D_ERR_UNSUPPORTED, "libnccl.so.2 not found");
+	if(world < 1 || rank < 0 || rank >= world || !id256) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "rank / world");
+	if(p->commFrame) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "communicators already initialised");
+	cudaSetDevice(p->device);
+	Ps3dNcclUniqueId ids[2];
+	memcpy(ids, id256, sizeof(ids));
+	NK(p, a->CommInitRank(&p->commFrame, world, ids[0], rank));
+	NK(p, a->CommInitRank(&p->commUpload, world, ids[1], rank));
+	CK(p, cudaStreamCreateWithFlags(&p->gatherStream, cudaStreamNonBlocking));
+	p->commRank = rank; p->commWorld = world;
+	return PS3D_OK;
+}
+int ps3d_comm_destroy(ps3d_pipe* p)
+{
+	const NcclApi* a = ncclApi();
+	if(p->gatherStream) { cudaStreamSynchronize(p->gatherStream); }
+	if(a && p->commFrame) { cudaStreamSynchronize(p->stream); a->CommDestroy(p->commFrame); }
+	if(a && p->commUpload) a->CommDestroy(p->commUpload);
+	if(p->gatherStream) cudaStreamDestroy(p->gatherStream);
+	p->commFrame = p->commUpload = nullptr; p->gatherStream = nullptr; p->commRank = 0; p->commWorld = 1;
+	return PS3D_OK;
+}
+// bands: 2 * world ints, raster rows [row0, row1) rendered by each rank. The colour target is top-down (fbo.cpp:104-105):
+// raster rows [r0, r1) are memory rows [H - r1, H - r0). One grouped send/recv on the pipe's stream behind the frame.
+int ps3d_composite_bands(ps3d_pipe* p, const int* bands)
+{
+	TRACE();
+	cudaSetDevice(p->device);
+	SETTLE(p);
+	const NcclApi* a = ncclApi();
+	if(!a || !p->commFrame) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "ps3d_comm_init first");
+	if(!bands) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "bands");
+	if(1 == p->commWorld) return PS3D_OK;
+	const size_t pitch = (size_t)p->width * 4;
+	uint8_t* target = p->display[p->back];
+	if(0 == p->commRank && p->readValid[p->back]) { CK(p, cudaStreamWaitEvent(p->stream, p->readDone[p->back], 0)); p->readValid[p->back] = false; }
+	NK(p, a->GroupStart());
+	for(int r = 1; r < p->commWorld; r++)
+	{
+		const int r0 = std::max(0, std::min(bands[2 * r], p->height)), r1 = std::max(r0, std::min(bands[2 * r + 1], p->height));
+		if(r1 == r0) continue;
+		uint8_t* at = target + (size_t)(p->height - r1) * pitch;
+		const size_t bytes = (size_t)(r1 - r0) * pitch;
+		if(0 == p->commRank) NK(p, a->Recv(at, bytes, PS_NCCL_UINT8, r, p->commFrame, p->stream));
+		else if(r == p->commRank) NK(p, a->Send(at, bytes, PS_NCCL_UINT8, 0, p->commFrame, p->stream));
+	}
+	NK(p, a->GroupEnd());
+	p->launches++;
+	return PS3D_OK;
+}
+// Sharded upload's exchange: rank r has written units [r * per, (r + 1) * per) of the VBO (ps3d_vbo_update_async, per =
+// unitCount / world); one in-place all-gather on the gather stream, behind that upload, makes them whole on every rank.
+// Draws wait for it through the VBO's ready event.
+int ps3d_vbo_all_gather(ps3d_pipe* p, int vbo)
+{
+	TRACE();
+	cudaSetDevice(p->device);
+	const NcclApi* a = ncclApi();
+	if(!a || !p->commUpload) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "ps3d_comm_init first");
+	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
+	Vbo& v = p->vbos[vbo];
+	if(1 == p->commWorld) return PS3D_OK;
+	{ const int rc = vboEvents(p, v); if(rc) return rc; }
+	const size_t perBytes = (v.unitCount / (size_t)p->commWorld) * v.unitBytes;
+	if(0 == perBytes) return PS3D_OK;
+	// behind the asynchronous upload of this rank's shard (which itself waited for the last draw that read the VBO)
+	if(v.readyValid) CK(p, cudaStreamWaitEvent(p->gatherStream, v.ready, 0));
+	else if(v.readValid) CK(p, cudaStreamWaitEvent(p->gatherStream, v.lastRead, 0));
+	NK(p, a->AllGather(v.data + (size_t)p->commRank * perBytes, v.data, perBytes, PS_NCCL_UINT8, p->commUpload, p->gatherStream));
+	CK(p, cudaEventRecord(v.ready, p->gatherStream));
+	v.readyValid = true;
+	p->launches++;
 	return PS3D_OK;
 }
 

@@ -112,6 +112,10 @@ class PuresoftVBO:
         self._pipe._check(self._pipe._lib.ps3d_vbo_device_ptr(self._pipe._h, self.handle, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def allGather(self):
+        """Sharded upload: completes the VBO from every rank's shard (ps3d_vbo_all_gather)."""
+        self._pipe._check(self._pipe._lib.ps3d_vbo_all_gather(self._pipe._h, self.handle))
+
     def deviceWritten(self, cuda_stream):
         self._pipe._check(self._pipe._lib.ps3d_vbo_device_written(self._pipe._h, self.handle, C.c_void_p(cuda_stream)))
 
@@ -341,6 +345,24 @@ class PuresoftPipeline:
     def readColourAsync(self, pinned_ptr, pitchBytes=None):
         """Colour target into PINNED host memory behind the work enqueued so far; complete after finish()."""
         self._check(self._lib.ps3d_read_colour_async(self._h, C.c_void_p(pinned_ptr), int(pitchBytes or self.width * 4)))
+
+    # ---- sort-first exchange steps inside the library (include/ps3d.h) ---------------------------------------
+    def commUniqueId(self):
+        """Rank 0: 256 opaque bytes every rank passes to commInit."""
+        buf = (C.c_uint8 * 256)()
+        self._check(self._lib.ps3d_comm_unique_id(C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def commInit(self, rank, world, unique_id):
+        buf = (C.c_uint8 * 256).from_buffer_copy(unique_id)
+        self._check(self._lib.ps3d_comm_init(self._h, int(rank), int(world), C.cast(buf, C.c_void_p)))
+
+    def commDestroy(self):
+        self._lib.ps3d_comm_destroy(self._h)
+
+    def compositeBands(self, bands):
+        flat = (C.c_int * (2 * len(bands)))(*[int(v) for b in bands for v in b])
+        self._check(self._lib.ps3d_composite_bands(self._h, flat))
 
     def deviceJoin(self):
         """The pipe's stream waits for everything enqueued so far on the copy and read-back streams."""

@@ -50,6 +50,30 @@ def gather_bands(colour, bands, rank, world, height):
             req.wait()
 
 
+def init_native_comm(pipe, rank, world, device):
+    """The library's own NCCL communicators (ps3d_comm_init): rank 0 draws the unique ids, torch.distributed carries the
+    256 bytes to every rank — the only thing the host language does for the exchange steps; the composite and the upload
+    all-gathers are then issued from inside the library on the pipe's streams. Returns False (torch path stays) when
+    PS3D_SORTFIRST=torch or libnccl cannot be bound."""
+    import os
+    if world == 1 or os.environ.get("PS3D_SORTFIRST", "native") == "torch":
+        return False
+    buf = torch.zeros(257, dtype=torch.uint8, device=device)
+    if rank == 0:
+        try:
+            ids = pipe.commUniqueId()
+            buf[:256] = torch.frombuffer(bytearray(ids), dtype=torch.uint8).to(device)
+            buf[256] = 1
+        except Exception:  # noqa: BLE001 — libnccl not bindable: every rank learns it from the flag below
+            pass
+    dist.broadcast(buf, 0)
+    host = buf.cpu().numpy()
+    if host[256] != 1:
+        return False
+    pipe.commInit(rank, world, bytes(host[:256]))
+    return True
+
+
 class _DevicePtr:
     def __init__(self, ptr, shape, typestr="<i4"):
         self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
@@ -58,10 +82,11 @@ class _DevicePtr:
 class Compositor:
     """Binds a pipe's device colour target to torch and gathers the bands on the pipe's own stream."""
 
-    def __init__(self, pipe, rank, world, device, ext_stream):
+    def __init__(self, pipe, rank, world, device, ext_stream, native=False):
         self.pipe, self.rank, self.world, self.device, self.ext = pipe, rank, world, device, ext_stream
         self.bands = row_bands(pipe.height, world)
         self.band = self.bands[rank]
+        self.native = native          # ps3d_composite_bands (the library's own communicator) instead of torch.distributed
         self._views = {}
 
     def _colour(self):
@@ -72,6 +97,9 @@ class Compositor:
         return self._views[ptr]
 
     def gather_to_rank0(self):
+        if self.native:
+            self.pipe.compositeBands(self.bands)
+            return
         with torch.cuda.stream(self.ext):
             gather_bands(self._colour(), self.bands, self.rank, self.world, self.pipe.height)
 
@@ -98,18 +126,19 @@ class ShardedUpload:
     next step's uploads never wait for a collective. Draws wait for the gathered streams through the VBOs' ready events
     (ps3d_vbo_device_written); nothing blocks the host."""
 
-    def __init__(self, pipe, vbos, rank, world, device):
-        """vbos: [(PuresoftVBO, pinned uint8 torch tensor holding the WHOLE stream's bytes)]"""
-        self.pipe, self.rank, self.world = pipe, rank, world
+    def __init__(self, pipe, vbos, rank, world, device, native=False):
+        """vbos: [(PuresoftVBO, pinned uint8 torch tensor holding the WHOLE stream's bytes)]. native: the all-gathers are
+        issued by the library itself (ps3d_vbo_all_gather, its own communicator and gather stream)."""
+        self.pipe, self.rank, self.world, self.native = pipe, rank, world, native
         self.copy_stream = pipe.deviceCopyStream()
         self.ext = torch.cuda.ExternalStream(self.copy_stream, device=device)
-        self.gather = torch.cuda.Stream(device=device) if world > 1 else None
+        self.gather = torch.cuda.Stream(device=device) if (world > 1 and not native) else None
         self.items = []
         for vbo, host in vbos:
             ptr, nbytes = vbo.devicePtr()
             per, rem = shard_units(vbo.unitCount, world)
-            flat = torch.as_tensor(_DevicePtr(ptr, (nbytes,), "|u1"), device=device) if world > 1 else None
-            self.items.append((vbo, host, per, rem, flat, torch.cuda.Event() if world > 1 else None))
+            flat = torch.as_tensor(_DevicePtr(ptr, (nbytes,), "|u1"), device=device) if (world > 1 and not native) else None
+            self.items.append((vbo, host, per, rem, flat, torch.cuda.Event() if (world > 1 and not native) else None))
         self.h2d_bytes = sum((per + rem) * vbo.unitBytes for vbo, _, per, rem, _, _ in self.items)
 
     def step(self):
@@ -119,7 +148,9 @@ class ShardedUpload:
             vbo.updateContentAsync(base + r * per * vbo.unitBytes, r * per, per)
             if rem:
                 vbo.updateContentAsync(base + w * per * vbo.unitBytes, w * per, rem)
-            if w > 1:
+            if w > 1 and self.native:
+                vbo.allGather()
+            elif w > 1:
                 # the copy stream has also waited for the last draw that read this VBO (ps3d_vbo_update_async), so the
                 # gather behind this event cannot overwrite a stream a geometry kernel is still reading
                 ev.record(self.ext)
