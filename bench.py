@@ -219,8 +219,10 @@ def main():
     if comp:
         pipe.setRowBand(*comp.band)
 
+    replay_frame = scenes.compile_replay(pipe, sc, up)   # the frame's command list with its ctypes arguments prepared once
+
     def frame():
-        scenes.replay(pipe, sc, up, finish=False)
+        replay_frame()
         if comp:
             comp.gather_to_rank0()
 
@@ -287,10 +289,12 @@ def main():
     h2d = int(h2d_t.item())          # all ranks together
     d2h = host_colour[0].numel() * 4
 
+    replay_set = [replay_frame, scenes.compile_replay(pipe, sc, ups[1])]
+
     def frame_e2e(i):
         s = i & 1
         uploaders[s].step()
-        scenes.replay(pipe, sc, ups[s], finish=False)
+        replay_set[s]()
         if comp:
             comp.gather_to_rank0()
         if rank == 0:

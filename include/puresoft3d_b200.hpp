@@ -83,6 +83,18 @@ PS3D_DECLARE_FAMILY(DEF04, PS3D_FN_DEF04) // skybox.h
 PS3D_DECLARE_FAMILY(DEF05, PS3D_FN_DEF05) // shadow.h
 #undef PS3D_DECLARE_FAMILY
 
+// proc.h:89-94. The reference's process(threadIndex, threadCount, frame, depth) body becomes a device functor named by id.
+class PuresoftPostProcessor
+{
+public:
+	explicit PuresoftPostProcessor(int functor) : m_functor(functor) {}
+	virtual ~PuresoftPostProcessor() {}
+	int functor() const { return m_functor; }
+private:
+	int m_functor;
+};
+class PP_DepthofField : public PuresoftPostProcessor { public: PP_DepthofField() : PuresoftPostProcessor(PS3D_POST_DEPTHOFFIELD) {} }; // src/test2/testpost.h
+
 class PuresoftPipeline;
 
 namespace ps3d_detail
@@ -109,6 +121,9 @@ public:
 	~PuresoftVBO();
 	void updateContent(const void* src);           // vbo.cpp:28-31 — whole-buffer, synchronous
 	void updateContentDevice(const void* devSrc);  // source already in HBM
+	// pipelined transfers (include/ps3d.h): units [firstUnit, firstUnit + unitCount) from PINNED host memory, returns at once
+	void updateContentAsync(const void* pinnedSrc, size_t firstUnit, size_t unitCount);
+	void allGather();                              // sharded upload's exchange step (after PuresoftPipeline::commInit)
 	int handle() const { return m_handle; }
 	size_t unitBytes() const { return m_unitBytes; }
 	size_t unitCount() const { return m_unitCount; }
@@ -205,6 +220,7 @@ public:
 	void drawVAO(int vao, bool callerThrdForFragProc = false) { check(ps3d_draw_vao(m_pipe, vao, callerThrdForFragProc ? 1 : 0)); }
 	void finish(void) { check(ps3d_finish(m_pipe)); }
 	void swapBuffers(void) { check(ps3d_swap_buffers(m_pipe)); }
+	void postProcess(PuresoftPostProcessor* processor) { check(ps3d_post_process(m_pipe, processor->functor())); } // post.cpp:3-19
 	void enable(int behavior) { check(ps3d_enable(m_pipe, behavior)); }
 	void disable(int behavior) { check(ps3d_disable(m_pipe, behavior)); }
 	void clearDepth(float furthest = 1.0f) { check(ps3d_clear_depth(m_pipe, furthest)); }
@@ -215,6 +231,11 @@ public:
 	void readDepth(float* depth, size_t pitchBytes) { check(ps3d_read_depth(m_pipe, depth, pitchBytes)); }
 	ps3d_stats getStats(void) { ps3d_stats s; check(ps3d_get_stats(m_pipe, &s)); return s; }
 	void setRowBand(int row0 = -1, int row1 = -1) { check(ps3d_set_row_band(m_pipe, row0, row1)); }
+	// asynchronous read-back into PINNED host memory (complete after finish()), and the sort-first exchange steps
+	void readColourAsync(void* pinnedBgra, size_t pitchBytes) { check(ps3d_read_colour_async(m_pipe, pinnedBgra, pitchBytes)); }
+	static void commUniqueId(void* id256) { ps3d_detail::raise(NULL, ps3d_comm_unique_id(id256)); }
+	void commInit(int rank, int world, const void* id256) { check(ps3d_comm_init(m_pipe, rank, world, id256)); }
+	void compositeBands(const int* bands) { check(ps3d_composite_bands(m_pipe, bands)); }
 
 	int deviceWidth() const { return m_width; }
 	int deviceHeight() const { return m_height; }
@@ -255,4 +276,6 @@ inline PuresoftVBO::~PuresoftVBO()
 	if(m_pipe && m_handle >= 0) ps3d_vbo_destroy(m_pipe, m_handle);
 }
 inline void PuresoftVBO::updateContent(const void* src) { ps3d_detail::raise(m_pipe, ps3d_vbo_update(m_pipe, m_handle, src)); }
+inline void PuresoftVBO::updateContentAsync(const void* pinnedSrc, size_t firstUnit, size_t unitCount) { ps3d_detail::raise(m_pipe, ps3d_vbo_update_async(m_pipe, m_handle, firstUnit, unitCount, pinnedSrc)); }
+inline void PuresoftVBO::allGather() { ps3d_detail::raise(m_pipe, ps3d_vbo_all_gather(m_pipe, m_handle)); }
 inline void PuresoftVBO::updateContentDevice(const void* devSrc) { ps3d_detail::raise(m_pipe, ps3d_vbo_update_device(m_pipe, m_handle, devSrc)); }

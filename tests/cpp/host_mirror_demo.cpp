@@ -100,6 +100,11 @@ int main()
 	       (unsigned long long)st.spans, (unsigned long long)st.fragments_tested, (unsigned long long)st.fragments_shaded);
 	printf("colour %016llx\n", fnv(colour.data(), colour.size() * 4));
 	printf("depth %016llx\n", fnv(depth.data(), depth.size() * 4));
+	// post-processing hook, as src/test2/puresoft.cpp:243 would call it
+	PP_DepthofField depthofField;
+	pipeline.postProcess(&depthofField);
+	pipeline.readColour(colour.data(), W * 4);
+	printf("post %016llx\n", fnv(colour.data(), colour.size() * 4));
 	pipeline.destroyVAO(vao); // takes vp, vn(attached? no: displaced), vc with it (pipeline.cpp:194-201)
 	delete vn;                // handed back by attachVBO, so it is ours
 	return ok ? 0 : 1;

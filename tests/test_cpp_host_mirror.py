@@ -27,6 +27,7 @@ def test_host_mirror_against_oracle_library(tmp_path, built):
     assert out["backend"] == "oracle-c"
     assert out["errors"] == "ok" and out["ownership"] == "ok"
     assert int(out["stats"].split()[4]) > 1000
+    assert out["post"] != out["colour"]
 
 
 @pytest.mark.gpu
@@ -35,5 +36,5 @@ def test_host_mirror_cuda_equals_oracle(tmp_path, built):
     b = build_and_run(tmp_path, ORACLE_SO, "oracle")
     assert a["backend"] == "cuda-sm100a"
     assert a["errors"] == "ok" and a["ownership"] == "ok"
-    for key in ("stats", "depth", "colour"):
+    for key in ("stats", "depth", "colour", "post"):
         assert a[key] == b[key], key

@@ -199,3 +199,20 @@ def test_demo2_from_plane_objx_oracle_equals_reference(oracle_lib, ref_lib, buil
     assert np.array_equal(a["depth"].view(np.uint32), b["depth"].view(np.uint32))
     assert np.array_equal(a["counts"], b["counts"])
     assert a["stats"]["fragments_shaded"] == b["stats"]["fragments_shaded"] > 100000
+
+
+def test_compiled_replay_is_the_same_frame(oracle_lib, built):
+    """scenes.compile_replay (the command list with its ctypes arguments prepared once) against scenes.replay."""
+    from _scenes_small import SMALL
+    from puresoft3d_b200.pipeline import PuresoftPipeline
+    for name in ("c3_demo2_desk", "demo2_post", "c4_blend_overdraw"):
+        sc = SMALL[name]()
+        want = render_all(oracle_lib, sc, capture=False)
+        p = PuresoftPipeline(sc.width, sc.height, lib=oracle_lib)
+        up = scenes.upload(p, sc)
+        frame = scenes.compile_replay(p, sc, up)
+        frame()
+        p.finish()
+        assert np.array_equal(p.readColour(), want["colour"]), name
+        assert np.array_equal(p.readDepth().view(np.uint32), want["depth"].view(np.uint32)), name
+        p.close()
