@@ -215,7 +215,9 @@ def main():
     up = scenes.upload(pipe, sc)
     ext = torch.cuda.ExternalStream(pipe.deviceStream(), device=dev)
     native = sortfirst.init_native_comm(pipe, rank, world, dev) if world > 1 else False
-    comp = sortfirst.Compositor(pipe, rank, world, dev, ext, native=native) if world > 1 else None
+    native_comp = False
+    native_comp = native and os.environ.get("PS3D_SORTFIRST_COMPOSITE", "native") != "torch"
+    comp = sortfirst.Compositor(pipe, rank, world, dev, ext, native=native_comp) if world > 1 else None
     if comp:
         pipe.setRowBand(*comp.band)
 
@@ -370,7 +372,7 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "scene": sc.name, "triangles": sc.meta.get("triangles"), "resolution": [sc.width, sc.height],
                        "shader": "DEF03 (Blinn-Phong + normal map)", "textures": "2 x %d^2 BGRA nearest" % sc.textures[0]["width"], "fragments_per_frame": frags_per_frame, "fragments_tested_per_frame": tested_per_frame,
-                       "parallelism": ("sort-first row bands x%d, NCCL send/recv to rank 0 (%s)" % (world, "issued by the library on the pipe's stream" if native else "torch.distributed")) if world > 1 else "single GPU",
+                       "parallelism": ("sort-first row bands x%d, NCCL send/recv to rank 0 (%s)" % (world, "issued by the library on the pipe's stream" if native_comp else "torch.distributed")) if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (%d MB vertex streams + %d MB textures + header/varying/survivor intermediates of the same order per frame vs 126 MB L2)" % (vertex_b // 1000000, sum(a.nbytes for t in sc.textures for a in t["layers"]) // 1000000),
                        "approx": "x86 rcpps/rsqrtss tables bits=%s" % (pipe.hostApproxInfo(),)},
             "clocks": clocks,
