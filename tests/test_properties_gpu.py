@@ -33,7 +33,8 @@ def test_tile_and_binning_paths_agree(kind, built):
     base = run_hash(kind)
     assert base["stats"]["fragments_shaded"] == base["counts_sum"] > 0
     for env in ({"PS3D_TILE_PATH": "ordered"}, {"PS3D_TILE_PATH": "immediate"}, {"PS3D_BINNING": "radix"},
-                {"PS3D_RASTER_PARTS": "1"}, {"PS3D_RASTER_PARTS": "2"}, {"PS3D_RASTER_PARTS": "4"}):
+                {"PS3D_RASTER_PARTS": "1"}, {"PS3D_RASTER_PARTS": "2"}, {"PS3D_RASTER_PARTS": "4"},
+                {"PS3D_SPECULATE": "0"}):
         other = run_hash(kind, **env)
         for key in ("depth", "counts", "colour"):
             assert other[key] == base[key], (env, key)
