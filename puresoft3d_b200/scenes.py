@@ -598,22 +598,48 @@ def tex_cloud(rng, w, h):
     return out
 
 
-def scene_planets(width=800, height=500, shadow=480, seed=3, stacks=16, slices=32, tex_size=256):
+DEMO1_PICTURES = {   # src/test/testobjs.cpp:12-18, :63-64, :119-122, :188-196 (cube faces: xpos, xneg, ypos, yneg, zpos, zneg)
+    "diffuse": "earth.jpg", "bump": "earth.dot3.png", "spec": "earth.spac.png", "night": "earth.night.png", "cloud": "earth.cloud.png",
+    "moon_d": "moon.jpg", "moon_b": "moon.dot3.png",
+    "sky": ["purplenebula_rt.png", "purplenebula_lf.png", "purplenebula_up.png", "purplenebula_dn.png", "purplenebula_ft.png", "purplenebula_bk.png"],
+}
+
+
+def scene_planets(width=800, height=500, shadow=480, seed=3, stacks=16, slices=32, tex_size=256, sphere_objx=None, picture_dir=None):
     """Demo 1 (src/test/puresoft.cpp:113-206): shadow pass into a float texture (earth + moon with DEF05, cloud layer with the
     discarding CloudShadow triple), then skybox (DEF04, depth off), earth (VP/IP_Planet + FP_Earth), moon (FP_Satellite) and the
     alpha-blended cloud layer (VP/IP/FP_Cloud). Uniform slots as src/test/testobjs.cpp:45-145."""
     rng = np.random.default_rng(seed)
-    sc = Scene("demo1-planets-%dx%d" % (width, height), width, height)
-    diffuse = sc.add_texture(tex_size, tex_size, 4, tex_smooth_bgra(rng, tex_size, tex_size))
-    bump = sc.add_texture(tex_size, tex_size, 4, tex_smooth_bgra(rng, tex_size, tex_size, normal_map=True))
-    spec = sc.add_texture(tex_size, tex_size, 4, tex_smooth_bgra(rng, tex_size, tex_size))
-    night = sc.add_texture(tex_size, tex_size, 4, (tex_smooth_bgra(rng, tex_size, tex_size) // 3).astype(np.uint8))
-    cloud = sc.add_texture(tex_size, tex_size, 4, tex_cloud(rng, tex_size, tex_size))
-    moon_d = sc.add_texture(tex_size // 2, tex_size // 2, 4, tex_smooth_bgra(rng, tex_size // 2, tex_size // 2))
-    moon_b = sc.add_texture(tex_size // 2, tex_size // 2, 4, tex_smooth_bgra(rng, tex_size // 2, tex_size // 2, normal_map=True))
-    sky = sc.add_texture(64, 64, 4, layers=[tex_smooth_bgra(rng, 64, 64) for _ in range(6)])
+    sc = Scene("demo1-planets-%dx%d%s" % (width, height, "-objx" if sphere_objx else ""), width, height)
+
+    def tex(key, synthetic):
+        """The demo's own picture (picture_dir given and the file is there: SceneObject::findOrCreateTexture,
+        src/test/scenobj.cpp:165-200, through objx.load_picture) or a seeded synthetic stand-in."""
+        pix = synthetic()
+        if picture_dir and os.path.exists(os.path.join(picture_dir, DEMO1_PICTURES[key])):
+            from . import objx
+            pix = objx.load_picture(os.path.join(picture_dir, DEMO1_PICTURES[key]))
+        return sc.add_texture(pix.shape[1], pix.shape[0], 4, np.ascontiguousarray(pix))
+
+    diffuse = tex("diffuse", lambda: tex_smooth_bgra(rng, tex_size, tex_size))
+    bump = tex("bump", lambda: tex_smooth_bgra(rng, tex_size, tex_size, normal_map=True))
+    spec = tex("spec", lambda: tex_smooth_bgra(rng, tex_size, tex_size))
+    night = tex("night", lambda: (tex_smooth_bgra(rng, tex_size, tex_size) // 3).astype(np.uint8))
+    cloud = tex("cloud", lambda: tex_cloud(rng, tex_size, tex_size))
+    moon_d = tex("moon_d", lambda: tex_smooth_bgra(rng, tex_size // 2, tex_size // 2))
+    moon_b = tex("moon_b", lambda: tex_smooth_bgra(rng, tex_size // 2, tex_size // 2, normal_map=True))
+    faces = [tex_smooth_bgra(rng, 64, 64) for _ in range(6)]
+    if picture_dir and all(os.path.exists(os.path.join(picture_dir, f)) for f in DEMO1_PICTURES["sky"]):
+        from . import objx
+        faces = [np.ascontiguousarray(objx.load_picture(os.path.join(picture_dir, f))) for f in DEMO1_PICTURES["sky"]]
+    sky = sc.add_texture(faces[0].shape[1], faces[0].shape[0], 4, layers=faces)
     shadow_tex = sc.add_texture(shadow, shadow, 4, None)   # float depth, created empty (puresoft.cpp:141-147)
-    sphere = sc.add_vao(_std_slots(sphere_mesh(stacks, slices, radius=0.5)))
+    if sphere_objx:
+        # SceneObject::findOrCreateVao("sphere.objx"), src/test/scenobj.cpp:88-163: first mesh of the file, w = 1, binormals
+        from . import objx
+        sphere = sc.add_vao(objx.mesh_slots(objx.read_objx(sphere_objx)[1][0]))
+    else:
+        sphere = sc.add_vao(_std_slots(sphere_mesh(stacks, slices, radius=0.5)))
     quad = sc.add_vao({0: (16, np.array([(-1, 1, 0, 1), (-1, -1, 0, 1), (1, -1, 0, 1), (1, -1, 0, 1), (1, 1, 0, 1), (-1, 1, 0, 1)], F32))})
     p_shadow = sc.add_programme(K.FN_DEF05)
     p_cloudshadow = sc.add_programme(K.FN_CLOUDSHADOW)

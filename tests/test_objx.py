@@ -216,3 +216,16 @@ def test_compiled_replay_is_the_same_frame(oracle_lib, built):
         assert np.array_equal(p.readColour(), want["colour"]), name
         assert np.array_equal(p.readDepth().view(np.uint32), want["depth"].view(np.uint32)), name
         p.close()
+
+
+@needs_reference
+def test_demo1_from_sphere_objx_oracle_equals_reference(oracle_lib, ref_lib, built):
+    """Demo 1's frame (src/test/puresoft.cpp:162-206) with the reference's own sphere.objx and pictures: earth (diffuse, dot3,
+    specular, night maps), cloud layer (blended, discarding shadow pass), moon, cube-map skybox, projective shadow lookup."""
+    sc = scenes.scene_planets(640, 400, shadow=480, sphere_objx=REF_TEST + "/sphere.objx", picture_dir=REF_TEST)
+    assert (sc.textures[0]["width"], sc.textures[0]["height"]) == (2048, 1024) and len(sc.textures[7]["layers"]) == 6
+    a, b = render_all(oracle_lib, sc), render_all(ref_lib, sc)
+    assert np.array_equal(a["colour"], b["colour"])
+    assert np.array_equal(a["depth"].view(np.uint32), b["depth"].view(np.uint32))
+    assert np.array_equal(a["counts"], b["counts"])
+    assert a["stats"]["fragments_shaded"] == b["stats"]["fragments_shaded"] > 300000
