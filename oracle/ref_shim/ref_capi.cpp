@@ -155,6 +155,7 @@ struct ps3d_pipe
 	std::vector<size_t> vboBytes;
 	std::string err;
 	uint64_t draws;
+	uint64_t triangles;   // complete triangles: per draw, vertex-processor calls / 3 (a dangling vertex or two never forms one)
 };
 
 #define PS3D_TRY(p) try {
@@ -182,7 +183,7 @@ int ps3d_create(int width, int height, int, ps3d_pipe** out)
 {
 	if(!out || width <= 0 || height <= 0) return PS3D_ERR_INVALID_ARGUMENT;
 	ps3d_pipe* p = new ps3d_pipe;
-	p->width = width; p->height = height; p->draws = 0;
+	p->width = width; p->height = height; p->draws = 0; p->triangles = 0;
 	p->sh = new Shared;
 	p->sh->counters.reset();
 	const char* env = getenv("PS3D_REF_COUNTING");
@@ -477,7 +478,9 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 {
 	PS3D_TRY(p)
 	if(vao >= 0 && vao < (int)p->pipe->m_vaoPool.size() && !p->pipe->m_vaoPool[vao]) return PS3D_OK;
+	const uint64_t before = p->sh->counters.vertices[0].v;
 	p->pipe->drawVAO(vao, callerThread != 0);
+	p->triangles += (p->sh->counters.vertices[0].v - before) / 3;
 	p->draws++;
 	PS3D_CATCH(p)
 }
@@ -550,7 +553,7 @@ int ps3d_get_stats(ps3d_pipe* p, ps3d_stats* out)
 {
 	memset(out, 0, sizeof(*out));
 	const Counters& c = p->sh->counters;
-	out->triangles_submitted = c.vertices[0].v / 3;
+	out->triangles_submitted = p->triangles;
 	out->triangles_rasterised = 0; // not observable from outside the reference
 	out->spans = c.spans[0].v;
 	out->fragments_tested = c.sum(c.tested, 64);
@@ -559,7 +562,7 @@ int ps3d_get_stats(ps3d_pipe* p, ps3d_stats* out)
 	return PS3D_OK;
 }
 
-int ps3d_reset_stats(ps3d_pipe* p) { p->sh->counters.reset(); p->draws = 0; return PS3D_OK; }
+int ps3d_reset_stats(ps3d_pipe* p) { p->sh->counters.reset(); p->draws = 0; p->triangles = 0; return PS3D_OK; }
 
 int ps3d_debug_capture(ps3d_pipe* p, int width, int height)
 {

@@ -956,3 +956,83 @@ def scene_desk_objx(path, width=1024, height=640, shadow=1024, picture_dir=None,
     sc.meta["triangles"] = ntri
     sc.meta["components"] = [c["component"] for (c, _, _, _, _) in drawn]
     return sc
+
+
+# ---- edge cases of the inputs themselves -----------------------------------------------------------------------------
+
+def scene_ragged_streams(width=200, height=120, seed=21):
+    """What the draw does with awkward vertex streams (vertthrd.cpp:21-31: all attached slots advance in lock-step and the draw
+    ends when ANY of them runs out): slots of different lengths, a vertex count that is not a multiple of 3 (the trailing
+    vertices never form a triangle), an EMPTY stream, an attached slot the functor does not read that is shorter than the
+    ones it reads, and a draw with fewer than 3 vertices — several draws of one frame, DEF02 (position, normal, colour)."""
+    rng = np.random.default_rng(seed)
+    sc = Scene("ragged-streams-%dx%d" % (width, height), width, height)
+    prog = sc.add_programme(K.FN_DEF02)
+
+    def streams(n_pos, n_nrm, n_col, extra=None, z=0.0):
+        n = max(n_pos, n_nrm, n_col, 3)
+        xy = rng.uniform(-0.9, 0.9, size=(n, 2))
+        pos = np.concatenate([xy, np.full((n, 1), z), np.ones((n, 1))], axis=1).astype(F32)
+        nrm = np.tile(np.array([0, 0, 1, 0], F32), (n, 1))
+        col = np.concatenate([rng.uniform(40, 255, size=(n, 3)), np.full((n, 1), 255.0)], axis=1).astype(F32)
+        slots = {0: (16, pos[:n_pos]), 1: (16, nrm[:n_nrm]), 2: (16, col[:n_col])}
+        if extra is not None:
+            slots[7] = (8, np.zeros((extra, 2), F32))      # a slot DEF02 never reads still ends the draw when it runs out
+        return sc.add_vao(slots)
+
+    vaos = [streams(30, 27, 29, z=0.1),        # 27 vertices = 9 triangles
+            streams(31, 31, 31, z=0.0),        # 31 vertices = 10 triangles + 1 dangling vertex
+            streams(12, 12, 0, z=-0.1),        # empty colour stream: nothing is drawn
+            streams(24, 24, 24, extra=7, z=-0.2),   # the unread slot 7 has 7 units: 2 triangles
+            streams(2, 2, 2, z=-0.3)]          # fewer than one triangle
+    ident = colmajor(mat_identity())
+    sc.cmd("viewport", width, height); sc.cmd("depth", -1); sc.cmd("clearDepth", 1.0); sc.cmd("clearColour", 0xFF202020)
+    sc.cmd("uniform", 3, ident); sc.cmd("uniform", 4, ident); sc.cmd("uniform", 5, ident)
+    sc.cmd("uniform", 7, vec4(0.3, 0.4, 2.0)); sc.cmd("uniform", 8, vec4(0.0, 0.0, 3.0))
+    sc.cmd("disable", K.BEHAVIOR_FACE_CULLING)
+    sc.cmd("use", prog)
+    for v in vaos:
+        sc.cmd("draw", v)
+    sc.cmd("enable", K.BEHAVIOR_FACE_CULLING)
+    sc.meta["triangles"] = 9 + 10 + 0 + 2 + 0
+    return sc
+
+
+def scene_crowded_tile(width=320, height=200, seed=22, crowd=3000):
+    """Extremes of the binning: `crowd` tiny triangles inside ONE 16x16 tile (a tile list longer than the shared-memory sort
+    takes: the draw's speculated tail is refused on the device and the exact retry takes the radix path), triangles hundreds
+    of times larger than the viewport (the whole-rectangle path of the tile mask), one with a vertex behind the eye
+    (w < 0: the perspective divide mirrors it, nothing is clipped) — in submission order that matters
+    (depth dead band, fragthrd.cpp:227)."""
+    rng = np.random.default_rng(seed)
+    sc = Scene("crowded-tile-%dx%d-%d" % (width, height, crowd), width, height)
+    pos, col, nrm = [], [], []
+
+    def tri(p, w=(1.0, 1.0, 1.0)):
+        for (x, y, z), ww in zip(p, w):
+            pos.append((x * ww, y * ww, z * ww, ww))
+            col.append(tuple(rng.uniform(30, 255, size=3)) + (255.0,))
+            nrm.append((0.0, 0.0, 1.0, 0.0))
+
+    tri([(-60.0, -55.0, 0.9), (70.0, -50.0, 0.9), (3.0, 90.0, 0.9)])                      # covers everything, far
+    cx, cy = (40.0 - width // 2) / (width // 2), (72.0 - height // 2) / (height // 2)     # tile (2, 4)
+    px, py = 2.0 / width, 2.0 / height
+    for i in range(crowd):
+        c = np.array([cx, cy]) + rng.uniform(-6, 6, size=2) * (px, py)
+        d = rng.uniform(-2.5, 2.5, size=(3, 2)) * (px, py)
+        z = 0.5 - 0.0003 * (i % 1000) + rng.uniform(-0.00005, 0.00005, size=3)                # inside and around the 1e-4 dead band
+        tri([(c[0] + d[k, 0], c[1] + d[k, 1], z[k]) for k in range(3)])
+    tri([(-0.5, -40.0, 0.3), (0.5, -40.0, 0.3), (0.0, 45.0, 0.3)])                         # a tall spike through every tile row
+    tri([(-0.8, -0.6, 0.2), (0.8, -0.6, 0.2), (0.0, 0.7, 0.2)], w=(1.0, 1.0, -0.5))        # one vertex behind the eye
+    vao = sc.add_vao({0: (16, np.array(pos, F32)), 1: (16, np.array(nrm, F32)), 2: (16, np.array(col, F32))})
+    prog = sc.add_programme(K.FN_DEF02)
+    ident = colmajor(mat_identity())
+    sc.cmd("viewport", width, height); sc.cmd("depth", -1); sc.cmd("clearDepth", 1.0); sc.cmd("clearColour", 0xFF101010)
+    sc.cmd("uniform", 3, ident); sc.cmd("uniform", 4, ident); sc.cmd("uniform", 5, ident)
+    sc.cmd("uniform", 7, vec4(0.3, 0.4, 2.0)); sc.cmd("uniform", 8, vec4(0.0, 0.0, 3.0))
+    sc.cmd("disable", K.BEHAVIOR_FACE_CULLING)
+    sc.cmd("use", prog)
+    sc.cmd("draw", vao)
+    sc.cmd("enable", K.BEHAVIOR_FACE_CULLING)
+    sc.meta["triangles"] = len(pos) // 3
+    return sc

@@ -33,6 +33,10 @@ SMALL = {
     "demo1_planets": lambda: scenes.scene_planets(400, 250, shadow=240, stacks=12, slices=24, tex_size=128),
     "c3_demo2_desk": lambda: scenes.scene_desk(384, 240, shadow=256, clutter=10, tex_size=128),
     "demo2_objx_file": _demo2_from_objx,
+    # awkward inputs: ragged / empty / dangling vertex streams; a tile list too long for the shared-memory sort (device-side
+    # refusal of the speculated tail + exact retry on the radix path), triangles far larger than the viewport, w < 0
+    "ragged_streams": lambda: scenes.scene_ragged_streams(200, 120),
+    "crowded_tile": lambda: scenes.scene_crowded_tile(320, 200, crowd=3000),
     # + the post-processing hook (PP_DepthofField through the reference's own postProcess)
     "demo2_post": lambda: _demo2_from_objx(post=True),
 }
