@@ -82,7 +82,56 @@ PS_D void mbarWait(uint64_t* bar, uint32_t parity)
 		             : "=r"(done) : "r"(smemAddr(bar)), "r"(parity) : "memory");
 }
 
+// One tall triangle (held by lane `src`) walked by the whole warp, lane = every 32nd row: its spans and clamped fragments are
+// added to the calling lanes' counters, its extent comes back reduced. Out of line: its registers stay out of the main path.
+struct TallExtent { int minX, maxX, minY, maxY; unsigned spans, frags; };
+__device__ __noinline__ TallExtent tallWalk(const DrawParams& P, uint32_t tri, int lane)
+{
+	unsigned spans = 0, frags = 0;
+	// the triangle's record was stored by its owner lane before the __syncwarp() in front of this call: read it back (L2)
+	const uint4* rec = (const uint4*)(P.hdr + tri);
+	const uint4 q0 = __ldcg(rec), q1 = __ldcg(rec + 1), q3 = __ldcg(rec + 3);
+	float vx[3], vy[3];
+	vx[0] = __uint_as_float(q0.x); vy[0] = __uint_as_float(q0.y);
+	vx[1] = __uint_as_float(q0.z); vy[1] = __uint_as_float(q0.w);
+	vx[2] = __uint_as_float(q1.x); vy[2] = __uint_as_float(q1.y);
+	const uint32_t rows = q3.x, half0 = q3.y, half1 = q3.z, plan = q3.w;
+	const int firstRow = (int)(rows & 0xffff), lastRow = (int)(rows >> 16);
+	const int l0 = (int)(half1 & 0xffff), l1 = (int)(half1 >> 16);
+	const int u0 = (int)(half0 & 0xffff), u1 = (int)(half0 >> 16);
+	const int selL = (int)((plan >> 8) & 0xff), selU = (int)(plan & 0xff);
+	const Edge LU = makeEdge(vx, vy, selU & 3, (selU >> 2) & 3), RU = makeEdge(vx, vy, (selU >> 4) & 3, (selU >> 6) & 3);
+	Edge LL = LU, RL = RU;
+	if(l0 <= l1) { LL = makeEdge(vx, vy, selL & 3, (selL >> 2) & 3); RL = makeEdge(vx, vy, (selL >> 4) & 3, (selL >> 6) & 3); }
+	int minX = 0x7fffffff, maxX = -1, minY = 0x7fffffff, maxY = -1;
+#pragma unroll 1
+	for(int iy = firstRow + lane; iy <= lastRow; iy += 32)
+	{
+		const bool lower = iy >= l0 && iy <= l1;
+		if(!lower && !(iy >= u0 && iy <= u1)) continue;
+		const float y = (float)iy;
+		const Edge& L = lower ? LL : LU;
+		const Edge& R = lower ? RL : RU;
+		const int left = cvtt(fadd(edgeAt(L, y), 0.5f)), right = cvtt(fadd(edgeAt(R, y), 0.5f));   // rasterizer.cpp:98-117
+		if(left == right) continue;                            // drawvao.cpp:72
+		spans++;
+		if(iy < P.band0 || iy >= P.band1) continue;
+		const int x1 = left < 0 ? 0 : left;                     // RESULT_ROW::leftClamped
+		const int x2 = right >= P.vpW ? P.vpW - 1 : right;      // RESULT_ROW::rightClamped
+		if(x1 > x2) continue;
+		frags += (unsigned)(x2 - x1 + 1);
+		minX = min(minX, x1); maxX = max(maxX, x2);
+		minY = min(minY, iy); maxY = max(maxY, iy);
+	}
+	minX = __reduce_min_sync(PS_FULL, minX); maxX = __reduce_max_sync(PS_FULL, maxX);
+	minY = __reduce_min_sync(PS_FULL, minY); maxY = __reduce_max_sync(PS_FULL, maxY);
+	TallExtent e;
+	e.minX = minX; e.maxX = maxX; e.minY = minY; e.maxY = maxY; e.spans = spans; e.frags = frags;
+	return e;
+}
+
 #define PS_GEOM_THREADS 128
+#define PS_TALL_ROWS 64        // triangles this many rows high are walked by a whole warp
 
 // STAGED: the block's vertex range (PS_GEOM_THREADS x 3 consecutive elements, contiguous in the un-indexed stream) of the
 // POSITION slot — slot 0 in every vertex functor of the reference — is brought into shared memory by one bulk copy; the
@@ -216,6 +265,8 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_setup_kernel(const __gri
 	}
 
 	// ---- part B, thread = surviving triangle (dense when compacted): records, varyings, the row walk that finds the tiles really touched
+	uint32_t wCount = 0, wRect0 = 0, wRect1 = 0, wMask = 0;
+	bool tall = false, bigPending = false;
 	if(work)
 	{
 		const float vx[3] = { h.vx0, h.vx1, h.vx2 }, vy[3] = { h.vy0, h.vy1, h.vy2 };
@@ -250,6 +301,11 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_setup_kernel(const __gri
 					}
 				}
 				const int firstRow = (int)(h.rows & 0xffff), lastRow = (int)(h.rows >> 16);
+				// a triangle PS_TALL_ROWS rows high or more is walked by the whole warp further down (a 4096-row shadow-map
+				// triangle would keep this one thread busy for a millisecond)
+				tall = lastRow - firstRow >= PS_TALL_ROWS;
+				if(!tall)
+				{
 				int minX = 0x7fffffff, maxX = -1, minY = 0x7fffffff, maxY = -1;
 				// for the first four tile rows the triangle touches: the tile columns its spans reach (lo | hi << 16)
 				uint32_t tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0;
@@ -309,8 +365,7 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_setup_kernel(const __gri
 						// large triangle: the whole rectangle of tiles (the tile kernels drop rows that miss a tile)
 						mask = 0xffffffffu;
 						count = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
-						for(int ty = ty0; ty <= ty1; ty++)
-							for(int tx = tx0; tx <= tx1; tx++) atomicAdd(&P.tileCount[ty * P.tilesX + tx], 1u);
+						bigPending = true;                              // its tiles are counted by the whole warp further down
 					}
 					else
 					{
@@ -330,12 +385,54 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_setup_kernel(const __gri
 						}
 					}
 				}
+				}
 			}
 		}
-		P.triCount[wtri] = count;
-		P.triRect[3 * wtri] = rect0;
-		P.triRect[3 * wtri + 1] = rect1;
-		P.triRect[3 * wtri + 2] = mask;
+		wCount = count; wRect0 = rect0; wRect1 = rect1; wMask = mask;
+	}
+	// ---- tall triangles: the warp walks one at a time, lane = every 32nd row. Only the extent is needed: they are binned
+	// by their whole rectangle (a rectangle of fewer than 8 x 4 tiles included: a superset of the tiles touched is harmless,
+	// the tile kernels drop the rows that miss a tile).
+	__syncwarp();
+	{
+		const int lane = threadIdx.x & 31;
+		uint32_t todo = __ballot_sync(PS_FULL, work && tall);
+		while(todo)
+		{
+			const int src = __ffs(todo) - 1;
+			todo &= todo - 1;
+			const TallExtent te = tallWalk(P, __shfl_sync(PS_FULL, wtri, src), lane);
+			const int minX = te.minX, maxX = te.maxX, minY = te.minY, maxY = te.maxY;
+			spans += te.spans; frags += te.frags;
+			if(lane == src && maxX >= 0)
+			{
+				const int tx0 = minX / PS_TILE, tx1 = maxX / PS_TILE, ty0 = minY / PS_TILE, ty1 = maxY / PS_TILE;
+				wRect0 = (uint32_t)tx0 | ((uint32_t)tx1 << 16);
+				wRect1 = (uint32_t)ty0 | ((uint32_t)ty1 << 16);
+				wMask = 0xffffffffu;
+				wCount = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+				bigPending = true;
+			}
+		}
+		if(work)
+		{
+			P.triCount[wtri] = wCount;
+			P.triRect[3 * wtri] = wRect0;
+			P.triRect[3 * wtri + 1] = wRect1;
+			P.triRect[3 * wtri + 2] = wMask;
+		}
+		// ---- whole-rectangle triangles: the warp counts one's tiles at a time, lane = every 32nd tile
+		todo = __ballot_sync(PS_FULL, bigPending);
+		while(todo)
+		{
+			const int src = __ffs(todo) - 1;
+			todo &= todo - 1;
+			const uint32_t r0 = __shfl_sync(PS_FULL, wRect0, src), r1 = __shfl_sync(PS_FULL, wRect1, src);
+			const int tx0 = (int)(r0 & 0xffff), tx1 = (int)(r0 >> 16), ty0 = (int)(r1 & 0xffff), ty1 = (int)(r1 >> 16);
+			const uint32_t w = (uint32_t)(tx1 - tx0 + 1), total = w * (uint32_t)(ty1 - ty0 + 1);
+			for(uint32_t i = (uint32_t)lane; i < total; i += 32)
+				atomicAdd(&P.tileCount[(ty0 + (int)(i / w)) * P.tilesX + tx0 + (int)(i % w)], 1u);
+		}
 	}
 	// counters: one set of atomics per block, on the block's replica
 	__shared__ unsigned long long blockSums[PS_GEOM_THREADS / 32][3];
@@ -478,7 +575,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ 
                                                         uint32_t* poison, DrawReport* report, uint32_t* __restrict__ tileOrder)
 {
 	__shared__ uint32_t warpTotals[32];
-	__shared__ uint32_t carryS, longestS;
+	__shared__ uint32_t carryS, longestS, passTotalS, nonEmptyS;
 	__shared__ unsigned long long boundS;
 	__shared__ uint32_t hist[256];                     // tiles per length class, longest lists first
 	if(0 == threadIdx.x) { carryS = 0; longestS = 0; }
@@ -494,12 +591,15 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ 
 	}
 	__syncthreads();
 	uint32_t longest = 0;
+	if(ntiles <= 16384)
+	{
+	// one tile per thread, 1024 per pass (C2's 8160 tiles: measured faster than the 8-per-thread form below)
 	for(uint32_t base = 0; base < ntiles + 1; base += 1024)
 	{
 		const uint32_t i = base + threadIdx.x;
 		const uint32_t v = i < ntiles ? tileCount[i] : 0;
 		longest = max(longest, v);
-		if(i < ntiles) atomicAdd(&hist[255u - min(v >> 2, 255u)], 1u);
+		if(i < ntiles && v) atomicAdd(&hist[255u - min(v >> 2, 255u)], 1u);
 		uint32_t incl = v;
 #pragma unroll
 		for(int d = 1; d < 32; d <<= 1)
@@ -512,10 +612,64 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ 
 		uint32_t warpBase = 0;
 		for(int w = 0; w < warp; w++) warpBase += warpTotals[w];
 		const uint32_t carry = carryS;
-		if(i < ntiles + 1) { tileStart[i] = carry + warpBase + incl - v; if(i < ntiles) { tileFill[i] = 0; tileCount[i] = 0; } }
+		if(i < ntiles + 1) { tileStart[i] = carry + warpBase + incl - v; if(i < ntiles && v) { tileFill[i] = 0; tileCount[i] = 0; } }
 		__syncthreads();
 		if(1023 == threadIdx.x) carryS = carry + warpBase + incl;
 		__syncthreads();
+	}
+	}
+	else
+	{
+	// 8 consecutive tiles per thread, 8192 per pass: thread-local prefix, one block-wide scan of the thread sums, carry
+	// between passes. (No faster than 1024-tile passes on C2's 8160 tiles, but a 4096^2 shadow map has 65536: 8 passes, not 64.)
+	for(uint32_t base = 0; base < ntiles + 1; base += 8192)
+	{
+		const uint32_t i0 = base + threadIdx.x * 8;
+		uint32_t v[8], sum = 0;
+#pragma unroll
+		for(int k = 0; k < 8; k++)
+		{
+			v[k] = i0 + k < ntiles ? tileCount[i0 + k] : 0;
+			longest = max(longest, v[k]);
+			if(i0 + k < ntiles && v[k]) atomicAdd(&hist[255u - min(v[k] >> 2, 255u)], 1u);
+			sum += v[k];
+		}
+		uint32_t incl = sum;
+#pragma unroll
+		for(int d = 1; d < 32; d <<= 1)
+		{
+			const uint32_t t = __shfl_up_sync(PS_FULL, incl, d);
+			if(lane >= d) incl += t;
+		}
+		if(31 == lane) warpTotals[warp] = incl;
+		__syncthreads();
+		if(0 == warp)
+		{
+			const uint32_t w = warpTotals[lane];
+			uint32_t wi = w;
+#pragma unroll
+			for(int d = 1; d < 32; d <<= 1)
+			{
+				const uint32_t t = __shfl_up_sync(PS_FULL, wi, d);
+				if(lane >= d) wi += t;
+			}
+			warpTotals[lane] = wi - w;                     // exclusive
+			if(31 == lane) passTotalS = wi;
+		}
+		__syncthreads();
+		const uint32_t carry = carryS;
+		uint32_t run = carry + warpTotals[warp] + incl - sum;
+#pragma unroll
+		for(int k = 0; k < 8; k++)
+		{
+			if(i0 + k < ntiles + 1) tileStart[i0 + k] = run;
+			if(i0 + k < ntiles && v[k]) { tileFill[i0 + k] = 0; tileCount[i0 + k] = 0; }
+			run += v[k];
+		}
+		__syncthreads();
+		if(0 == threadIdx.x) carryS = carry + passTotalS;
+		__syncthreads();
+	}
 	}
 	longest = __reduce_max_sync(PS_FULL, longest);
 	if(0 == lane && longest) atomicMax(&longestS, longest);
@@ -538,13 +692,16 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ 
 		uint32_t run = incl - sum;
 #pragma unroll
 		for(int k = 0; k < 8; k++) { hist[lane * 8 + k] = run; run += h[k]; }
+		if(31 == lane) nonEmptyS = run;
 	}
 	__syncthreads();
+	// only tiles with a list are ordered; tileOrder[ntiles] = how many there are (the tile kernels stop there)
 	for(uint32_t i = threadIdx.x; i < ntiles; i += 1024)
 	{
 		const uint32_t v = tileStart[i + 1] - tileStart[i];
-		tileOrder[atomicAdd(&hist[255u - min(v >> 2, 255u)], 1u)] = i;
+		if(v) tileOrder[atomicAdd(&hist[255u - min(v >> 2, 255u)], 1u)] = i;
 	}
+	if(0 == threadIdx.x) tileOrder[ntiles] = nonEmptyS;
 	if(0 == threadIdx.x)
 	{
 		const uint32_t total = carryS, lng = longestS;
@@ -560,41 +717,68 @@ __global__ void __launch_bounds__(128) bin_fill_kernel(const uint32_t* __restric
                                                       const uint32_t* __restrict__ tileStart, uint32_t* __restrict__ tileFill,
                                                       uint32_t* __restrict__ lists, uint32_t ntris, int tilesX, const uint32_t* __restrict__ poison)
 {
+	// triangles binned by their whole rectangle (more than 8 x 4 tiles — up to every tile of the target): the BLOCK takes
+	// them one at a time, every thread four tiles per step, so that hundreds of the (returning) atomics are in flight
+	// instead of one thread's one (a 4096^2 shadow map's ground quad is 2 x 23 000 tiles: 12 ms per triangle serially)
+	__shared__ uint32_t bigTri[128], bigR0[128], bigR1[128];
+	__shared__ uint32_t nBig;
 	if(*poison) return;
+	if(0 == threadIdx.x) nBig = 0;
+	__syncthreads();
 	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
-	if(tri >= ntris) return;
-	if(0 == triCount[tri]) return;
-	const uint32_t r0 = triRect[3 * tri], r1 = triRect[3 * tri + 1], mask = triRect[3 * tri + 2];
-	const int tx0 = (int)(r0 & 0xffff), tx1 = (int)(r0 >> 16), ty0 = (int)(r1 & 0xffff), ty1 = (int)(r1 >> 16);
-	if(0xffffffffu == mask)
+	if(tri < ntris && 0 != triCount[tri])
 	{
-		for(int ty = ty0; ty <= ty1; ty++)
-			for(int tx = tx0; tx <= tx1; tx++)
+		const uint32_t r0 = triRect[3 * tri], r1 = triRect[3 * tri + 1], mask = triRect[3 * tri + 2];
+		if(0xffffffffu == mask)
+		{
+			const uint32_t k = atomicAdd(&nBig, 1u);
+			bigTri[k] = tri; bigR0[k] = r0; bigR1[k] = r1;
+		}
+		else
+		{
+			const int tx0 = (int)(r0 & 0xffff), ty0 = (int)(r1 & 0xffff);
+			for(uint32_t m = mask; m; m &= m - 1)
 			{
-				const uint32_t tile = (uint32_t)(ty * tilesX + tx);
+				const int bit = __ffs(m) - 1;
+				const uint32_t tile = (uint32_t)((ty0 + (bit >> 3)) * tilesX + tx0 + (bit & 7));
 				lists[tileStart[tile] + atomicAdd(&tileFill[tile], 1u)] = tri;
 			}
+		}
 	}
-	else
+	__syncthreads();
+	const uint32_t n = nBig;
+	for(uint32_t k = 0; k < n; k++)
 	{
-		for(uint32_t m = mask; m; m &= m - 1)
+		const uint32_t t = bigTri[k], r0 = bigR0[k], r1 = bigR1[k];
+		const int tx0 = (int)(r0 & 0xffff), tx1 = (int)(r0 >> 16), ty0 = (int)(r1 & 0xffff), ty1 = (int)(r1 >> 16);
+		const uint32_t w = (uint32_t)(tx1 - tx0 + 1), total = w * (uint32_t)(ty1 - ty0 + 1);
+		for(uint32_t base = threadIdx.x; base < total; base += 4 * 128)
 		{
-			const int bit = __ffs(m) - 1;
-			const uint32_t tile = (uint32_t)((ty0 + (bit >> 3)) * tilesX + tx0 + (bit & 7));
-			lists[tileStart[tile] + atomicAdd(&tileFill[tile], 1u)] = tri;
+			uint32_t tile[4], at[4];
+#pragma unroll
+			for(int u = 0; u < 4; u++)
+			{
+				const uint32_t i = base + (uint32_t)u * 128;
+				tile[u] = i < total ? (uint32_t)((ty0 + (int)(i / w)) * tilesX + tx0 + (int)(i % w)) : 0xffffffffu;
+			}
+#pragma unroll
+			for(int u = 0; u < 4; u++) at[u] = tile[u] != 0xffffffffu ? tileStart[tile[u]] + atomicAdd(&tileFill[tile[u]], 1u) : 0;
+#pragma unroll
+			for(int u = 0; u < 4; u++) if(tile[u] != 0xffffffffu) lists[at[u]] = t;
 		}
 	}
 }
 
 // one warp per tile: bitonic sort of its list (<= PS_SORT_LIMIT ids) in shared memory
 __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_list_sort_kernel(const uint32_t* __restrict__ tileStart, uint32_t* __restrict__ lists, uint32_t ntiles,
-                                                                                const uint32_t* __restrict__ poison)
+                                                                                const uint32_t* __restrict__ poison, const uint32_t* __restrict__ tileOrder)
 {
 	__shared__ uint32_t buf[PS_WARPS_PER_BLOCK][PS_SORT_LIMIT];
 	if(*poison) return;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	const uint32_t tile = blockIdx.x * PS_WARPS_PER_BLOCK + w;
-	if(tile >= ntiles) return;
+	const uint32_t slot = blockIdx.x * PS_WARPS_PER_BLOCK + w;
+	if(slot >= tileOrder[ntiles]) return;              // tiles with a list
+	const uint32_t tile = tileOrder[slot];
 	const uint32_t begin = tileStart[tile], n = tileStart[tile + 1] - begin;
 	if(n < 2 || n > PS_SORT_LIMIT) return;
 	uint32_t* a = buf[w];
@@ -780,7 +964,7 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_imm
 	if(*P.poison) return;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const int tileSlot = blockIdx.x * PS_WARPS_PER_BLOCK + w;
-	if(tileSlot >= P.tilesX * P.tilesY) return;
+	if(tileSlot >= (int)P.tileOrder[P.tilesX * P.tilesY]) return;   // tiles with a list
 	const int tile = (int)P.tileOrder[tileSlot];         // longest lists first (tile_scan_kernel)
 	const uint32_t listBegin = tileStart[tile], listEnd = tileStart[tile + 1];
 	if(listBegin == listEnd) return;
@@ -1117,7 +1301,7 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_shade_ord
 	if(*P.poison) return;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const int tileSlot = blockIdx.x * PS_WARPS_PER_BLOCK + w;
-	if(tileSlot >= P.tilesX * P.tilesY) return;
+	if(tileSlot >= (int)P.tileOrder[P.tilesX * P.tilesY]) return;   // tiles with a list
 	const int tile = (int)P.tileOrder[tileSlot];         // longest lists first (tile_scan_kernel)
 	const uint32_t listBegin = tileStart[tile], listEnd = tileStart[tile + 1];
 	if(listBegin == listEnd) return;
@@ -1587,7 +1771,7 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_raster_depth_ker
 	// rasteriser, so when there are fewer tiles than the GPU has warp slots (a sort-first band, a small target) a tile is
 	// cut into `parts` (1, 2 or 4) groups of PS_TILE / parts rows, one warp each, all reading the same list.
 	const int warpSlot = blockIdx.x * PS_WARPS_PER_BLOCK + w;
-	if(warpSlot >= P.tilesX * P.tilesY * parts) return;
+	if(warpSlot >= (int)P.tileOrder[P.tilesX * P.tilesY] * parts) return;   // tiles with a list
 	const int tile = (int)P.tileOrder[warpSlot / parts];   // longest lists first (tile_scan_kernel)
 	const int rowsPer = PS_TILE / parts, partRow0 = (warpSlot % parts) * rowsPer;
 	const uint32_t listBegin = tileStart[tile], listEnd = tileStart[tile + 1];

@@ -408,7 +408,7 @@ static int launchTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe, in
 		// lists filled with atomics in arrival order, then every tile's list sorted by triangle id = submission order
 		ProfScope ps(p, CLS_BIN);
 		bin_fill_kernel<<<(P.ntris + 127) / 128, 128, 0, p->stream>>>(p->triCount.p, p->triRect.p, p->tileStart.p, p->tileFill.p, p->valsA.p, P.ntris, P.tilesX, p->poisonDev);
-		tile_list_sort_kernel<<<(ntiles + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK, 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(p->tileStart.p, p->valsA.p, ntiles, p->poisonDev);
+		tile_list_sort_kernel<<<(ntiles + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK, 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(p->tileStart.p, p->valsA.p, ntiles, p->poisonDev, p->tileOrder.p);
 		p->launches += 2;
 		CK(p, cudaGetLastError());
 		sortedTris = p->valsA.p;

@@ -69,9 +69,12 @@ def main():
         ms = e0.elapsed_time(e1) / steps
         st = pipe.getStats()
         frags = st["fragments_shaded"] / steps
+        pipe.close()
+        # the parity frame on a FRESH pipe, like the reference's below: clear4 never touches the last buffer row (fbo.cpp:336),
+        # so on a long-lived target a blending scene accumulates there from frame to frame — on both sides
+        pipe = PuresoftPipeline(sc.width, sc.height, device=0)
         pipe.debugCapture(sc.width, sc.height)
-        frame()
-        pipe.finish()
+        scenes.render(pipe, sc)
         g = dict(colour=pipe.readColour(), depth=pipe.readDepth(), counts=pipe.debugReadShadeCounts())
         pipe.close()
         # ---- the reference's own renderer: counted frame (parity), then timed frames with the counting decorators off
