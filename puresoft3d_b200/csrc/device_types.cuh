@@ -56,6 +56,9 @@ struct alignas(128) DeviceStats
 	unsigned long long fragments_shaded;
 	// per draw (reset by tile_scan_kernel):
 	unsigned long long fragBound;   // sum of clamped span lengths = upper bound of the draw's depth-test survivors
+	// the range of tile indices the draw binned anything to, as two maxima so that all-zero means "none": ~lowest, highest + 1.
+	// tile_scan_kernel scans only that range (a small object on a 4096^2 shadow map touches a few hundred of 65536 tiles)
+	unsigned tileLoInv, tileHi1;
 };
 
 // What the host learns about a draw after its geometry + tile scan, written by tile_scan_kernel into mapped pinned host

@@ -436,6 +436,14 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_setup_kernel(const __gri
 	}
 	// counters: one set of atomics per block, on the block's replica
 	__shared__ unsigned long long blockSums[PS_GEOM_THREADS / 32][3];
+	__shared__ unsigned blockRange[PS_GEOM_THREADS / 32][2];
+	{
+		// the draw's range of tile indices: corners of every binned triangle's rectangle (bounds of the tiles it touches)
+		const unsigned loInv = wCount ? ~((wRect1 & 0xffff) * (unsigned)P.tilesX + (wRect0 & 0xffff)) : 0u;
+		const unsigned hi1 = wCount ? (wRect1 >> 16) * (unsigned)P.tilesX + (wRect0 >> 16) + 1u : 0u;
+		const unsigned a = __reduce_max_sync(PS_FULL, loInv), b = __reduce_max_sync(PS_FULL, hi1);
+		if(0 == (threadIdx.x & 31)) { blockRange[threadIdx.x >> 5][0] = a; blockRange[threadIdx.x >> 5][1] = b; }
+	}
 	const unsigned long long r = warpSumU64(rasterised), s = warpSumU64(spans);
 	unsigned long long f = frags;
 #pragma unroll
@@ -449,6 +457,14 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_setup_kernel(const __gri
 		for(int w = 0; w < PS_GEOM_THREADS / 32; w++) v += blockSums[w][threadIdx.x];
 		DeviceStats* st = P.stats + (blockIdx.x & (PS_STATS_COPIES - 1));
 		if(v) atomicAdd(0 == threadIdx.x ? &st->triangles_rasterised : (1 == threadIdx.x ? &st->spans : &st->fragBound), v);
+	}
+	else if(threadIdx.x < 5)
+	{
+		unsigned v = 0;
+#pragma unroll
+		for(int w = 0; w < PS_GEOM_THREADS / 32; w++) v = max(v, blockRange[w][threadIdx.x - 3]);
+		DeviceStats* st = P.stats + (blockIdx.x & (PS_STATS_COPIES - 1));
+		if(v) atomicMax(3 == threadIdx.x ? &st->tileLoInv : &st->tileHi1, v);
 	}
 }
 
@@ -577,6 +593,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ 
 	__shared__ uint32_t warpTotals[32];
 	__shared__ uint32_t carryS, longestS, passTotalS, nonEmptyS;
 	__shared__ unsigned long long boundS;
+	__shared__ uint32_t rangeLoS, rangeHiS;            // the draw binned to tiles [lo, hi) only (geom_setup's replicas, folded below)
 	__shared__ uint32_t hist[256];                     // tiles per length class, longest lists first
 	if(0 == threadIdx.x) { carryS = 0; longestS = 0; }
 	if(threadIdx.x < 256) hist[threadIdx.x] = 0;
@@ -588,18 +605,24 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ 
 #pragma unroll
 		for(int d = 16; d > 0; d >>= 1) b += __shfl_xor_sync(PS_FULL, b, d);
 		if(0 == lane) boundS = b;
+		unsigned loInv = lane < PS_STATS_COPIES ? stats[lane].tileLoInv : 0u, hi1 = lane < PS_STATS_COPIES ? stats[lane].tileHi1 : 0u;
+		if(lane < PS_STATS_COPIES) { stats[lane].tileLoInv = 0; stats[lane].tileHi1 = 0; }
+		loInv = __reduce_max_sync(PS_FULL, loInv); hi1 = __reduce_max_sync(PS_FULL, hi1);
+		if(0 == lane) { rangeLoS = hi1 ? min(~loInv, ntiles) : ntiles; rangeHiS = min(hi1, ntiles); }
 	}
 	__syncthreads();
+	// everything outside [lo, hi) is empty: its tileStart is never read (only tiles with a list are ordered and visited)
+	const uint32_t lo = rangeLoS, hi = max(rangeHiS, rangeLoS);
 	uint32_t longest = 0;
 	if(ntiles <= 16384)
 	{
 	// one tile per thread, 1024 per pass (C2's 8160 tiles: measured faster than the 8-per-thread form below)
-	for(uint32_t base = 0; base < ntiles + 1; base += 1024)
+	for(uint32_t base = lo; base < hi + 1; base += 1024)
 	{
 		const uint32_t i = base + threadIdx.x;
-		const uint32_t v = i < ntiles ? tileCount[i] : 0;
+		const uint32_t v = i < hi ? tileCount[i] : 0;
 		longest = max(longest, v);
-		if(i < ntiles && v) atomicAdd(&hist[255u - min(v >> 2, 255u)], 1u);
+		if(i < hi && v) atomicAdd(&hist[255u - min(v >> 2, 255u)], 1u);
 		uint32_t incl = v;
 #pragma unroll
 		for(int d = 1; d < 32; d <<= 1)
@@ -612,7 +635,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ 
 		uint32_t warpBase = 0;
 		for(int w = 0; w < warp; w++) warpBase += warpTotals[w];
 		const uint32_t carry = carryS;
-		if(i < ntiles + 1) { tileStart[i] = carry + warpBase + incl - v; if(i < ntiles && v) { tileFill[i] = 0; tileCount[i] = 0; } }
+		if(i < hi + 1) { tileStart[i] = carry + warpBase + incl - v; if(i < hi && v) { tileFill[i] = 0; tileCount[i] = 0; } }
 		__syncthreads();
 		if(1023 == threadIdx.x) carryS = carry + warpBase + incl;
 		__syncthreads();
@@ -622,16 +645,16 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ 
 	{
 	// 8 consecutive tiles per thread, 8192 per pass: thread-local prefix, one block-wide scan of the thread sums, carry
 	// between passes. (No faster than 1024-tile passes on C2's 8160 tiles, but a 4096^2 shadow map has 65536: 8 passes, not 64.)
-	for(uint32_t base = 0; base < ntiles + 1; base += 8192)
+	for(uint32_t base = lo; base < hi + 1; base += 8192)
 	{
 		const uint32_t i0 = base + threadIdx.x * 8;
 		uint32_t v[8], sum = 0;
 #pragma unroll
 		for(int k = 0; k < 8; k++)
 		{
-			v[k] = i0 + k < ntiles ? tileCount[i0 + k] : 0;
+			v[k] = i0 + k < hi ? tileCount[i0 + k] : 0;
 			longest = max(longest, v[k]);
-			if(i0 + k < ntiles && v[k]) atomicAdd(&hist[255u - min(v[k] >> 2, 255u)], 1u);
+			if(i0 + k < hi && v[k]) atomicAdd(&hist[255u - min(v[k] >> 2, 255u)], 1u);
 			sum += v[k];
 		}
 		uint32_t incl = sum;
@@ -662,8 +685,8 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ 
 #pragma unroll
 		for(int k = 0; k < 8; k++)
 		{
-			if(i0 + k < ntiles + 1) tileStart[i0 + k] = run;
-			if(i0 + k < ntiles && v[k]) { tileFill[i0 + k] = 0; tileCount[i0 + k] = 0; }
+			if(i0 + k < hi + 1) tileStart[i0 + k] = run;
+			if(i0 + k < hi && v[k]) { tileFill[i0 + k] = 0; tileCount[i0 + k] = 0; }
 			run += v[k];
 		}
 		__syncthreads();
@@ -696,7 +719,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ 
 	}
 	__syncthreads();
 	// only tiles with a list are ordered; tileOrder[ntiles] = how many there are (the tile kernels stop there)
-	for(uint32_t i = threadIdx.x; i < ntiles; i += 1024)
+	for(uint32_t i = lo + threadIdx.x; i < hi; i += 1024)
 	{
 		const uint32_t v = tileStart[i + 1] - tileStart[i];
 		if(v) tileOrder[atomicAdd(&hist[255u - min(v >> 2, 255u)], 1u)] = i;
