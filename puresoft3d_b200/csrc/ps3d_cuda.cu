@@ -1340,8 +1340,7 @@ int ps3d_composite_bands(ps3d_pipe* p, const int* bands)
 		else if(r == p->commRank) NK(p, a->Send(at, bytes, PS_NCCL_UINT8, 0, p->commFrame, p->stream));
 	}
 	NK(p, a->GroupEnd());
-	p->launches++;
-	return PS3D_OK;
+	return PS3D_OK;           // (not counted in ps3d_device_launch_count: the kernel is NCCL's)
 }
 // Sharded upload's exchange: rank r has written units [r * per, (r + 1) * per) of the VBO (ps3d_vbo_update_async, per =
 // unitCount / world); one in-place all-gather on the gather stream, behind that upload, makes them whole on every rank.
@@ -1364,7 +1363,6 @@ int ps3d_vbo_all_gather(ps3d_pipe* p, int vbo)
 	NK(p, a->AllGather(v.data + (size_t)p->commRank * perBytes, v.data, perBytes, PS_NCCL_UINT8, p->commUpload, p->gatherStream));
 	CK(p, cudaEventRecord(v.ready, p->gatherStream));
 	v.readyValid = true;
-	p->launches++;
 	return PS3D_OK;
 }
 
