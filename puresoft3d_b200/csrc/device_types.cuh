@@ -105,6 +105,8 @@ struct DrawParams
 	uint32_t* triRect;          // per triangle 3 words: tx0 | tx1 << 16, ty0 | ty1 << 16, mask of touched tiles (bit = (ty-ty0)*8 + tx-tx0;
 	                            // ~0 when the rectangle exceeds 8 x 4 tiles and is used whole)
 	uint32_t* tileCount;        // per tile: triangles binned to it (atomics in geom_setup)
+	uint32_t* workList;         // sort-first, two-kernel geometry: indices of the triangles the position half kept, any order
+	uint32_t* workCount;
 	const uint32_t* tileOrder;  // the tiles by descending list length (tile_scan_kernel): the order the tile kernels take them in
 	DeviceStats* stats;         // PS_STATS_COPIES replicas
 	const uint32_t* poison;     // != 0: a speculated capacity of this draw was too small, every kernel behind the tile scan returns at once

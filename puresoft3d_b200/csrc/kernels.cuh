@@ -139,11 +139,22 @@ __device__ __noinline__ TallExtent tallWalk(const DrawParams& P, uint32_t tri, i
 // other slots are read straight from global memory by the varyings pass, i.e. only for triangles that survive culling
 // and (sort-first) lie in this rank's band: at N ranks most triangles never touch them.
 #define PS_GEOM_STAGE_SLOTS 1u
-template<class PROG, bool STAGED>
+// MODE: PS_GEOM_FUSED  one kernel does everything (whole frames).
+//       PS_GEOM_APPEND the position half only: survivors of the sort-first band get their header stored and their index
+//                      appended to one global list (warp-aggregated).
+//       PS_GEOM_LIST   the varyings / row-walk half as a dense kernel over that list. With a band a rank keeps ~1/N of a
+//                      shuffled stream; compaction inside a block does not shorten this half in proportion (the block pays
+//                      its latency whatever the lane count), a grid over the list does.
+#define PS_GEOM_FUSED 0
+#define PS_GEOM_APPEND 1
+#define PS_GEOM_LIST 2
+template<class PROG, bool STAGED, int MODE>
 __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_setup_kernel(const __grid_constant__ DrawParams P)
 {
 	constexpr int NV = PROG::NV;
+	static_assert(!(STAGED && PS_GEOM_LIST == MODE), "the list-driven half reads global memory");
 	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+	if(PS_GEOM_LIST == MODE && blockIdx.x * blockDim.x >= *P.workCount) return;   // (the grid is sized for every triangle)
 	extern __shared__ __align__(128) uint8_t stage[];
 	__shared__ uint64_t stageBar;
 	uint32_t stageOff[16];
@@ -184,7 +195,7 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_setup_kernel(const __gri
 	__shared__ uint32_t warpAlive[PS_GEOM_THREADS / 32];
 	bool alive = false;
 	TriHeader h;
-	if(tri < P.ntris)
+	if(PS_GEOM_LIST != MODE && tri < P.ntris)
 	{
 		float ndcX[3], ndcY[3], rw[3], pz[3];
 		F4 pos[3];
@@ -230,9 +241,36 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_setup_kernel(const __gri
 	}
 	// Compaction pays when survivors are sparse in the block — a sort-first band on a shuffled stream; on a whole frame of
 	// front-facing triangles it only adds two barriers (C2, one GPU: 0.127 -> 0.141 ms), so it is taken with a band only.
-	const bool compact = P.band0 > 0 || P.band1 < P.vpH;
+	const bool compact = PS_GEOM_FUSED == MODE && (P.band0 > 0 || P.band1 < P.vpH);
 	bool work = alive;
 	uint32_t wtri = tri;
+	if(PS_GEOM_APPEND == MODE)
+	{
+		// survivors: header to its final place, index to the list (one atomic per warp; the list's order does not matter)
+		const uint32_t aliveBallot = __ballot_sync(PS_FULL, alive);
+		uint32_t base = 0;
+		if(0 == (threadIdx.x & 31) && aliveBallot) base = atomicAdd(P.workCount, (uint32_t)__popc(aliveBallot));
+		base = __shfl_sync(PS_FULL, base, 0);
+		if(alive)
+		{
+			P.workList[base + (uint32_t)__popc(aliveBallot & ((1u << (threadIdx.x & 31)) - 1))] = tri;
+			uint4* dst = (uint4*)(P.hdr + tri);
+			const uint4* src = (const uint4*)&h;
+			dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+		}
+		work = false;
+	}
+	if(PS_GEOM_LIST == MODE)
+	{
+		work = tri < *P.workCount;
+		if(work)
+		{
+			wtri = P.workList[tri];
+			const uint4* src = (const uint4*)(P.hdr + wtri);
+			uint4* dst = (uint4*)&h;
+			dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+		}
+	}
 	if(compact)
 	{
 		const uint32_t aliveBallot = __ballot_sync(PS_FULL, alive);

@@ -86,18 +86,33 @@ template<class PROG> void launchGeom(const DrawParams& P, cudaStream_t s)
 			bytes += ((size_t)PS_GEOM_THREADS * 3 * P.stride[i] + 127) & ~(size_t)127;
 			aligned = aligned && 0 == ((uintptr_t)P.slot[i] & 15);
 		}
-	if(geomStagingOn() && aligned && bytes > 0 && bytes <= 96 * 1024)
+	const bool staged = geomStagingOn() && aligned && bytes > 0 && bytes <= 96 * 1024;
+	// with a sort-first band: the position half appends the band's survivors to a list, the other half runs over the list
+	const bool split = P.workList && (P.band0 > 0 || P.band1 < P.vpH);
+	if(staged)
 	{
 		static size_t attr = 0;
 		if(bytes > attr)
 		{
-			cudaFuncSetAttribute(geom_setup_kernel<PROG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024));
+			cudaFuncSetAttribute(geom_setup_kernel<PROG, true, PS_GEOM_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024));
+			cudaFuncSetAttribute(geom_setup_kernel<PROG, true, PS_GEOM_APPEND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024));
 			attr = 96 * 1024;
 		}
-		geom_setup_kernel<PROG, true><<<blocks, PS_GEOM_THREADS, bytes, s>>>(P);
+		if(split) geom_setup_kernel<PROG, true, PS_GEOM_APPEND><<<blocks, PS_GEOM_THREADS, bytes, s>>>(P);
+		else geom_setup_kernel<PROG, true, PS_GEOM_FUSED><<<blocks, PS_GEOM_THREADS, bytes, s>>>(P);
 	}
 	else
-		geom_setup_kernel<PROG, false><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
+	{
+		if(split) geom_setup_kernel<PROG, false, PS_GEOM_APPEND><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
+		else geom_setup_kernel<PROG, false, PS_GEOM_FUSED><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
+	}
+	if(split) geom_setup_kernel<PROG, false, PS_GEOM_LIST><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
+}
+bool geomSplitWanted(int bandRows, int vpH)
+{
+	static int mode = -2;   // -1 = by band size, 0 = never, 1 = always
+	if(-2 == mode) { const char* e = getenv("PS3D_GEOM_SPLIT"); mode = !e ? -1 : (e[0] == '0' ? 0 : 1); }
+	return mode < 0 ? (long long)bandRows * 6 <= vpH : 1 == mode;
 }
 // PS3D_RASTER_PARTS=1|2|4 forces the number of row groups a tile is cut into (A/B checks, tests)
 int rasterPartsForced() { static int v = -2; if(-2 == v) { const char* e = getenv("PS3D_RASTER_PARTS"); v = e ? atoi(e) : 0; if(v != 1 && v != 2 && v != 4) v = 0; } return v; }
@@ -227,7 +242,7 @@ struct ps3d_pipe
 	// per-draw scratch
 	DevBuf<TriHeader> hdr;
 	DevBuf<F4> vary;
-	DevBuf<uint32_t> triCount, triOffset, triRect, scanSums, keysA, valsA, keysB, valsB, tileCount, tileStart, tileFill, tileOrder, sortCounts;
+	DevBuf<uint32_t> triCount, triOffset, triRect, scanSums, keysA, valsA, keysB, valsB, tileCount, tileStart, tileFill, tileOrder, sortCounts, workList;
 	DevBuf<uint32_t> svTri, svMisc, svWinner;   // survivor stream of the draw in flight (split path)
 	DevBuf<int> svLeft, svRight;
 	DevBuf<float> svInv;
@@ -601,7 +616,7 @@ int ps3d_destroy(ps3d_pipe* p)
 	if(p->rcpDev) cudaFree(p->rcpDev);
 	if(p->rsqrtDev) cudaFree(p->rsqrtDev);
 	p->hdr.release(); p->vary.release(); p->triCount.release(); p->triOffset.release(); p->triRect.release(); p->scanSums.release();
-	p->keysA.release(); p->valsA.release(); p->keysB.release(); p->valsB.release(); p->tileCount.release(); p->tileStart.release(); p->tileFill.release(); p->tileOrder.release(); p->sortCounts.release();
+	p->keysA.release(); p->valsA.release(); p->keysB.release(); p->valsB.release(); p->tileCount.release(); p->tileStart.release(); p->tileFill.release(); p->tileOrder.release(); p->sortCounts.release(); p->workList.release();
 	for(auto& s : p->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
 	for(auto& e : p->eventPool) cudaEventDestroy(e);
 	cudaStreamDestroy(p->stream); cudaStreamDestroy(p->copyStream); cudaStreamDestroy(p->readStream);
@@ -1073,6 +1088,14 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	}
 	P.hdr = p->hdr.p; P.vary = p->vary.p; P.triCount = p->triCount.p; P.triRect = p->triRect.p; P.tileCount = p->tileCount.p; P.tileOrder = p->tileOrder.p;
 	P.poison = p->poisonDev;
+	// two-kernel geometry pays below about a sixth of the rows (band probe: an eighth 0.085 -> 0.067 ms, a quarter 0.092 -> 0.100 ms:
+	// the list-driven half reads its vertex streams sparsely); PS3D_GEOM_SPLIT=1 forces it for any band, =0 never
+	if(geomSplitWanted(P.band1 - P.band0, P.vpH) && (P.band0 > 0 || P.band1 < P.vpH))
+	{
+		CK(p, p->workList.ensure(ntris + 4));
+		P.workList = p->workList.p + 4; P.workCount = p->workList.p;      // the counter lives in front of the list
+		CK(p, cudaMemsetAsync(P.workCount, 0, 4, p->stream));
+	}
 
 	// which tile path (kernels.cuh): a functor that may discard() makes the depth write wait for the shading
 	// (fragthrd.cpp:234-237) -> immediate; a draw that blends needs its colours applied in submission order -> ordered;

@@ -50,7 +50,8 @@ def test_c2_full_size_is_idempotent_and_plausible(built):
     assert a["stats"]["fragments_shaded"] >= a["covered"]
 
 
-@pytest.mark.parametrize("name,world", [("c2_heightfield_small", 2), ("c4_blend_overdraw", 3), ("soup_odd_size", 4)])
+@pytest.mark.parametrize("name,world", [("c2_heightfield_small", 2), ("c4_blend_overdraw", 3), ("soup_odd_size", 4), ("c2_heightfield_tiny_tris", 8),
+                                        ("crowded_tile", 7)])
 def test_row_bands_tile_the_frame(name, world, cuda_lib, oracle_lib):
     """Sort-first on one GPU: band by band into separate pipes; each band equals the oracle's band, their union the frame."""
     sc = SMALL[name]()
