@@ -1,29 +1,37 @@
-// kernels.cuh — the hot path: geom_setup -> ordered binning -> tile_raster_shade.
+// kernels.cuh — the hot path: geom_setup -> ordered binning -> tile raster + depth -> shade.
 //
 // Reference call stack replaced: PuresoftPipeline::drawVAO (drawvao.cpp:3-133) with
 // processVertices / isBackFace (vertthrd.cpp), PuresoftRasterizer::pushTriangle (rasterizer.cpp),
 // PuresoftInterpolater (interp.cpp), the per-scanline ring queues (rinque.h) and fragmentThread (fragthrd.cpp).
+// One draw = these kernels enqueued back to back on the pipe's stream, no host synchronisation:
 //
-//   geom_setup<PROG>          one thread per triangle: vertex functor x3, perspective divide, back-face, whole-triangle z
-//                             reject, pushTriangle's setup; writes the 64-byte TriHeader + the varyings, and the
-//                             rectangle of 16x16 tiles its spans touch.
-//   scan / emit / radix sort  (tile, triangle) pairs emitted in triangle order and stably sorted by tile id: every tile
-//                             gets its triangles in SUBMISSION ORDER, which the depth dead-band and blend4 require (§9.7).
-//   tile_raster_shade<PROG>   one warp per 16x16 tile, depth + colour tile staged in shared memory for the whole draw.
-//                             Per chunk of 32 triangles (submission order):
-//                               A1  lane = triangle: header -> shared memory, rows inside the tile, warp scan => span list
-//                               A2  lane = span (triangle,row), dense: the reference's RESULT_ROW arithmetic, the span's
-//                                   interpolation set-up (interp.cpp:26-80) and the chain advanced to the tile's edge
-//                               B   lane = pixel owner (row, 8-pixel segment): walks the spans of its row in submission
-//                                   order replaying the exact serial chains (§9.6), depth-tests against shared memory,
-//                                   pushes every survivor into a shared-memory queue
-//                               C   lane = survivor, dense, 32 at a time: varyings, fragment functor, ordered commit
-//                             One write-back per tile.
+//   geom_setup<PROG, STAGED, MODE>
+//                        thread = triangle. Position half: vertex functor x3 (positions staged by one TMA bulk copy per
+//                        block), perspective divide, back-face, whole-triangle z reject, pushTriangle's set-up, sort-first
+//                        band reject. Other half, for survivors: 64-byte TriHeader + varyings, the reference's per-row spans
+//                        to find the tiles really touched, per-tile counts. Tall triangles are walked by a whole warp, whole-
+//                        rectangle ones counted by a warp. Fused for whole frames; with a small band the two halves are two
+//                        kernels around one global survivor list (PS_GEOM_APPEND / PS_GEOM_LIST).
+//   tile_scan            one block: exclusive scan of the per-tile counts over the draw's tile range, the verdict on the
+//                        capacities the host speculated with (poison), the tiles ordered by list length.
+//   bin_fill, tile_list_sort
+//                        lists filled in arrival order (atomics; whole-rectangle triangles by the whole block), then every
+//                        tile's list sorted by triangle id = SUBMISSION ORDER, which the depth dead band and blend4 require
+//                        (SURVEY.md §9.7). Lists too long for shared memory: emit_pairs + stable LSD radix sort.
+//   tile_raster_depth    (split path, the default) one warp per 16x16 tile or per group of 8 / 4 of its rows, longest lists
+//                        first, depth tile in shared memory for the whole draw; per chunk of 32 triangles: A1 lane = triangle,
+//                        X lane = (triangle, row), Y lane = span, B lane = pixel — exact serial chains (§9.6), the depth rule
+//                        in submission order; every survivor appended to a stream, the last one of each pixel remembered.
+//   shade<PROG>          flat loop over the survivor stream: varyings, fragment functor once per survivor (fragthrd.cpp:231),
+//                        the pixel's last survivor stores its colour.
+//   tile_raster_shade_ordered<PROG>
+//                        one-kernel tile path with colours committed in submission order: draws that blend (blend4 is not
+//                        commutative).
 //   tile_raster_shade_immediate<PROG>
-//                             the first version (lane = row segment does everything, fragment functor called inside
-//                             the pixel loop). Kept for functors that may discard() while depth writes are on — there
-//                             the depth write depends on the functor's result (fragthrd.cpp:234-237) — and as an A/B
-//                             switch (PS3D_TILE_IMMEDIATE=1).
+//                        the first version (fragment functor inside the pixel loop): functors that may discard() while depth
+//                        writes are on — there the depth write depends on the functor's result (fragthrd.cpp:234-237).
+//   clear_depth / clear_colour / post_process<POST>
+//                        fbo.cpp:332-371 (clear4 skips the last buffer row, replicated); post.cpp:3-19.
 #pragma once
 #include "shaders.cuh"
 #include "raster.cuh"

@@ -6,6 +6,12 @@ raster rows, one per rank (tile-row aligned). Every rank holds all vertex stream
 geometry stage for every triangle, bins only the spans inside its band (ps3d_set_row_band) and shades them; then the
 finished colour bands are gathered onto rank 0 — the path's one exchange step — with NCCL send/recv over NVLink.
 No pixel is touched by two ranks, so the composite is a plain copy and sharding cannot change a result.
+
+Both exchange steps (the band composite, and the all-gather that completes vertex streams of which every rank uploaded
+only its 1/N — ShardedUpload) are issued by the library itself on the pipe's streams once init_native_comm() has handed
+it NCCL ids (ps3d_comm_init / ps3d_composite_bands / ps3d_vbo_all_gather); the torch.distributed forms below
+(gather_bands, all_gather_shards) are the same steps on torch tensors: the CPU (gloo) tests run them, and
+PS3D_SORTFIRST=torch selects them on GPUs for A/B runs.
 """
 import torch
 import torch.distributed as dist
