@@ -83,6 +83,28 @@ PS3D_DECLARE_FAMILY(DEF04, PS3D_FN_DEF04) // skybox.h
 PS3D_DECLARE_FAMILY(DEF05, PS3D_FN_DEF05) // shadow.h
 #undef PS3D_DECLARE_FAMILY
 
+// The demos' own shader classes (src/test/testproc.h, src/test2/testproc.h) under their own names; the two demos reuse
+// names (VP_Shadow, IP_Null, ...), hence one namespace per demo.
+#define PS3D_DEMO_V(NAME, FN) class NAME : public PuresoftVertexProcessor { public: NAME() : PuresoftVertexProcessor(FN) {} };
+#define PS3D_DEMO_I(NAME, FN) class NAME : public PuresoftInterpolationProcessor { public: NAME() : PuresoftInterpolationProcessor(FN) {} };
+#define PS3D_DEMO_F(NAME, FN) class NAME : public PuresoftFragmentProcessor { public: NAME() : PuresoftFragmentProcessor(FN) {} };
+namespace ps3d_demo1   // src/test/testproc.h
+{
+PS3D_DEMO_V(VP_Planet, PS3D_FN_PLANET) PS3D_DEMO_I(IP_Planet, PS3D_FN_PLANET) PS3D_DEMO_F(FP_Earth, PS3D_FN_PLANET) PS3D_DEMO_F(FP_Satellite, PS3D_FN_SATELLITE)
+PS3D_DEMO_V(VP_Cloud, PS3D_FN_CLOUD) PS3D_DEMO_I(IP_Cloud, PS3D_FN_CLOUD) PS3D_DEMO_F(FP_Cloud, PS3D_FN_CLOUD)
+PS3D_DEMO_V(VP_CloudShadow, PS3D_FN_CLOUDSHADOW) PS3D_DEMO_I(IP_CloudShadow, PS3D_FN_CLOUDSHADOW) PS3D_DEMO_F(FP_CloudShadow, PS3D_FN_CLOUDSHADOW)
+}
+namespace ps3d_demo2   // src/test2/testproc.h
+{
+PS3D_DEMO_V(VP_PositionOnly, PS3D_FN_POSITIONONLY) PS3D_DEMO_I(IP_Null, PS3D_FN_POSITIONONLY) PS3D_DEMO_F(FP_SingleColourNoLighting, PS3D_FN_POSITIONONLY)
+PS3D_DEMO_V(VP_SingleColour, PS3D_FN_SINGLECOLOUR) PS3D_DEMO_I(IP_SingleColour, PS3D_FN_SINGLECOLOUR) PS3D_DEMO_F(FP_SingleColour, PS3D_FN_SINGLECOLOUR)
+PS3D_DEMO_V(VP_DiffuseOnly, PS3D_FN_DIFFUSEONLY) PS3D_DEMO_I(IP_DiffuseOnly, PS3D_FN_DIFFUSEONLY) PS3D_DEMO_F(FP_DiffuseOnly, PS3D_FN_DIFFUSEONLY)
+PS3D_DEMO_V(VP_Shadow, PS3D_FN_SHADOW2) PS3D_DEMO_F(FP_Null, PS3D_FN_SHADOW2)
+}
+#undef PS3D_DEMO_V
+#undef PS3D_DEMO_I
+#undef PS3D_DEMO_F
+
 // proc.h:89-94. The reference's process(threadIndex, threadCount, frame, depth) body becomes a device functor named by id.
 class PuresoftPostProcessor
 {
