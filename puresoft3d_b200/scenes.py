@@ -1036,3 +1036,64 @@ def scene_crowded_tile(width=320, height=200, seed=22, crowd=3000):
     sc.cmd("enable", K.BEHAVIOR_FACE_CULLING)
     sc.meta["triangles"] = len(pos) // 3
     return sc
+
+
+def scene_state_fuzz(seed, width=None, height=None, draws=None):
+    """A seeded frame of several draws with the pipeline's state changing between them: behaviour bits (depth test / depth
+    write / culling / blending; never 'test on, write off', where the reference reads a depth cursor it did not position,
+    SURVEY.md §9.12), viewport sizes up to the target's, DEF01 / DEF02 / DEF03 / DEF04 programmes, CLAMP and WRAP textures,
+    triangle soups of all sizes with perspective w. Identity view, so positions are clip space."""
+    rng = np.random.default_rng(1000 + seed)
+    width = int(width or rng.integers(40, 200))
+    if width % 4 == 1:
+        width += 1          # pipeline.cpp:31 under-allocates the default depth rows when W % 4 == 1 (SURVEY.md §9.12): not a width to pin on
+    height = int(height or rng.integers(30, 150))
+    sc = Scene("state-fuzz-%d-%dx%d" % (seed, width, height), width, height)
+    tsz = int(rng.choice([8, 32, 64]))
+    tex2d = sc.add_texture(tsz, tsz, 4, tex_random_bgra(rng, tsz, tsz), wrap=int(rng.choice([K.WRAP_CLAMP, K.WRAP_WRAP])))
+    bump = sc.add_texture(tsz, tsz, 4, tex_smooth_bgra(rng, tsz, tsz, normal_map=True))
+    cube = sc.add_texture(16, 16, 4, layers=[tex_random_bgra(rng, 16, 16) for _ in range(6)])
+    progs = {f: sc.add_programme(f) for f in (K.FN_DEF01, K.FN_DEF02, K.FN_DEF03, K.FN_DEF04)}
+    ident = colmajor(mat_identity())
+    sc.cmd("depth", -1); sc.cmd("clearDepth", 1.0); sc.cmd("clearColour", int(rng.integers(0, 2 ** 32)))
+    for u in (3, 4, 5):
+        sc.cmd("uniform", u, ident)
+    sc.cmd("uniform", 7, vec4(*rng.uniform(-2, 2, size=3))); sc.cmd("uniform", 8, vec4(0.0, 0.0, 3.0))
+    sc.cmd("uniform", 1, ident)                                            # DEF04: view matrix in slot 1, cube map id in slot 2
+    sc.cmd("tex_uniform", 2, cube); sc.cmd("tex_uniform", 9, tex2d); sc.cmd("tex_uniform", 10, bump)
+    all_bits = K.BEHAVIOR_UPDATE_DEPTH | K.BEHAVIOR_TEST_DEPTH | K.BEHAVIOR_FACE_CULLING | K.BEHAVIOR_ALPHABLEND
+    ntri = 0
+    for d in range(int(draws or rng.integers(2, 6))):
+        n = int(rng.integers(1, 60))
+        c = rng.uniform(-1.2, 1.2, size=(n, 1, 2))
+        size = rng.choice([0.02, 0.2, 0.8, 2.5], size=(n, 1, 1))
+        xy = c + rng.uniform(-1, 1, size=(n, 3, 2)) * size
+        z = rng.uniform(-1.05, 1.05, size=(n, 3, 1))
+        w = np.where(rng.random((n, 1, 1)) < 0.3, rng.uniform(0.4, 3.0, size=(n, 3, 1)), 1.0)
+        pos = (np.concatenate([xy, z, np.ones((n, 3, 1))], axis=2) * w).reshape(n * 3, 4).astype(F32)
+        nrm = np.tile(np.array([0, 0, 1, 0], F32), (n * 3, 1))
+        tan = np.tile(np.array([1, 0, 0, 0], F32), (n * 3, 1))
+        bin_ = np.tile(np.array([0, 1, 0, 0], F32), (n * 3, 1))
+        col = np.concatenate([rng.uniform(20, 255, size=(n * 3, 3)), np.full((n * 3, 1), 255.0)], axis=1).astype(F32)
+        uv = rng.uniform(-0.2, 1.6, size=(n * 3, 2)).astype(F32)
+        uv = np.abs(uv)                                                    # (unsigned)negative differs between x86 and CUDA; the scenes keep uv >= 0 (SURVEY.md §9.9)
+        fn = int(rng.choice([K.FN_DEF01, K.FN_DEF02, K.FN_DEF03, K.FN_DEF04]))
+        if fn == K.FN_DEF02:
+            slots = {0: (16, pos), 1: (16, nrm), 2: (16, col)}
+        elif fn == K.FN_DEF04:
+            slots = {0: (16, pos)}
+        else:
+            slots = {0: (16, pos), 1: (16, tan), 2: (16, bin_), 3: (16, nrm), 4: (8, uv)}
+        vao = sc.add_vao(slots)
+        bits = int(rng.integers(0, 16))
+        if (bits & K.BEHAVIOR_TEST_DEPTH) and not (bits & K.BEHAVIOR_UPDATE_DEPTH):
+            bits |= K.BEHAVIOR_UPDATE_DEPTH
+        sc.cmd("disable", all_bits); sc.cmd("enable", bits)
+        sc.cmd("viewport", int(rng.integers(max(2, width // 3), width + 1)), int(rng.integers(max(2, height // 3), height + 1)))
+        sc.cmd("use", progs[fn])
+        sc.cmd("draw", vao)
+        ntri += n
+    sc.cmd("disable", all_bits)
+    sc.cmd("enable", K.BEHAVIOR_UPDATE_DEPTH | K.BEHAVIOR_TEST_DEPTH | K.BEHAVIOR_FACE_CULLING)
+    sc.meta["triangles"] = ntri
+    return sc
