@@ -2,11 +2,18 @@
 viewport sizes, the five default programmes' vertex layouts, CLAMP / WRAP textures, cube maps, triangles of every size with
 perspective w. CPU: the restatement against the unmodified reference build, bit for bit (widens the oracle's pin beyond the
 hand-written scenes). GPU: the CUDA library against the restatement through the C-ABI."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
 from _compare import colour_stats, render_all
+from conftest import ROOT
 from puresoft3d_b200 import scenes
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from fuzz_hunt import family  # noqa: E402  (seeded variants of every scene family: demos, blend overdraw, crowded tile, height fields, soups)
 
 
 @pytest.mark.parametrize("seed", range(120))
@@ -29,5 +36,26 @@ def test_cuda_equals_oracle(seed, cuda_lib, oracle_lib):
     assert np.array_equal(a["counts"], b["counts"])
     frac, _ = colour_stats(a["colour"], b["colour"])
     assert frac >= 0.999
+    for key in ("triangles_submitted", "spans", "fragments_tested", "fragments_shaded"):
+        assert a["stats"][key] == b["stats"][key], key
+
+
+@pytest.mark.parametrize("seed", range(70))
+def test_scene_families_oracle_equals_reference(seed, oracle_lib, ref_lib):
+    sc = family(seed)
+    a, b = render_all(oracle_lib, sc), render_all(ref_lib, sc)
+    assert np.array_equal(a["colour"], b["colour"])
+    assert np.array_equal(a["depth"].view(np.uint32), b["depth"].view(np.uint32))
+    assert np.array_equal(a["counts"], b["counts"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(42))
+def test_scene_families_cuda_equals_oracle(seed, cuda_lib, oracle_lib):
+    sc = family(seed)
+    a, b = render_all(cuda_lib, sc), render_all(oracle_lib, sc)
+    assert np.array_equal(a["depth"].view(np.uint32), b["depth"].view(np.uint32))
+    assert np.array_equal(a["counts"], b["counts"])
+    assert colour_stats(a["colour"], b["colour"])[0] >= 0.999
     for key in ("triangles_submitted", "spans", "fragments_tested", "fragments_shaded"):
         assert a["stats"][key] == b["stats"][key], key
