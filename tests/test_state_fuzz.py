@@ -13,7 +13,7 @@ from conftest import ROOT
 from puresoft3d_b200 import scenes
 
 sys.path.insert(0, os.path.join(ROOT, "tools"))
-from fuzz_hunt import family  # noqa: E402  (seeded variants of every scene family: demos, blend overdraw, crowded tile, height fields, soups)
+from fuzz_hunt import family, render_band  # noqa: E402  (seeded variants of every scene family: demos, blend overdraw, crowded tile, height fields, soups)
 
 
 @pytest.mark.parametrize("seed", range(120))
@@ -59,3 +59,20 @@ def test_scene_families_cuda_equals_oracle(seed, cuda_lib, oracle_lib):
     assert colour_stats(a["colour"], b["colour"])[0] >= 0.999
     for key in ("triangles_submitted", "spans", "fragments_tested", "fragments_shaded"):
         assert a["stats"][key] == b["stats"][key], key
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(36))
+def test_scene_families_with_a_sort_first_band(seed, cuda_lib, oracle_lib):
+    """One rank's band of a random world size (2..9): small bands take the two-kernel geometry and the row-group split."""
+    from puresoft3d_b200 import sortfirst
+    rng = np.random.default_rng(9000 + seed)
+    sc = family(seed)
+    world = int(rng.integers(2, 10))
+    band = sortfirst.row_bands(sc.height, world)[int(rng.integers(0, world))]
+    a, b = render_band(cuda_lib, sc, band), render_band(oracle_lib, sc, band)
+    assert np.array_equal(a["depth"].view(np.uint32), b["depth"].view(np.uint32))
+    m0, m1 = sortfirst.memory_rows(band, sc.height)
+    if m1 > m0:
+        assert colour_stats(a["colour"][m0:m1], b["colour"][m0:m1])[0] >= 0.999
+    assert a["stats"]["fragments_tested"] == b["stats"]["fragments_tested"] and a["stats"]["fragments_shaded"] == b["stats"]["fragments_shaded"]

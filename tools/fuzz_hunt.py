@@ -1,7 +1,9 @@
 """Bug hunt beyond the test-suite's seeds: seeded variants of every scene family, CUDA against the restatement (on a GPU box),
 or — `--cpu` — the restatement against the reference build (in the build container).
 
-    python tools/fuzz_hunt.py [--cpu] [first_seed] [count]
+    python tools/fuzz_hunt.py [--cpu] [--bands] [first_seed] [count]
+
+--bands: every frame restricted to one rank's sort-first band of a random world size (ps3d_set_row_band) on both sides.
 """
 import os
 import sys
@@ -39,9 +41,44 @@ def family(seed):
     return scenes.scene_soup(w, h, seed=seed, count=int(rng.integers(10, 500)), cull=bool(rng.integers(0, 2)))
 
 
+def render_band(lib, sc, band):
+    from puresoft3d_b200.pipeline import PuresoftPipeline
+    p = PuresoftPipeline(sc.width, sc.height, lib=lib)
+    try:
+        p.setRowBand(*band)
+        scenes.render(p, sc)
+        return dict(colour=p.readColour(), depth=p.readDepth(), stats=p.getStats())
+    finally:
+        p.close()
+
+
+def main_bands(first, count):
+    from puresoft3d_b200 import sortfirst
+    oracle = _capi.bind(os.path.join(ROOT, "oracle", "libps3d_oracle.so"))
+    cuda = _capi.load_product()
+    bad = []
+    for seed in range(first, first + count):
+        rng = np.random.default_rng(9000 + seed)
+        sc = family(seed)
+        world = int(rng.integers(2, 10))
+        bands = sortfirst.row_bands(sc.height, world)
+        band = bands[int(rng.integers(0, world))]
+        a, b = render_band(cuda, sc, band), render_band(oracle, sc, band)
+        m0, m1 = sortfirst.memory_rows(band, sc.height)
+        ok = (np.array_equal(a["depth"].view(np.uint32), b["depth"].view(np.uint32)),
+              colour_stats(a["colour"][m0:m1], b["colour"][m0:m1])[0] >= 0.999 if m1 > m0 else True,
+              all(a["stats"][k] == b["stats"][k] for k in ("fragments_tested", "fragments_shaded")))
+        if not all(ok):
+            bad.append(seed)
+            print(seed, sc.name, "world", world, "band", band, "depth/colour/stats", ok, flush=True)
+    print("cuda vs restatement with a sort-first band, seeds %d..%d: mismatching %s" % (first, first + count - 1, bad))
+
+
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     cpu = "--cpu" in sys.argv
+    if "--bands" in sys.argv:
+        return main_bands(int(args[0]) if args else 0, int(args[1]) if len(args) > 1 else 150)
     first, count = (int(args[0]) if args else 0), (int(args[1]) if len(args) > 1 else 200)
     oracle = _capi.bind(os.path.join(ROOT, "oracle", "libps3d_oracle.so"))
     other = _capi.bind(os.path.join(ROOT, "oracle", "_ref", "libps3d_ref.so")) if cpu else _capi.load_product()
