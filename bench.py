@@ -11,14 +11,18 @@ A step = one frame of the hot path: clearDepth + clearColour + uniforms + drawVA
 metric/value : shaded fragments/s, whole job. A shaded fragment is one FragmentProcessor::process invocation
                (fragthrd.cpp:231) — counted on the device; identical on every backend because parity is bit-exact.
 value        : inputs resident in HBM when the timed region starts; CUDA events on the pipe's own stream, max over ranks.
-e2e          : same metric through the public API with HOST buffers: every step re-uploads the five vertex streams
-               from pinned host memory (updateContent), renders, and reads the colour target back.
+e2e          : same metric through the public API with HOST buffers: every step uploads the five vertex streams from
+               pinned host memory, renders, and reads the colour target back into pinned host memory — through the
+               pipelined forms of those calls (ps3d_vbo_update_async / ps3d_read_colour_async, two VBO sets, two display
+               targets), so step i+1's upload overlaps step i's frame; at N > 1 every rank uploads 1/N of each stream and
+               the shards are all-gathered over NVLink (the inputs cross PCIe once in total).
 roofline     : the dominant kernel class, live CUDA-event time on its launching stream (ps3d_profile_*), against
                MEASURED_PEAKS.json; frame_roofline is SURVEY.md §8(d)'s whole-frame formula.
 cpu_baseline : the reference's own renderer (oracle/_ref, the unmodified sources through the shim) on this host's cores.
 
 N > 1 (torchrun): sort-first — rank r renders raster rows [r*H/N, (r+1)*H/N) of the SAME frame (strong scaling); every
-rank runs the geometry stage for all triangles; finished colour bands are gathered to rank 0 over NCCL (NVLink).
+rank runs the position half of the geometry stage for all triangles; finished colour bands land in rank 0's target over
+NCCL (NVLink), issued by the library itself on the pipe's stream (PS3D_SORTFIRST=torch: by torch.distributed).
 --impl reference: the reference's CPU renderer alone (rank 0 only), same scene, same metric.
 """
 import argparse

@@ -198,8 +198,9 @@ int ps3d_debug_read_shade_counts(ps3d_pipe* p, uint32_t* counts /* height*width 
 int ps3d_debug_clear_shade_counts(ps3d_pipe* p);
 
 /* Sort-first sharding (new; the reference has no multi-device path): restrict rasterisation to raster rows
- * [row0, row1) of the viewport. Geometry still runs for every triangle; spans outside the band are dropped
- * before binning. (-1,-1) = whole viewport. */
+ * [row0, row1) of the viewport. The position half of the geometry stage still runs for every triangle; a triangle whose
+ * rows all miss the band leaves nothing behind, spans outside the band are dropped before binning.
+ * (-1,-1) = whole viewport. */
 int ps3d_set_row_band(ps3d_pipe* p, int row0, int row1);
 
 /* The exchange steps of sort-first rendering issued from inside the library (NCCL over NVLink on the pipe's own streams;
