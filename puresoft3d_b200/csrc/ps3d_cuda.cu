@@ -742,7 +742,9 @@ int ps3d_vbo_update(ps3d_pipe* p, int vbo, const void* src)
 	cudaSetDevice(p->device);
 	SETTLE(p);
 	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
-	// vbo.cpp:28-31 copies synchronously: the caller may free `src` on return
+	// vbo.cpp:28-31 copies synchronously: the caller may free `src` on return. (An asynchronous write still in flight on the copy
+	// or gather stream lands first.)
+	if(p->vbos[vbo].readyValid) CK(p, cudaStreamWaitEvent(p->stream, p->vbos[vbo].ready, 0));
 	CK(p, cudaMemcpyAsync(p->vbos[vbo].data, src, p->vbos[vbo].unitBytes * p->vbos[vbo].unitCount, cudaMemcpyHostToDevice, p->stream));
 	CK(p, cudaStreamSynchronize(p->stream));
 	return PS3D_OK;
@@ -753,6 +755,7 @@ int ps3d_vbo_update_device(ps3d_pipe* p, int vbo, const void* devSrc)
 	cudaSetDevice(p->device);
 	SETTLE(p);
 	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
+	if(p->vbos[vbo].readyValid) CK(p, cudaStreamWaitEvent(p->stream, p->vbos[vbo].ready, 0));
 	CK(p, cudaMemcpyAsync(p->vbos[vbo].data, devSrc, p->vbos[vbo].unitBytes * p->vbos[vbo].unitCount, cudaMemcpyDeviceToDevice, p->stream));
 	if(p->vbos[vbo].lastRead) { CK(p, cudaEventRecord(p->vbos[vbo].lastRead, p->stream)); p->vbos[vbo].readValid = true; }
 	return PS3D_OK;
@@ -815,6 +818,7 @@ int ps3d_vbo_destroy(ps3d_pipe* p, int vbo)
 	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
 	cudaStreamSynchronize(p->stream);
 	cudaStreamSynchronize(p->copyStream);
+	if(p->gatherStream) cudaStreamSynchronize(p->gatherStream);
 	freeVbo(p->vbos[vbo]);
 	for(Vao& a : p->vaos) if(a.alive) for(int s = 0; s < PS3D_MAX_VBOS; s++) if(a.vbo[s] == vbo) a.vbo[s] = -1;
 	return PS3D_OK;
