@@ -12,7 +12,7 @@ from _compare import colour_stats, render_all
 from conftest import ROOT
 from puresoft3d_b200 import scenes
 
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))
 from fuzz_hunt import family, render_band  # noqa: E402  (seeded variants of every scene family: demos, blend overdraw, crowded tile, height fields, soups)
 
 

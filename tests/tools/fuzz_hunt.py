@@ -1,14 +1,14 @@
 """Bug hunt beyond the test-suite's seeds: seeded variants of every scene family, CUDA against the restatement (on a GPU box),
 or — `--cpu` — the restatement against the reference build (in the build container).
 
-    python tools/fuzz_hunt.py [--cpu] [--bands] [first_seed] [count]
+    python tests/tools/fuzz_hunt.py [--cpu] [--bands] [first_seed] [count]
 
 --bands: every frame restricted to one rank's sort-first band of a random world size (ps3d_set_row_band) on both sides.
 """
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np

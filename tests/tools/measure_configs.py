@@ -1,9 +1,9 @@
 #!/usr/bin/env python3
 """every BASELINE.json config at its full size on one B200, beside the reference's own renderer on the
 same box's host cores, with the parity gates evaluated on those very frames (the reference build is the checker here:
-this is measurement + test tooling, not the product path).
+this is measurement + test tooling — it lives under tests/ because it loads the checkers under oracle/ — not the product path).
 
-    python tools/measure_configs.py [--configs C1,C2,C3,C4,C5-4k] > gpurun_out/configs.jsonl
+    python tests/tools/measure_configs.py [--configs C1,C2,C3,C4,C5-4k] > gpurun_out/configs.jsonl
 """
 import argparse
 import json
@@ -11,7 +11,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
