@@ -66,6 +66,7 @@ struct ps3d_objx
 	uint32_t nv = 0, ni = 0, nextOffset = 0;
 	bool hasTex = false, hasNrm = false, hasTan = false;
 	long payloadStart = 0;
+	long fileBytes = 0;     // reader: a header that promises more bytes than the file holds is refused before anything is allocated for it
 };
 
 namespace {
@@ -141,6 +142,7 @@ int ps3d_objx_open(const char* filename, ps3d_objx_scene* scene, ps3d_objx** out
 	if(!f) return PS3D_OBJX_ERR_IO;
 	ps3d_objx* h = new ps3d_objx();
 	h->file = f;
+	if(0 == fseek(f, 0, SEEK_END)) { h->fileBytes = ftell(f); rewind(f); }
 	if(1 != fread(h->fileHeader, FILE_HEADER_BYTES, 1, f)) { fclose(f); delete h; return PS3D_OBJX_ERR_FORMAT; }
 	const uint32_t version = getU32(h->fileHeader);
 	h->numMeshes = getU32(h->fileHeader + 4);
@@ -192,6 +194,7 @@ int ps3d_objx_read_mesh_header(ps3d_objx* h, ps3d_objx_mesh* mesh)
 	h->payloadStart = ftell(h->file);
 	h->headerPending = true;
 	if(payloadBytes(h->nv, h->ni, h->hasTex, h->hasNrm, h->hasTan) > h->nextOffset) return PS3D_OBJX_ERR_FORMAT;
+	if(h->fileBytes > 0 && (unsigned long long)h->payloadStart + h->nextOffset > (unsigned long long)h->fileBytes) return PS3D_OBJX_ERR_FORMAT;
 	return PS3D_OBJX_OK;
 }
 

@@ -229,3 +229,29 @@ def test_demo1_from_sphere_objx_oracle_equals_reference(oracle_lib, ref_lib, bui
     assert np.array_equal(a["depth"].view(np.uint32), b["depth"].view(np.uint32))
     assert np.array_equal(a["counts"], b["counts"])
     assert a["stats"]["fragments_shaded"] == b["stats"]["fragments_shaded"] > 300000
+
+
+def test_corrupted_files_never_crash_the_reader(tmp_path, built):
+    """Random byte corruption of a valid file: the native reader either reads it or refuses it (ObjxError) — a header that
+    promises more than the file holds is refused before anything is allocated for it."""
+    rng = np.random.default_rng(99)
+    good = tmp_path / "g.objx"
+    objx.write_objx(good, {"camera_pos": (1, 2, 3, 0)}, [_tri_mesh("o/a", 6, rng), _tri_mesh("o/b", 3, rng, indices=np.arange(9, dtype=np.int32))])
+    raw = np.frombuffer(good.read_bytes(), dtype=np.uint8)
+    refused = read = 0
+    for k in range(400):
+        bad = raw.copy()
+        n = int(rng.integers(1, 6))
+        at = rng.integers(0, 176 + 1627 if k % 2 else bad.size, size=n)     # half of the runs aim at the headers
+        bad[at] = rng.integers(0, 256, size=n, dtype=np.uint8)
+        if k % 7 == 0:
+            bad = bad[:int(rng.integers(10, bad.size))]                     # truncation
+        path = tmp_path / "bad.objx"
+        path.write_bytes(bad.tobytes())
+        try:
+            _, meshes = objx.read_objx(path)
+            read += 1
+            assert all(m["vertices"].shape[0] < 10 ** 6 for m in meshes)
+        except objx.ObjxError:
+            refused += 1
+    assert refused > 0 and read > 0
