@@ -618,3 +618,110 @@ int ps3d_profile_read(ps3d_pipe*, ps3d_profile*) { return PS3D_ERR_UNSUPPORTED; 
 int ps3d_host_approx_info(int* rcpBits, int* rsqrtBits) { *rcpBits = -1; *rsqrtBits = -1; return PS3D_OK; } // the hardware instructions themselves
 
 } // extern "C"
+
+// ---- function-level test hooks (NOT part of include/ps3d.h; tests/cpp/functors_vs_reference.cpp binds them) ---------------
+// The reference's own processor classes and PuresoftFBO driven one call at a time, in plain C types, so that the product's
+// device functors — compiled for the host by the test — can be compared with them input by input.
+namespace
+{
+struct CaptureOutput : public FragmentProcessorOutput          // proc.h:51-63; FBOBridge: write never blends, write4 does (fragthrd.cpp:54-82)
+{
+	uint32_t bgra; int flags;                                    // bit 0 wrote, bit 1 discarded, bit 2 through write4
+	CaptureOutput() : bgra(0), flags(0) {}
+	void discard(void) { flags |= 2; }
+	void read(int, void* d, size_t n) { memset(d, 0, n); }
+	void read1(int, void* d) { memset(d, 0, 1); }
+	void read4(int, void* d) { memset(d, 0, 4); }
+	void read16(int, void* d) { memset(d, 0, 16); }
+	void write(int, const void* d, size_t n) { memcpy(&bgra, d, n < 4 ? n : 4); flags |= 1; }
+	void write1(int, const void* d) { memcpy(&bgra, d, 1); flags |= 1; }
+	void write4(int, const void* d) { memcpy(&bgra, d, 4); flags |= 1 | 4; }
+	void write16(int, const void* d) { memcpy(&bgra, d, 4); flags |= 1; }
+};
+struct RefProc
+{
+	PuresoftProcessor* proc;
+	int kind;
+	std::vector<PURESOFTUNIFORM> uniforms;
+	std::vector<std::vector<unsigned char> > store;
+	const void* textures[MAX_TEXTURES];
+	RefProc() : proc(NULL), kind(0), uniforms(MAX_UNIFORMS), store(MAX_UNIFORMS) { memset(&uniforms[0], 0, sizeof(PURESOFTUNIFORM) * MAX_UNIFORMS); memset(textures, 0, sizeof(textures)); }
+};
+}
+extern "C" {
+void* ps3d_ref_fbo_create(int width, int height, int elemLen, int wrapMode, int layers, const void* const* pixels)
+{
+	PuresoftFBO* f = new PuresoftFBO(width, width * elemLen, height, elemLen, false, NULL, (PuresoftFBO::WRAPMODE)wrapMode, layers - 1);
+	for(int l = 0; l < layers; l++)
+	{
+		PuresoftFBO* layer = 0 == l ? f : f->getExtraLayer((PuresoftFBO::LAYER)l);   // tex.cpp: extra layers are FBOs of their own
+		if(layer && pixels && pixels[l]) memcpy(layer->getBuffer(), pixels[l], (size_t)width * elemLen * height);
+	}
+	return f;
+}
+void ps3d_ref_fbo_destroy(void* f) { delete (PuresoftFBO*)f; }
+void* ps3d_ref_proc_create(int kind, int functor)
+{
+	PuresoftProcessor* pr = makeProcessor(kind, functor);
+	if(!pr) return NULL;
+	RefProc* r = new RefProc(); r->proc = pr; r->kind = kind;
+	return r;
+}
+void ps3d_ref_proc_destroy(void* h) { RefProc* r = (RefProc*)h; delete r->proc; delete r; }
+size_t ps3d_ref_proc_user_bytes(void* h) { return ((RefProc*)h)->proc->userDataBytes(); }
+void ps3d_ref_proc_set_uniform(void* h, int slot, const void* data, size_t len)
+{
+	RefProc* r = (RefProc*)h;
+	r->store[slot].assign((const unsigned char*)data, (const unsigned char*)data + len);
+	r->store[slot].resize(len + 64);                              // room for the aligned copy below
+	unsigned char* at = &r->store[slot][0];
+	at += (16 - ((uintptr_t)at & 15)) & 15;                       // mcemath loads uniforms with movaps
+	memmove(at, data, len);
+	r->uniforms[slot].data = at; r->uniforms[slot].capacity = len;
+}
+void ps3d_ref_proc_set_texture(void* h, int index, void* fbo) { ((RefProc*)h)->textures[index] = fbo; }
+void ps3d_ref_proc_prepare(void* h)
+{
+	RefProc* r = (RefProc*)h;
+	if(PS3D_PROC_VERTEX == r->kind) dynamic_cast<PuresoftVertexProcessor*>(r->proc)->preprocess(&r->uniforms[0]);
+	else if(PS3D_PROC_INTERPOLATION == r->kind) dynamic_cast<PuresoftInterpolationProcessor*>(r->proc)->preprocess(&r->uniforms[0]);
+	else dynamic_cast<PuresoftFragmentProcessor*>(r->proc)->preprocess(&r->uniforms[0], r->textures);
+}
+// user: the interpolated varyings (PROCDATA_*), 16-byte aligned
+int ps3d_ref_fp_process(void* h, int x, int y, void* user, uint32_t* bgra)
+{
+	FragmentProcessorInput in; in.position[0] = x; in.position[1] = y; in.user = user;
+	CaptureOutput out;
+	dynamic_cast<PuresoftFragmentProcessor*>(((RefProc*)h)->proc)->process(&in, &out);
+	*bgra = out.bgra;
+	return out.flags;
+}
+// The interpolater's use of an interpolation processor on one span (interp.cpp:26-92): start / end from the two ends' corrected
+// contributions, step = calcStep, optional left-clip skip, `steps` single steps, then correctInterpolation. All buffers 16-byte
+// aligned, userDataBytes() each; contributes: 4 floats per end.
+void ps3d_ref_ip_span(void* h, const void* v0, const void* v1, const void* v2, const float* contribL, const float* contribR, int stepCount, int skip, int steps,
+                      float correctionFactor2, void* start, void* step, void* fragment)
+{
+	PuresoftInterpolationProcessor* ip = dynamic_cast<PuresoftInterpolationProcessor*>(((RefProc*)h)->proc);
+	const void* verts[3] = { v0, v1, v2 };
+	const size_t bytes = ip->userDataBytes();
+	void* end = NULL;
+	if(0 != posix_memalign(&end, 16, bytes ? bytes : 16)) return;
+	ip->interpolateByContributes(start, verts, contribL);
+	ip->interpolateByContributes(end, verts, contribR);
+	ip->calcStep(step, start, end, stepCount);
+	if(skip > 0) ip->stepForward(start, step, skip);
+	for(int i = 0; i < steps; i++) ip->stepForward(start, step, 1);
+	ip->correctInterpolation(fragment, start, correctionFactor2);
+	free(end);
+}
+// slots: 16 pointers to this vertex's element in every attached stream (NULL = not attached); user: 16-byte aligned PROCDATA_*
+void ps3d_ref_vp_process(void* h, const void* const* slots, float* position4, void* user)
+{
+	VertexProcessorInput in;
+	for(size_t i = 0; i < MAX_VBOS; i++) in.data[i] = slots[i];
+	VertexProcessorOutput out; out.user = user;
+	dynamic_cast<PuresoftVertexProcessor*>(((RefProc*)h)->proc)->process(&in, &out);
+	memcpy(position4, out.position, 16);
+}
+}
