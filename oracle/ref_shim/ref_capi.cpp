@@ -715,6 +715,20 @@ void ps3d_ref_ip_span(void* h, const void* v0, const void* v1, const void* v2, c
 	ip->correctInterpolation(fragment, start, correctionFactor2);
 	free(end);
 }
+// PuresoftFBO::blend4 (fbo.cpp:208-229, MMX asm -> intrinsics in this build) on one pixel: dst is written, src blended over it through
+// the sequential cursor the fragment thread uses (fragthrd.cpp:70-82), the result read back
+uint32_t ps3d_ref_blend4(uint32_t src, uint32_t dst)
+{
+	static PuresoftFBO* f = NULL;
+	if(!f) f = new PuresoftFBO(4, 16, 2, 4);
+	f->directWrite4(0, 1, &dst);
+	f->setCurRow(0, 0);
+	f->setCurCol(0, 1);
+	f->blend4(0, (const unsigned char*)&src);
+	uint32_t out = 0;
+	f->directRead4(0, 1, &out);
+	return out;
+}
 // slots: 16 pointers to this vertex's element in every attached stream (NULL = not attached); user: 16-byte aligned PROCDATA_*
 void ps3d_ref_vp_process(void* h, const void* const* slots, float* position4, void* user)
 {

@@ -991,24 +991,7 @@ __global__ void __launch_bounds__(256) post_process_kernel(TargetDesc colour, Ta
 // tile raster + shade
 // ======================================================================================================================
 
-// fbo.cpp:208-229 blend4 : per channel dst + ((sat_u16(src - dst) * srcA) >> 8), 16-bit lanes, unsigned-saturating pack
-PS_D uint32_t blend4(uint32_t src, uint32_t dst)
-{
-	const uint32_t a = src >> 24;
-	uint32_t out = 0;
-#pragma unroll
-	for(int ch = 0; ch < 4; ch++)
-	{
-		const uint32_t s = (src >> (8 * ch)) & 0xff, d = (dst >> (8 * ch)) & 0xff;
-		const uint32_t diff = s > d ? s - d : 0;           // _mm_subs_pu16
-		const uint32_t prod = (diff * a) & 0xffff;          // _mm_mullo_pi16
-		const uint32_t sum = ((prod >> 8) + d) & 0xffff;    // _mm_srli_pi16 + _mm_add_pi16
-		const int ssum = (int)(short)sum;                   // _mm_packs_pu16 saturates a SIGNED 16-bit value to 0..255
-		const uint32_t byte = ssum < 0 ? 0u : (ssum > 255 ? 255u : (uint32_t)ssum);
-		out |= byte << (8 * ch);
-	}
-	return out;
-}
+// (blend4 — fbo.cpp:208-229 — lives in shaders.cuh next to FragmentProcessorOutput: host/device code, pinned on the host too)
 
 struct TileSmem
 {

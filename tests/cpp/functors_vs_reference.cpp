@@ -36,6 +36,7 @@ int ps3d_ref_fp_process(void* h, int x, int y, void* user, uint32_t* bgra);
 void ps3d_ref_vp_process(void* h, const void* const* slots, float* position4, void* user);
 void ps3d_ref_ip_span(void* h, const void* v0, const void* v1, const void* v2, const float* contribL, const float* contribR, int stepCount, int skip, int steps,
                       float correctionFactor2, void* start, void* step, void* fragment);
+uint32_t ps3d_ref_blend4(uint32_t src, uint32_t dst);
 }
 enum { KIND_V = 0, KIND_I = 1, KIND_F = 2 };   // PS3D_PROC_*
 
@@ -236,6 +237,23 @@ int main(int argc, char** argv)
 	failing += vertexCase<ProgSingleColour>("V_SingleColour", 33, 33, n, ap);
 	failing += vertexCase<ProgDiffuseOnly>("V_DiffuseOnly", 34, 34, n, ap);
 	failing += vertexCase<ProgShadow2>("V_Shadow2", 35, 32, n, ap);
+	// ---- blend4 (fbo.cpp:208-229): every (source, destination, alpha) of one channel with the other channels random: 16.7 M blends
+	{
+		long long checked = 0, bad = 0;
+		for(uint32_t a = 0; a < 256; a++)
+			for(uint32_t sv = 0; sv < 256; sv++)
+				for(uint32_t dv = 0; dv < 256; dv += (n >= 1000000 ? 1 : 5))
+				{
+					const int ch = (int)(rnd32() % 3);
+					const uint32_t r = rnd32(), q = rnd32();
+					const uint32_t src = ((r & 0x00ffffffu) & ~(0xffu << (8 * ch))) | (sv << (8 * ch)) | (a << 24);
+					const uint32_t dst = (q & ~(0xffu << (8 * ch))) | (dv << (8 * ch));
+					checked++;
+					if(blend4(src, dst) != ps3d_ref_blend4(src, dst)) bad++;
+				}
+		printf("blend4 %lld %lld\n", checked, bad);
+		failing += bad != 0;
+	}
 	// ---- interpolation processors
 	failing += interpolationCase<ProgDEF01>("I_DEF01", 1, n);
 	failing += interpolationCase<ProgDEF02>("I_DEF02", 2, n);
