@@ -152,6 +152,7 @@ public:
 private:
 	friend class PuresoftPipeline;
 	ps3d_pipe* m_pipe;
+	PuresoftPipeline* m_owner;                     // the pipeline that tracks this object; cleared when the pipeline dies first
 	int m_handle;
 	size_t m_unitBytes, m_unitCount;
 	PuresoftVBO(const PuresoftVBO&);
@@ -174,7 +175,14 @@ public:
 	{
 		// pipeline.cpp:64-116: the pipeline owns processors, textures, VAOs and the VBOs still attached to them
 		for(size_t i = 0; i < m_procs.size(); i++) delete m_procs[i];
-		for(size_t i = 0; i < m_vbos.size(); i++) if(m_vbos[i]) { m_vbos[i]->m_pipe = NULL; if(m_owned[i]) delete m_vbos[i]; }
+		for(size_t i = 0; i < m_vbos.size(); i++)
+			if(m_vbos[i])
+			{
+				PuresoftVBO* v = m_vbos[i];
+				m_vbos[i] = NULL;
+				v->m_pipe = NULL; v->m_owner = NULL;   // a VBO the caller still holds outlives the pipeline as an empty shell
+				if(m_owned[i]) delete v;
+			}
 		if(m_pipe) ps3d_destroy(m_pipe);
 	}
 
@@ -231,7 +239,7 @@ public:
 		for(size_t i = 0; i < attached.size(); i++)
 		{
 			const int h = attached[i];
-			if((size_t)h < m_vbos.size() && m_vbos[h]) { PuresoftVBO* v = m_vbos[h]; m_vbos[h] = NULL; v->m_handle = -1; if(m_owned[h]) delete v; }
+			if((size_t)h < m_vbos.size() && m_vbos[h]) { PuresoftVBO* v = m_vbos[h]; m_vbos[h] = NULL; v->m_handle = -1; v->m_owner = NULL; if(m_owned[h]) delete v; }
 		}
 	}
 
@@ -270,7 +278,14 @@ private:
 	{
 		const int h = v->handle();
 		if((size_t)h >= m_vbos.size()) { m_vbos.resize(h + 1, NULL); m_owned.resize(h + 1, false); }
+		// a handle slot the library reused: whoever sat here before is gone from the library's point of view
+		if(m_vbos[h] && m_vbos[h] != v) { m_vbos[h]->m_handle = -1; m_vbos[h]->m_owner = NULL; }
 		m_vbos[h] = v; m_owned[h] = owned;
+	}
+	void untrack(PuresoftVBO* v)
+	{
+		const int h = v->handle();
+		if(h >= 0 && (size_t)h < m_vbos.size() && m_vbos[h] == v) { m_vbos[h] = NULL; m_owned[h] = false; }
 	}
 	PuresoftVBO* release(int h)
 	{
@@ -288,13 +303,14 @@ private:
 };
 
 inline PuresoftVBO::PuresoftVBO(PuresoftPipeline& pipeline, size_t unitBytes, size_t unitCount)
-	: m_pipe(pipeline.m_pipe), m_handle(-1), m_unitBytes(unitBytes), m_unitCount(unitCount)
+	: m_pipe(pipeline.m_pipe), m_owner(&pipeline), m_handle(-1), m_unitBytes(unitBytes), m_unitCount(unitCount)
 {
 	ps3d_detail::raise(m_pipe, ps3d_vbo_create(m_pipe, unitBytes, unitCount, &m_handle));
 	pipeline.track(this, false);
 }
 inline PuresoftVBO::~PuresoftVBO()
 {
+	if(m_owner) m_owner->untrack(this);            // the pipeline must not keep (or later write through) a dangling pointer
 	if(m_pipe && m_handle >= 0) ps3d_vbo_destroy(m_pipe, m_handle);
 }
 inline void PuresoftVBO::updateContent(const void* src) { ps3d_detail::raise(m_pipe, ps3d_vbo_update(m_pipe, m_handle, src)); }

@@ -73,6 +73,10 @@ bool radixBinningForced() { static int on = -1; if(on < 0) { const char* e = get
 // PS3D_GEOM_STAGE=0 turns the shared-memory staging of the vertex streams off (A/B checks)
 bool geomStagingOn() { static int on = -1; if(on < 0) { const char* e = getenv("PS3D_GEOM_STAGE"); on = (e && e[0] == '0') ? 0 : 1; } return on == 1; }
 
+// function-local launch state (attributes set, occupancy) is kept per device ordinal
+#define PS_MAX_DEVICES 64
+int currentDevice() { int d = 0; cudaGetDevice(&d); return d >= 0 && d < PS_MAX_DEVICES ? d : 0; }
+
 template<class PROG> void launchGeom(const DrawParams& P, cudaStream_t s)
 {
 	const unsigned blocks = (P.ntris + PS_GEOM_THREADS - 1) / PS_GEOM_THREADS;
@@ -91,12 +95,14 @@ template<class PROG> void launchGeom(const DrawParams& P, cudaStream_t s)
 	const bool split = P.workList && (P.band0 > 0 || P.band1 < P.vpH);
 	if(staged)
 	{
-		static size_t attr = 0;
-		if(bytes > attr)
+		// cudaFuncSetAttribute is per device: one flag per device ordinal (a process may own pipes on several GPUs)
+		static bool attrSet[PS_MAX_DEVICES] = { false };
+		const int dev = currentDevice();
+		if(!attrSet[dev])
 		{
 			cudaFuncSetAttribute(geom_setup_kernel<PROG, true, PS_GEOM_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024));
 			cudaFuncSetAttribute(geom_setup_kernel<PROG, true, PS_GEOM_APPEND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024));
-			attr = 96 * 1024;
+			attrSet[dev] = true;
 		}
 		if(split) geom_setup_kernel<PROG, true, PS_GEOM_APPEND><<<blocks, PS_GEOM_THREADS, bytes, s>>>(P);
 		else geom_setup_kernel<PROG, true, PS_GEOM_FUSED><<<blocks, PS_GEOM_THREADS, bytes, s>>>(P);
@@ -128,11 +134,12 @@ template<class PROG> void launchTileOrdered(const DrawParams& P, const uint32_t*
 template<class PROG> void launchShade(const DrawParams& P, const SurvivorStream& Q, cudaStream_t s)
 {
 	// a flat grid-stride loop over the survivor stream: exactly one resident wave
-	static int perSM = 0, sms = 0;
+	static int perSMs[PS_MAX_DEVICES] = { 0 }, smss[PS_MAX_DEVICES] = { 0 };
+	const int dev = currentDevice();
+	int& perSM = perSMs[dev];
+	int& sms = smss[dev];
 	if(0 == perSM)
 	{
-		int dev = 0;
-		cudaGetDevice(&dev);
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shade_kernel<PROG>, 128, 0) != cudaSuccess || perSM <= 0) perSM = 4;
 	}
@@ -874,10 +881,18 @@ int ps3d_vao_destroy(ps3d_pipe* p, int vao)
 	if(vao < 0 || vao >= (int)p->vaos.size()) return fail(p, PS3D_ERR_OUT_OF_RANGE, "PuresoftPipeline::attachVBO vao"); // pipeline.cpp:185-188
 	if(!p->vaos[vao].alive) return PS3D_OK;
 	cudaStreamSynchronize(p->stream);
+	// an asynchronous upload or all-gather may still be writing one of the VBOs about to be freed
+	cudaStreamSynchronize(p->copyStream);
+	if(p->gatherStream) cudaStreamSynchronize(p->gatherStream);
 	for(int s = 0; s < PS3D_MAX_VBOS; s++) // pipeline.cpp:194-201: the pipeline owns attached VBOs
 	{
 		const int v = p->vaos[vao].vbo[s];
-		if(v >= 0 && p->vbos[v].alive) freeVbo(p->vbos[v]);
+		if(v >= 0 && p->vbos[v].alive)
+		{
+			freeVbo(p->vbos[v]);
+			// the handle may be reused: no other VAO may keep pointing at it (as ps3d_vbo_destroy does)
+			for(Vao& a : p->vaos) if(a.alive) for(int t = 0; t < PS3D_MAX_VBOS; t++) if(a.vbo[t] == v) a.vbo[t] = -1;
+		}
 	}
 	p->vaos[vao].alive = false;
 	return PS3D_OK;
@@ -1133,10 +1148,13 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	}
 	CK(p, cudaGetLastError());
 	// the geometry kernel is the only reader of the vertex streams: asynchronous uploads may overwrite them behind it
+	// (every attached VBO, also one that has only ever been written synchronously: its first asynchronous write or
+	// all-gather must wait for THIS read, not for the creation-time fill)
 	for(int s = 0; s < PS3D_MAX_VBOS; s++)
-		if(va.vbo[s] >= 0 && p->vbos[va.vbo[s]].readyValid)
+		if(va.vbo[s] >= 0)
 		{
 			Vbo& v = p->vbos[va.vbo[s]];
+			{ const int rc = vboEvents(p, v); if(rc) return rc; }
 			CK(p, cudaEventRecord(v.lastRead, p->stream));
 			v.readValid = true;
 		}
@@ -1245,7 +1263,7 @@ int ps3d_get_stats(ps3d_pipe* p, ps3d_stats* out)
 	TRACE();
 	cudaSetDevice(p->device);
 	SETTLE(p);
-	static DeviceStats d[PS_STATS_COPIES];
+	DeviceStats d[PS_STATS_COPIES];                // per call: two pipes (two devices, two threads) must not share a host buffer
 	CK(p, cudaMemcpyAsync(d, p->statsDev, sizeof(d), cudaMemcpyDeviceToHost, p->stream));
 	CK(p, cudaStreamSynchronize(p->stream));
 	*out = p->stats;

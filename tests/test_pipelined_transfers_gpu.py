@@ -62,3 +62,29 @@ def test_pipelined_frames_equal_synchronous_frames(name, cuda_lib, oracle_lib):
     with pytest.raises(Exception):
         vbo.updateContentAsync(host.data_ptr(), vbo.unitCount, 1)
     pipe.close()
+
+
+def test_async_write_waits_for_a_draw_of_a_synchronously_filled_vbo(cuda_lib):
+    """A VBO filled only by the synchronous updateContent and then drawn: the first asynchronous write must wait for that
+    draw's geometry kernel (its lastRead event is recorded for EVERY attached VBO, not only for ones written asynchronously
+    before). Sync update, draw without finish, async update with different data, draw: frame 1 must be the frame of the first
+    data, frame 2 the frame of the second."""
+    sc = SMALL["c2_heightfield_small"]()
+    want_a = render_all(cuda_lib, sc)["colour"].view(np.uint32)
+    images = [torch.zeros((sc.height, sc.width), dtype=torch.int32).pin_memory() for _ in range(2)]
+    for rep in range(3):                    # several rounds on fresh pipes: a race does not lose every time
+        pipe = PuresoftPipeline(sc.width, sc.height, lib=cuda_lib)
+        up = scenes.upload(pipe, sc)        # synchronous updateContent on every VBO, nothing asynchronous before the draw
+        junk = [torch.from_numpy(np.full(arr.size * arr.itemsize // 4, 2.0e9, dtype=np.float32)).pin_memory() for _, arr in up.vbos]
+        scenes.replay(pipe, sc, up, finish=False)                       # draw, no finish
+        pipe.readColourAsync(images[0].data_ptr(), sc.width * 4)
+        pipe.swapBuffers()
+        for (vbo, arr), j in zip(up.vbos, junk):                        # different data, asynchronously, right behind the draw
+            vbo.updateContentAsync(j.data_ptr(), 0, vbo.unitCount)
+        scenes.replay(pipe, sc, up, finish=False)
+        pipe.readColourAsync(images[1].data_ptr(), sc.width * 4)
+        pipe.swapBuffers()
+        pipe.finish()
+        assert np.array_equal(images[0].numpy().view(np.uint32)[:-1], want_a[:-1]), "the asynchronous write overtook the draw (round %d)" % rep
+        assert not np.array_equal(images[1].numpy().view(np.uint32)[:-1], want_a[:-1]), "the second draw did not see the asynchronous write"
+        pipe.close()
