@@ -119,6 +119,25 @@ def build_scene(args):
     raise SystemExit("unknown workload")
 
 
+def bench_config(args, sc):
+    """The workload, named identically by both arms (the driver compares the two dicts): static properties of the scene only.
+    What differs between the arms (threads, ranks, transfers, counters of the run) lives in other keys of the line."""
+    vertex_mb = sc.vertex_bytes_read() // 1000000
+    tex_mb = sum(a.nbytes for t in sc.textures for a in t["layers"] if a is not None) // 1000000
+    return {"workload": args.workload, "scene": sc.name, "triangles": sc.meta.get("triangles"), "resolution": [sc.width, sc.height],
+            "shader": "DEF03 (Blinn-Phong + normal map)", "textures": "2 x %d^2 BGRA nearest" % sc.textures[0]["width"],
+            "state": "depth test + write, back-face culling, no blending",
+            "l2": "inputs larger than L2, no flush between steps: %d MB of vertex streams + %d MB of textures are read every step (126 MB L2)" % (vertex_mb, tex_mb)}
+
+
+def frame_hashes(colour, depth):
+    """sha256 of the frame's colour words (top-down BGRA8, W*4 per row) and depth words (bottom-up float32): equal hashes on
+    1, 2, 4, 8 GPUs and on the reference arm are the check that sort-first sharding changes no result."""
+    import hashlib
+    return (hashlib.sha256(np.ascontiguousarray(colour).view(np.uint8).tobytes()).hexdigest(),
+            hashlib.sha256(np.ascontiguousarray(depth).view(np.uint8).tobytes()).hexdigest())
+
+
 def algorithmic_bytes(scene, tex_samples):
     """vertex bytes read once + every bound target written once + targets loaded because the clear is a
     separate pass here? No: the formula counts clears as fused (0 B) — kept as specified — + min(texture bytes, 4 B x samples)."""
@@ -151,6 +170,7 @@ def run_reference(args, rank):
     up = scenes.upload(p, sc)
     scenes.replay(p, sc, up)
     frags = p.getStats()["fragments_shaded"]
+    colour_sha, depth_sha = frame_hashes(p.readColour(), p.readDepth())
     p.close()
     # pass 2 (timed, decorators off): the stock code path
     os.environ["PS3D_REF_COUNTING"] = "0"
@@ -171,8 +191,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "shaded_fragments_per_s", "value": value, "unit": "fragments/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "frames_per_s": 1000.0 / ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "scene": sc.name, "triangles": sc.meta.get("triangles"), "resolution": [sc.width, sc.height],
-                   "shader": "DEF03", "fragments_per_frame": frags},
+        "config": bench_config(args, sc), "parallelism": "%d host threads" % threads,
+        "fragments_per_frame": frags, "colour_sha256": colour_sha, "depth_sha256": depth_sha,
         "cpu_baseline": {"value": value, "unit": "fragments/s", "cores": threads, "kind": kind,
                          "sample": "%d full frames of the workload, %d warm-up" % (args.steps, args.warmup)},
         "e2e": {"value": value, "unit": "fragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -335,6 +355,14 @@ def main():
         want = pipe.readColour().view(np.uint32)
         e2e_check = bool(np.array_equal(want, host_colour[0].numpy().view(np.uint32)) and np.array_equal(want, host_colour[1].numpy().view(np.uint32)))
     clocks = sampler.stop()   # sampled across both timed regions
+    # the frame's hashes (rank 0's colour target holds the composite; depth bands are collected here, outside any timed region)
+    depth_full = pipe.readDepth()
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, (comp.band, depth_full[comp.band[0]:comp.band[1]].copy()))
+        for (b0, b1), rows in parts:
+            depth_full[b0:b1] = rows
+    colour_sha, depth_sha = frame_hashes(pipe.readColour(), depth_full) if rank == 0 else (None, None)
 
     # ---- roofline ------------------------------------------------------------------------------------------------
     peak, peak_src = load_peaks()
@@ -374,11 +402,11 @@ def main():
             "metric": "shaded_fragments_per_s", "value": value, "unit": "fragments/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "frames_per_s": 1000.0 / ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "scene": sc.name, "triangles": sc.meta.get("triangles"), "resolution": [sc.width, sc.height],
-                       "shader": "DEF03 (Blinn-Phong + normal map)", "textures": "2 x %d^2 BGRA nearest" % sc.textures[0]["width"], "fragments_per_frame": frags_per_frame, "fragments_tested_per_frame": tested_per_frame,
-                       "parallelism": ("sort-first row bands x%d, NCCL send/recv to rank 0 (%s)" % (world, "issued by the library on the pipe's stream" if native_comp else "torch.distributed")) if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2 (%d MB vertex streams + %d MB textures + header/varying/survivor intermediates of the same order per frame vs 126 MB L2)" % (vertex_b // 1000000, sum(a.nbytes for t in sc.textures for a in t["layers"]) // 1000000),
-                       "approx": "x86 rcpps/rsqrtss tables bits=%s" % (pipe.hostApproxInfo(),)},
+            "config": bench_config(args, sc),
+            "parallelism": ("sort-first row bands x%d, composite to rank 0 %s" % (world, comp.how)) if world > 1 else "single GPU",
+            "fragments_per_frame": frags_per_frame, "fragments_tested_per_frame": tested_per_frame,
+            "approx": "x86 rcpps/rsqrtss tables bits=%s" % (pipe.hostApproxInfo(),),
+            "colour_sha256": colour_sha, "depth_sha256": depth_sha,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(t.item()) / e2e_steps, "steps": e2e_steps,

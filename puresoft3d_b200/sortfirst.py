@@ -93,6 +93,7 @@ class Compositor:
         self.bands = row_bands(pipe.height, world)
         self.band = self.bands[rank]
         self.native = native          # ps3d_composite_bands (the library's own communicator) instead of torch.distributed
+        self.how = "by NCCL send/recv issued by the library on the pipe's stream" if native else "by torch.distributed send/recv"
         self._views = {}
 
     def _colour(self):

@@ -15,6 +15,7 @@ PRODUCT_SO = os.path.join(ROOT, "puresoft3d_b200", "libps3d_b200.so")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: minutes of CPU reference time; runs only with PS3D_SLOW=1")
 
 
 @pytest.fixture(scope="session")

@@ -44,3 +44,47 @@ def test_render_is_idempotent(cuda_lib):
     sc = SMALL["c2_heightfield_small"]()
     a, b = render_all(cuda_lib, sc), render_all(cuda_lib, sc)
     assert np.array_equal(a["colour"], b["colour"]) and np.array_equal(a["depth"].view(np.uint32), b["depth"].view(np.uint32))
+
+
+# ---- every BASELINE.json config at its FULL size, against the reference's own renderer (oracle/_ref) ------------------------
+# The reference needs 1.3 s (C2), 0.2 s (C3), 0.8 s (C4) per frame on the GPU box's host cores: cheap enough for the suite.
+# C5 (10 M triangles at 4K: 17 s per reference frame + the scene build) runs when PS3D_SLOW=1.
+
+def _full_configs():
+    from puresoft3d_b200 import scenes
+    return {
+        "C1": lambda: scenes.scene_cube(640, 480),
+        "C2": lambda: scenes.scene_heightfield(1920, 1080, grid=354, layers=4, seed=2, tex_size=2048),
+        "C3": lambda: scenes.scene_desk(1920, 1080, shadow=4096, clutter=24, tex_size=512),
+        "C4": lambda: scenes.scene_blend_overdraw(1920, 1080),
+        "C5-4k": lambda: scenes.scene_heightfield(3840, 2160, grid=1118, layers=4, seed=5, tex_size=2048),
+    }
+
+
+def _render_ref_counted(ref_lib, sc):
+    import os
+    old = os.environ.get("PS3D_REF_COUNTING")
+    os.environ["PS3D_REF_COUNTING"] = "1"
+    os.environ.setdefault("PS3D_REF_THREADS", str(os.cpu_count() or 2))
+    try:
+        return render_all(ref_lib, sc)
+    finally:
+        if old is None:
+            os.environ.pop("PS3D_REF_COUNTING", None)
+        else:
+            os.environ["PS3D_REF_COUNTING"] = old
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4", pytest.param("C5-4k", marks=pytest.mark.slow)])
+def test_full_size_config_matches_reference_build(name, cuda_lib, ref_lib):
+    import os
+    if name == "C5-4k" and os.environ.get("PS3D_SLOW") != "1":
+        pytest.skip("set PS3D_SLOW=1 (the reference needs ~20 s per 10 M-triangle frame)")
+    sc = _full_configs()[name]()
+    a, b = render_all(cuda_lib, sc), _render_ref_counted(ref_lib, sc)
+    assert np.array_equal(a["counts"], b["counts"]), "per-pixel FragmentProcessor::process counts differ from the reference"
+    assert np.array_equal(a["depth"].view(np.uint32), b["depth"].view(np.uint32)), "depth words differ from the reference"
+    frac, worst = colour_stats(a["colour"], b["colour"])
+    assert frac >= COLOUR_FRACTION, (frac, worst)
+    for key in ("triangles_submitted", "fragments_shaded"):
+        assert a["stats"][key] == b["stats"][key], key
