@@ -239,18 +239,35 @@ def main():
     up = scenes.upload(pipe, sc)
     ext = torch.cuda.ExternalStream(pipe.deviceStream(), device=dev)
     native = sortfirst.init_native_comm(pipe, rank, world, dev) if world > 1 else False
-    native_comp = False
-    native_comp = native and os.environ.get("PS3D_SORTFIRST_COMPOSITE", "native") != "torch"
-    comp = sortfirst.Compositor(pipe, rank, world, dev, ext, native=native_comp) if world > 1 else None
+    # the composite: peer stores into rank 0's target over NVLink (default) | the library's NCCL send/recv | torch.distributed
+    peer_comp = sortfirst.init_peer_composite(pipe, rank, world, dev) if world > 1 else False
+    native_comp = native and not peer_comp and os.environ.get("PS3D_SORTFIRST_COMPOSITE", "peer") != "torch"
+    comp = sortfirst.Compositor(pipe, rank, world, dev, ext, native=native_comp, peer=peer_comp) if world > 1 else None
     if comp:
         pipe.setRowBand(*comp.band)
 
     replay_frame = scenes.compile_replay(pipe, sc, up)   # the frame's command list with its ctypes arguments prepared once
 
-    def frame():
+    def frame_calls():
         replay_frame()
         if comp:
             comp.gather_to_rank0()
+
+    # The frame as ONE launch: its calls are captured once into a CUDA graph (ps3d_graph_*) and replayed. What a frame costs the
+    # host matters when its kernels take tens of microseconds (8 ranks). A composite made of NCCL calls stays outside.
+    use_graph = os.environ.get("PS3D_GRAPH", "1") != "0" and (comp is None or peer_comp)
+    graphs = {}
+
+    def capture(key, calls):
+        pipe.graphBegin()
+        calls()
+        graphs[key] = pipe.graphEnd()
+
+    def frame():
+        if use_graph and "frame" in graphs:
+            pipe.graphLaunch(graphs["frame"])
+        else:
+            frame_calls()
 
     def barrier():
         if world > 1:
@@ -261,8 +278,20 @@ def main():
     for _ in range(args.warmup):
         frame()
     pipe.finish()
-    pipe.resetStats()
+    # per-kernel-class times (roofline, kernel_ms_per_frame): a pass of the same frames with an event pair around every kernel
+    # class (ps3d_profile_*), before the timed region — a captured frame carries no such events, and they are not free
     pipe.profileEnable(True)
+    for _ in range(args.steps):
+        frame_calls()
+    pipe.finish()
+    prof = pipe.profileRead()
+    pipe.profileEnable(False)
+    if use_graph:
+        capture("frame", frame_calls)
+        for _ in range(3):
+            frame()
+        pipe.finish()
+    pipe.resetStats()
     launches0 = pipe.deviceLaunchCount()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
@@ -275,8 +304,6 @@ def main():
     ev1.synchronize()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
-    prof = pipe.profileRead()
-    pipe.profileEnable(False)
     launches = pipe.deviceLaunchCount() - launches0
     stats = pipe.getStats()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -349,7 +376,7 @@ def main():
         dist.all_reduce(frag_t, op=dist.ReduceOp.SUM)
     e2e_value = float(frag_t.item()) / (float(t.item()) / 1000.0)
     # the images the pipelined steps read back must be the frame the kernel-only leg renders (rank 0 holds the composite)
-    frame()
+    frame_calls()
     e2e_check = None
     if rank == 0:
         want = pipe.readColour().view(np.uint32)
@@ -404,6 +431,7 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": bench_config(args, sc),
             "parallelism": ("sort-first row bands x%d, composite to rank 0 %s" % (world, comp.how)) if world > 1 else "single GPU",
+            "frame_launch": "one CUDA graph launch per frame (ps3d_graph_*)" if use_graph else "one launch per kernel",
             "fragments_per_frame": frags_per_frame, "fragments_tested_per_frame": tested_per_frame,
             "approx": "x86 rcpps/rsqrtss tables bits=%s" % (pipe.hostApproxInfo(),),
             "colour_sha256": colour_sha, "depth_sha256": depth_sha,

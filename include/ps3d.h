@@ -220,6 +220,35 @@ int ps3d_comm_destroy(ps3d_pipe* p);
 int ps3d_composite_bands(ps3d_pipe* p, const int* bands);
 int ps3d_vbo_all_gather(ps3d_pipe* p, int vbo);
 
+/* The composite without a copy step: over NVLink peer memory every rank renders its band STRAIGHT INTO rank 0's colour target
+ * (the shade kernel's stores are peer stores), so what is left of the exchange is a pair of counters per frame.
+ *  ps3d_peer_export     PS3D_PEER_BLOB bytes describing this rank's display targets and flag block (CUDA IPC handles); hand
+ *                       every rank's blob to every rank by any host transport (one all-gather at start-up).
+ *  ps3d_peer_import     blobs = world x PS3D_PEER_BLOB bytes in rank order. Ranks != 0 map rank 0's targets; from here on their
+ *                       draws write rank 0's colour target (their own row band of it, ps3d_set_row_band) and their
+ *                       ps3d_clear_colour is rank 0's business.
+ *  ps3d_composite_peer  behind every frame, on every rank: ranks != 0 publish "frame written" (release at system scope), rank 0
+ *                       waits on its stream until every rank has. No rank overwrites a target rank 0 has not handed out again
+ *                       (rank 0 hands it out with its next clear / draw into it, i.e. behind a read-back it enqueued).
+ * Every rank must issue the same sequence of clear / draw / swap / composite calls. */
+#define PS3D_PEER_BLOB 256
+int ps3d_peer_export(ps3d_pipe* p, void* blob);
+int ps3d_peer_import(ps3d_pipe* p, int rank, int world, const void* blobs);
+int ps3d_composite_peer(ps3d_pipe* p);
+
+/* Captured frames (CUDA library only). The calls between ps3d_graph_begin and ps3d_graph_end (clears, uniforms, draws, the
+ * composite) are recorded once into a CUDA graph instead of being run; ps3d_graph_launch replays them as ONE launch — what a
+ * frame costs the host when its kernels take tens of microseconds (C2 on 8 GPUs). Contract: run the same frame once normally
+ * first (buffers are sized by then: a captured frame cannot allocate), keep resources, state and uniforms of the frame
+ * unchanged between launches (uniform values are latched at capture), and capture once per (VBO set, display target)
+ * combination the frame is launched with. Vertex data may change between launches (ps3d_vbo_update*): the streams are read
+ * through the same pointers. A replayed frame whose intermediates no longer fit the buffers it was captured with is reported
+ * by the next ps3d_finish as PS3D_ERR_INVALID_ARGUMENT ("re-capture"). */
+int ps3d_graph_begin(ps3d_pipe* p);
+int ps3d_graph_end(ps3d_pipe* p, int* graph);
+int ps3d_graph_launch(ps3d_pipe* p, int graph);
+int ps3d_graph_destroy(ps3d_pipe* p, int graph);
+
 /* Device-resident access for the benchmark and the multi-GPU composite (CUDA library only; the CPU
  * libraries return PS3D_ERR_UNSUPPORTED). Pointers are CUDA device pointers owned by the pipe. */
 int ps3d_device_colour_ptr(ps3d_pipe* p, void** devPtr, size_t* pitchBytes);

@@ -266,6 +266,15 @@ public:
 	static void commUniqueId(void* id256) { ps3d_detail::raise(NULL, ps3d_comm_unique_id(id256)); }
 	void commInit(int rank, int world, const void* id256) { check(ps3d_comm_init(m_pipe, rank, world, id256)); }
 	void compositeBands(const int* bands) { check(ps3d_composite_bands(m_pipe, bands)); }
+	// composite over NVLink peer memory: every rank renders straight into rank 0's colour target (include/ps3d.h)
+	void peerExport(void* blob) { check(ps3d_peer_export(m_pipe, blob)); }
+	void peerImport(int rank, int world, const void* blobs) { check(ps3d_peer_import(m_pipe, rank, world, blobs)); }
+	void compositePeer() { check(ps3d_composite_peer(m_pipe)); }
+	// captured frames: record the calls of one frame once, replay them as one launch (include/ps3d.h)
+	void graphBegin() { check(ps3d_graph_begin(m_pipe)); }
+	int graphEnd() { int g = -1; check(ps3d_graph_end(m_pipe, &g)); return g; }
+	void graphLaunch(int graph) { check(ps3d_graph_launch(m_pipe, graph)); }
+	void graphDestroy(int graph) { check(ps3d_graph_destroy(m_pipe, graph)); }
 
 	int deviceWidth() const { return m_width; }
 	int deviceHeight() const { return m_height; }

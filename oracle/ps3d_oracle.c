@@ -1485,6 +1485,13 @@ int ps3d_comm_unique_id(void* id) { (void)id; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_comm_init(ps3d_pipe* p, int r, int w, const void* id) { (void)p; (void)r; (void)w; (void)id; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_comm_destroy(ps3d_pipe* p) { (void)p; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_composite_bands(ps3d_pipe* p, const int* b) { (void)p; (void)b; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_peer_export(ps3d_pipe* p, void* b) { (void)p; (void)b; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_peer_import(ps3d_pipe* p, int r, int w, const void* b) { (void)p; (void)r; (void)w; (void)b; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_composite_peer(ps3d_pipe* p) { (void)p; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_graph_begin(ps3d_pipe* p) { (void)p; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_graph_end(ps3d_pipe* p, int* g) { (void)p; (void)g; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_graph_launch(ps3d_pipe* p, int g) { (void)p; (void)g; return PS3D_ERR_UNSUPPORTED; }
+int ps3d_graph_destroy(ps3d_pipe* p, int g) { (void)p; (void)g; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_vbo_all_gather(ps3d_pipe* p, int vbo) { (void)p; (void)vbo; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_device_launch_count(ps3d_pipe* p, uint64_t* n) { (void)p; if(n) *n = 0; return PS3D_OK; }
 int ps3d_profile_enable(ps3d_pipe* p, int on) { (void)p; (void)on; return PS3D_ERR_UNSUPPORTED; }

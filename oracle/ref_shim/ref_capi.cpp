@@ -611,6 +611,13 @@ int ps3d_comm_unique_id(void*) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_comm_init(ps3d_pipe*, int, int, const void*) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_comm_destroy(ps3d_pipe*) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_composite_bands(ps3d_pipe*, const int*) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_peer_export(ps3d_pipe*, void*) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_peer_import(ps3d_pipe*, int, int, const void*) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_composite_peer(ps3d_pipe*) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_graph_begin(ps3d_pipe*) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_graph_end(ps3d_pipe*, int*) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_graph_launch(ps3d_pipe*, int) { return PS3D_ERR_UNSUPPORTED; }
+int ps3d_graph_destroy(ps3d_pipe*, int) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_vbo_all_gather(ps3d_pipe*, int) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_device_launch_count(ps3d_pipe*, uint64_t* n) { if(n) *n = 0; return PS3D_OK; }
 int ps3d_profile_enable(ps3d_pipe*, int) { return PS3D_ERR_UNSUPPORTED; }

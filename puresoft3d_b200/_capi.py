@@ -120,6 +120,13 @@ PROTOTYPES = {
     "ps3d_comm_destroy": (C.c_int, [_P]),
     "ps3d_composite_bands": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "ps3d_vbo_all_gather": (C.c_int, [_P, C.c_int]),
+    "ps3d_peer_export": (C.c_int, [_P, C.c_void_p]),
+    "ps3d_peer_import": (C.c_int, [_P, C.c_int, C.c_int, C.c_void_p]),
+    "ps3d_composite_peer": (C.c_int, [_P]),
+    "ps3d_graph_begin": (C.c_int, [_P]),
+    "ps3d_graph_end": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "ps3d_graph_launch": (C.c_int, [_P, C.c_int]),
+    "ps3d_graph_destroy": (C.c_int, [_P, C.c_int]),
     "ps3d_device_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "ps3d_profile_enable": (C.c_int, [_P, C.c_int]),
     "ps3d_profile_read": (C.c_int, [_P, C.POINTER(Profile)]),

@@ -59,6 +59,9 @@ struct alignas(128) DeviceStats
 	// the range of tile indices the draw binned anything to, as two maxima so that all-zero means "none": ~lowest, highest + 1.
 	// tile_scan_kernel scans only that range (a small object on a 4096^2 shadow map touches a few hundred of 65536 tiles)
 	unsigned tileLoInv, tileHi1;
+	// span path, per draw: what the geometry kernel counted; tile_plan_kernel adds them to the totals above only when the
+	// draw's speculated capacities held (a draw that is run again must not be counted twice), and resets them
+	unsigned long long dRasterised, dSpans, dTested;
 };
 
 // What the host learns about a draw after its geometry + tile scan, written by tile_scan_kernel into mapped pinned host
@@ -68,8 +71,10 @@ struct DrawReport
 	unsigned int bad;               // a speculated capacity was too small (or a list too long): the guarded tail did nothing
 	unsigned int pairs;             // (tile, triangle) pairs = sum of the per-tile counts
 	unsigned int longest;           // longest tile list
-	unsigned int pad;
+	unsigned int spans;             // span path: span records the draw needs
 	unsigned long long fragBound;
+	unsigned int sticky;            // set with `bad`, cleared only by the host: a replayed captured frame (ps3d_graph_launch) is checked here
+	unsigned int pad;
 };
 
 // Survivors of the depth test, one record per FragmentProcessor::process call still to make (split path): structure of
@@ -85,6 +90,47 @@ struct SurvivorStream
 	uint32_t* winner;     // vpW x vpH: 1 + index of the LAST record of each pixel (only that one's colour lands); 0 = none
 	uint32_t capacity;
 };
+
+// ---- span path (kernels_span.cuh): every RESULT_ROW of every surviving triangle is evaluated ONCE, by a dense
+// (triangle, row) lane of the geometry kernel, together with the depth half of interpolateStartAndStep; the tile kernel
+// reads these records instead of re-deriving spans from triangle headers.
+// One record per raster row of a surviving triangle, 32 bytes = one sector, read by the tile kernel (all of it) and by the shade
+// kernel (the first half).
+struct alignas(32) SpanRec
+{
+	int left, right;          // RESULT_ROW::left / right (unclamped; an empty row is stored as 1, 0)
+	float zmin;               // conservative lower bound of z over the clamped span; -inf: none; NaN: too long for a precomputed bound
+	uint32_t triEdges;        // triangle id of the draw (24 bits) | the row's edge plan << 24 (2-bit vertex ids: l0, l1, r0, r1)
+	float cf2, cf2Step, z0, zStep;   // correctionFactor2 / projected z chains at the CLAMPED start column (interp.cpp:26-80)
+};
+#define PS_SPAN_MAX_TRIS 0x1000000u   // triangle ids must fit 24 bits on the span path
+struct SpanStreams
+{
+	SpanRec* rec;
+	uint2* tri;           // per triangle: index of its first record, first row | last row << 16 of the records (inside band and targets)
+	uint32_t* count;      // records allocated so far in this draw (one atomicAdd per geometry block)
+	uint32_t capacity;
+};
+
+// per-tile triangle lists of fixed capacity, appended to directly by the geometry kernel (any order), sorted by the list sort
+struct TileLists
+{
+	uint32_t* fill;       // per tile: entries appended in the draw in flight (may exceed cap: the plan kernel then raises poison); zeroed by the plan kernel
+	uint32_t* len;        // per tile: the finished count, written by the plan kernel
+	uint32_t* ids;        // tile * cap + slot
+	uint32_t cap;
+};
+
+// survivors of the depth test on the span path: 12 bytes each
+struct SurvivorStream2
+{
+	uint32_t* span;       // index of the span record
+	uint32_t* xy;         // x | y << 13 | PS_SV_WINNER
+	float* inv;           // 1 / correctionFactor2 at the pixel (interp.cpp:85)
+	uint32_t* count;
+	uint32_t capacity;
+};
+#define PS_SV_WINNER 0x80000000u   // the LAST survivor of its pixel: the only one whose colour lands
 
 struct DrawParams
 {
@@ -112,4 +158,6 @@ struct DrawParams
 	const uint32_t* poison;     // != 0: a speculated capacity of this draw was too small, every kernel behind the tile scan returns at once
 	uint32_t* cap;              // per-pixel FragmentProcessor::process counts (parity hook) or NULL
 	int capW, capH;
+	SpanStreams sp;             // span path
+	TileLists tl;
 };

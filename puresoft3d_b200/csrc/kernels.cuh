@@ -777,6 +777,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ 
 		const unsigned long long bound = boundS;
 		const uint32_t bad = (total > pairCap || bound > survivorCap || lng > listLimit) ? 1u : 0u;
 		report->pairs = total; report->longest = lng; report->fragBound = bound; report->bad = bad;
+		if(bad) report->sticky = 1;
 		__threadfence_system();
 		*poison = bad;
 	}

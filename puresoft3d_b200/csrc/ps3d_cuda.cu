@@ -15,6 +15,7 @@
 #include <dlfcn.h>
 #include "ps3d.h"
 #include "kernels.cuh"
+#include "kernels_span.cuh"
 #include "x86_approx.h"
 
 // the few NCCL types the run-time binding below needs (stable NCCL 2 ABI: a 128-byte unique id by value, an opaque communicator)
@@ -40,6 +41,7 @@ struct Prog { int vp, ip, fp; };
 typedef void (*LaunchGeom)(const DrawParams&, cudaStream_t);
 typedef void (*LaunchTile)(const DrawParams&, const uint32_t*, const uint32_t*, cudaStream_t);
 typedef void (*LaunchShade)(const DrawParams&, const SurvivorStream&, cudaStream_t);
+typedef void (*LaunchShade2)(const DrawParams&, const SurvivorStream2&, cudaStream_t);
 
 struct ProgEntry
 {
@@ -53,6 +55,8 @@ struct ProgEntry
 	LaunchGeom geom;
 	LaunchTile tileImmediate, tileOrdered;
 	LaunchShade shade;
+	LaunchGeom geomSpan;        // span path (kernels_span.cuh)
+	LaunchShade2 shadeSpan;
 };
 
 // PS3D_TILE_PATH=immediate|ordered|split forces one tile path for every draw (A/B checks); default: chosen per draw
@@ -145,6 +149,54 @@ template<class PROG> void launchShade(const DrawParams& P, const SurvivorStream&
 	}
 	shade_kernel<PROG><<<sms * perSM, 128, 0, s>>>(P, Q);
 }
+// ---- span path launchers ----------------------------------------------------------------------------------------------
+template<class PROG> void launchGeomSpan(const DrawParams& P, cudaStream_t s)
+{
+	const unsigned blocks = (P.ntris + PS_GEOM_THREADS - 1) / PS_GEOM_THREADS;
+	size_t bytes = 0;
+	bool aligned = true;
+	for(int i = 0; i < 16; i++)
+		if(((PROG::V::SLOTS & PS_GEOM_STAGE_SLOTS) >> i) & 1)
+		{
+			bytes += ((size_t)PS_GEOM_THREADS * 3 * P.stride[i] + 127) & ~(size_t)127;
+			aligned = aligned && 0 == ((uintptr_t)P.slot[i] & 15);
+		}
+	const bool staged = geomStagingOn() && aligned && bytes > 0 && bytes <= 64 * 1024;
+	// sort-first band: the rows-only pre-cull in front of the vertex work (PS3D_GEOM_PRECULL=0 turns it off for A/B runs)
+	static int precull = -1;
+	if(precull < 0) { const char* e = getenv("PS3D_GEOM_PRECULL"); precull = (e && e[0] == '0') ? 0 : 1; }
+	const bool banded = precull && (P.band0 > 0 || P.band1 < P.vpH);
+	if(staged)
+	{
+		static bool attrSet[PS_MAX_DEVICES] = { false };
+		const int dev = currentDevice();
+		if(!attrSet[dev])
+		{
+			cudaFuncSetAttribute(geom_span_kernel<PROG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(64 * 1024));
+			cudaFuncSetAttribute(geom_span_kernel<PROG, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(64 * 1024));
+			attrSet[dev] = true;
+		}
+		if(banded) geom_span_kernel<PROG, true, true><<<blocks, PS_GEOM_THREADS, bytes, s>>>(P);
+		else geom_span_kernel<PROG, true, false><<<blocks, PS_GEOM_THREADS, bytes, s>>>(P);
+	}
+	else if(banded) geom_span_kernel<PROG, false, true><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
+	else geom_span_kernel<PROG, false, false><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
+}
+template<class PROG> void launchShadeSpan(const DrawParams& P, const SurvivorStream2& Q, cudaStream_t s)
+{
+	const size_t smem = 0;
+	static int perSMs[PS_MAX_DEVICES] = { 0 }, smss[PS_MAX_DEVICES] = { 0 };
+	const int dev = currentDevice();
+	int& perSM = perSMs[dev];
+	int& sms = smss[dev];
+	if(0 == perSM)
+	{
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shade_span_kernel<PROG>, PS_SHADE_THREADS, smem) != cudaSuccess || perSM <= 0) perSM = 4;
+	}
+	shade_span_kernel<PROG><<<sms * perSM, PS_SHADE_THREADS, smem, s>>>(P, Q);
+}
+
 template<class PROG> ProgEntry makeEntry(int fnV, int fnI, int fnF)
 {
 	ProgEntry e;
@@ -160,6 +212,8 @@ template<class PROG> ProgEntry makeEntry(int fnV, int fnI, int fnF)
 	e.tileImmediate = launchTileImmediate<PROG>;
 	e.tileOrdered = launchTileOrdered<PROG>;
 	e.shade = launchShade<PROG>;
+	e.geomSpan = launchGeomSpan<PROG>;
+	e.shadeSpan = launchShadeSpan<PROG>;
 	return e;
 }
 
@@ -196,6 +250,9 @@ bool functorKnown(int kind, int fn)
 	return false;
 }
 
+// set while a frame is being captured (ps3d_graph_begin .. ps3d_graph_end): nothing may be allocated or freed then
+thread_local bool g_capturing = false;
+
 template<typename T> struct DevBuf
 {
 	T* p = nullptr;
@@ -203,6 +260,7 @@ template<typename T> struct DevBuf
 	cudaError_t ensure(size_t n)
 	{
 		if(n <= cap) return cudaSuccess;
+		if(g_capturing) return cudaErrorStreamCaptureUnsupported;   // run the frame once normally before capturing it
 		if(p) cudaFree(p);
 		p = nullptr;
 		size_t want = n + n / 4 + 1024;
@@ -254,6 +312,33 @@ struct ps3d_pipe
 	DevBuf<int> svLeft, svRight;
 	DevBuf<float> svInv;
 	uint32_t* svCountDev;
+	// span path (kernels_span.cuh): span records, per-triangle record index, fixed-capacity tile lists, 12-byte survivors
+	DevBuf<SpanRec> spRec;
+	DevBuf<uint2> spTri;
+	DevBuf<uint32_t> tlFill, tlLen, tlIds;
+	DevBuf<uint32_t> sv2Span, sv2XY;
+	DevBuf<float> sv2Inv;
+	uint32_t* spanCountDev;
+	size_t spanHigh, listHigh;     // high-water marks of earlier draws: the next speculation
+	std::vector<uint8_t> vaoLegacy; // VAOs whose last draw needed the first path (a tile list too long for the shared-memory sort)
+	// sort-first composite over peer memory (ps3d_peer_*): rank 0's display targets and flag block mapped into every rank
+	struct Peer
+	{
+		bool active; int rank, world;
+		uint8_t* display0[2];       // rank 0's display targets (ranks != 0: cudaIpc mappings; rank 0: its own)
+		PeerFlags* flags0;          // rank 0's flag block (ranks != 0: mapping)
+		PeerFlags* flagsOwn;        // every rank allocates one (only rank 0's is used) so that the export blob has one shape
+		PeerCounters* ctr;
+		bool needTake;              // no colour write since the last composite: the next one takes (rank 0: hands out) the target first
+	} peer;
+	// captured frames (ps3d_graph_*)
+	struct Graph { cudaGraphExec_t exec; uint64_t launches; uint64_t draws, tris; std::vector<int> vaos; int back, backAfter; bool alive; };
+	std::vector<Graph> graphs;
+	bool capturing, graphLaunched;
+	int capBack;
+	uint64_t capLaunches0, capDraws0, capTris0;
+	std::vector<int> capVaos;
+
 	uint32_t* totalDev;
 	DeviceStats* statsDev;      // PS_STATS_COPIES replicas
 	// asynchronous draws: the tail of a draw (binning, raster, shade) is enqueued behind the tile scan with SPECULATED
@@ -264,7 +349,7 @@ struct ps3d_pipe
 	cudaEvent_t scanEvent;
 	bool speculate;
 	size_t pairHigh, survivorHigh;   // high-water marks of earlier draws: the next speculation
-	struct Pending { bool valid; DrawParams P; const ProgEntry* pe; int path; bool radix; } pending;
+	struct Pending { bool valid; DrawParams P; const ProgEntry* pe; int path; bool radix; bool span; bool tailLaunched; int vao; } pending;
 	ps3d_stats stats;
 	uint32_t* capDev;
 	int capW, capH;
@@ -311,6 +396,10 @@ struct ProfScope
 #define CK(p, call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { (p)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return PS3D_ERR_DEVICE; } } while(0)
 
 static int settle(ps3d_pipe* p);
+static int peerFirstWrite(ps3d_pipe* p);
+static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe);
+static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao, size_t spans, size_t longest, size_t survivors);
+static int enqueueLegacy(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int path, int vao);
 
 // ---- NCCL, bound at run time ------------------------------------------------------------------------------------------
 // The sort-first exchange steps (band composite to rank 0, all-gather of the sharded vertex upload) are issued from inside
@@ -468,6 +557,7 @@ static int launchTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe, in
 		}
 		sortedTris = vIn;
 	}
+	{ const int rc = peerFirstWrite(p); if(rc) return rc; }
 	if(0 == path) { ProfScope ps(p, CLS_TILE); pe->tileImmediate(P, p->tileStart.p, sortedTris, p->stream); p->launches++; }
 	else if(1 == path) { ProfScope ps(p, CLS_TILE); pe->tileOrdered(P, p->tileStart.p, sortedTris, p->stream); p->launches++; }
 	else
@@ -512,6 +602,30 @@ static int settle(ps3d_pipe* p)
 	const ProgEntry* pe = p->pending.pe;
 	int path = p->pending.path;
 	p->profPairs += p->profiling ? r.pairs : 0;
+	if(p->pending.span)
+	{
+		// span path: the geometry kernel itself depends on a speculated capacity (span records, list capacity), so a draw whose
+		// sizes did not hold is run again from its geometry kernel with the exact sizes (its counters were not added, its lists
+		// and counts were reset by the plan kernel); a list too long for the shared-memory sort sends the draw down the first path
+		if(r.spans > p->spanHigh) p->spanHigh = r.spans;
+		if(r.longest > p->listHigh) p->listHigh = r.longest;
+		if(r.fragBound > p->survivorHigh) p->survivorHigh = (size_t)r.fragBound;
+		if(!r.bad)
+		{
+			if(p->pending.tailLaunched) return PS3D_OK;
+			return launchSpanTail(p, P, pe);
+		}
+		CK(p, cudaMemsetAsync(p->poisonDev, 0, 4, p->stream));
+		const int vao = p->pending.vao;
+		if(r.longest > PS_SORT_LIMIT || r.fragBound >= 0xfffffff0ull || r.spans >= 0xfffffff0u)
+		{
+			if(vao >= 0) { if((int)p->vaoLegacy.size() <= vao) p->vaoLegacy.resize(vao + 1, 0); p->vaoLegacy[vao] = 1; }
+			const DrawParams P2 = P;
+			return enqueueLegacy(p, P2, pe, r.fragBound >= 0xfffffff0ull ? 1 : 2, vao);
+		}
+		const DrawParams P2 = P;
+		return enqueueSpan(p, P2, pe, vao, r.spans, r.longest, (size_t)r.fragBound);
+	}
 	if(r.pairs > p->pairHigh) p->pairHigh = r.pairs;
 	if(2 == path && r.fragBound > p->survivorHigh) p->survivorHigh = (size_t)r.fragBound;
 	if(p->speculate && !radixBinningForced() && !r.bad) return PS3D_OK;   // the guarded tail ran
@@ -523,6 +637,207 @@ static int settle(ps3d_pipe* p)
 	CK(p, p->valsA.ensure(r.pairs));
 	if(2 == path) { int rc = ensureSurvivors(p, (size_t)r.fragBound, P); if(rc) return rc; }
 	return launchTail(p, P, pe, path, radix);
+}
+
+// VBO read events: the geometry kernels are the only readers of the vertex streams; asynchronous uploads may overwrite them behind
+// the last one. (Every attached VBO, also one that has only ever been written synchronously: its first asynchronous write or
+// all-gather must wait for THIS read, not for the creation-time fill.)
+static int recordVboReads(ps3d_pipe* p, int vao)
+{
+	if(vao < 0 || vao >= (int)p->vaos.size() || !p->vaos[vao].alive) return PS3D_OK;
+	if(p->capturing) { p->capVaos.push_back(vao); return PS3D_OK; }   // recorded behind every launch of the captured frame instead
+	const Vao& va = p->vaos[vao];
+	for(int s = 0; s < PS3D_MAX_VBOS; s++)
+		if(va.vbo[s] >= 0 && p->vbos[va.vbo[s]].alive)
+		{
+			Vbo& v = p->vbos[va.vbo[s]];
+			{ const int rc = vboEvents(p, v); if(rc) return rc; }
+			CK(p, cudaEventRecord(v.lastRead, p->stream));
+			v.readValid = true;
+		}
+	return PS3D_OK;
+}
+
+// Sort-first over peer memory: the first colour write of a frame takes rank 0's target (ranks != 0: wait until rank 0 has handed
+// it out) or hands it out (rank 0). Called in front of every kernel that writes colour.
+static int peerFirstWrite(ps3d_pipe* p)
+{
+	if(!p->peer.active || !p->peer.needTake) return PS3D_OK;
+	p->peer.needTake = false;
+	if(0 == p->peer.rank) peer_release_kernel<<<1, 1, 0, p->stream>>>(p->peer.ctr, p->peer.flags0, p->back);
+	else peer_take_kernel<<<1, 1, 0, p->stream>>>(p->peer.ctr, p->peer.flags0, p->back);
+	p->launches++;
+	CK(p, cudaGetLastError());
+	return PS3D_OK;
+}
+
+static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe)
+{
+	const uint32_t ntiles = (uint32_t)(P.tilesX * P.tilesY);
+	SurvivorStream2 Q;
+	Q.span = p->sv2Span.p; Q.xy = p->sv2XY.p; Q.inv = p->sv2Inv.p; Q.count = p->svCountDev;
+	Q.capacity = (uint32_t)std::min<size_t>(p->sv2Span.cap, 0xfffffff0u);
+	{
+		ProfScope ps(p, CLS_BIN);
+		tile_list_sort_cap_kernel<<<(ntiles + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK, 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(P.tl, ntiles, p->poisonDev, p->tileOrder.p);
+		p->launches++;
+	}
+	CK(p, cudaMemsetAsync(p->svCountDev, 0, 4, p->stream));
+	{
+		ProfScope ps(p, CLS_TILE);
+		// fewer tiles in play than warp slots on the GPU: cut every tile into 2 or 4 row groups, one warp each
+		const int bandRows = std::max(0, std::min(P.band1, P.vpH) - std::max(P.band0, 0));
+		const long long tilesInPlay = (long long)P.tilesX * ((bandRows + PS_TILE - 1) / PS_TILE);
+		const long long warpSlots = (long long)p->smCount * 32;      // resident warps of this kernel
+		int parts = rasterPartsForced();
+		if(parts <= 0) parts = tilesInPlay * 4 * 4 <= warpSlots * 5 ? 4 : (tilesInPlay * 2 * 4 <= warpSlots * 5 ? 2 : 1);
+		const unsigned blocks = (ntiles * (unsigned)parts + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK;
+		// PS3D_RASTER_MINB=8|10|12: blocks per SM the kernel is compiled for (64 / 51 / 40 registers) — A/B switch
+		static int minb = -1;
+		if(minb < 0) { const char* e = getenv("PS3D_RASTER_MINB"); minb = e ? atoi(e) : 8; }
+		if(12 == minb) tile_raster_span_kernel<12><<<blocks, 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(P, Q, parts);
+		else if(10 == minb) tile_raster_span_kernel<10><<<blocks, 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(P, Q, parts);
+		else tile_raster_span_kernel<8><<<blocks, 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(P, Q, parts);
+		p->launches++;
+	}
+	{ const int rc = peerFirstWrite(p); if(rc) return rc; }
+	{
+		ProfScope ps(p, CLS_SHADE);
+		pe->shadeSpan(P, Q, p->stream);
+		p->launches++;
+	}
+	CK(p, cudaGetLastError());
+	return PS3D_OK;
+}
+
+// The span path (kernels_span.cuh). spans / longest / survivors = 0: capacities speculated from the high-water marks of earlier
+// draws; otherwise the exact sizes a first attempt reported (settle()).
+static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao, size_t spans, size_t longest, size_t survivors)
+{
+	const uint32_t ntiles = (uint32_t)(P.tilesX * P.tilesY);
+	const size_t ntris = P.ntris;
+	const bool exact = spans || longest || survivors;
+	CK(p, p->hdr.ensure(ntris));
+	CK(p, p->vary.ensure(ntris * 3 * (size_t)(pe->nv > 0 ? pe->nv : 1)));
+	CK(p, p->spTri.ensure(ntris));
+	const size_t spanCap = exact ? spans + 1 : std::max(p->spanHigh + p->spanHigh / 4, ntris * 6 + 4096);
+	CK(p, p->spRec.ensure(spanCap));
+	size_t listCap = exact ? longest : std::max(p->listHigh + p->listHigh / 4, (size_t)128);
+	listCap = std::min<size_t>((listCap + 31) & ~(size_t)31, PS_SORT_LIMIT);
+	CK(p, p->tlIds.ensure((size_t)ntiles * listCap));
+	{
+		// tile_plan_kernel leaves the per-tile fill counts zeroed behind every draw; a fresh allocation starts zeroed
+		const uint32_t* before = p->tlFill.p;
+		CK(p, p->tlFill.ensure(ntiles + 1)); CK(p, p->tlLen.ensure(ntiles + 1)); CK(p, p->tileOrder.ensure(ntiles + 1));
+		if(p->tlFill.p != before) CK(p, cudaMemsetAsync(p->tlFill.p, 0, p->tlFill.cap * 4, p->stream));
+	}
+	const size_t svCap = exact ? survivors + 1 : std::max(p->survivorHigh + p->survivorHigh / 4, (size_t)P.vpW * P.vpH * 2);
+	CK(p, p->sv2Span.ensure(svCap)); CK(p, p->sv2XY.ensure(svCap)); CK(p, p->sv2Inv.ensure(svCap));
+	P.hdr = p->hdr.p; P.vary = p->vary.p; P.tileOrder = p->tileOrder.p; P.poison = p->poisonDev;
+	P.sp.rec = p->spRec.p; P.sp.tri = p->spTri.p; P.sp.count = p->spanCountDev;
+	P.sp.capacity = (uint32_t)std::min<size_t>(p->spRec.cap, 0xfffffff0u);
+	P.tl.fill = p->tlFill.p; P.tl.len = p->tlLen.p; P.tl.ids = p->tlIds.p; P.tl.cap = (uint32_t)listCap;
+	{
+		ProfScope ps(p, CLS_GEOM);
+		pe->geomSpan(P, p->stream);
+		p->launches++;
+	}
+	CK(p, cudaGetLastError());
+	{ const int rc = recordVboReads(p, vao); if(rc) return rc; }
+	{
+		ProfScope ps(p, CLS_BIN);
+		tile_plan_kernel<<<1, 1024, 0, p->stream>>>(P.tl, ntiles, p->statsDev, p->spanCountDev, P.sp.capacity,
+		                                          (unsigned long long)std::min<size_t>(p->sv2Span.cap, 0xfffffff0u), PS_SORT_LIMIT,
+		                                          p->poisonDev, p->reportDev, p->tileOrder.p);
+		p->launches++;
+	}
+	if(p->capturing)
+	{
+		// a captured frame cannot be judged by the host draw by draw: its tail is guarded by the poison word as always, and a
+		// replay that did not fit is reported through DrawReport::sticky at the next ps3d_finish
+		const int rc = launchSpanTail(p, P, pe);
+		return rc;
+	}
+	CK(p, cudaEventRecord(p->scanEvent, p->stream));
+	p->pending.valid = true; p->pending.P = P; p->pending.pe = pe; p->pending.path = 2; p->pending.span = true; p->pending.vao = vao;
+	p->pending.tailLaunched = false;
+	if(!p->speculate && !exact) return settle(p);      // sizes checked on the host before anything else is enqueued
+	p->pending.tailLaunched = true;
+	const int rc = launchSpanTail(p, P, pe);
+	if(rc) { p->pending.valid = false; return rc; }
+	return PS3D_OK;
+}
+
+// The first path (kernels.cuh): geometry with per-thread row walks, counted binning (tile scan + fill + sort), tile kernels that
+// re-derive spans from triangle headers. Draws that blend or may discard, and the fallback of the span path.
+static int enqueueLegacy(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int path, int vao)
+{
+	const uint32_t ntiles = (uint32_t)(P.tilesX * P.tilesY);
+	const size_t ntris = P.ntris;
+	CK(p, p->hdr.ensure(ntris));
+	CK(p, p->vary.ensure(ntris * 3 * (size_t)(pe->nv > 0 ? pe->nv : 1)));
+	CK(p, p->triCount.ensure(ntris));
+	CK(p, p->triRect.ensure(ntris * 3));
+	{
+		// tile_scan_kernel leaves the per-tile counts zeroed behind every draw; a fresh allocation starts zeroed
+		const uint32_t* before = p->tileCount.p;
+		CK(p, p->tileCount.ensure(ntiles + 1)); CK(p, p->tileStart.ensure(ntiles + 1)); CK(p, p->tileFill.ensure(ntiles + 1)); CK(p, p->tileOrder.ensure(ntiles + 1));
+		if(p->tileCount.p != before) CK(p, cudaMemsetAsync(p->tileCount.p, 0, p->tileCount.cap * 4, p->stream));
+	}
+	P.hdr = p->hdr.p; P.vary = p->vary.p; P.triCount = p->triCount.p; P.triRect = p->triRect.p; P.tileCount = p->tileCount.p; P.tileOrder = p->tileOrder.p;
+	P.poison = p->poisonDev;
+	// two-kernel geometry pays below about a sixth of the rows (band probe: an eighth 0.085 -> 0.067 ms, a quarter 0.092 -> 0.100 ms:
+	// the list-driven half reads its vertex streams sparsely); PS3D_GEOM_SPLIT=1 forces it for any band, =0 never
+	if(geomSplitWanted(P.band1 - P.band0, P.vpH) && (P.band0 > 0 || P.band1 < P.vpH))
+	{
+		CK(p, p->workList.ensure(ntris + 4));
+		P.workList = p->workList.p + 4; P.workCount = p->workList.p;      // the counter lives in front of the list
+		CK(p, cudaMemsetAsync(P.workCount, 0, 4, p->stream));
+	}
+
+	// Speculation: the draw's tail is enqueued right behind the tile scan, sized by the high-water marks of earlier draws;
+	// the scan checks the sizes on the device and the host reads its verdict at the next API call (settle()).
+	const bool speculate = p->speculate && !radixBinningForced();
+	uint32_t pairCap = 0xffffffffu, listLimit = 0xffffffffu;
+	unsigned long long survivorCap = ~0ull;
+	if(speculate)
+	{
+		const size_t pairGuess = std::max(p->pairHigh + p->pairHigh / 4, ntris + ntris / 2 + 1024);
+		CK(p, p->valsA.ensure(pairGuess));
+		pairCap = (uint32_t)std::min<size_t>(p->valsA.cap, 0xffffffffu);
+		listLimit = PS_SORT_LIMIT;
+		if(2 == path)
+		{
+			const size_t svGuess = std::max(p->survivorHigh + p->survivorHigh / 4, (size_t)P.vpW * P.vpH * 2);
+			{ const int rc = ensureSurvivors(p, svGuess, P); if(rc) return rc; }
+			survivorCap = std::min<size_t>(p->svTri.cap, 0xfffffff0u);
+		}
+	}
+	{
+		ProfScope ps(p, CLS_GEOM);
+		pe->geom(P, p->stream);
+		p->launches++;
+	}
+	CK(p, cudaGetLastError());
+	{ const int rc = recordVboReads(p, vao); if(rc) return rc; }
+	{
+		ProfScope ps(p, CLS_BIN);
+		tile_scan_kernel<<<1, 1024, 0, p->stream>>>(p->tileCount.p, p->tileStart.p, p->tileFill.p, ntiles, p->statsDev,
+		                                          pairCap, survivorCap, listLimit, p->poisonDev, p->reportDev, p->tileOrder.p);
+		p->launches++;
+	}
+	if(p->capturing)
+	{
+		if(!speculate) return fail(p, PS3D_ERR_UNSUPPORTED, "a captured frame needs speculated capacities (PS3D_SPECULATE=0 / PS3D_BINNING=radix are set)");
+		return launchTail(p, P, pe, path, false);
+	}
+	CK(p, cudaEventRecord(p->scanEvent, p->stream));
+	p->pending.valid = true; p->pending.P = P; p->pending.pe = pe; p->pending.path = path; p->pending.span = false; p->pending.tailLaunched = true; p->pending.vao = vao;
+	if(!speculate) return settle(p);          // exact sizes after a host sync in the middle of the draw
+	int rc = launchTail(p, P, pe, path, false);
+	if(rc) { p->pending.valid = false; return rc; }
+	CK(p, cudaGetLastError());
+	return PS3D_OK;
 }
 
 extern "C" {
@@ -574,8 +889,17 @@ int ps3d_create(int width, int height, int device, ps3d_pipe** out)
 		p->speculate = !(e && e[0] == '0');
 	}
 	ok = ok && cudaMalloc((void**)&p->svCountDev, 16) == cudaSuccess;
+	ok = ok && cudaMalloc((void**)&p->spanCountDev, 16) == cudaSuccess;
+	memset(&p->peer, 0, sizeof(p->peer));
+	p->capturing = false; p->graphLaunched = false; p->capBack = 0;
+	ok = ok && cudaMalloc((void**)&p->peer.flagsOwn, sizeof(PeerFlags)) == cudaSuccess;
+	ok = ok && cudaMalloc((void**)&p->peer.ctr, sizeof(PeerCounters)) == cudaSuccess;
+	if(ok) { cudaMemsetAsync(p->peer.flagsOwn, 0, sizeof(PeerFlags), p->stream); cudaMemsetAsync(p->peer.ctr, 0, sizeof(PeerCounters), p->stream); }
+	p->spanHigh = p->listHigh = 0;
+	p->pending.span = false; p->pending.tailLaunched = false; p->pending.vao = -1;
 	if(ok)
 	{
+		cudaMemsetAsync(p->spanCountDev, 0, 16, p->stream);
 		cudaMemsetAsync(p->display[0], 0, cbytes, p->stream);
 		cudaMemsetAsync(p->display[1], 0, cbytes, p->stream);
 		cudaMemsetAsync(p->defaultDepth, 0, dbytes, p->stream);
@@ -618,6 +942,15 @@ int ps3d_destroy(ps3d_pipe* p)
 	for(Vbo& v : p->vbos) if(v.alive) freeVbo(v);
 	cudaFree(p->display[0]); cudaFree(p->display[1]); cudaFree(p->defaultDepth);
 	cudaFree(p->totalDev); cudaFree(p->statsDev); cudaFree(p->svCountDev); cudaFree(p->poisonDev); cudaFreeHost(p->report); cudaEventDestroy(p->scanEvent);
+	cudaFree(p->spanCountDev);
+	for(auto& g : p->graphs) if(g.alive) cudaGraphExecDestroy(g.exec);
+	if(p->peer.active && p->peer.rank != 0)
+	{
+		cudaIpcCloseMemHandle(p->peer.display0[0]); cudaIpcCloseMemHandle(p->peer.display0[1]); cudaIpcCloseMemHandle(p->peer.flags0);
+	}
+	cudaFree(p->peer.flagsOwn); cudaFree(p->peer.ctr);
+	p->spRec.release(); p->spTri.release(); p->tlFill.release(); p->tlLen.release(); p->tlIds.release();
+	p->sv2Span.release(); p->sv2XY.release(); p->sv2Inv.release();
 	p->svTri.release(); p->svMisc.release(); p->svWinner.release(); p->svLeft.release(); p->svRight.release(); p->svInv.release();
 	if(p->capDev) cudaFree(p->capDev);
 	if(p->rcpDev) cudaFree(p->rcpDev);
@@ -774,8 +1107,9 @@ int ps3d_vbo_update_async(ps3d_pipe* p, int vbo, size_t firstUnit, size_t unitCo
 {
 	TRACE();
 	cudaSetDevice(p->device);
-	// no settle(): nothing here touches the pipe's stream, and a draw waiting for its retry re-runs only its tail, which
-	// does not read vertex streams — so the host can queue the next frame's upload while the last frame is in flight
+	// a draw on the span path whose speculated sizes did not hold runs again from its geometry kernel, which reads the vertex
+	// streams: its verdict (ready once its geometry + plan kernels are through — a fraction of the frame) is read first
+	SETTLE(p);
 	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
 	Vbo& v = p->vbos[vbo];
 	if(firstUnit > v.unitCount || unitCount > v.unitCount - firstUnit) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo range");
@@ -791,6 +1125,7 @@ int ps3d_vbo_device_written(ps3d_pipe* p, int vbo, void* cudaStream)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
 	Vbo& v = p->vbos[vbo];
 	{ const int rc = vboEvents(p, v); if(rc) return rc; }
@@ -1013,11 +1348,12 @@ int ps3d_clear_colour(ps3d_pipe* p, uint32_t bgra) // pipeline.cpp:340-343 -> cl
 	cudaSetDevice(p->device);
 	SETTLE(p);
 	if(p->height < 2) return PS3D_OK;
-	if(p->readValid[p->back]) { CK(p, cudaStreamWaitEvent(p->stream, p->readDone[p->back], 0)); p->readValid[p->back] = false; }
+	if(p->peer.active && p->peer.rank != 0) return PS3D_OK;   // sort-first over peer memory: the target is rank 0's, and so is its clear
+	if(!p->capturing && p->readValid[p->back]) { CK(p, cudaStreamWaitEvent(p->stream, p->readDone[p->back], 0)); p->readValid[p->back] = false; }
 	clear_colour_kernel<<<148 * 8, 256, 0, p->stream>>>(p->display[p->back], p->width, p->height - 1, p->width * 4, bgra);
 	p->launches++;
 	CK(p, cudaGetLastError());
-	return PS3D_OK;
+	return peerFirstWrite(p);                          // rank 0 hands the cleared target out to the other ranks
 }
 
 // ---- the draw (drawvao.cpp:3-133) ------------------------------------------------------------------------------------
@@ -1053,10 +1389,14 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	for(int s = 0; s < PS3D_MAX_VBOS; s++)
 		if(((pe->slots >> s) & 1) && !P.slot[s]) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "vertex functor reads a VBO slot that is not attached");
 	// asynchronous uploads (ps3d_vbo_update_async / ps3d_vbo_device_written) of the streams this draw reads must have landed
-	for(int s = 0; s < PS3D_MAX_VBOS; s++)
-		if(va.vbo[s] >= 0 && p->vbos[va.vbo[s]].readyValid) CK(p, cudaStreamWaitEvent(p->stream, p->vbos[va.vbo[s]].ready, 0));
-	// ... and an asynchronous read-back of the target this draw writes must have left it
-	if(p->readValid[p->back]) { CK(p, cudaStreamWaitEvent(p->stream, p->readDone[p->back], 0)); p->readValid[p->back] = false; }
+	// (a captured frame waits for both in front of every launch instead: ps3d_graph_launch)
+	if(!p->capturing)
+	{
+		for(int s = 0; s < PS3D_MAX_VBOS; s++)
+			if(va.vbo[s] >= 0 && p->vbos[va.vbo[s]].readyValid) CK(p, cudaStreamWaitEvent(p->stream, p->vbos[va.vbo[s]].ready, 0));
+		// ... and an asynchronous read-back of the target this draw writes must have left it
+		if(p->readValid[p->back]) { CK(p, cudaStreamWaitEvent(p->stream, p->readDone[p->back], 0)); p->readValid[p->back] = false; }
+	}
 	const size_t ntris = nverts / 3;
 	if(ntris > 0x7fffffffu / 3) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "too many triangles in one draw");
 	// uniforms are latched now (the reference latches pointers in preprocess(), drawvao.cpp:18-20)
@@ -1088,89 +1428,24 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	P.band1 = p->band1 > p->vpH ? p->vpH : p->band1;
 	P.tilesX = (p->vpW + PS_TILE - 1) / PS_TILE;
 	P.tilesY = (p->vpH + PS_TILE - 1) / PS_TILE;
-	P.colour.ptr = p->display[p->back]; P.colour.width = p->width; P.colour.height = p->height; P.colour.scanline = p->width * 4; P.colour.topDown = 1;
+	P.colour.ptr = (p->peer.active && p->peer.rank != 0) ? p->peer.display0[p->back] : p->display[p->back]; P.colour.width = p->width; P.colour.height = p->height; P.colour.scanline = p->width * 4; P.colour.topDown = 1;
 	P.depth = depthTarget(p);
 	P.approx = p->approx;
 	P.stats = p->statsDev;
 	P.cap = p->capDev; P.capW = p->capW; P.capH = p->capH;
 
-	const uint32_t ntiles = (uint32_t)(P.tilesX * P.tilesY);
-	CK(p, p->hdr.ensure(ntris));
-	CK(p, p->vary.ensure(ntris * 3 * (size_t)(pe->nv > 0 ? pe->nv : 1)));
-	CK(p, p->triCount.ensure(ntris));
-	CK(p, p->triRect.ensure(ntris * 3));
-	{
-		// tile_scan_kernel leaves the per-tile counts zeroed behind every draw; a fresh allocation starts zeroed
-		const uint32_t* before = p->tileCount.p;
-		CK(p, p->tileCount.ensure(ntiles + 1)); CK(p, p->tileStart.ensure(ntiles + 1)); CK(p, p->tileFill.ensure(ntiles + 1)); CK(p, p->tileOrder.ensure(ntiles + 1));
-		if(p->tileCount.p != before) CK(p, cudaMemsetAsync(p->tileCount.p, 0, p->tileCount.cap * 4, p->stream));
-	}
-	P.hdr = p->hdr.p; P.vary = p->vary.p; P.triCount = p->triCount.p; P.triRect = p->triRect.p; P.tileCount = p->tileCount.p; P.tileOrder = p->tileOrder.p;
-	P.poison = p->poisonDev;
-	// two-kernel geometry pays below about a sixth of the rows (band probe: an eighth 0.085 -> 0.067 ms, a quarter 0.092 -> 0.100 ms:
-	// the list-driven half reads its vertex streams sparsely); PS3D_GEOM_SPLIT=1 forces it for any band, =0 never
-	if(geomSplitWanted(P.band1 - P.band0, P.vpH) && (P.band0 > 0 || P.band1 < P.vpH))
-	{
-		CK(p, p->workList.ensure(ntris + 4));
-		P.workList = p->workList.p + 4; P.workCount = p->workList.p;      // the counter lives in front of the list
-		CK(p, cudaMemsetAsync(P.workCount, 0, 4, p->stream));
-	}
-
 	// which tile path (kernels.cuh): a functor that may discard() makes the depth write wait for the shading
 	// (fragthrd.cpp:234-237) -> immediate; a draw that blends needs its colours applied in submission order -> ordered;
-	// everything else -> split (raster + depth kernel, survivor stream, flat shade kernel)
+	// everything else -> split: raster + depth kernel, survivor stream, flat shade kernel — over span records computed once
+	// by the geometry kernel (kernels_span.cuh, the default) or, PS3D_TILE_PATH=split, re-derived per tile (kernels.cuh)
 	int path = pe->mayDiscard ? 0 : (((p->behavior & PS3D_BEHAVIOR_ALPHABLEND) && pe->usesWrite4) ? 1 : 2);
-	if(tilePathForced() >= 0 && !(pe->mayDiscard)) path = tilePathForced() == 2 && 1 == path ? 1 : tilePathForced();
-	if(2 == path && (P.vpW > 8191 || P.vpH > 8191)) path = 1;      // the survivor record packs x and y in 13 bits each
-
-	// Speculation: the draw's tail is enqueued right behind the tile scan, sized by the high-water marks of earlier draws;
-	// the scan checks the sizes on the device and the host reads its verdict at the next API call (settle()).
-	const bool speculate = p->speculate && !radixBinningForced();
-	uint32_t pairCap = 0xffffffffu, listLimit = 0xffffffffu;
-	unsigned long long survivorCap = ~0ull;
-	if(speculate)
-	{
-		const size_t pairGuess = std::max(p->pairHigh + p->pairHigh / 4, ntris + ntris / 2 + 1024);
-		CK(p, p->valsA.ensure(pairGuess));
-		pairCap = (uint32_t)std::min<size_t>(p->valsA.cap, 0xffffffffu);
-		listLimit = PS_SORT_LIMIT;
-		if(2 == path)
-		{
-			const size_t svGuess = std::max(p->survivorHigh + p->survivorHigh / 4, (size_t)P.vpW * P.vpH * 2);
-			{ const int rc = ensureSurvivors(p, svGuess, P); if(rc) return rc; }
-			survivorCap = std::min<size_t>(p->svTri.cap, 0xfffffff0u);
-		}
-	}
-	{
-		ProfScope ps(p, CLS_GEOM);
-		pe->geom(P, p->stream);
-		p->launches++;
-	}
-	CK(p, cudaGetLastError());
-	// the geometry kernel is the only reader of the vertex streams: asynchronous uploads may overwrite them behind it
-	// (every attached VBO, also one that has only ever been written synchronously: its first asynchronous write or
-	// all-gather must wait for THIS read, not for the creation-time fill)
-	for(int s = 0; s < PS3D_MAX_VBOS; s++)
-		if(va.vbo[s] >= 0)
-		{
-			Vbo& v = p->vbos[va.vbo[s]];
-			{ const int rc = vboEvents(p, v); if(rc) return rc; }
-			CK(p, cudaEventRecord(v.lastRead, p->stream));
-			v.readValid = true;
-		}
-	{
-		ProfScope ps(p, CLS_BIN);
-		tile_scan_kernel<<<1, 1024, 0, p->stream>>>(p->tileCount.p, p->tileStart.p, p->tileFill.p, ntiles, p->statsDev,
-		                                          pairCap, survivorCap, listLimit, p->poisonDev, p->reportDev, p->tileOrder.p);
-		p->launches++;
-	}
-	CK(p, cudaEventRecord(p->scanEvent, p->stream));
-	p->pending.valid = true; p->pending.P = P; p->pending.pe = pe; p->pending.path = path;
-	if(!speculate) return settle(p);          // exact sizes after a host sync in the middle of the draw
-	int rc = launchTail(p, P, pe, path, false);
-	if(rc) { p->pending.valid = false; return rc; }
-	CK(p, cudaGetLastError());
-	return PS3D_OK;
+	bool span = 2 == path;
+	if(tilePathForced() >= 0 && !(pe->mayDiscard)) { path = tilePathForced() == 2 && 1 == path ? 1 : tilePathForced(); span = false; }
+	if(2 == path && (P.vpW > 8191 || P.vpH > 8191)) { path = 1; span = false; }      // the survivor record packs x and y in 13 bits each
+	if(radixBinningForced() || ntris >= PS_SPAN_MAX_TRIS) span = false;
+	if(span && vao < (int)p->vaoLegacy.size() && p->vaoLegacy[vao]) span = false;
+	if(span) return enqueueSpan(p, P, pe, vao, 0, 0, 0);
+	return enqueueLegacy(p, P, pe, path, vao);
 }
 
 int ps3d_finish(ps3d_pipe* p)
@@ -1182,6 +1457,12 @@ int ps3d_finish(ps3d_pipe* p)
 	CK(p, cudaStreamSynchronize(p->copyStream));
 	CK(p, cudaStreamSynchronize(p->readStream));
 	if(p->gatherStream) CK(p, cudaStreamSynchronize(p->gatherStream));
+	if(p->graphLaunched && p->report->sticky)
+	{
+		p->report->sticky = 0; p->graphLaunched = false;
+		return fail(p, PS3D_ERR_INVALID_ARGUMENT, "a captured frame no longer fits the buffers it was captured with: run the frame normally once and re-capture");
+	}
+	p->graphLaunched = false;
 	return PS3D_OK;
 }
 int ps3d_swap_buffers(ps3d_pipe* p) { p->back ^= 1; return PS3D_OK; } // pipeline.cpp:314-322
@@ -1394,6 +1675,7 @@ int ps3d_vbo_all_gather(ps3d_pipe* p, int vbo)
 {
 	TRACE();
 	cudaSetDevice(p->device);
+	SETTLE(p);
 	const NcclApi* a = ncclApi();
 	if(!a || !p->commUpload) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "ps3d_comm_init first");
 	if(!vboOk(p, vbo)) return fail(p, PS3D_ERR_OUT_OF_RANGE, "vbo");
@@ -1408,6 +1690,147 @@ int ps3d_vbo_all_gather(ps3d_pipe* p, int vbo)
 	NK(p, a->AllGather(v.data + (size_t)p->commRank * perBytes, v.data, perBytes, PS_NCCL_UINT8, p->commUpload, p->gatherStream));
 	CK(p, cudaEventRecord(v.ready, p->gatherStream));
 	v.readyValid = true;
+	return PS3D_OK;
+}
+
+// ---- sort-first composite over NVLink peer memory (include/ps3d.h) ---------------------------------------------------------
+
+int ps3d_peer_export(ps3d_pipe* p, void* blob)
+{
+	TRACE();
+	cudaSetDevice(p->device);
+	SETTLE(p);
+	if(!blob) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "blob");
+	static_assert(3 * sizeof(cudaIpcMemHandle_t) <= PS3D_PEER_BLOB, "blob too small");
+	cudaIpcMemHandle_t h[3];
+	CK(p, cudaIpcGetMemHandle(&h[0], p->display[0]));
+	CK(p, cudaIpcGetMemHandle(&h[1], p->display[1]));
+	CK(p, cudaIpcGetMemHandle(&h[2], p->peer.flagsOwn));
+	memset(blob, 0, PS3D_PEER_BLOB);
+	memcpy(blob, h, sizeof(h));
+	return PS3D_OK;
+}
+int ps3d_peer_import(ps3d_pipe* p, int rank, int world, const void* blobs)
+{
+	TRACE();
+	cudaSetDevice(p->device);
+	SETTLE(p);
+	if(world < 1 || world > 64 || rank < 0 || rank >= world || !blobs) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "rank / world");
+	if(p->peer.active) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "peer targets already imported");
+	CK(p, cudaStreamSynchronize(p->stream));
+	p->peer.rank = rank; p->peer.world = world;
+	if(0 == rank)
+	{
+		p->peer.display0[0] = p->display[0]; p->peer.display0[1] = p->display[1]; p->peer.flags0 = p->peer.flagsOwn;
+	}
+	else
+	{
+		cudaIpcMemHandle_t h[3];
+		memcpy(h, blobs, sizeof(h));                   // rank 0's blob comes first
+		CK(p, cudaIpcOpenMemHandle((void**)&p->peer.display0[0], h[0], cudaIpcMemLazyEnablePeerAccess));
+		CK(p, cudaIpcOpenMemHandle((void**)&p->peer.display0[1], h[1], cudaIpcMemLazyEnablePeerAccess));
+		CK(p, cudaIpcOpenMemHandle((void**)&p->peer.flags0, h[2], cudaIpcMemLazyEnablePeerAccess));
+	}
+	p->peer.active = world > 1;
+	p->peer.needTake = true;
+	return PS3D_OK;
+}
+int ps3d_composite_peer(ps3d_pipe* p)
+{
+	TRACE();
+	cudaSetDevice(p->device);
+	SETTLE(p);
+	if(!p->peer.active) return p->peer.world == 1 ? PS3D_OK : fail(p, PS3D_ERR_INVALID_ARGUMENT, "ps3d_peer_import first");
+	// a frame that wrote no colour at all still takes part in the hand-over of the target
+	{ const int rc = peerFirstWrite(p); if(rc) return rc; }
+	if(0 == p->peer.rank) peer_wait_done_kernel<<<1, 64, 0, p->stream>>>(p->peer.ctr, p->peer.flags0, p->peer.world);
+	else peer_signal_done_kernel<<<1, 1, 0, p->stream>>>(p->peer.ctr, p->peer.flags0, p->peer.rank);
+	p->launches++;
+	CK(p, cudaGetLastError());
+	p->peer.needTake = true;
+	return PS3D_OK;
+}
+
+// ---- captured frames (include/ps3d.h) ---------------------------------------------------------------------------------------
+
+int ps3d_graph_begin(ps3d_pipe* p)
+{
+	TRACE();
+	cudaSetDevice(p->device);
+	SETTLE(p);
+	if(p->capturing) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "a frame is already being captured");
+	if(p->profiling) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "per-kernel event timing is on: a captured frame has no such events");
+	if(!p->speculate) return fail(p, PS3D_ERR_UNSUPPORTED, "PS3D_SPECULATE=0: a captured frame cannot size its buffers after a host sync");
+	CK(p, cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+	p->capturing = true; g_capturing = true;
+	p->capLaunches0 = p->launches; p->capDraws0 = p->stats.draws; p->capTris0 = p->stats.triangles_submitted;
+	p->capBack = p->back;
+	p->capVaos.clear();
+	return PS3D_OK;
+}
+int ps3d_graph_end(ps3d_pipe* p, int* graph)
+{
+	TRACE();
+	cudaSetDevice(p->device);
+	if(!p->capturing) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "no frame is being captured");
+	p->capturing = false; g_capturing = false;
+	cudaGraph_t g = nullptr;
+	const cudaError_t e = cudaStreamEndCapture(p->stream, &g);
+	// the recorded calls did not run: what they counted belongs to the launches
+	ps3d_pipe::Graph G;
+	G.launches = p->launches - p->capLaunches0; G.draws = p->stats.draws - p->capDraws0; G.tris = p->stats.triangles_submitted - p->capTris0;
+	p->launches = p->capLaunches0; p->stats.draws = p->capDraws0; p->stats.triangles_submitted = p->capTris0;
+	G.back = p->capBack; G.backAfter = p->back;
+	p->back = p->capBack;
+	G.vaos = p->capVaos; G.alive = true; G.exec = nullptr;
+	if(e != cudaSuccess || !g) { cudaGetLastError(); p->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e); return PS3D_ERR_DEVICE; }
+	const cudaError_t e2 = cudaGraphInstantiate(&G.exec, g, 0);
+	cudaGraphDestroy(g);
+	if(e2 != cudaSuccess) { p->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e2); return PS3D_ERR_DEVICE; }
+	size_t slot = 0;
+	for(; slot < p->graphs.size(); slot++) if(!p->graphs[slot].alive) break;
+	if(slot == p->graphs.size()) p->graphs.push_back(G); else p->graphs[slot] = G;
+	if(graph) *graph = (int)slot;
+	return PS3D_OK;
+}
+int ps3d_graph_launch(ps3d_pipe* p, int graph)
+{
+	TRACE();
+	cudaSetDevice(p->device);
+	SETTLE(p);
+	if(graph < 0 || graph >= (int)p->graphs.size() || !p->graphs[graph].alive) return fail(p, PS3D_ERR_OUT_OF_RANGE, "graph");
+	if(p->capturing) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "a frame is being captured");
+	ps3d_pipe::Graph& G = p->graphs[graph];
+	if(p->back != G.back) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "the frame was captured with the other display target current");
+	// what the recorded calls would have waited for one by one: asynchronous uploads of the streams the frame reads, and an
+	// asynchronous read-back still leaving the target it writes
+	for(int vao : G.vaos)
+		if(vao >= 0 && vao < (int)p->vaos.size() && p->vaos[vao].alive)
+			for(int s = 0; s < PS3D_MAX_VBOS; s++)
+			{
+				const int v = p->vaos[vao].vbo[s];
+				if(v >= 0 && p->vbos[v].alive && p->vbos[v].readyValid) CK(p, cudaStreamWaitEvent(p->stream, p->vbos[v].ready, 0));
+			}
+	if(p->readValid[p->back]) { CK(p, cudaStreamWaitEvent(p->stream, p->readDone[p->back], 0)); p->readValid[p->back] = false; }
+	// (draws enqueued one by one are judged by settle(); their verdicts do not concern the captured frames)
+	if(!p->graphLaunched) p->report->sticky = 0;
+	CK(p, cudaGraphLaunch(G.exec, p->stream));
+	p->graphLaunched = true;
+	p->capturing = false;
+	for(int vao : G.vaos) { const int rc = recordVboReads(p, vao); if(rc) return rc; }
+	p->launches += G.launches; p->stats.draws += G.draws; p->stats.triangles_submitted += G.tris;
+	p->back = G.backAfter;
+	return PS3D_OK;
+}
+int ps3d_graph_destroy(ps3d_pipe* p, int graph)
+{
+	TRACE();
+	cudaSetDevice(p->device);
+	SETTLE(p);
+	if(graph < 0 || graph >= (int)p->graphs.size() || !p->graphs[graph].alive) return fail(p, PS3D_ERR_OUT_OF_RANGE, "graph");
+	CK(p, cudaStreamSynchronize(p->stream));
+	cudaGraphExecDestroy(p->graphs[graph].exec);
+	p->graphs[graph].alive = false;
 	return PS3D_OK;
 }
 

@@ -116,6 +116,27 @@ PS_D int setupTriangle(int vpW, int vpH, int halfW, int halfH, const float* ndcX
 	return 1;
 }
 
+// The row range pushTriangle derives from the three viewport y (rasterizer.cpp:73-90,149-168) and nothing else: what a
+// sort-first rank needs to know to drop a triangle whose rows are all another rank's, before it pays for the rest of the
+// vertex work. Same operations as setupTriangle above. Returns false where the triangle walks no row.
+PS_D bool rowRangeOnly(int vpH, int halfH, const float* ndcY, int& firstRow, int& lastRow)
+{
+	float vy[3];
+	firstRow = lastRow = 0;
+#pragma unroll
+	for(int i = 0; i < 3; i++)
+	{
+		vy[i] = fadd(fmul((float)halfH, ndcY[i]), (float)halfH);
+		if(0 == i) firstRow = lastRow = cvtt(vy[0]);
+		else if(vy[i] > (float)lastRow) lastRow = cvtt(vy[i]);
+		else if(vy[i] < (float)firstRow) firstRow = cvtt(vy[i]);
+	}
+	if(firstRow >= vpH || lastRow < 0) { firstRow = 0; lastRow = -1; }
+	if(firstRow < 0) firstRow = 0;
+	if(lastRow >= vpH) lastRow = vpH - 1;
+	return firstRow < lastRow;
+}
+
 struct RowSpan
 {
 	int left, right; // RESULT_ROW::left / right, unclamped (rasterizer.cpp:100,107)

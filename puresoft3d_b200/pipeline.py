@@ -364,6 +364,38 @@ class PuresoftPipeline:
         flat = (C.c_int * (2 * len(bands)))(*[int(v) for b in bands for v in b])
         self._check(self._lib.ps3d_composite_bands(self._h, flat))
 
+    PEER_BLOB = 256
+
+    def peerExport(self):
+        """This rank's display targets and flag block as CUDA IPC handles (PEER_BLOB opaque bytes) for peerImport on every rank."""
+        buf = (C.c_uint8 * self.PEER_BLOB)()
+        self._check(self._lib.ps3d_peer_export(self._h, C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def peerImport(self, rank, world, blobs):
+        """blobs: world x PEER_BLOB bytes in rank order. From here on ranks != 0 render straight into rank 0's colour target."""
+        buf = (C.c_uint8 * (self.PEER_BLOB * world)).from_buffer_copy(blobs)
+        self._check(self._lib.ps3d_peer_import(self._h, int(rank), int(world), C.cast(buf, C.c_void_p)))
+
+    def compositePeer(self):
+        """Behind every frame on every rank: 'my band is written' / rank 0 waits for every rank (include/ps3d.h)."""
+        self._check(self._lib.ps3d_composite_peer(self._h))
+
+    # ---- captured frames (include/ps3d.h) --------------------------------------------------------------------------
+    def graphBegin(self):
+        self._check(self._lib.ps3d_graph_begin(self._h))
+
+    def graphEnd(self):
+        g = C.c_int(-1)
+        self._check(self._lib.ps3d_graph_end(self._h, C.byref(g)))
+        return g.value
+
+    def graphLaunch(self, graph):
+        self._check(self._lib.ps3d_graph_launch(self._h, int(graph)))
+
+    def graphDestroy(self, graph):
+        self._check(self._lib.ps3d_graph_destroy(self._h, int(graph)))
+
     def deviceJoin(self):
         """The pipe's stream waits for everything enqueued so far on the copy and read-back streams."""
         self._check(self._lib.ps3d_device_join(self._h))

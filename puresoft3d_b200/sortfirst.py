@@ -80,6 +80,28 @@ def init_native_comm(pipe, rank, world, device):
     return True
 
 
+def init_peer_composite(pipe, rank, world, device):
+    """The composite over NVLink peer memory (ps3d_peer_*): every rank exports CUDA IPC handles of its display targets and flag
+    block, one all-gather hands them round, ranks != 0 map rank 0's targets and render their band straight into them. Returns
+    False (another composite stays in charge) when PS3D_SORTFIRST_COMPOSITE names one or the handles cannot be had."""
+    import os
+    if world == 1 or os.environ.get("PS3D_SORTFIRST_COMPOSITE", "peer") != "peer":
+        return False
+    blob = torch.zeros(pipe.PEER_BLOB, dtype=torch.uint8, device=device)
+    ok = torch.ones(1, dtype=torch.int32, device=device)
+    try:
+        blob.copy_(torch.frombuffer(bytearray(pipe.peerExport()), dtype=torch.uint8))
+    except Exception:  # noqa: BLE001 — every rank learns it from the flag below
+        ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) != 1:
+        return False
+    blobs = torch.empty(world * pipe.PEER_BLOB, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(blobs, blob)
+    pipe.peerImport(rank, world, bytes(blobs.cpu().numpy()))
+    return True
+
+
 class _DevicePtr:
     def __init__(self, ptr, shape, typestr="<i4"):
         self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
@@ -88,12 +110,14 @@ class _DevicePtr:
 class Compositor:
     """Binds a pipe's device colour target to torch and gathers the bands on the pipe's own stream."""
 
-    def __init__(self, pipe, rank, world, device, ext_stream, native=False):
+    def __init__(self, pipe, rank, world, device, ext_stream, native=False, peer=False):
         self.pipe, self.rank, self.world, self.device, self.ext = pipe, rank, world, device, ext_stream
         self.bands = row_bands(pipe.height, world)
         self.band = self.bands[rank]
         self.native = native          # ps3d_composite_bands (the library's own communicator) instead of torch.distributed
-        self.how = "by NCCL send/recv issued by the library on the pipe's stream" if native else "by torch.distributed send/recv"
+        self.peer = peer              # ps3d_composite_peer: the bands were rendered straight into rank 0's target over NVLink
+        self.how = ("by peer stores of the shade kernel into rank 0's target over NVLink (no copy step; two counters per frame)" if peer else
+                    "by NCCL send/recv issued by the library on the pipe's stream" if native else "by torch.distributed send/recv")
         self._views = {}
 
     def _colour(self):
@@ -104,6 +128,9 @@ class Compositor:
         return self._views[ptr]
 
     def gather_to_rank0(self):
+        if self.peer:
+            self.pipe.compositePeer()
+            return
         if self.native:
             self.pipe.compositeBands(self.bands)
             return

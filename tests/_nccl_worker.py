@@ -30,12 +30,25 @@ def main():
     sc = SMALL[scene_name]()
     p = PuresoftPipeline(sc.width, sc.height, device=local)
     ext = torch.cuda.ExternalStream(p.deviceStream(), device=dev)
+    mode = sys.argv[3] if len(sys.argv) > 3 else "peer"
+    os.environ["PS3D_SORTFIRST_COMPOSITE"] = mode
     native = sortfirst.init_native_comm(p, rank, world, dev)
-    comp = sortfirst.Compositor(p, rank, world, dev, ext, native=native)
+    peer = sortfirst.init_peer_composite(p, rank, world, dev)
+    comp = sortfirst.Compositor(p, rank, world, dev, ext, native=native and not peer, peer=peer)
     p.setRowBand(*comp.band)
     up = scenes.upload(p, sc)
     msgs = []
-    for rep in range(3):                       # several frames in flight back to back: the composite must not race the next frame's clear
+    for rep in range(2):                       # several frames in flight back to back: the composite must not race the next frame's clear
+        scenes.replay(p, sc, up, finish=False)
+        comp.gather_to_rank0()
+    # ... and once as a captured frame (ps3d_graph_*), where the composite can be captured (no NCCL call inside)
+    if peer:
+        p.graphBegin()
+        scenes.replay(p, sc, up, finish=False)
+        comp.gather_to_rank0()
+        g = p.graphEnd()
+        p.graphLaunch(g)
+    else:
         scenes.replay(p, sc, up, finish=False)
         comp.gather_to_rank0()
     p.finish()
