@@ -274,10 +274,37 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # Frames in flight: a frame is a chain of kernels, several of them latency-bound (a tile's list, a block's phases), and a
+    # sort-first rank's share of a frame does not fill the GPU: a second pipe (own stream, own scratch buffers and targets; on
+    # ranks != 0 peer-mapped to rank 0's second pipe) renders frame i + 1 while frame i is still in flight. Same frames, same
+    # images, counted once each. PS3D_FRAMES_IN_FLIGHT=1 turns it off.
+    n_flight = max(1, int(os.environ.get("PS3D_FRAMES_IN_FLIGHT", "2")))
+    if comp is not None and not peer_comp:
+        n_flight = 1
+    flights = [dict(pipe=pipe, ext=ext, calls=frame_calls, launch=frame)]
+    for _ in range(1, n_flight):
+        q = PuresoftPipeline(sc.width, sc.height, device=local_rank)
+        q_up = scenes.upload(q, sc)
+        q_ext = torch.cuda.ExternalStream(q.deviceStream(), device=dev)
+        q_comp = None
+        if world > 1:
+            assert sortfirst.init_peer_composite(q, rank, world, dev)
+            q_comp = sortfirst.Compositor(q, rank, world, dev, q_ext, peer=True)
+            q.setRowBand(*q_comp.band)
+        q_replay = scenes.compile_replay(q, sc, q_up)
+
+        def q_calls(q_replay=q_replay, q_comp=q_comp):
+            q_replay()
+            if q_comp:
+                q_comp.gather_to_rank0()
+        flights.append(dict(pipe=q, ext=q_ext, calls=q_calls, launch=q_calls))
+
     # ---- kernel-only: inputs resident in HBM ------------------------------------------------------------------
     for _ in range(args.warmup):
-        frame()
-    pipe.finish()
+        for f in flights:
+            f["calls"]()
+    for f in flights:
+        f["pipe"].finish()
     # per-kernel-class times (roofline, kernel_ms_per_frame): a pass of the same frames with an event pair around every kernel
     # class (ps3d_profile_*), before the timed region — a captured frame carries no such events, and they are not free
     pipe.profileEnable(True)
@@ -288,28 +315,47 @@ def main():
     pipe.profileEnable(False)
     if use_graph:
         capture("frame", frame_calls)
+        for f in flights[1:]:
+            f["pipe"].graphBegin()
+            f["calls"]()
+            g = f["pipe"].graphEnd()
+            f["launch"] = (lambda q=f["pipe"], g=g: q.graphLaunch(g))
         for _ in range(3):
-            frame()
-        pipe.finish()
-    pipe.resetStats()
-    launches0 = pipe.deviceLaunchCount()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for f in flights:
+                f["launch"]()
+        for f in flights:
+            f["pipe"].finish()
+    for f in flights:
+        f["pipe"].resetStats()
+    launches0 = sum(f["pipe"].deviceLaunchCount() for f in flights)
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ends = [torch.cuda.Event(enable_timing=True) for _ in flights]
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    ev0.record(ext)
-    for _ in range(args.steps):
-        frame()
-    ev1.record(ext)
-    ev1.synchronize()
+    ev0.record(ext)                       # every stream is idle here (barrier + device synchronize)
+    for i in range(args.steps):
+        flights[i % len(flights)]["launch"]()
+    for f, e in zip(flights, ends):
+        e.record(f["ext"])
+    for e in ends:
+        e.synchronize()
     barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = pipe.deviceLaunchCount() - launches0
+    ms_total = max(ev0.elapsed_time(e) for e in ends)
+    launches = sum(f["pipe"].deviceLaunchCount() for f in flights) - launches0
     stats = pipe.getStats()
+    for f in flights[1:]:
+        st = f["pipe"].getStats()
+        for k in ("fragments_shaded", "fragments_tested", "draws"):
+            stats[k] += st[k]
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     frag_t = torch.tensor([float(stats["fragments_shaded"])], dtype=torch.float64, device=dev)
     tested_per_frame = stats["fragments_tested"] / args.steps
+    per_rank_ms = [ms_total / args.steps]
     if world > 1:
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        per_rank_ms = [float(v.item()) / args.steps for v in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(frag_t, op=dist.ReduceOp.SUM)
     ms_total = float(t.item())
@@ -364,6 +410,7 @@ def main():
     for i in range(e2e_steps):
         frame_e2e(i)
     pipe.deviceJoin()                # the last read-back belongs to the timed region
+    ev1 = torch.cuda.Event(enable_timing=True)
     ev1.record(ext)
     ev1.synchronize()
     pipe.finish()
@@ -432,6 +479,7 @@ def main():
             "config": bench_config(args, sc),
             "parallelism": ("sort-first row bands x%d, composite to rank 0 %s" % (world, comp.how)) if world > 1 else "single GPU",
             "frame_launch": "one CUDA graph launch per frame (ps3d_graph_*)" if use_graph else "one launch per kernel",
+            "frames_in_flight": len(flights), "ms_per_step_by_rank": per_rank_ms,
             "fragments_per_frame": frags_per_frame, "fragments_tested_per_frame": tested_per_frame,
             "approx": "x86 rcpps/rsqrtss tables bits=%s" % (pipe.hostApproxInfo(),),
             "colour_sha256": colour_sha, "depth_sha256": depth_sha,
@@ -453,6 +501,10 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, frags_per_frame)
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+    for f in flights[1:]:
+        f["pipe"].close()
     pipe.close()
     if world > 1:
         dist.destroy_process_group()

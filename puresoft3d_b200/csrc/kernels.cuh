@@ -946,6 +946,15 @@ __global__ void clear_depth_kernel(float4* __restrict__ buf, size_t quads, float
 __global__ void clear_colour_kernel(uint8_t* __restrict__ buf, int width, int rows, int scanline, uint32_t v)
 {
 	const size_t total = (size_t)width * rows;
+	if(scanline == width * 4 && 0 == ((uintptr_t)buf & 15))
+	{
+		// the rows are contiguous (the display targets, fbo.cpp:104-105): one flat fill, 128-bit stores
+		const size_t quads = total >> 2;
+		const uint4 q = make_uint4(v, v, v, v);
+		for(size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < quads; i += (size_t)gridDim.x * blockDim.x) ((uint4*)buf)[i] = q;
+		if(0 == blockIdx.x && threadIdx.x < (total & 3)) ((uint32_t*)buf)[(quads << 2) + threadIdx.x] = v;
+		return;
+	}
 	for(size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
 	{
 		const size_t y = i / width, x = i - y * width;

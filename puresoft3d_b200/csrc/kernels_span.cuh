@@ -87,13 +87,46 @@ PS_D void evalSpan(const TriHeader& h, int iy, int vpW, int limitX, SpanOut& o)
 	else o.zmin = __int_as_float(0x7fc00000);               // too long for the closed-form estimate: the tile kernel estimates per tile
 }
 
-// BANDED (sort-first, a rank renders a band of rows): every rank sees every triangle, so what a rank spends on triangles of
-// other bands bounds the scaling. Phase A0 computes only the three viewport y (the vertex functor's y and w: the compiler
-// drops the rest) and the row range; triangles with no row in the band leave the block there, the others are compacted and
-// phase A runs on dense warps.
-template<class PROG, bool STAGED, bool BANDED>
+// Sort-first (a rank renders a band of rows): every rank sees every triangle, so what a rank spends on triangles of other
+// bands bounds the scaling. geom_precull computes only the three viewport y (the vertex functor's y and w: the compiler drops
+// the rest) and the row range, and appends the triangles with a row in the band to one list (any order: tile lists are sorted
+// by triangle id later, span records are allocated block by block anyway); geom_span<LISTED> then runs over that list on
+// dense blocks.
+template<class PROG>
+__global__ void __launch_bounds__(256) geom_precull_kernel(const __grid_constant__ DrawParams P)
+{
+	constexpr int NV = PROG::NV;
+	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	bool keep = false;
+	if(tri < P.ntris)
+	{
+		float ndcY[3];
+#pragma unroll
+		for(int i = 0; i < 3; i++)
+		{
+			VertexProcessorInput in;
+#pragma unroll
+			for(int s = 0; s < 16; s++)
+				in.data[s] = (PROG::V::SLOTS >> s) & 1 ? P.slot[s] + (size_t)(tri * 3 + i) * P.stride[s] : nullptr;
+			VertexProcessorOutput<NV> vo;
+			PROG::V::process(in, vo, P);
+			ndcY[i] = fmul(vo.position.y, fdiv(1.0f, vo.position.w));   // vertthrd.cpp:37-38
+		}
+		int firstRow, lastRow;
+		keep = rowRangeOnly(P.vpH, P.halfH, ndcY, firstRow, lastRow) && lastRow >= P.band0 && firstRow < P.band1;
+	}
+	const uint32_t keepBallot = __ballot_sync(PS_FULL, keep);
+	uint32_t base = 0;
+	if(0 == lane && keepBallot) base = atomicAdd(P.workCount, (uint32_t)__popc(keepBallot));
+	base = __shfl_sync(PS_FULL, base, 0);
+	if(keep) P.workList[base + (uint32_t)__popc(keepBallot & ((1u << lane) - 1))] = tri;
+}
+
+template<class PROG, bool STAGED, bool LISTED>
 __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_span_kernel(const __grid_constant__ DrawParams P)
 {
+	static_assert(!(STAGED && LISTED), "the list-driven form gathers its vertices from global memory");
 	constexpr int NV = PROG::NV;
 	const uint32_t tri0 = blockIdx.x * PS_GEOM_THREADS;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -106,8 +139,7 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_span_kernel(const __grid
 	__shared__ uint8_t sOwner[PS_SPAN_WINDOW];           // (triangle, row) lane of the window -> survivor
 	__shared__ uint32_t sInfo[PS_SPAN_WINDOW];           // tile columns reached by that row: lo | hi << 12 | valid << 31
 	__shared__ uint32_t sWarpAlive[PS_GEOM_THREADS / 32], sWarpRows[PS_GEOM_THREADS / 32];
-	__shared__ uint32_t sWarpCand[PS_GEOM_THREADS / 32];
-	__shared__ uint8_t sCand[PS_GEOM_THREADS];           // BANDED: triangles of the block with a row in this rank's band
+	__shared__ uint32_t sTri[PS_GEOM_THREADS];           // survivor -> its triangle id in the draw
 	__shared__ uint32_t sSpanBase;
 	uint32_t stageOff[16];
 	if(STAGED)
@@ -140,48 +172,19 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_span_kernel(const __grid
 	const int limitX = useDepth ? P.depth.width - 1 : 0x7fffffff;
 	const int limitY = useDepth ? P.depth.height - 1 : 0x7fffffff;
 
-	// ---- A0 (BANDED), thread = triangle: row range only ----------------------------------------------------------------------
-	uint32_t orig = threadIdx.x;                       // the triangle of the block this thread takes through phase A
-	bool candidate = tri0 + threadIdx.x < P.ntris;
-	if(BANDED)
+	// the triangle this thread takes through phase A
+	const uint32_t orig = threadIdx.x;
+	uint32_t tri = tri0 + threadIdx.x;
+	bool candidate = tri < P.ntris;
+	if(LISTED)
 	{
-		bool keep = false;
-		if(candidate)
-		{
-			float ndcY[3];
-#pragma unroll
-			for(int i = 0; i < 3; i++)
-			{
-				VertexProcessorInput in;
-#pragma unroll
-				for(int s = 0; s < 16; s++)
-					in.data[s] = (PROG::V::SLOTS >> s) & 1 ? ((STAGED && ((PS_GEOM_STAGE_SLOTS >> s) & 1)) ? stage + stageOff[s] + (size_t)(threadIdx.x * 3 + i) * P.stride[s]
-					                                                  : P.slot[s] + (size_t)((tri0 + threadIdx.x) * 3 + i) * P.stride[s]) : nullptr;
-				VertexProcessorOutput<NV> vo;
-				PROG::V::process(in, vo, P);
-				ndcY[i] = fmul(vo.position.y, fdiv(1.0f, vo.position.w));   // vertthrd.cpp:37-38
-			}
-			int firstRow, lastRow;
-			keep = rowRangeOnly(P.vpH, P.halfH, ndcY, firstRow, lastRow) && lastRow >= P.band0 && firstRow < P.band1;
-		}
-		const uint32_t keepBallot = __ballot_sync(PS_FULL, keep);
-		if(0 == lane) sWarpCand[warp] = (uint32_t)__popc(keepBallot);
-		__syncthreads();
-		uint32_t base = 0, nCand = 0;
-#pragma unroll
-		for(int w = 0; w < PS_GEOM_THREADS / 32; w++)
-		{
-			if(w < warp) base += sWarpCand[w];
-			nCand += sWarpCand[w];
-		}
-		if(keep) sCand[base + (uint32_t)__popc(keepBallot & ((1u << lane) - 1))] = (uint8_t)threadIdx.x;
-		__syncthreads();
-		candidate = threadIdx.x < nCand;
-		orig = candidate ? sCand[threadIdx.x] : 0u;
+		const uint32_t nList = *P.workCount;
+		if(tri0 >= nList) return;                       // (the grid is sized for every triangle)
+		candidate = tri < nList;
+		tri = candidate ? P.workList[tri] : 0u;
 	}
-	const uint32_t tri = tri0 + orig;
 
-	// ---- A, thread = triangle (BANDED: = candidate, dense) -------------------------------------------------------------------
+	// ---- A, thread = triangle (LISTED: of this rank's band, dense) --------------------------------------------------------------
 	unsigned rasterised = 0;
 	bool alive = false;
 	int row0 = 0, nrows = 0;
@@ -256,6 +259,7 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_span_kernel(const __grid
 		sRowBase[slot] = rowBase + rowsIncl - (uint32_t)nrows;
 		sRow0[slot] = row0;
 		sOrig[slot] = (uint8_t)orig;
+		sTri[slot] = tri;
 	}
 	if(0 == threadIdx.x)
 	{
@@ -299,7 +303,7 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_span_kernel(const __grid
 			if(fits)
 			{
 				int4* dst = (int4*)(P.sp.rec + spanBase + s);
-				dst[0] = make_int4(sp.left, sp.right, __float_as_int(sp.zmin), (int)((tri0 + sOrig[o]) | ((uint32_t)sp.edges << 24)));
+				dst[0] = make_int4(sp.left, sp.right, __float_as_int(sp.zmin), (int)(sTri[o] | ((uint32_t)sp.edges << 24)));
 				dst[1] = make_int4(__float_as_int(sp.cf2), __float_as_int(sp.cf2Step), __float_as_int(sp.z0), __float_as_int(sp.zStep));
 			}
 		}
@@ -340,7 +344,7 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_span_kernel(const __grid
 	if(k < nAlive && maxTx >= 0)
 	{
 		const uint32_t orig = sOrig[k];
-		wtri = tri0 + orig;
+		wtri = sTri[k];
 		binned = 1;
 		{
 			// 64-byte record as four 16-byte stores
@@ -464,12 +468,16 @@ __global__ void __launch_bounds__(1024) tile_plan_kernel(TileLists tl, uint32_t 
                                                         uint32_t* __restrict__ tileOrder)
 {
 	__shared__ uint32_t hist[256];                     // tiles per length class, longest lists first
+	// one histogram per warp: most tiles of a frame fall into a handful of classes, and ~8000 atomics of a whole block on five
+	// shared-memory addresses were most of this kernel's time (MATCH-aggregated adds were slower still: 14 -> 21 us)
+	__shared__ uint32_t whist[32][256];
 	__shared__ uint32_t longestS, nonEmptyS, pairsS;
 	__shared__ unsigned long long boundS, foldS[3];
 	__shared__ uint32_t rangeLoS, rangeHiS;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	if(0 == threadIdx.x) { longestS = 0; pairsS = 0; }
 	if(threadIdx.x < 256) hist[threadIdx.x] = 0;
+	for(int q = threadIdx.x; q < 32 * 256; q += 1024) (&whist[0][0])[q] = 0;
 	if(0 == warp)
 	{
 		unsigned long long b = 0, a0 = 0, a1 = 0, a2 = 0;
@@ -520,14 +528,22 @@ __global__ void __launch_bounds__(1024) tile_plan_kernel(TileLists tl, uint32_t 
 				{
 					tl.fill[i] = 0;
 					longest = max(longest, v[q]); pairs += v[q];
-					atomicAdd(&hist[255u - min(v[q] >> 2, 255u)], 1u);
 				}
 			}
+			if(i < hi && v[q]) atomicAdd(&whist[warp][255u - min(v[q] >> 2, 255u)], 1u);
 		}
 	}
 	longest = __reduce_max_sync(PS_FULL, longest);
 	pairs = __reduce_add_sync(PS_FULL, pairs);
 	if(0 == lane) { if(longest) atomicMax(&longestS, longest); if(pairs) atomicAdd(&pairsS, pairs); }
+	__syncthreads();
+	if(threadIdx.x < 256)
+	{
+		// class totals; whist[w][c] becomes warp w's first slot inside class c
+		uint32_t run = 0;
+		for(int w = 0; w < 32; w++) { const uint32_t c = whist[w][threadIdx.x]; whist[w][threadIdx.x] = run; run += c; }
+		hist[threadIdx.x] = run;
+	}
 	__syncthreads();
 	if(0 == warp)
 	{
@@ -553,7 +569,11 @@ __global__ void __launch_bounds__(1024) tile_plan_kernel(TileLists tl, uint32_t 
 		for(int q = 0; q < 8; q++)
 		{
 			const uint32_t i = lo + q * 1024 + threadIdx.x;
-			if(i < hi && keep[q]) tileOrder[atomicAdd(&hist[255u - min(keep[q] >> 2, 255u)], 1u)] = i;
+			if(i < hi && keep[q])
+			{
+				const uint32_t cls = 255u - min(keep[q] >> 2, 255u);
+				tileOrder[hist[cls] + atomicAdd(&whist[warp][cls], 1u)] = i;
+			}
 		}
 	}
 	else
@@ -561,7 +581,7 @@ __global__ void __launch_bounds__(1024) tile_plan_kernel(TileLists tl, uint32_t 
 		for(uint32_t i = lo + threadIdx.x; i < hi; i += 1024)
 		{
 			const uint32_t v = tl.len[i];
-			if(v) tileOrder[atomicAdd(&hist[255u - min(v >> 2, 255u)], 1u)] = i;
+			if(v) { const uint32_t cls = 255u - min(v >> 2, 255u); tileOrder[hist[cls] + atomicAdd(&whist[warp][cls], 1u)] = i; }
 		}
 	}
 	if(0 == threadIdx.x)
@@ -646,7 +666,8 @@ __global__ void peer_take_kernel(PeerCounters* mine, const PeerFlags* rank0, int
 	while((int)(ldAcquireSys(&rank0->released[b]) - v) < 0) __nanosleep(200);
 }
 
-// one warp per tile: bitonic sort of its list (<= PS_SORT_LIMIT ids) in shared memory; lists at tile * cap
+// one warp per tile: bitonic sort of its list (<= PS_SORT_LIMIT ids) in shared memory; lists at tile * cap. (A block per tile with a
+// block barrier per stage: 13.3 -> 10.6 us for a sort-first eighth, but 32 -> 44 us for the whole frame: dropped.)
 __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK) tile_list_sort_cap_kernel(TileLists tl, uint32_t ntiles, const uint32_t* __restrict__ poison,
                                                                                     const uint32_t* __restrict__ tileOrder)
 {

@@ -125,7 +125,7 @@ bool geomSplitWanted(int bandRows, int vpH)
 	return mode < 0 ? (long long)bandRows * 6 <= vpH : 1 == mode;
 }
 // PS3D_RASTER_PARTS=1|2|4 forces the number of row groups a tile is cut into (A/B checks, tests)
-int rasterPartsForced() { static int v = -2; if(-2 == v) { const char* e = getenv("PS3D_RASTER_PARTS"); v = e ? atoi(e) : 0; if(v != 1 && v != 2 && v != 4) v = 0; } return v; }
+int rasterPartsForced() { static int v = -2; if(-2 == v) { const char* e = getenv("PS3D_RASTER_PARTS"); v = e ? atoi(e) : 0; if(v != 1 && v != 2 && v != 4 && v != 8) v = 0; } return v; }
 unsigned tileBlocks(const DrawParams& P) { return ((unsigned)(P.tilesX * P.tilesY) + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK; }
 template<class PROG> void launchTileImmediate(const DrawParams& P, const uint32_t* tileStart, const uint32_t* sortedTris, cudaStream_t s)
 {
@@ -162,10 +162,16 @@ template<class PROG> void launchGeomSpan(const DrawParams& P, cudaStream_t s)
 			aligned = aligned && 0 == ((uintptr_t)P.slot[i] & 15);
 		}
 	const bool staged = geomStagingOn() && aligned && bytes > 0 && bytes <= 64 * 1024;
-	// sort-first band: the rows-only pre-cull in front of the vertex work (PS3D_GEOM_PRECULL=0 turns it off for A/B runs)
+	// sort-first band: the rows-only pre-cull into a list, then the geometry kernel over the list (PS3D_GEOM_PRECULL=0: every
+	// rank takes every triangle through the whole position half — A/B runs)
 	static int precull = -1;
 	if(precull < 0) { const char* e = getenv("PS3D_GEOM_PRECULL"); precull = (e && e[0] == '0') ? 0 : 1; }
-	const bool banded = precull && (P.band0 > 0 || P.band1 < P.vpH);
+	if(precull && P.workList && (P.band0 > 0 || P.band1 < P.vpH))
+	{
+		geom_precull_kernel<PROG><<<(P.ntris + 255) / 256, 256, 0, s>>>(P);
+		geom_span_kernel<PROG, false, true><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
+		return;
+	}
 	if(staged)
 	{
 		static bool attrSet[PS_MAX_DEVICES] = { false };
@@ -173,13 +179,10 @@ template<class PROG> void launchGeomSpan(const DrawParams& P, cudaStream_t s)
 		if(!attrSet[dev])
 		{
 			cudaFuncSetAttribute(geom_span_kernel<PROG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(64 * 1024));
-			cudaFuncSetAttribute(geom_span_kernel<PROG, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(64 * 1024));
 			attrSet[dev] = true;
 		}
-		if(banded) geom_span_kernel<PROG, true, true><<<blocks, PS_GEOM_THREADS, bytes, s>>>(P);
-		else geom_span_kernel<PROG, true, false><<<blocks, PS_GEOM_THREADS, bytes, s>>>(P);
+		geom_span_kernel<PROG, true, false><<<blocks, PS_GEOM_THREADS, bytes, s>>>(P);
 	}
-	else if(banded) geom_span_kernel<PROG, false, true><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
 	else geom_span_kernel<PROG, false, false><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
 }
 template<class PROG> void launchShadeSpan(const DrawParams& P, const SurvivorStream2& Q, cudaStream_t s)
@@ -689,8 +692,10 @@ static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe
 		const int bandRows = std::max(0, std::min(P.band1, P.vpH) - std::max(P.band0, 0));
 		const long long tilesInPlay = (long long)P.tilesX * ((bandRows + PS_TILE - 1) / PS_TILE);
 		const long long warpSlots = (long long)p->smCount * 32;      // resident warps of this kernel
+		// (a tile's list is one dependent chain, ~100 us on C2 whatever the load: as soon as the tiles in play no longer fill the
+		// GPU's warp slots about twice over, shorter chains win — 2, 4 or 8 row groups per tile)
 		int parts = rasterPartsForced();
-		if(parts <= 0) parts = tilesInPlay * 4 * 4 <= warpSlots * 5 ? 4 : (tilesInPlay * 2 * 4 <= warpSlots * 5 ? 2 : 1);
+		if(parts <= 0) parts = tilesInPlay * 4 <= warpSlots ? 8 : (tilesInPlay * 2 <= warpSlots ? 4 : (tilesInPlay * 5 <= warpSlots * 6 ? 2 : 1));
 		const unsigned blocks = (ntiles * (unsigned)parts + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK;
 		// PS3D_RASTER_MINB=8|10|12: blocks per SM the kernel is compiled for (64 / 51 / 40 registers) — A/B switch
 		static int minb = -1;
@@ -734,13 +739,19 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 	const size_t svCap = exact ? survivors + 1 : std::max(p->survivorHigh + p->survivorHigh / 4, (size_t)P.vpW * P.vpH * 2);
 	CK(p, p->sv2Span.ensure(svCap)); CK(p, p->sv2XY.ensure(svCap)); CK(p, p->sv2Inv.ensure(svCap));
 	P.hdr = p->hdr.p; P.vary = p->vary.p; P.tileOrder = p->tileOrder.p; P.poison = p->poisonDev;
+	if(P.band0 > 0 || P.band1 < P.vpH)
+	{
+		CK(p, p->workList.ensure(ntris + 4));
+		P.workList = p->workList.p + 4; P.workCount = p->workList.p;      // the counter lives in front of the list
+		CK(p, cudaMemsetAsync(P.workCount, 0, 4, p->stream));
+	}
 	P.sp.rec = p->spRec.p; P.sp.tri = p->spTri.p; P.sp.count = p->spanCountDev;
 	P.sp.capacity = (uint32_t)std::min<size_t>(p->spRec.cap, 0xfffffff0u);
 	P.tl.fill = p->tlFill.p; P.tl.len = p->tlLen.p; P.tl.ids = p->tlIds.p; P.tl.cap = (uint32_t)listCap;
 	{
 		ProfScope ps(p, CLS_GEOM);
 		pe->geomSpan(P, p->stream);
-		p->launches++;
+		p->launches += P.workList ? 2 : 1;
 	}
 	CK(p, cudaGetLastError());
 	{ const int rc = recordVboReads(p, vao); if(rc) return rc; }
@@ -772,6 +783,7 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 // re-derive spans from triangle headers. Draws that blend or may discard, and the fallback of the span path.
 static int enqueueLegacy(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int path, int vao)
 {
+	P.workList = nullptr; P.workCount = nullptr;       // (a draw handed over by the span path brings its own)
 	const uint32_t ntiles = (uint32_t)(P.tilesX * P.tilesY);
 	const size_t ntris = P.ntris;
 	CK(p, p->hdr.ensure(ntris));
