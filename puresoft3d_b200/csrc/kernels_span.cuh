@@ -91,7 +91,9 @@ PS_D void evalSpan(const TriHeader& h, int iy, int vpW, int limitX, SpanOut& o)
 // bands bounds the scaling. geom_precull computes only the three viewport y (the vertex functor's y and w: the compiler drops
 // the rest) and the row range, and appends the triangles with a row in the band to one list (any order: tile lists are sorted
 // by triangle id later, span records are allocated block by block anyway); geom_span<LISTED> then runs over that list on
-// dense blocks.
+// dense blocks. (Tried and dropped: the pre-cull inside the geometry kernel, a block queueing the survivors of 8 chunks into
+// dense batches — 90 registers and an eighth of the blocks: 66 us against 29 + 38 us for an eighth of C2's rows, 204 against
+// 34 + 130 us for half of them; and the pre-cull in front of phase A of every block without the queue: 145 us for half.)
 template<class PROG>
 __global__ void __launch_bounds__(256) geom_precull_kernel(const __grid_constant__ DrawParams P)
 {
@@ -123,15 +125,16 @@ __global__ void __launch_bounds__(256) geom_precull_kernel(const __grid_constant
 	if(keep) P.workList[base + (uint32_t)__popc(keepBallot & ((1u << lane) - 1))] = tri;
 }
 
-template<class PROG, bool STAGED, bool LISTED>
-__global__ void __launch_bounds__(PS_GEOM_THREADS) geom_span_kernel(const __grid_constant__ DrawParams P)
+struct GeomAcc { unsigned rasterised, spans; unsigned long long frags; unsigned loInv, hi1; };
+
+// One batch of up to 128 triangles (one per thread; `candidate` false: none) through phases A, S and B. `orig` is the
+// triangle's place in the staged copy of the block's vertex range (STAGED only). Ends with a block barrier, so batches can
+// follow each other in one block.
+template<class PROG, bool STAGED>
+PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candidate, const uint8_t* stage, const uint32_t* stageOff, GeomAcc& acc)
 {
-	static_assert(!(STAGED && LISTED), "the list-driven form gathers its vertices from global memory");
 	constexpr int NV = PROG::NV;
-	const uint32_t tri0 = blockIdx.x * PS_GEOM_THREADS;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	extern __shared__ __align__(128) uint8_t stage[];
-	__shared__ uint64_t stageBar;
 	__shared__ TriHeader sHdr[PS_GEOM_THREADS];          // survivors, compacted (submission order kept)
 	__shared__ uint32_t sRowBase[PS_GEOM_THREADS + 1];   // first (triangle, row) lane of each survivor
 	__shared__ int sRow0[PS_GEOM_THREADS];
@@ -141,48 +144,9 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_span_kernel(const __grid
 	__shared__ uint32_t sWarpAlive[PS_GEOM_THREADS / 32], sWarpRows[PS_GEOM_THREADS / 32];
 	__shared__ uint32_t sTri[PS_GEOM_THREADS];           // survivor -> its triangle id in the draw
 	__shared__ uint32_t sSpanBase;
-	uint32_t stageOff[16];
-	if(STAGED)
-	{
-		const uint32_t nt = min((uint32_t)PS_GEOM_THREADS, P.ntris - tri0);
-		uint32_t off = 0;
-#pragma unroll
-		for(int s = 0; s < 16; s++)
-		{
-			stageOff[s] = off;
-			if(((PROG::V::SLOTS & PS_GEOM_STAGE_SLOTS) >> s) & 1) off += (PS_GEOM_THREADS * 3 * P.stride[s] + 127u) & ~127u;
-		}
-		if(0 == threadIdx.x) mbarInit(&stageBar, 1);
-		__syncthreads();
-		if(0 == threadIdx.x)
-		{
-			uint32_t total = 0;
-#pragma unroll
-			for(int s = 0; s < 16; s++)
-				if(((PROG::V::SLOTS & PS_GEOM_STAGE_SLOTS) >> s) & 1) total += (nt * 3 * P.stride[s] + 15u) & ~15u;
-			mbarExpectTx(&stageBar, total);
-#pragma unroll
-			for(int s = 0; s < 16; s++)
-				if(((PROG::V::SLOTS & PS_GEOM_STAGE_SLOTS) >> s) & 1)
-					bulkCopyG2S(stage + stageOff[s], P.slot[s] + (size_t)tri0 * 3 * P.stride[s], (nt * 3 * P.stride[s] + 15u) & ~15u, &stageBar);
-		}
-		mbarWait(&stageBar, 0);
-	}
 	const bool useDepth = 0 != (P.behavior & (PS_BEHAVIOR_TEST_DEPTH | PS_BEHAVIOR_UPDATE_DEPTH));
 	const int limitX = useDepth ? P.depth.width - 1 : 0x7fffffff;
 	const int limitY = useDepth ? P.depth.height - 1 : 0x7fffffff;
-
-	// the triangle this thread takes through phase A
-	const uint32_t orig = threadIdx.x;
-	uint32_t tri = tri0 + threadIdx.x;
-	bool candidate = tri < P.ntris;
-	if(LISTED)
-	{
-		const uint32_t nList = *P.workCount;
-		if(tri0 >= nList) return;                       // (the grid is sized for every triangle)
-		candidate = tri < nList;
-		tri = candidate ? P.workList[tri] : 0u;
-	}
 
 	// ---- A, thread = triangle (LISTED: of this rank's band, dense) --------------------------------------------------------------
 	unsigned rasterised = 0;
@@ -426,17 +390,24 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_span_kernel(const __grid
 			}
 		}
 	}
-	// counters: one set of atomics per block, on the block's replica (per-draw fields: the plan kernel folds them)
+	acc.rasterised += rasterised; acc.spans += spans; acc.frags += frags;
+	acc.loInv = max(acc.loInv, binned ? ~((rect1 & 0xffff) * (unsigned)P.tilesX + (rect0 & 0xffff)) : 0u);
+	acc.hi1 = max(acc.hi1, binned ? (rect1 >> 16) * (unsigned)P.tilesX + (rect0 >> 16) + 1u : 0u);
+	__syncthreads();
+}
+
+// counters: one set of atomics per block, on the block's replica (per-draw fields: the plan kernel folds them)
+PS_D void geomFinish(const DrawParams& P, const GeomAcc& acc)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	__shared__ unsigned long long blockSums[PS_GEOM_THREADS / 32][3];
 	__shared__ unsigned blockRange[PS_GEOM_THREADS / 32][2];
 	{
-		const unsigned loInv = binned ? ~((rect1 & 0xffff) * (unsigned)P.tilesX + (rect0 & 0xffff)) : 0u;
-		const unsigned hi1 = binned ? (rect1 >> 16) * (unsigned)P.tilesX + (rect0 >> 16) + 1u : 0u;
-		const unsigned a = __reduce_max_sync(PS_FULL, loInv), b = __reduce_max_sync(PS_FULL, hi1);
+		const unsigned a = __reduce_max_sync(PS_FULL, acc.loInv), b = __reduce_max_sync(PS_FULL, acc.hi1);
 		if(0 == lane) { blockRange[warp][0] = a; blockRange[warp][1] = b; }
 	}
-	const unsigned long long r = warpSumU64(rasterised), s = warpSumU64(spans);
-	unsigned long long f = frags;
+	const unsigned long long r = warpSumU64(acc.rasterised), s = warpSumU64(acc.spans);
+	unsigned long long f = acc.frags;
 #pragma unroll
 	for(int d = 16; d > 0; d >>= 1) f += __shfl_xor_sync(PS_FULL, f, d);
 	if(0 == lane) { blockSums[warp][0] = r; blockSums[warp][1] = s; blockSums[warp][2] = f; }
@@ -457,6 +428,60 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_span_kernel(const __grid
 		DeviceStats* st = P.stats + (blockIdx.x & (PS_STATS_COPIES - 1));
 		if(v) atomicMax(3 == threadIdx.x ? &st->tileLoInv : &st->tileHi1, v);
 	}
+}
+
+template<class PROG, bool STAGED, bool LISTED>
+__global__ void __launch_bounds__(PS_GEOM_THREADS) geom_span_kernel(const __grid_constant__ DrawParams P)
+{
+	static_assert(!(STAGED && LISTED), "the list-driven form gathers its vertices from global memory");
+	constexpr int NV = PROG::NV;
+	const uint32_t tri0 = blockIdx.x * PS_GEOM_THREADS;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	extern __shared__ __align__(128) uint8_t stage[];
+	__shared__ uint64_t stageBar;
+	uint32_t stageOff[16];
+	if(STAGED)
+	{
+		const uint32_t nt = min((uint32_t)PS_GEOM_THREADS, P.ntris - tri0);
+		uint32_t off = 0;
+#pragma unroll
+		for(int s = 0; s < 16; s++)
+		{
+			stageOff[s] = off;
+			if(((PROG::V::SLOTS & PS_GEOM_STAGE_SLOTS) >> s) & 1) off += (PS_GEOM_THREADS * 3 * P.stride[s] + 127u) & ~127u;
+		}
+		if(0 == threadIdx.x) mbarInit(&stageBar, 1);
+		__syncthreads();
+		if(0 == threadIdx.x)
+		{
+			uint32_t total = 0;
+#pragma unroll
+			for(int s = 0; s < 16; s++)
+				if(((PROG::V::SLOTS & PS_GEOM_STAGE_SLOTS) >> s) & 1) total += (nt * 3 * P.stride[s] + 15u) & ~15u;
+			mbarExpectTx(&stageBar, total);
+#pragma unroll
+			for(int s = 0; s < 16; s++)
+				if(((PROG::V::SLOTS & PS_GEOM_STAGE_SLOTS) >> s) & 1)
+					bulkCopyG2S(stage + stageOff[s], P.slot[s] + (size_t)tri0 * 3 * P.stride[s], (nt * 3 * P.stride[s] + 15u) & ~15u, &stageBar);
+		}
+		mbarWait(&stageBar, 0);
+	}
+
+	// the triangle this thread takes through phase A
+	const uint32_t orig = threadIdx.x;
+	uint32_t tri = tri0 + threadIdx.x;
+	bool candidate = tri < P.ntris;
+	if(LISTED)
+	{
+		const uint32_t nList = *P.workCount;
+		if(tri0 >= nList) return;                       // (the grid is sized for every triangle)
+		candidate = tri < nList;
+		tri = candidate ? P.workList[tri] : 0u;
+	}
+
+	GeomAcc acc = { 0, 0, 0, 0, 0 };
+	geomBatch<PROG, STAGED>(P, tri, orig, candidate, stage, stageOff, acc);
+	geomFinish(P, acc);
 }
 
 // ======================================================================================================================

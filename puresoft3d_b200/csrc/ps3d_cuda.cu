@@ -162,11 +162,12 @@ template<class PROG> void launchGeomSpan(const DrawParams& P, cudaStream_t s)
 			aligned = aligned && 0 == ((uintptr_t)P.slot[i] & 15);
 		}
 	const bool staged = geomStagingOn() && aligned && bytes > 0 && bytes <= 64 * 1024;
-	// sort-first band: the rows-only pre-cull into a list, then the geometry kernel over the list (PS3D_GEOM_PRECULL=0: every
-	// rank takes every triangle through the whole position half — A/B runs)
-	static int precull = -1;
-	if(precull < 0) { const char* e = getenv("PS3D_GEOM_PRECULL"); precull = (e && e[0] == '0') ? 0 : 1; }
-	if(precull && P.workList && (P.band0 > 0 || P.band1 < P.vpH))
+	// sort-first band: triangles with no row in the band leave after a rows-only look at their vertices (a pre-cull kernel fills a
+	// list, the geometry kernel runs over it). PS3D_GEOM_BAND=none: every rank takes every triangle through the whole position
+	// half (A/B runs)
+	static int bandMode = -1;
+	if(bandMode < 0) { const char* e = getenv("PS3D_GEOM_BAND"); bandMode = (e && !strcmp(e, "none")) ? 0 : 1; }
+	if(bandMode && P.workList && (P.band0 > 0 || P.band1 < P.vpH))
 	{
 		geom_precull_kernel<PROG><<<(P.ntris + 255) / 256, 256, 0, s>>>(P);
 		geom_span_kernel<PROG, false, true><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
@@ -751,7 +752,7 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 	{
 		ProfScope ps(p, CLS_GEOM);
 		pe->geomSpan(P, p->stream);
-		p->launches += P.workList ? 2 : 1;
+		p->launches++;
 	}
 	CK(p, cudaGetLastError());
 	{ const int rc = recordVboReads(p, vao); if(rc) return rc; }
