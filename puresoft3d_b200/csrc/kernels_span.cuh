@@ -1106,8 +1106,8 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK, MINB) tile_raster_spa
 // varyings): the stream words are read two iterations ahead and the span record one ahead, so only the last level's latency
 // is exposed. (Tried and dropped: that level staged through shared memory by 16-byte asynchronous copies, all issued together —
 // LDGSTS neither merges the lanes that name the same triangle nor uses L1, the kernel went 0.205 -> 0.355 ms.)
-template<class PROG>
-__global__ void __launch_bounds__(PS_SHADE_THREADS) shade_span_kernel(const __grid_constant__ DrawParams P, const SurvivorStream2 Q)
+template<class PROG, int MINB>
+__global__ void __launch_bounds__(PS_SHADE_THREADS, MINB) shade_span_kernel(const __grid_constant__ DrawParams P, const SurvivorStream2 Q)
 {
 	constexpr int NV = PROG::NV;
 	if(*P.poison) return;

@@ -188,17 +188,25 @@ template<class PROG> void launchGeomSpan(const DrawParams& P, cudaStream_t s)
 }
 template<class PROG> void launchShadeSpan(const DrawParams& P, const SurvivorStream2& Q, cudaStream_t s)
 {
-	const size_t smem = 0;
-	static int perSMs[PS_MAX_DEVICES] = { 0 }, smss[PS_MAX_DEVICES] = { 0 };
+	// a flat grid-stride loop over the survivor stream: exactly one resident wave. PS3D_SHADE_MINB=5|7|8: the variant compiled for
+	// that many blocks per SM (A/B switch)
+	static int perSMs[PS_MAX_DEVICES][3] = { { 0 } }, smss[PS_MAX_DEVICES] = { 0 };
+	static int minb = -1;                              // 0: 5 blocks (100 registers), 1: 7 blocks (72, default), 2: 8 blocks (64)
+	if(minb < 0) { const char* e = getenv("PS3D_SHADE_MINB"); const int v = e ? atoi(e) : 7; minb = v <= 5 ? 0 : (v >= 8 ? 2 : 1); }
 	const int dev = currentDevice();
-	int& perSM = perSMs[dev];
+	int& perSM = perSMs[dev][minb];
 	int& sms = smss[dev];
 	if(0 == perSM)
 	{
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shade_span_kernel<PROG>, PS_SHADE_THREADS, smem) != cudaSuccess || perSM <= 0) perSM = 4;
+		const cudaError_t e = 2 == minb ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shade_span_kernel<PROG, 8>, PS_SHADE_THREADS, 0)
+		                    : (1 == minb ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shade_span_kernel<PROG, 7>, PS_SHADE_THREADS, 0)
+		                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shade_span_kernel<PROG, 5>, PS_SHADE_THREADS, 0));
+		if(e != cudaSuccess || perSM <= 0) perSM = 4;
 	}
-	shade_span_kernel<PROG><<<sms * perSM, PS_SHADE_THREADS, smem, s>>>(P, Q);
+	if(2 == minb) shade_span_kernel<PROG, 8><<<sms * perSM, PS_SHADE_THREADS, 0, s>>>(P, Q);
+	else if(1 == minb) shade_span_kernel<PROG, 7><<<sms * perSM, PS_SHADE_THREADS, 0, s>>>(P, Q);
+	else shade_span_kernel<PROG, 5><<<sms * perSM, PS_SHADE_THREADS, 0, s>>>(P, Q);
 }
 
 template<class PROG> ProgEntry makeEntry(int fnV, int fnI, int fnF)
