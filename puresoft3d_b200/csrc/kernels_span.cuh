@@ -125,12 +125,17 @@ __global__ void __launch_bounds__(256) geom_precull_kernel(const __grid_constant
 	if(keep) P.workList[base + (uint32_t)__popc(keepBallot & ((1u << lane) - 1))] = tri;
 }
 
+// STAGED: 0 = every slot read from global memory, 1 = the position slot (slot 0 of every vertex functor) staged in shared memory by
+// one TMA bulk copy per block, 2 = every slot the functor reads staged (all of a block's vertex bytes in flight at once, phase B
+// reads no global memory; 28 KB per block for DEF03)
+template<int STAGED> __host__ __device__ constexpr uint32_t stageMask(uint32_t slots) { return 2 == STAGED ? slots : (1 == STAGED ? (slots & 1u) : 0u); }
+
 struct GeomAcc { unsigned rasterised, spans; unsigned long long frags; unsigned loInv, hi1; };
 
 // One batch of up to 128 triangles (one per thread; `candidate` false: none) through phases A, S and B. `orig` is the
 // triangle's place in the staged copy of the block's vertex range (STAGED only). Ends with a block barrier, so batches can
 // follow each other in one block.
-template<class PROG, bool STAGED>
+template<class PROG, int STAGED>
 PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candidate, const uint8_t* stage, const uint32_t* stageOff, GeomAcc& acc)
 {
 	constexpr int NV = PROG::NV;
@@ -165,7 +170,7 @@ PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candi
 			VertexProcessorInput in;
 #pragma unroll
 			for(int s = 0; s < 16; s++)
-				in.data[s] = (PROG::V::SLOTS >> s) & 1 ? ((STAGED && ((PS_GEOM_STAGE_SLOTS >> s) & 1)) ? stage + stageOff[s] + (size_t)(orig * 3 + i) * P.stride[s]
+				in.data[s] = (PROG::V::SLOTS >> s) & 1 ? ((0 != ((stageMask<STAGED>(PROG::V::SLOTS) >> s) & 1)) ? stage + stageOff[s] + (size_t)(orig * 3 + i) * P.stride[s]
 				                                                  : P.slot[s] + (size_t)(tri * 3 + i) * P.stride[s]) : nullptr;
 			VertexProcessorOutput<NV> vo;
 			PROG::V::process(in, vo, P);
@@ -326,7 +331,7 @@ PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candi
 				VertexProcessorInput in;
 #pragma unroll
 				for(int s = 0; s < 16; s++)
-					in.data[s] = (PROG::V::SLOTS >> s) & 1 ? ((STAGED && ((PS_GEOM_STAGE_SLOTS >> s) & 1)) ? stage + stageOff[s] + (size_t)(orig * 3 + i) * P.stride[s]
+					in.data[s] = (PROG::V::SLOTS >> s) & 1 ? ((0 != ((stageMask<STAGED>(PROG::V::SLOTS) >> s) & 1)) ? stage + stageOff[s] + (size_t)(orig * 3 + i) * P.stride[s]
 					                                                  : P.slot[s] + (size_t)(wtri * 3 + i) * P.stride[s]) : nullptr;
 				VertexProcessorOutput<NV> vo;
 				PROG::V::process(in, vo, P);
@@ -430,7 +435,7 @@ PS_D void geomFinish(const DrawParams& P, const GeomAcc& acc)
 	}
 }
 
-template<class PROG, bool STAGED, bool LISTED>
+template<class PROG, int STAGED, bool LISTED>
 __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_span_kernel(const __grid_constant__ DrawParams P)
 {
 	static_assert(!(STAGED && LISTED), "the list-driven form gathers its vertices from global memory");
@@ -448,7 +453,7 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_span_kernel(const __grid
 		for(int s = 0; s < 16; s++)
 		{
 			stageOff[s] = off;
-			if(((PROG::V::SLOTS & PS_GEOM_STAGE_SLOTS) >> s) & 1) off += (PS_GEOM_THREADS * 3 * P.stride[s] + 127u) & ~127u;
+			if((stageMask<STAGED>(PROG::V::SLOTS) >> s) & 1) off += (PS_GEOM_THREADS * 3 * P.stride[s] + 127u) & ~127u;
 		}
 		if(0 == threadIdx.x) mbarInit(&stageBar, 1);
 		__syncthreads();
@@ -457,11 +462,11 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_span_kernel(const __grid
 			uint32_t total = 0;
 #pragma unroll
 			for(int s = 0; s < 16; s++)
-				if(((PROG::V::SLOTS & PS_GEOM_STAGE_SLOTS) >> s) & 1) total += (nt * 3 * P.stride[s] + 15u) & ~15u;
+				if((stageMask<STAGED>(PROG::V::SLOTS) >> s) & 1) total += (nt * 3 * P.stride[s] + 15u) & ~15u;
 			mbarExpectTx(&stageBar, total);
 #pragma unroll
 			for(int s = 0; s < 16; s++)
-				if(((PROG::V::SLOTS & PS_GEOM_STAGE_SLOTS) >> s) & 1)
+				if((stageMask<STAGED>(PROG::V::SLOTS) >> s) & 1)
 					bulkCopyG2S(stage + stageOff[s], P.slot[s] + (size_t)tri0 * 3 * P.stride[s], (nt * 3 * P.stride[s] + 15u) & ~15u, &stageBar);
 		}
 		mbarWait(&stageBar, 0);
@@ -765,10 +770,43 @@ struct RasterCtx2
 	uint32_t qCount;           // warp-uniform
 	unsigned survived;
 	bool depthWrote;           // per lane
+	uint32_t reserved;         // lane 0: first stream index of the group in flight (the atomic's answer, not waited for until flushEnd)
+	bool pending;              // warp-uniform: a group sits in registers, its slots being reserved
+	uint32_t pSpan, pXY;       // per lane: that group's record
+	float pInv;
 };
+#define PS_SV_HOLE 0xffffffffu     // survivor stream: a reserved slot that no survivor took (the last, partial group of a tile)
 
-PS_D void flushSurvivors2(const SurvivorStream2& Q, RasterSmem2& S, int lane, uint32_t n, int tx0, int ty0)
+// A full group of 32 survivors leaves the queue in two steps: flushBegin takes the records into registers and issues the atomic
+// that reserves their stream slots; flushEnd — at the next flush or the end of the tile — stores them. The atomic's ~1 us round
+// trip (7 % of this kernel's stall samples when waited for on the spot) passes while the next pixels are tested, and the stream
+// stays dense. (Tried: slots reserved 32 at a time ahead of need, the last partial group padded with holes the shade kernel
+// skips — same gain here, but 4 % more warps for the shade kernel.)
+PS_D void flushEnd(const SurvivorStream2& Q, RasterSmem2& S, RasterCtx2& C)
 {
+	if(!C.pending) return;                             // (warp-uniform)
+	C.pending = false;
+	const uint32_t i = __shfl_sync(PS_FULL, C.reserved, 0) + (uint32_t)C.lane;
+	if(i < Q.capacity)
+	{
+		Q.span[i] = C.pSpan; Q.inv[i] = C.pInv;
+		Q.xy[i] = (uint32_t)(C.tx0 + (int)(C.pXY & 15)) | ((uint32_t)(C.ty0 + (int)((C.pXY >> 4) & 15)) << 13);
+	}
+	// queue order = submission order inside a pixel and a warp's reservations grow with time: the latest record has the highest index
+	atomicMax(&S.lastIdx[C.pXY & 0xff], i + 1);
+}
+PS_D void flushBegin(const SurvivorStream2& Q, RasterSmem2& S, RasterCtx2& C)
+{
+	flushEnd(Q, S, C);
+	C.pSpan = S.qSpan[C.lane]; C.pXY = S.qXY[C.lane]; C.pInv = S.qInv[C.lane];
+	if(0 == C.lane) C.reserved = atomicAdd(Q.count, 32u);
+	C.pending = true;
+}
+// the last, partial group of a tile: n < 32 records, reserved and stored on the spot
+PS_D void flushRest(const SurvivorStream2& Q, RasterSmem2& S, RasterCtx2& C, uint32_t n)
+{
+	flushEnd(Q, S, C);
+	const int lane = C.lane;
 	uint32_t base = 0;
 	if(0 == lane) base = atomicAdd(Q.count, n);
 	base = __shfl_sync(PS_FULL, base, 0);
@@ -779,9 +817,8 @@ PS_D void flushSurvivors2(const SurvivorStream2& Q, RasterSmem2& S, int lane, ui
 		if(i < Q.capacity)
 		{
 			Q.span[i] = S.qSpan[lane]; Q.inv[i] = S.qInv[lane];
-			Q.xy[i] = (uint32_t)(tx0 + (int)(m & 15)) | ((uint32_t)(ty0 + (int)((m >> 4) & 15)) << 13);
+			Q.xy[i] = (uint32_t)(C.tx0 + (int)(m & 15)) | ((uint32_t)(C.ty0 + (int)((m >> 4) & 15)) << 13);
 		}
-		// queue order = submission order inside a pixel and bases grow with time: the latest record has the highest index
 		atomicMax(&S.lastIdx[m & 0xff], i + 1);
 	}
 	__syncwarp();
@@ -815,14 +852,22 @@ PS_D void pixelPass(const SurvivorStream2& Q, RasterSmem2& S, RasterCtx2& C, uin
 		const bool act = p < totalPix;
 		const int slot = startedBefore + __popc(starts & (C.ltMask | (1u << lane))) - 1;
 		startedBefore += __popc(starts);
-		uint32_t pix = 0x1000u + lane, span = 0;
+		uint32_t pix = 0x1000u + lane, span = 0, pos = 0;
+		int kk = 0;
+		if(act)
+		{
+			pos = (head + (uint32_t)slot) & (PS_SLOTS - 1);
+			kk = (int)(p - S.pixBase[slot]);
+			const uint32_t smisc = S.sMisc[pos];
+			span = S.sSpan[pos];
+			pix = (((smisc >> 4) & 15) << 4) | ((smisc & 15) + (uint32_t)kk);
+		}
+		// fragments of one pixel are tested in lane order = submission order (§9.7). (The match is issued before the chain replay
+		// and the divide, which do not depend on it: its latency was 9 % of this kernel's stall samples.)
+		const uint32_t peers = __match_any_sync(PS_FULL, pix);
 		float z = 0, inv = 0;
 		if(act)
 		{
-			const uint32_t pos = (head + (uint32_t)slot) & (PS_SLOTS - 1);
-			const int kk = (int)(p - S.pixBase[slot]);
-			const uint32_t smisc = S.sMisc[pos];
-			span = S.sSpan[pos];
 			float c2 = S.sCf2[pos], zz = S.sZ[pos];
 			const float c2Step = S.sCf2Step[pos], zzStep = S.sZStep[pos];
 #pragma unroll 1
@@ -834,10 +879,7 @@ PS_D void pixelPass(const SurvivorStream2& Q, RasterSmem2& S, RasterCtx2& C, uin
 			// interpolateNextStep, interp.cpp:82-92
 			inv = fdiv(1.0f, c2);
 			z = fmul(zz, inv);
-			pix = (((smisc >> 4) & 15) << 4) | ((smisc & 15) + (uint32_t)kk);
 		}
-		// fragments of one pixel are tested in lane order = submission order (§9.7)
-		const uint32_t peers = __match_any_sync(PS_FULL, pix);
 		const int rank = __popc(peers & C.ltMask);
 		const int maxRank = __reduce_max_sync(PS_FULL, act ? rank : 0);
 		bool pass = false;
@@ -866,7 +908,7 @@ PS_D void pixelPass(const SurvivorStream2& Q, RasterSmem2& S, RasterCtx2& C, uin
 		__syncwarp();
 		if(C.qCount >= 32)
 		{
-			flushSurvivors2(Q, S, lane, 32, C.tx0, C.ty0);
+			flushBegin(Q, S, C);
 			C.survived += 32;
 			const uint32_t rem = C.qCount - 32;
 			uint32_t a = 0, d = 0; float f = 0;
@@ -936,6 +978,7 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK, MINB) tile_raster_spa
 	C.testDepth = testDepth; C.updateDepth = updateDepth;
 	C.ltMask = (1u << lane) - 1;
 	C.qCount = 0; C.survived = 0; C.depthWrote = false;
+	C.reserved = 0; C.pending = false; C.pSpan = 0; C.pXY = 0; C.pInv = 0.0f;
 	const int tileX1 = tx0 + PS_TILE - 1;
 	const int depthLimitX = useDepth ? P.depth.width - 1 : 0x7fffffff;
 	uint32_t head = 0, waiting = 0;                    // ring of spans waiting for the pixel phase (warp-uniform)
@@ -985,6 +1028,13 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK, MINB) tile_raster_spa
 		}
 		__syncwarp();
 
+		// every record of the chunk is asked into L2 now (no register holds a prefetch); the loads below, one pass ahead of their
+		// use, then meet L2 latency instead of DRAM's
+		for(uint32_t s = (uint32_t)lane; s < total; s += 32)
+		{
+			const SpanRec* r = P.sp.rec + (S.triBase[S.owner[s]] + s);
+			asm volatile("prefetch.global.L2 [%0];" :: "l"(r));
+		}
 		// the first pass's records
 		int4 recA = make_int4(1, 0, 0, 0), recD = make_int4(0, 0, 0, 0);
 		int rowNext = 0;
@@ -1069,7 +1119,8 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK, MINB) tile_raster_spa
 		__syncwarp();
 	}
 	if(waiting) pixelPass(Q, S, C, head, waiting);
-	if(C.qCount) { flushSurvivors2(Q, S, lane, C.qCount, tx0, ty0); C.survived += C.qCount; }
+	flushRest(Q, S, C, C.qCount);
+	C.survived += C.qCount;
 
 	// ---- write back: depth tile (128-bit stores), and the flag of each pixel's last survivor
 	if(__any_sync(PS_FULL, C.depthWrote) && depthRowOk && mine)
@@ -1114,8 +1165,10 @@ __global__ void __launch_bounds__(PS_SHADE_THREADS, MINB) shade_span_kernel(cons
 	const uint32_t n = min(*Q.count, Q.capacity);
 	const uint32_t stride = gridDim.x * blockDim.x;
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	// pipeline registers: item i (xy, inv, record), item i + stride (stream words); item i + 2 * stride is read inside the loop
-	uint32_t xy0 = 0, sp1 = 0, xy1 = 0;
+	// pipeline registers: item i (xy, inv, record), item i + stride (stream words); item i + 2 * stride is read inside the loop.
+	// (Tried and dropped: the record two items ahead and the next item's header + varyings asked into L1 by prefetch
+	// instructions while this one is shaded: 0.186 -> 0.196 ms.)
+	uint32_t xy0 = PS_SV_HOLE, sp1 = 0, xy1 = PS_SV_HOLE;
 	float inv0 = 0, inv1 = 0;
 	int4 rec0 = make_int4(1, 0, 0, 0);
 	if(NV > 0)
@@ -1132,15 +1185,18 @@ __global__ void __launch_bounds__(PS_SHADE_THREADS, MINB) shade_span_kernel(cons
 			xy = xy0;
 			const float inv = inv0;
 			const int4 A = rec0;
+			// the pipeline moves on
+			{
+				const uint32_t i1 = i + stride, i2 = i + 2 * stride;
+				xy0 = xy1; inv0 = inv1;
+				if(i1 < n && i1 >= i) rec0 = __ldg((const int4*)(P.sp.rec + sp1));
+				if(i2 < n && i2 >= i1 && i1 >= i) { xy1 = Q.xy[i2]; inv1 = Q.inv[i2]; sp1 = Q.span[i2]; }
+			}
+			if(PS_SV_HOLE == xy) continue;                                 // a reserved slot no survivor took
 			const uint32_t tri = (uint32_t)A.w & 0xffffffu;
 			const uint4* src = (const uint4*)(P.hdr + tri);
 			const uint4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
 			const F4* v = P.vary + (size_t)tri * 3 * NV;
-			// the pipeline moves on
-			const uint32_t i1 = i + stride, i2 = i + 2 * stride;
-			xy0 = xy1; inv0 = inv1;
-			if(i1 < n && i1 >= i) rec0 = __ldg((const int4*)(P.sp.rec + sp1));
-			if(i2 < n && i2 >= i1 && i1 >= i) { xy1 = Q.xy[i2]; inv1 = Q.inv[i2]; sp1 = Q.span[i2]; }
 			const int x = (int)(xy & 0x1fff), y = (int)((xy >> 13) & 0x1fff);
 			const int left = A.x, right = A.y, e = (int)((uint32_t)A.w >> 24);
 			const float vx[3] = { __uint_as_float(q0.x), __uint_as_float(q0.z), __uint_as_float(q1.x) };
@@ -1175,7 +1231,7 @@ __global__ void __launch_bounds__(PS_SHADE_THREADS, MINB) shade_span_kernel(cons
 			for(int q = x1; q < x; q++) IP::stepForward(vStart, vStep, 1);    // interp.cpp:88, one rounded add per pixel
 			IP::correctInterpolation(frag, vStart, inv);
 		}
-		else xy = Q.xy[i];
+		else { xy = Q.xy[i]; if(PS_SV_HOLE == xy) continue; }
 		const int x = (int)(xy & 0x1fff), y = (int)((xy >> 13) & 0x1fff);
 		FragmentProcessorOutput out;
 		out.discarded = false; out.wrote = false; out.blendable = false; out.bgra = 0;

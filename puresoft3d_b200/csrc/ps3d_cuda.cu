@@ -150,18 +150,32 @@ template<class PROG> void launchShade(const DrawParams& P, const SurvivorStream&
 	shade_kernel<PROG><<<sms * perSM, 128, 0, s>>>(P, Q);
 }
 // ---- span path launchers ----------------------------------------------------------------------------------------------
-template<class PROG> void launchGeomSpan(const DrawParams& P, cudaStream_t s)
+template<class PROG, int STAGED> bool launchGeomSpanStaged(const DrawParams& P, unsigned blocks, cudaStream_t s)
 {
-	const unsigned blocks = (P.ntris + PS_GEOM_THREADS - 1) / PS_GEOM_THREADS;
+	// bytes of the block's vertex range of the staged slots (bulk copies need 16-byte aligned sources: the block's first element
+	// sits at a multiple of 384 * stride bytes from the 256-byte aligned VBO base)
 	size_t bytes = 0;
 	bool aligned = true;
 	for(int i = 0; i < 16; i++)
-		if(((PROG::V::SLOTS & PS_GEOM_STAGE_SLOTS) >> i) & 1)
+		if((stageMask<STAGED>(PROG::V::SLOTS) >> i) & 1)
 		{
 			bytes += ((size_t)PS_GEOM_THREADS * 3 * P.stride[i] + 127) & ~(size_t)127;
-			aligned = aligned && 0 == ((uintptr_t)P.slot[i] & 15);
+			aligned = aligned && 0 == ((uintptr_t)P.slot[i] & 15) && 0 == ((PS_GEOM_THREADS * 3 * P.stride[i]) & 15);
 		}
-	const bool staged = geomStagingOn() && aligned && bytes > 0 && bytes <= 64 * 1024;
+	if(!aligned || 0 == bytes || bytes > 64 * 1024) return false;
+	static bool attrSet[PS_MAX_DEVICES] = { false };
+	const int dev = currentDevice();
+	if(!attrSet[dev])
+	{
+		cudaFuncSetAttribute(geom_span_kernel<PROG, STAGED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(64 * 1024));
+		attrSet[dev] = true;
+	}
+	geom_span_kernel<PROG, STAGED, false><<<blocks, PS_GEOM_THREADS, bytes, s>>>(P);
+	return true;
+}
+template<class PROG> void launchGeomSpan(const DrawParams& P, cudaStream_t s)
+{
+	const unsigned blocks = (P.ntris + PS_GEOM_THREADS - 1) / PS_GEOM_THREADS;
 	// sort-first band: triangles with no row in the band leave after a rows-only look at their vertices (a pre-cull kernel fills a
 	// list, the geometry kernel runs over it). PS3D_GEOM_BAND=none: every rank takes every triangle through the whole position
 	// half (A/B runs)
@@ -170,21 +184,13 @@ template<class PROG> void launchGeomSpan(const DrawParams& P, cudaStream_t s)
 	if(bandMode && P.workList && (P.band0 > 0 || P.band1 < P.vpH))
 	{
 		geom_precull_kernel<PROG><<<(P.ntris + 255) / 256, 256, 0, s>>>(P);
-		geom_span_kernel<PROG, false, true><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
+		geom_span_kernel<PROG, 0, true><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
 		return;
 	}
-	if(staged)
-	{
-		static bool attrSet[PS_MAX_DEVICES] = { false };
-		const int dev = currentDevice();
-		if(!attrSet[dev])
-		{
-			cudaFuncSetAttribute(geom_span_kernel<PROG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(64 * 1024));
-			attrSet[dev] = true;
-		}
-		geom_span_kernel<PROG, true, false><<<blocks, PS_GEOM_THREADS, bytes, s>>>(P);
-	}
-	else geom_span_kernel<PROG, false, false><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
+	// PS3D_GEOM_STAGE=0: nothing staged (A/B runs); default: the position slot staged in shared memory by one TMA bulk copy per block.
+	// (Every slot staged — STAGED = 2, 28 KB per block for DEF03, phase B off global memory — measured 0.194 -> 0.215 ms on C2: dropped.)
+	if(geomStagingOn() && launchGeomSpanStaged<PROG, 1>(P, blocks, s)) return;
+	geom_span_kernel<PROG, 0, false><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
 }
 template<class PROG> void launchShadeSpan(const DrawParams& P, const SurvivorStream2& Q, cudaStream_t s)
 {
@@ -745,7 +751,8 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 		CK(p, p->tlFill.ensure(ntiles + 1)); CK(p, p->tlLen.ensure(ntiles + 1)); CK(p, p->tileOrder.ensure(ntiles + 1));
 		if(p->tlFill.p != before) CK(p, cudaMemsetAsync(p->tlFill.p, 0, p->tlFill.cap * 4, p->stream));
 	}
-	const size_t svCap = exact ? survivors + 1 : std::max(p->survivorHigh + p->survivorHigh / 4, (size_t)P.vpW * P.vpH * 2);
+	const size_t svSlack = 0;
+	const size_t svCap = (exact ? survivors + 1 : std::max(p->survivorHigh + p->survivorHigh / 4, (size_t)P.vpW * P.vpH * 2)) + svSlack;
 	CK(p, p->sv2Span.ensure(svCap)); CK(p, p->sv2XY.ensure(svCap)); CK(p, p->sv2Inv.ensure(svCap));
 	P.hdr = p->hdr.p; P.vary = p->vary.p; P.tileOrder = p->tileOrder.p; P.poison = p->poisonDev;
 	if(P.band0 > 0 || P.band1 < P.vpH)
@@ -767,7 +774,7 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 	{
 		ProfScope ps(p, CLS_BIN);
 		tile_plan_kernel<<<1, 1024, 0, p->stream>>>(P.tl, ntiles, p->statsDev, p->spanCountDev, P.sp.capacity,
-		                                          (unsigned long long)std::min<size_t>(p->sv2Span.cap, 0xfffffff0u), PS_SORT_LIMIT,
+		                                          (unsigned long long)(std::min<size_t>(p->sv2Span.cap, 0xfffffff0u) - svSlack), PS_SORT_LIMIT,
 		                                          p->poisonDev, p->reportDev, p->tileOrder.p);
 		p->launches++;
 	}
