@@ -148,6 +148,11 @@ PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candi
 	__shared__ uint32_t sInfo[PS_SPAN_WINDOW];           // tile columns reached by that row: lo | hi << 12 | valid << 31
 	__shared__ uint32_t sWarpAlive[PS_GEOM_THREADS / 32], sWarpRows[PS_GEOM_THREADS / 32];
 	__shared__ uint32_t sTri[PS_GEOM_THREADS];           // survivor -> its triangle id in the draw
+	// survivors PS_TALL_ROWS rows high or more (a 4096-row shadow-map triangle): their extent in tiles is reduced by the whole
+	// block instead of being walked row by row by their own thread (min tx, max tx, first ty, last ty)
+	__shared__ uint32_t sTallExt[PS_GEOM_THREADS][4];
+	__shared__ uint32_t sTallList[PS_GEOM_THREADS];
+	__shared__ uint32_t sTallCount;
 	__shared__ uint32_t sSpanBase;
 	const bool useDepth = 0 != (P.behavior & (PS_BEHAVIOR_TEST_DEPTH | PS_BEHAVIOR_UPDATE_DEPTH));
 	const int limitX = useDepth ? P.depth.width - 1 : 0x7fffffff;
@@ -235,9 +240,20 @@ PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candi
 		sRowBase[nAlive] = totalRows;
 		sSpanBase = totalRows ? atomicAdd(P.sp.count, totalRows) : 0u;
 	}
+	if(0 == threadIdx.x) sTallCount = 0;
 	__syncthreads();
 	const uint32_t spanBase = sSpanBase;
 	const bool fits = totalRows <= P.sp.capacity && spanBase <= P.sp.capacity - totalRows;   // else: the plan kernel raises poison, the draw runs again
+	{
+		const bool tallK = threadIdx.x < nAlive && sRowBase[threadIdx.x + 1] - sRowBase[threadIdx.x] >= PS_TALL_ROWS;
+		if(tallK)
+		{
+			sTallList[atomicAdd(&sTallCount, 1u)] = threadIdx.x;
+			sTallExt[threadIdx.x][0] = 0xffffffffu; sTallExt[threadIdx.x][1] = 0; sTallExt[threadIdx.x][2] = 0xffffffffu; sTallExt[threadIdx.x][3] = 0;
+		}
+	}
+	__syncthreads();
+	const uint32_t nTall = sTallCount;
 
 	// ---- S, lane = (triangle, row): one record per row -------------------------------------------------------------------------
 	const uint32_t k = threadIdx.x;                    // B: this thread's survivor
@@ -245,6 +261,7 @@ PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candi
 	unsigned spans = 0;
 	unsigned long long frags = 0;
 	const int myRow0 = k < nAlive ? sRow0[k] : 0, tyBase = myRow0 / PS_TILE;
+	const bool myTall = myRows1 - myRows0 >= PS_TALL_ROWS;
 	uint32_t trLo[4] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu }, trHi[4] = { 0, 0, 0, 0 };
 	int tyLast = -1;
 	for(uint32_t w0 = 0; w0 < totalRows; w0 += PS_SPAN_WINDOW)
@@ -280,6 +297,7 @@ PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candi
 		// B's view of its triangle, row by row from what the lanes left in shared memory: the tile columns its spans reach in the
 		// four tile rows from the one its first row lies in (rows further down fold into the last slot). (Tried instead, all slower
 		// on C2: shared-memory atomics by every lane 0.196 -> 0.214 ms, a segmented reduction by shuffles 0.214, MATCH + group REDUX 0.297.)
+		if(!myTall)
 		{
 			const uint32_t a = max(myRows0, w0), b = min(myRows1, wEnd);
 			for(uint32_t s = a; s < b; s++)
@@ -295,16 +313,48 @@ PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candi
 				tyLast = ty;
 			}
 		}
-		if(wEnd < totalRows) __syncthreads();          // the next window overwrites sOwner / sInfo
+		// tall survivors: the block reduces the extent of each one's rows of this window
+		for(uint32_t q = 0; q < nTall; q++)
+		{
+			const uint32_t kt = sTallList[q];
+			const uint32_t a = max(sRowBase[kt], w0), b = min(sRowBase[kt + 1], wEnd);
+			uint32_t lo = 0xffffffffu, hi = 0, t0 = 0xffffffffu, t1 = 0;
+			for(uint32_t s = a + threadIdx.x; s < b; s += PS_GEOM_THREADS)
+			{
+				const uint32_t info = sInfo[s - w0];
+				if(0 == (info & 0x80000000u)) continue;
+				const uint32_t ty = (uint32_t)((sRow0[kt] + (int)(s - sRowBase[kt])) / PS_TILE);
+				lo = min(lo, info & 0xfff); hi = max(hi, (info >> 12) & 0xfff);
+				t0 = min(t0, ty); t1 = max(t1, ty);
+			}
+			lo = __reduce_min_sync(PS_FULL, lo); hi = __reduce_max_sync(PS_FULL, hi);
+			t0 = __reduce_min_sync(PS_FULL, t0); t1 = __reduce_max_sync(PS_FULL, t1);
+			if(0 == lane && lo != 0xffffffffu)
+			{
+				atomicMin(&sTallExt[kt][0], lo); atomicMax(&sTallExt[kt][1], hi);
+				atomicMin(&sTallExt[kt][2], t0); atomicMax(&sTallExt[kt][3], t1);
+			}
+		}
+		__syncthreads();                               // the next window overwrites sOwner / sInfo; B reads the tall extents
 	}
 	int minTx = 0x7fffffff, maxTx = -1, tyFirst = -1;
-#pragma unroll
-	for(int r = 0; r < 4; r++)
-		if(trLo[r] != 0xffffffffu)
+	if(myTall)
+	{
+		if(sTallExt[k][0] != 0xffffffffu)
 		{
-			if(tyFirst < 0) tyFirst = tyBase + r;
-			minTx = min(minTx, (int)trLo[r]); maxTx = max(maxTx, (int)trHi[r]);
+			minTx = (int)sTallExt[k][0]; maxTx = (int)sTallExt[k][1]; tyFirst = (int)sTallExt[k][2]; tyLast = (int)sTallExt[k][3];
 		}
+	}
+	else
+	{
+#pragma unroll
+		for(int r = 0; r < 4; r++)
+			if(trLo[r] != 0xffffffffu)
+			{
+				if(tyFirst < 0) tyFirst = tyBase + r;
+				minTx = min(minTx, (int)trLo[r]); maxTx = max(maxTx, (int)trHi[r]);
+			}
+	}
 
 	// ---- B, thread = survivor (dense): records for the shade kernel, tile lists -----------------------------------------------
 	uint32_t binned = 0, rect0 = 0, rect1 = 0;
@@ -343,7 +393,7 @@ PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candi
 		const int tx0 = minTx, tx1 = maxTx, ty0 = tyFirst, ty1 = tyLast;
 		rect0 = (uint32_t)tx0 | ((uint32_t)tx1 << 16);
 		rect1 = (uint32_t)ty0 | ((uint32_t)ty1 << 16);
-		if(tx1 - tx0 >= 8 || ty1 - tyBase >= 4) bigPending = true;  // its whole rectangle, appended by the warp further down
+		if(myTall || tx1 - tx0 >= 8 || ty1 - tyBase >= 4) bigPending = true;  // its whole rectangle, appended by the warp further down
 		else
 		{
 			// small triangle (the common case): exactly the tiles some span of it reaches (bit = (ty - tyBase) * 8 + tx - tx0). Up to

@@ -28,6 +28,7 @@ CONFIGS = {
     "C3": lambda: scenes.scene_desk(1920, 1080, shadow=4096, clutter=24, tex_size=512),
     "C4": lambda: scenes.scene_blend_overdraw(1920, 1080),
     "C5-4k": lambda: scenes.scene_heightfield(3840, 2160, grid=1118, layers=4, seed=5, tex_size=2048),
+    "C5-8k": lambda: scenes.scene_heightfield(7680, 4320, grid=1118, layers=4, seed=5, tex_size=2048),
 }
 
 
@@ -58,8 +59,18 @@ def main():
         for _ in range(5):
             frame()
         pipe.finish()
+        if os.environ.get("PS3D_GRAPH", "1") != "0":
+            # the frame as one launch (ps3d_graph_*): what 54 draws of 12-triangle boxes (C3) cost is mostly launches
+            calls = frame
+            pipe.graphBegin()
+            calls()
+            g = pipe.graphEnd()
+            frame = (lambda pipe=pipe, g=g: pipe.graphLaunch(g))
+            for _ in range(3):
+                frame()
+            pipe.finish()
         pipe.resetStats()
-        steps = 50 if name != "C5-4k" else 10
+        steps = 50 if not name.startswith("C5") else 10
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(ext)
         for _ in range(steps):
