@@ -278,7 +278,7 @@ def main():
     # sort-first rank's share of a frame does not fill the GPU: a second pipe (own stream, own scratch buffers and targets; on
     # ranks != 0 peer-mapped to rank 0's second pipe) renders frame i + 1 while frame i is still in flight. Same frames, same
     # images, counted once each. PS3D_FRAMES_IN_FLIGHT=1 turns it off.
-    n_flight = max(1, int(os.environ.get("PS3D_FRAMES_IN_FLIGHT", "2")))
+    n_flight = max(1, int(os.environ.get("PS3D_FRAMES_IN_FLIGHT", "2" if world > 1 else "1")))   # (one GPU gains nothing: its kernels fill it)
     if comp is not None and not peer_comp:
         n_flight = 1
     flights = [dict(pipe=pipe, ext=ext, calls=frame_calls, launch=frame)]
