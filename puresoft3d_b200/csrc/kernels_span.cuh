@@ -87,6 +87,11 @@ PS_D void evalSpan(const TriHeader& h, int iy, int vpW, int limitX, SpanOut& o)
 	else o.zmin = __int_as_float(0x7fc00000);               // too long for the closed-form estimate: the tile kernel estimates per tile
 }
 
+// STAGED: 0 = every slot read from global memory, 1 = the position slot (slot 0 of every vertex functor) staged in shared memory by
+// one TMA bulk copy per block, 2 = every slot the functor reads staged (all of a block's vertex bytes in flight at once, phase B
+// reads no global memory; 28 KB per block for DEF03)
+template<int STAGED> __host__ __device__ constexpr uint32_t stageMask(uint32_t slots) { return 2 == STAGED ? slots : (1 == STAGED ? (slots & 1u) : 0u); }
+
 // Sort-first (a rank renders a band of rows): every rank sees every triangle, so what a rank spends on triangles of other
 // bands bounds the scaling. geom_precull computes only the three viewport y (the vertex functor's y and w: the compiler drops
 // the rest) and the row range, and appends the triangles with a row in the band to one list (any order: tile lists are sorted
@@ -94,12 +99,15 @@ PS_D void evalSpan(const TriHeader& h, int iy, int vpW, int limitX, SpanOut& o)
 // dense blocks. (Tried and dropped: the pre-cull inside the geometry kernel, a block queueing the survivors of 8 chunks into
 // dense batches — 90 registers and an eighth of the blocks: 66 us against 29 + 38 us for an eighth of C2's rows, 204 against
 // 34 + 130 us for half of them; and the pre-cull in front of phase A of every block without the queue: 145 us for half.)
+#define PS_PRECULL_THREADS 512
 template<class PROG>
-__global__ void __launch_bounds__(256) geom_precull_kernel(const __grid_constant__ DrawParams P)
+__global__ void __launch_bounds__(PS_PRECULL_THREADS) geom_precull_kernel(const __grid_constant__ DrawParams P)
 {
 	constexpr int NV = PROG::NV;
-	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
-	const int lane = threadIdx.x & 31;
+	const uint32_t tri = blockIdx.x * PS_PRECULL_THREADS + threadIdx.x;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	__shared__ uint32_t sWarpKeep[PS_PRECULL_THREADS / 32];
+	__shared__ uint32_t sBase;
 	bool keep = false;
 	if(tri < P.ntris)
 	{
@@ -118,17 +126,27 @@ __global__ void __launch_bounds__(256) geom_precull_kernel(const __grid_constant
 		int firstRow, lastRow;
 		keep = rowRangeOnly(P.vpH, P.halfH, ndcY, firstRow, lastRow) && lastRow >= P.band0 && firstRow < P.band1;
 	}
+	// one append per BLOCK: the list's counter is a single address, and 31 000 returning atomics on it (one per warp) were
+	// what this kernel took 28 us for on C2 — the arithmetic and the 48 MB of positions need a third of that
 	const uint32_t keepBallot = __ballot_sync(PS_FULL, keep);
-	uint32_t base = 0;
-	if(0 == lane && keepBallot) base = atomicAdd(P.workCount, (uint32_t)__popc(keepBallot));
-	base = __shfl_sync(PS_FULL, base, 0);
-	if(keep) P.workList[base + (uint32_t)__popc(keepBallot & ((1u << lane) - 1))] = tri;
+	if(0 == lane) sWarpKeep[warp] = (uint32_t)__popc(keepBallot);
+	__syncthreads();
+	if(0 == warp)
+	{
+		const uint32_t c = lane < PS_PRECULL_THREADS / 32 ? sWarpKeep[lane] : 0u;
+		uint32_t incl = c;
+#pragma unroll
+		for(int d = 1; d < 32; d <<= 1)
+		{
+			const uint32_t t = __shfl_up_sync(PS_FULL, incl, d);
+			if(lane >= d) incl += t;
+		}
+		if(lane < PS_PRECULL_THREADS / 32) sWarpKeep[lane] = incl - c;
+		if(31 == lane) sBase = incl ? atomicAdd(P.workCount, incl) : 0u;
+	}
+	__syncthreads();
+	if(keep) P.workList[sBase + sWarpKeep[warp] + (uint32_t)__popc(keepBallot & ((1u << lane) - 1))] = tri;
 }
-
-// STAGED: 0 = every slot read from global memory, 1 = the position slot (slot 0 of every vertex functor) staged in shared memory by
-// one TMA bulk copy per block, 2 = every slot the functor reads staged (all of a block's vertex bytes in flight at once, phase B
-// reads no global memory; 28 KB per block for DEF03)
-template<int STAGED> __host__ __device__ constexpr uint32_t stageMask(uint32_t slots) { return 2 == STAGED ? slots : (1 == STAGED ? (slots & 1u) : 0u); }
 
 struct GeomAcc { unsigned rasterised, spans; unsigned long long frags; unsigned loInv, hi1; };
 
@@ -204,6 +222,18 @@ PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candi
 			h.rw0 = rw[0]; h.rw1 = rw[1]; h.rw2 = rw[2];
 			h.z0 = pz[0]; h.z1 = pz[1]; h.z2 = pz[2];
 		}
+	}
+	// what phase B will read of this triangle's other vertex slots is asked into L2 now (phase S lies in between): survivors only
+	if(alive && NV > 0)
+	{
+#pragma unroll
+		for(int s = 0; s < 16; s++)
+			if(((PROG::V::SLOTS >> s) & 1) && 0 == ((stageMask<STAGED>(PROG::V::SLOTS) >> s) & 1))
+			{
+				const uint8_t* a0 = P.slot[s] + (size_t)tri * 3 * P.stride[s];
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(a0));
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(a0 + 3 * P.stride[s] - 1));
+			}
 	}
 	// compaction + exclusive scan of the row counts, both in thread order (dead threads add nothing, so a survivor's prefix
 	// is the same in either numbering)

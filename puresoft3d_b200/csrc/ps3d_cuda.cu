@@ -183,7 +183,7 @@ template<class PROG> void launchGeomSpan(const DrawParams& P, cudaStream_t s)
 	if(bandMode < 0) { const char* e = getenv("PS3D_GEOM_BAND"); bandMode = (e && !strcmp(e, "none")) ? 0 : 1; }
 	if(bandMode && P.workList && (P.band0 > 0 || P.band1 < P.vpH))
 	{
-		geom_precull_kernel<PROG><<<(P.ntris + 255) / 256, 256, 0, s>>>(P);
+		geom_precull_kernel<PROG><<<(P.ntris + PS_PRECULL_THREADS - 1) / PS_PRECULL_THREADS, PS_PRECULL_THREADS, 0, s>>>(P);
 		geom_span_kernel<PROG, 0, true><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
 		return;
 	}
