@@ -104,10 +104,11 @@ struct alignas(32) SpanRec
 	float cf2, cf2Step, z0, zStep;   // correctionFactor2 / projected z chains at the CLAMPED start column (interp.cpp:26-80)
 };
 #define PS_SPAN_MAX_TRIS 0x1000000u   // triangle ids must fit 24 bits on the span path
+struct alignas(8) TriSpan { uint32_t x, y; };   // (a plain struct: this header is also compiled for the host by the functor tests)
 struct SpanStreams
 {
 	SpanRec* rec;
-	uint2* tri;           // per triangle: index of its first record, first row | last row << 16 of the records (inside band and targets)
+	TriSpan* tri;         // per triangle: index of its first record, first row | last row << 16 of the records (inside band and targets)
 	uint32_t* count;      // records allocated so far in this draw (one atomicAdd per geometry block)
 	uint32_t capacity;
 };

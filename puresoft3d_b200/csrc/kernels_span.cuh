@@ -401,7 +401,7 @@ PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candi
 			const uint4* src = (const uint4*)&sHdr[k];
 			dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
 		}
-		P.sp.tri[wtri] = make_uint2(spanBase + myRows0, (uint32_t)sRow0[k] | ((uint32_t)(sRow0[k] + (int)(myRows1 - myRows0) - 1) << 16));
+		{ TriSpan tsv; tsv.x = spanBase + myRows0; tsv.y = (uint32_t)sRow0[k] | ((uint32_t)(sRow0[k] + (int)(myRows1 - myRows0) - 1) << 16); P.sp.tri[wtri] = tsv; }
 		if(NV > 0)
 		{
 			float4* vd = (float4*)(P.vary + (size_t)wtri * 3 * NV);
@@ -1068,7 +1068,7 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK, MINB) tile_raster_spa
 	// chunks ahead, the per-triangle words one chunk ahead, the span records one candidate pass ahead.
 	uint32_t idAhead = 0;
 	uint2 tsAhead = make_uint2(0, 0);
-	if((uint32_t)lane < listLen) tsAhead = __ldg(&P.sp.tri[list[lane]]);
+	if((uint32_t)lane < listLen) tsAhead = __ldg((const uint2*)&P.sp.tri[list[lane]]);
 	if(32u + lane < listLen) idAhead = list[32u + lane];
 
 	for(uint32_t chunk = 0; chunk < listLen; chunk += 32)
@@ -1076,7 +1076,7 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK, MINB) tile_raster_spa
 		// ---- lane = triangle of the chunk: where its records are, which of its rows lie in this warp's rows ----
 		const uint32_t li = chunk + lane;
 		const uint2 ts = tsAhead;
-		if(li + 32 < listLen) tsAhead = __ldg(&P.sp.tri[idAhead]);
+		if(li + 32 < listLen) tsAhead = __ldg((const uint2*)&P.sp.tri[idAhead]);
 		if(li + 64 < listLen) idAhead = list[li + 64];
 		int nrows = 0, ra = 0;
 		uint32_t recBase = 0;

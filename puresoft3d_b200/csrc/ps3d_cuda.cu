@@ -332,7 +332,7 @@ struct ps3d_pipe
 	uint32_t* svCountDev;
 	// span path (kernels_span.cuh): span records, per-triangle record index, fixed-capacity tile lists, 12-byte survivors
 	DevBuf<SpanRec> spRec;
-	DevBuf<uint2> spTri;
+	DevBuf<TriSpan> spTri;
 	DevBuf<uint32_t> tlFill, tlLen, tlIds;
 	DevBuf<uint32_t> sv2Span, sv2XY;
 	DevBuf<float> sv2Inv;
@@ -710,7 +710,7 @@ static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe
 		// (a tile's list is one dependent chain, ~100 us on C2 whatever the load: as soon as the tiles in play no longer fill the
 		// GPU's warp slots about twice over, shorter chains win — 2, 4 or 8 row groups per tile)
 		int parts = rasterPartsForced();
-		if(parts <= 0) parts = tilesInPlay * 4 <= warpSlots ? 8 : (tilesInPlay * 2 <= warpSlots ? 4 : (tilesInPlay * 5 <= warpSlots * 6 ? 2 : 1));
+		if(parts <= 0) parts = tilesInPlay * 4 <= warpSlots ? 8 : (tilesInPlay * 2 <= warpSlots ? 4 : (tilesInPlay <= warpSlots * 2 ? 2 : 1));
 		const unsigned blocks = (ntiles * (unsigned)parts + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK;
 		// PS3D_RASTER_MINB=8|10|12: blocks per SM the kernel is compiled for (64 / 51 / 40 registers) — A/B switch
 		static int minb = -1;
