@@ -290,7 +290,14 @@ typedef struct ps3d_profile
 } ps3d_profile;
 int ps3d_profile_enable(ps3d_pipe* p, int on);
 int ps3d_profile_read(ps3d_pipe* p, ps3d_profile* out);
-/* which rcpps / rsqrtss emulation the kernels use: table index bits measured on this host (0,0 = IEEE 1/x, 1/sqrt) */
+/* which rcpps / rsqrtss emulation the kernels use: table index bits measured on this host (0,0 = IEEE 1/x, 1/sqrt).
+ * NOTE — colour depends on the HOST CPU: the reference's fragment shaders use the approximate x86 instructions rcpps / rsqrtss
+ * (src/mcemath/vector.cpp:165,190,245), whose results differ between CPU models. At start-up this library measures the host's own
+ * instructions over all 2^23 mantissas and hands the tables to the kernels, so the GPU renders the colours the reference would
+ * render ON THIS MACHINE (bit for bit, which is what the parity tests observe); on a host with a different CPU the same scene can
+ * differ in the low bits of a colour channel, exactly as the reference's own output would. Coverage, depth and 1/w never use
+ * these instructions and do not depend on the host. PS3D_APPROX=ieee selects correctly rounded 1/x and 1/sqrt(x) instead
+ * (host-independent; colour then within the 1/255 gate, not bit-equal). */
 int ps3d_host_approx_info(int* rcpBits, int* rsqrtBits);
 
 #ifdef __cplusplus
