@@ -238,8 +238,8 @@ int ps3d_composite_peer(ps3d_pipe* p);
 
 /* Captured frames (CUDA library only). The calls between ps3d_graph_begin and ps3d_graph_end (clears, uniforms, draws, the
  * composite) are recorded once into a CUDA graph instead of being run; ps3d_graph_launch replays them as ONE launch — what a
- * frame costs the host when its kernels take tens of microseconds (C2 on 8 GPUs). Contract: run the same frame once normally
- * first (buffers are sized by then: a captured frame cannot allocate), keep resources, state and uniforms of the frame
+ * frame costs the host when its kernels take tens of microseconds (C2 on 8 GPUs). Contract: run the same frame normally
+ * first until its buffers have stopped growing (twice is enough: a captured frame cannot allocate), keep resources, state and uniforms of the frame
  * unchanged between launches (uniform values are latched at capture), and capture once per (VBO set, display target)
  * combination the frame is launched with. Vertex data may change between launches (ps3d_vbo_update*): the streams are read
  * through the same pointers. A replayed frame whose intermediates no longer fit the buffers it was captured with is reported

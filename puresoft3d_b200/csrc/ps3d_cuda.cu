@@ -740,10 +740,18 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 	CK(p, p->hdr.ensure(ntris));
 	CK(p, p->vary.ensure(ntris * 3 * (size_t)(pe->nv > 0 ? pe->nv : 1)));
 	CK(p, p->spTri.ensure(ntris));
-	const size_t spanCap = exact ? spans + 1 : std::max(p->spanHigh + p->spanHigh / 4, ntris * 6 + 4096);
+	// (a frame being captured cannot allocate: it takes the buffers the same frame ran in a moment ago as they are — they hold
+	// its high-water marks — instead of asking for the usual 25 % of head-room)
+	size_t spanCap = exact ? spans + 1 : std::max(p->spanHigh + p->spanHigh / 4, ntris * 6 + 4096);
+	if(p->capturing && p->spRec.cap >= p->spanHigh) spanCap = std::min(spanCap, p->spRec.cap);
 	CK(p, p->spRec.ensure(spanCap));
 	size_t listCap = exact ? longest : std::max(p->listHigh + p->listHigh / 4, (size_t)128);
 	listCap = std::min<size_t>((listCap + 31) & ~(size_t)31, PS_SORT_LIMIT);
+	if(p->capturing && (size_t)ntiles * listCap > p->tlIds.cap)
+	{
+		const size_t fits = (p->tlIds.cap / ntiles) & ~(size_t)31;
+		if(fits >= p->listHigh) listCap = fits;
+	}
 	CK(p, p->tlIds.ensure((size_t)ntiles * listCap));
 	{
 		// tile_plan_kernel leaves the per-tile fill counts zeroed behind every draw; a fresh allocation starts zeroed
@@ -752,7 +760,8 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 		if(p->tlFill.p != before) CK(p, cudaMemsetAsync(p->tlFill.p, 0, p->tlFill.cap * 4, p->stream));
 	}
 	const size_t svSlack = 0;
-	const size_t svCap = (exact ? survivors + 1 : std::max(p->survivorHigh + p->survivorHigh / 4, (size_t)P.vpW * P.vpH * 2)) + svSlack;
+	size_t svCap = (exact ? survivors + 1 : std::max(p->survivorHigh + p->survivorHigh / 4, (size_t)P.vpW * P.vpH * 2)) + svSlack;
+	if(p->capturing && p->sv2Span.cap >= p->survivorHigh) svCap = std::min(svCap, p->sv2Span.cap);
 	CK(p, p->sv2Span.ensure(svCap)); CK(p, p->sv2XY.ensure(svCap)); CK(p, p->sv2Inv.ensure(svCap));
 	P.hdr = p->hdr.p; P.vary = p->vary.p; P.tileOrder = p->tileOrder.p; P.poison = p->poisonDev;
 	if(P.band0 > 0 || P.band1 < P.vpH)
@@ -830,13 +839,15 @@ static int enqueueLegacy(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int pa
 	unsigned long long survivorCap = ~0ull;
 	if(speculate)
 	{
-		const size_t pairGuess = std::max(p->pairHigh + p->pairHigh / 4, ntris + ntris / 2 + 1024);
+		size_t pairGuess = std::max(p->pairHigh + p->pairHigh / 4, ntris + ntris / 2 + 1024);
+		if(p->capturing && p->valsA.cap >= p->pairHigh) pairGuess = std::min(pairGuess, p->valsA.cap);   // (a captured frame cannot allocate)
 		CK(p, p->valsA.ensure(pairGuess));
 		pairCap = (uint32_t)std::min<size_t>(p->valsA.cap, 0xffffffffu);
 		listLimit = PS_SORT_LIMIT;
 		if(2 == path)
 		{
-			const size_t svGuess = std::max(p->survivorHigh + p->survivorHigh / 4, (size_t)P.vpW * P.vpH * 2);
+			size_t svGuess = std::max(p->survivorHigh + p->survivorHigh / 4, (size_t)P.vpW * P.vpH * 2);
+			if(p->capturing && p->svTri.cap >= p->survivorHigh) svGuess = std::min(svGuess, p->svTri.cap);
 			{ const int rc = ensureSurvivors(p, svGuess, P); if(rc) return rc; }
 			survivorCap = std::min<size_t>(p->svTri.cap, 0xfffffff0u);
 		}
@@ -962,6 +973,15 @@ int ps3d_destroy(ps3d_pipe* p)
 	TRACE();
 	if(!p) return PS3D_ERR_INVALID_ARGUMENT;
 	cudaSetDevice(p->device);
+	if(p->capturing)
+	{
+		// a capture nobody ended: end it here, or the thread stays in capture mode
+		cudaGraph_t g = nullptr;
+		cudaStreamEndCapture(p->stream, &g);
+		if(g) cudaGraphDestroy(g);
+		cudaGetLastError();
+		p->capturing = false; g_capturing = false;
+	}
 	settle(p);
 	cudaStreamSynchronize(p->stream);
 	for(Texture* t : p->textures) if(t) { for(int i = 0; i < 6; i++) if(t->layer[i]) cudaFree(t->layer[i]); delete t; }
