@@ -8,7 +8,8 @@ CPU arm of bench.py. Nothing on the product path links or loads it.
 What the shim changes (no algorithmic change; BASELINE.json north_star / SURVEY.md §8c):
   * the three MSVC `__asm{}` blocks on the pipeline side are replaced by the equivalent SSE intrinsics
     (interp.cpp:55-66 haddps pair; fbo.cpp:353-370 and :377-393 16-byte fill loops);
-  * src/mcemath's asm routines are provided by oracle/ref_shim/mcemath_sse.cpp (same instruction order);
+  * src/mcemath is compiled from its own text, its asm blocks rewritten instruction by instruction (asm_translate.py);
+    oracle/ref_shim/mcemath_sse.cpp (round 1: a hand restatement) is kept only as a cross-check library;
   * `typedef __declspec(align(16)) struct {...} VertexProcessorOutput` (proc.h:20-24): alignment moved
     onto the struct so gcc accepts arrays of it;
   * Win32 threads/atomics/aligned malloc come from oracle/ref_shim/include/windows.h + win32_shim.cpp;
@@ -43,7 +44,7 @@ CXXFLAGS = [
     "-std=gnu++14", "-O2", "-fPIC", "-pthread", "-msse4.1", "-mmmx", "-mfpmath=sse", "-ffp-contract=off",
     "-fno-fast-math", "-fno-strict-aliasing", "-w",
     "-D__declspec(x)=__attribute__((x))", "-Dalign(x)=aligned(x)", "-D__stdcall=", "-D_stdcall=", "-D_cdecl=",
-    "-D__cdecl=", "-D__int64=long long", "-DNDEBUG",
+    "-D__cdecl=", "-D__int64=long long", "-DNDEBUG", "-D_declspec(x)=__attribute__((x))", "-D_copysign=copysign",
 ]
 
 # ---- the asm replacements -------------------------------------------------------------------------------------
@@ -192,6 +193,25 @@ def patch_testpost(text):
     return "#include <xmmintrin.h>\n#include <mmintrin.h>\n" + ASM_BLOCK.sub(lambda m: next(it), text)
 
 
+# src/mcemath: its C API (vector.cpp, matrix.cpp, quatern.cpp, matrxgl.cpp) is compiled from the reference's OWN text, every MSVC asm
+# block rewritten instruction by instruction by asm_translate.py (never by hand). wraprs.cpp (C++ wrapper classes) is not on the path.
+MCEMATH_SOURCES = ["vector.cpp", "matrix.cpp", "quatern.cpp", "matrxgl.cpp"]
+MCEMATH_BLOCKS = {"vector.cpp": 29, "matrix.cpp": 15, "quatern.cpp": 7, "matrxgl.cpp": 1}   # live blocks (SURVEY.md §8c counts 35 / 16 / 7 / 2 with the commented-out ones)
+
+
+def patch_mcemath(name, text):
+    import asm_translate
+    # lines that are comments from their first column on (the reference keeps a few dead asm blocks that way) go first: a
+    # commented `__asm{` must not open a block
+    text = "\n".join("" if ln.lstrip().startswith("//") else ln for ln in text.split("\n"))
+    text, n = asm_translate.translate_source(text, "src/mcemath/" + name)
+    if n != MCEMATH_BLOCKS[name]:
+        raise SystemExit("src/mcemath/%s: expected %d asm blocks, translated %d" % (name, MCEMATH_BLOCKS[name], n))
+    if "__asm" in text:
+        raise SystemExit("src/mcemath/%s: an asm block was left untranslated" % name)
+    return "#include <pmmintrin.h>\n#include <stdint.h>\n" + text
+
+
 def run(cmd):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
@@ -209,7 +229,14 @@ def main():
     os.makedirs(os.path.join(scratch, "p"))
     os.makedirs(os.path.join(scratch, "t1"))
     os.makedirs(os.path.join(scratch, "t2"))
+    os.makedirs(os.path.join(scratch, "m"))
+    sys.path.insert(0, HERE)
     try:
+        for fn in MCEMATH_SOURCES:
+            with open(os.path.join(REF, "src", "mcemath", fn), "r", encoding="latin-1") as f:
+                text = f.read()
+            with open(os.path.join(scratch, "m", fn), "w", encoding="latin-1") as f:
+                f.write(patch_mcemath(fn, text))
         src = os.path.join(REF, "src", "puresoft3d")
         for fn in sorted(os.listdir(src)):
             if fn.endswith(".h") or fn in PIPE_SOURCES:
@@ -239,7 +266,8 @@ def main():
         jobs += [] if not DEMOS else [(os.path.join(scratch, "t1", "testproc.cpp"), "t1_testproc.cpp"),
                  (os.path.join(scratch, "t2", "testproc.cpp"), "t2_testproc.cpp"), (os.path.join(scratch, "t2", "testpost.cpp"), "t2_testpost.cpp"),
                  (os.path.join(HERE, "demo_procs1.cpp"), "t1_demo_procs1.cpp"), (os.path.join(HERE, "demo_procs2.cpp"), "t2_demo_procs2.cpp")]
-        jobs += [(os.path.join(HERE, s), "s_" + s) for s in ("win32_shim.cpp", "mcemath_sse.cpp", "ref_capi.cpp")]
+        jobs += [(os.path.join(scratch, "m", s), "m_" + s) for s in MCEMATH_SOURCES]
+        jobs += [(os.path.join(HERE, s), "s_" + s) for s in ("win32_shim.cpp", "ref_capi.cpp")]
         for path, tag in jobs:
             obj = os.path.join(scratch, tag + ".o")
             extra = []
@@ -254,6 +282,11 @@ def main():
         os.makedirs(OUT_DIR, exist_ok=True)
         run(["g++", "-shared", "-pthread", "-o", OUT_SO] + objs)
         print("build_ref: wrote", OUT_SO)
+        # the hand-written restatement of the routines the pipeline calls (round 1's shim) stays as a CROSS-CHECK of the mechanical
+        # translation: its own library, compared routine by routine by tests/test_mcemath_translation.py
+        hand = os.path.join(OUT_DIR, "libmcemath_hand.so")
+        run(["g++"] + CXXFLAGS + ["-shared", "-o", hand, os.path.join(HERE, "mcemath_sse.cpp")])
+        print("build_ref: wrote", hand)
     finally:
         shutil.rmtree(scratch, ignore_errors=True)
     return 0

@@ -1,8 +1,9 @@
-// The `mcemaths_*` routines the Puresoft3D pipeline calls, restated as SSE intrinsics 1:1 from the MSVC inline
-// asm of src/mcemath (which gcc cannot assemble). TEST INFRASTRUCTURE ONLY — linked into oracle/_ref so the
-// unmodified reference pipeline runs as the parity pin. Every routine keeps the instruction ORDER of the asm
-// (separate mulps/addps, haddps pairing, hardware rcpps/rsqrtss) because that order defines the reference's
-// numerics. Built with -ffp-contract=off -mfpmath=sse.
+// ROUND 2: this file is no longer part of oracle/_ref/libps3d_ref.so. The reference build now compiles src/mcemath from its own
+// text, every MSVC asm block rewritten instruction by instruction by asm_translate.py. This hand-written restatement of the 26
+// `mcemaths_*` routines the pipeline calls (round 1's shim) is kept as an independent CROSS-CHECK of that translation: it is built
+// into oracle/_ref/libmcemath_hand.so and compared routine by routine by tests/test_mcemath_translation.py.
+// TEST INFRASTRUCTURE ONLY. Every routine keeps the instruction ORDER of the asm (separate mulps/addps, haddps pairing, hardware
+// rcpps/rsqrtss) because that order defines the reference's numerics. Built with -ffp-contract=off -mfpmath=sse.
 //
 // Citations: src/mcemath/vector.cpp, matrix.cpp, quatern.cpp (line ranges beside each function).
 #include <xmmintrin.h>

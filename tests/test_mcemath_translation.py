@@ -1,0 +1,98 @@
+"""oracle/_ref compiles src/mcemath from the reference's own text, every MSVC asm block rewritten instruction by instruction by
+oracle/ref_shim/asm_translate.py. Round 1's hand-written restatement of the 26 routines the pipeline calls
+(oracle/ref_shim/mcemath_sse.cpp -> oracle/_ref/libmcemath_hand.so) stays as an independent cross-check: both must return the same
+bytes, routine by routine, on random vectors, special values and the approximate instructions' whole input range."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import REF_SO, ROOT
+
+HAND_SO = os.path.join(ROOT, "oracle", "_ref", "libmcemath_hand.so")
+F = C.POINTER(C.c_float)
+
+# name -> (argument kinds, returns float); "o" = 16-float buffer written (and possibly read), "i" = 16-float input, "f" = float, "n" = int count
+SIGS = {
+    "mcemaths_add_3_4": ("oii", False), "mcemaths_sub_3_4": ("oii", False), "mcemaths_add_3_4_ip": ("oi", False),
+    "mcemaths_sub_3_4_ip": ("oi", False), "mcemaths_step_3_4_ip": ("oif", False), "mcemaths_dot_3_4": ("ii", True),
+    "mcemaths_cross_3": ("oii", False), "mcemaths_mul_3_4": ("of", False), "mcemaths_div_3_4": ("of", False),
+    "mcemaths_mulvec_3_4": ("oi", False), "mcemaths_divvec_3_4": ("oi", False), "mcemaths_len_3_4": ("i", True),
+    "mcemaths_norm_3_4": ("o", False), "mcemaths_zero_vec_ary": ("on", False), "mcemaths_clamp_3_4": ("off", False),
+    "mcemaths_mul_3": ("of", False), "mcemaths_div_3": ("of", False), "mcemaths_add_1to4": ("of", False), "mcemaths_sub_4by1": ("of", False),
+    "mcemaths_mat4transpose": ("o", False), "mcemaths_mat4cpy": ("oi", False), "mcemaths_transform_m4v4": ("oii", False),
+    "mcemaths_transform_m4v4_ip": ("oi", False), "mcemaths_transform_m4m4": ("oii", False), "mcemaths_make_tbn": ("oiii", False),
+    "mcemaths_quatcpy": ("oi", False),
+}
+
+
+def aligned(n=16):
+    raw = np.zeros(n + 8, dtype=np.float32)
+    off = (-raw.ctypes.data // 4) % 4
+    return raw[off:off + n]
+
+
+def call(lib, name, bufs, scalars):
+    kinds, ret_float = SIGS[name]
+    fn = getattr(lib, name)
+    fn.restype = C.c_float if ret_float else None
+    args, bi, si, argtypes = [], 0, 0, []
+    for k in kinds:
+        if k in "oi":
+            args.append(bufs[bi].ctypes.data_as(F)); argtypes.append(F); bi += 1
+        elif k == "f":
+            args.append(C.c_float(scalars[si])); argtypes.append(C.c_float); si += 1
+        else:
+            args.append(C.c_int(3)); argtypes.append(C.c_int)
+    fn.argtypes = argtypes
+    r = fn(*args)
+    return np.float32(r).view(np.uint32) if ret_float else None
+
+
+@pytest.fixture(scope="module")
+def libs(built):
+    if not (os.path.exists(REF_SO) and os.path.exists(HAND_SO)):
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    mode = getattr(os, "RTLD_LOCAL", 0) | getattr(os, "RTLD_NOW", 2)
+    return C.CDLL(REF_SO, mode=mode), C.CDLL(HAND_SO, mode=mode)
+
+
+@pytest.mark.parametrize("name", sorted(SIGS))
+def test_translated_routine_equals_the_hand_restatement(name, libs):
+    translated, hand = libs
+    rng = np.random.default_rng(abs(hash(name)) % (2 ** 32))
+    kinds, _ = SIGS[name]
+    nbuf = sum(1 for k in kinds if k in "oi")
+    specials = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-38, 1e-45, 3.4e38, 0.5, 255.0], dtype=np.float32)
+    for trial in range(400):
+        src = []
+        for _ in range(nbuf):
+            if trial % 4 == 0:
+                v = rng.choice(specials, size=16).astype(np.float32)
+            elif trial % 4 == 1:
+                v = rng.integers(0, 2 ** 32, size=16, dtype=np.uint64).astype(np.uint32).view(np.float32)   # any bit pattern
+            else:
+                v = (rng.standard_normal(16) * 10.0 ** rng.integers(-6, 7)).astype(np.float32)
+            src.append(v)
+        scalars = [np.float32(rng.standard_normal() * 10.0 ** rng.integers(-3, 4)), np.float32(rng.uniform(0, 300))]
+        if name == "mcemaths_clamp_3_4":
+            scalars = sorted(scalars)
+        outs = []
+        for lib in (translated, hand):
+            bufs = [aligned(16) for _ in range(nbuf)]
+            for b, v in zip(bufs, src):
+                b[:] = v
+            r = call(lib, name, bufs, scalars)
+            outs.append((r, [b.view(np.uint32).copy() for b in bufs]))
+        (ra, ba), (rb, bb) = outs
+        assert ra == rb or (ra is not None and np.isnan(np.uint32(ra).view(np.float32)) and np.isnan(np.uint32(rb).view(np.float32))), (name, trial)
+        for x, y in zip(ba, bb):
+            assert np.array_equal(x, y), (name, trial)
+
+
+def test_reference_build_exports_the_whole_c_api(libs):
+    """The mechanical build carries every mcemaths_* routine of vector / matrix / quatern / matrxgl.cpp, not only the 26 of the hand file."""
+    translated, _ = libs
+    for name in ("mcemaths_make_proj_perspective", "mcemaths_make_rotation", "mcemaths_mat4ident", "mcemaths_minpos_3_4"):
+        assert hasattr(translated, name), name
