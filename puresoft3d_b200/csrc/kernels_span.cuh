@@ -457,21 +457,37 @@ PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candi
 			}
 		}
 	}
-	// whole-rectangle triangles: the warp appends one's id to its tiles, lane = every 32nd tile
+	// whole-rectangle triangles: the BLOCK appends one's id to its tiles, every thread four tiles per step, so that hundreds of the
+	// (returning) atomics are in flight instead of one lane's one (a 4096^2 shadow map's ground quad is 2 x 65 536 tiles: a
+	// millisecond per triangle when one warp did it, an atomic's round trip per 32 tiles)
+	if(bigPending)
 	{
-		uint32_t todo = __ballot_sync(PS_FULL, bigPending);
-		while(todo)
+		const uint32_t q = atomicAdd(&sTallCount, 0x10000u) >> 16;   // (the tall list's counter: low half tall survivors, high half big ones)
+		sTallList[q] = k;                                             // (the tall list is dead by now: phase S is over)
+		sTallExt[k][0] = rect0; sTallExt[k][1] = rect1; sTallExt[k][2] = wtri;
+	}
+	__syncthreads();
+	{
+		const uint32_t nBig = sTallCount >> 16;
+		for(uint32_t q = 0; q < nBig; q++)
 		{
-			const int src = __ffs(todo) - 1;
-			todo &= todo - 1;
-			const uint32_t r0 = __shfl_sync(PS_FULL, rect0, src), r1 = __shfl_sync(PS_FULL, rect1, src), t = __shfl_sync(PS_FULL, wtri, src);
+			const uint32_t kb = sTallList[q];
+			const uint32_t r0 = sTallExt[kb][0], r1 = sTallExt[kb][1], t = sTallExt[kb][2];
 			const int tx0 = (int)(r0 & 0xffff), tx1 = (int)(r0 >> 16), ty0 = (int)(r1 & 0xffff), ty1 = (int)(r1 >> 16);
 			const uint32_t w = (uint32_t)(tx1 - tx0 + 1), total = w * (uint32_t)(ty1 - ty0 + 1);
-			for(uint32_t i = (uint32_t)lane; i < total; i += 32)
+			for(uint32_t base = threadIdx.x; base < total; base += 4 * PS_GEOM_THREADS)
 			{
-				const uint32_t tile = (uint32_t)((ty0 + (int)(i / w)) * P.tilesX + tx0 + (int)(i % w));
-				const uint32_t at = atomicAdd(&P.tl.fill[tile], 1u);
-				if(at < P.tl.cap) P.tl.ids[(size_t)tile * P.tl.cap + at] = t;
+				uint32_t tile[4], at[4];
+#pragma unroll
+				for(int u = 0; u < 4; u++)
+				{
+					const uint32_t i = base + (uint32_t)u * PS_GEOM_THREADS;
+					tile[u] = i < total ? (uint32_t)((ty0 + (int)(i / w)) * P.tilesX + tx0 + (int)(i % w)) : 0xffffffffu;
+				}
+#pragma unroll
+				for(int u = 0; u < 4; u++) at[u] = tile[u] != 0xffffffffu ? atomicAdd(&P.tl.fill[tile[u]], 1u) : 0xffffffffu;
+#pragma unroll
+				for(int u = 0; u < 4; u++) if(at[u] < P.tl.cap) P.tl.ids[(size_t)tile[u] * P.tl.cap + at[u]] = t;
 			}
 		}
 	}
