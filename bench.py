@@ -288,7 +288,8 @@ def main():
         q_ext = torch.cuda.ExternalStream(q.deviceStream(), device=dev)
         q_comp = None
         if world > 1:
-            assert sortfirst.init_peer_composite(q, rank, world, dev)
+            if not sortfirst.init_peer_composite(q, rank, world, dev):
+                raise SystemExit("the second pipe's peer composite could not be set up although the first one's was")
             q_comp = sortfirst.Compositor(q, rank, world, dev, q_ext, peer=True)
             q.setRowBand(*q_comp.band)
         q_replay = scenes.compile_replay(q, sc, q_up)

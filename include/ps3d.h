@@ -226,7 +226,8 @@ int ps3d_vbo_all_gather(ps3d_pipe* p, int vbo);
  *                       every rank's blob to every rank by any host transport (one all-gather at start-up).
  *  ps3d_peer_import     blobs = world x PS3D_PEER_BLOB bytes in rank order. Ranks != 0 map rank 0's targets; from here on their
  *                       draws write rank 0's colour target (their own row band of it, ps3d_set_row_band) and their
- *                       ps3d_clear_colour is rank 0's business.
+ *                       ps3d_clear_colour is rank 0's business. (rank = world = 0, blobs = NULL undoes an import: for a rank whose
+ *                       peers could not map rank 0's targets and that falls back to another composite with them.)
  *  ps3d_composite_peer  behind every frame, on every rank: ranks != 0 publish "frame written" (release at system scope), rank 0
  *                       waits on its stream until every rank has. No rank overwrites a target rank 0 has not handed out again
  *                       (rank 0 hands it out with its next clear / draw into it, i.e. behind a read-back it enqueued).

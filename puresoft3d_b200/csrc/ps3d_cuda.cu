@@ -1763,10 +1763,20 @@ int ps3d_peer_import(ps3d_pipe* p, int rank, int world, const void* blobs)
 	TRACE();
 	cudaSetDevice(p->device);
 	SETTLE(p);
+	if(0 == world && !blobs)
+	{
+		// undo an import (a rank whose peers could not map rank 0's targets falls back to another composite with them)
+		CK(p, cudaStreamSynchronize(p->stream));
+		if(p->peer.active && p->peer.rank != 0)
+		{
+			cudaIpcCloseMemHandle(p->peer.display0[0]); cudaIpcCloseMemHandle(p->peer.display0[1]); cudaIpcCloseMemHandle(p->peer.flags0);
+		}
+		p->peer.active = false; p->peer.rank = 0; p->peer.world = 1; p->peer.needTake = false;
+		return PS3D_OK;
+	}
 	if(world < 1 || world > 64 || rank < 0 || rank >= world || !blobs) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "rank / world");
 	if(p->peer.active) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "peer targets already imported");
 	CK(p, cudaStreamSynchronize(p->stream));
-	p->peer.rank = rank; p->peer.world = world;
 	if(0 == rank)
 	{
 		p->peer.display0[0] = p->display[0]; p->peer.display0[1] = p->display[1]; p->peer.flags0 = p->peer.flagsOwn;
@@ -1775,10 +1785,18 @@ int ps3d_peer_import(ps3d_pipe* p, int rank, int world, const void* blobs)
 	{
 		cudaIpcMemHandle_t h[3];
 		memcpy(h, blobs, sizeof(h));                   // rank 0's blob comes first
-		CK(p, cudaIpcOpenMemHandle((void**)&p->peer.display0[0], h[0], cudaIpcMemLazyEnablePeerAccess));
-		CK(p, cudaIpcOpenMemHandle((void**)&p->peer.display0[1], h[1], cudaIpcMemLazyEnablePeerAccess));
-		CK(p, cudaIpcOpenMemHandle((void**)&p->peer.flags0, h[2], cudaIpcMemLazyEnablePeerAccess));
+		void* m[3] = { nullptr, nullptr, nullptr };
+		for(int i = 0; i < 3; i++)
+			if(cudaIpcOpenMemHandle(&m[i], h[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+			{
+				const cudaError_t e = cudaGetLastError();
+				for(int j = 0; j < i; j++) cudaIpcCloseMemHandle(m[j]);
+				p->err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e) + " (no peer access to rank 0's GPU?)";
+				return PS3D_ERR_DEVICE;
+			}
+		p->peer.display0[0] = (uint8_t*)m[0]; p->peer.display0[1] = (uint8_t*)m[1]; p->peer.flags0 = (PeerFlags*)m[2];
 	}
+	p->peer.rank = rank; p->peer.world = world;
 	p->peer.active = world > 1;
 	p->peer.needTake = true;
 	return PS3D_OK;

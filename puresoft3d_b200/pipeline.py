@@ -377,6 +377,10 @@ class PuresoftPipeline:
         buf = (C.c_uint8 * (self.PEER_BLOB * world)).from_buffer_copy(blobs)
         self._check(self._lib.ps3d_peer_import(self._h, int(rank), int(world), C.cast(buf, C.c_void_p)))
 
+    def peerReset(self):
+        """Undo peerImport (every rank does when one rank's import failed: fall back to another composite together)."""
+        self._check(self._lib.ps3d_peer_import(self._h, 0, 0, None))
+
     def compositePeer(self):
         """Behind every frame on every rank: 'my band is written' / rank 0 waits for every rank (include/ps3d.h)."""
         self._check(self._lib.ps3d_composite_peer(self._h))

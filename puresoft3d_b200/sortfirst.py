@@ -98,7 +98,14 @@ def init_peer_composite(pipe, rank, world, device):
         return False
     blobs = torch.empty(world * pipe.PEER_BLOB, dtype=torch.uint8, device=device)
     dist.all_gather_into_tensor(blobs, blob)
-    pipe.peerImport(rank, world, bytes(blobs.cpu().numpy()))
+    try:
+        pipe.peerImport(rank, world, bytes(blobs.cpu().numpy()))
+    except Exception:  # noqa: BLE001 — e.g. no peer access between two GPUs of the box
+        ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) != 1:
+        pipe.peerReset()
+        return False
     return True
 
 
