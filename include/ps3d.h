@@ -278,6 +278,14 @@ int ps3d_read_colour_async(ps3d_pipe* p, void* pinnedBgra, size_t pitchBytes);
 int ps3d_device_join(ps3d_pipe* p);
 /* number of kernels this pipe has launched since creation (bench.py's gpu_launches) */
 int ps3d_device_launch_count(ps3d_pipe* p, uint64_t* launches);
+/* Batches of small draws. Consecutive ps3d_draw_vao calls of at most 16384 triangles each, into the same targets with the same
+ * viewport and behaviour bits (any programmes that neither blend nor discard), are collected and run as ONE pass when the next
+ * call arrives that is not such a draw: their triangles are numbered in submission order across the draws, so depth and colour
+ * resolve exactly as if the draws had run one after the other (drawvao.cpp:78-96 ends before the next call starts), but a
+ * tile is loaded, walked and stored once for all of them. Uniforms and texture bindings are latched per draw at the call, as
+ * always. Errors of a collected draw's launch surface at the call that launches the batch. PS3D_BATCH=0 turns this off.
+ * ps3d_debug_batch_counts: batches launched / draws that ran inside one, since creation (tests, bench). */
+int ps3d_debug_batch_counts(ps3d_pipe* p, uint64_t* batches, uint64_t* draws);
 
 /* Per-kernel-class device timing with CUDA events recorded on the pipe's own stream (bench.py's roofline figures).
  * While enabled every draw brackets its geometry kernel, its binning kernels, its raster/tile kernel and its shade kernel with event pairs;

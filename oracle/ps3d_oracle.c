@@ -1494,6 +1494,7 @@ int ps3d_graph_launch(ps3d_pipe* p, int g) { (void)p; (void)g; return PS3D_ERR_U
 int ps3d_graph_destroy(ps3d_pipe* p, int g) { (void)p; (void)g; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_vbo_all_gather(ps3d_pipe* p, int vbo) { (void)p; (void)vbo; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_device_launch_count(ps3d_pipe* p, uint64_t* n) { (void)p; if(n) *n = 0; return PS3D_OK; }
+int ps3d_debug_batch_counts(ps3d_pipe* p, uint64_t* b, uint64_t* d) { (void)p; if(b) *b = 0; if(d) *d = 0; return PS3D_OK; }
 int ps3d_profile_enable(ps3d_pipe* p, int on) { (void)p; (void)on; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_profile_read(ps3d_pipe* p, ps3d_profile* out) { (void)p; (void)out; return PS3D_ERR_UNSUPPORTED; }
 int ps3d_host_approx_info(int* rcpBits, int* rsqrtBits) { *rcpBits = -1; *rsqrtBits = -1; return PS3D_OK; } /* the hardware instructions themselves */

@@ -620,6 +620,7 @@ int ps3d_graph_launch(ps3d_pipe*, int) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_graph_destroy(ps3d_pipe*, int) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_vbo_all_gather(ps3d_pipe*, int) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_device_launch_count(ps3d_pipe*, uint64_t* n) { if(n) *n = 0; return PS3D_OK; }
+int ps3d_debug_batch_counts(ps3d_pipe*, uint64_t* b, uint64_t* d) { if(b) *b = 0; if(d) *d = 0; return PS3D_OK; }
 int ps3d_profile_enable(ps3d_pipe*, int) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_profile_read(ps3d_pipe*, ps3d_profile*) { return PS3D_ERR_UNSUPPORTED; }
 int ps3d_host_approx_info(int* rcpBits, int* rsqrtBits) { *rcpBits = -1; *rsqrtBits = -1; return PS3D_OK; } // the hardware instructions themselves

@@ -128,6 +128,7 @@ PROTOTYPES = {
     "ps3d_graph_launch": (C.c_int, [_P, C.c_int]),
     "ps3d_graph_destroy": (C.c_int, [_P, C.c_int]),
     "ps3d_device_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "ps3d_debug_batch_counts": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ps3d_profile_enable": (C.c_int, [_P, C.c_int]),
     "ps3d_profile_read": (C.c_int, [_P, C.POINTER(Profile)]),
     "ps3d_host_approx_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -585,6 +585,48 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_span_kernel(const __grid
 	geomFinish(P, acc);
 }
 
+// ---- batches of small draws (ps3d_cuda.cu: Batch) ---------------------------------------------------------------------------
+// Consecutive small draws into the same targets with the same behaviour bits share ONE pass: their triangles are numbered in
+// submission order across the draws (every draw starts a new block of PS_GEOM_THREADS ids, so a block of ids belongs to one
+// draw), one geometry launch per programme present fills the shared span records and tile lists, one plan / sort / raster pass
+// resolves depth in that order (which is the order the draws would have run in: drawvao.cpp:78-96 ends before the next call
+// starts), one shade launch per programme takes its own survivors. What differs from draw to draw — vertex streams, latched
+// uniforms, textures — sits in global memory, one DrawParams per draw (its stream pointers and triangle count shifted by the
+// draw's first id, so that the functors index them with the batch-wide id).
+struct BatchView
+{
+	const DrawParams* items;    // per draw
+	const uint32_t* blockDraw;  // per block of ids: draw | programme group << 16
+	const uint32_t* blockList;  // the blocks of this launch's programme group
+	uint32_t group;
+};
+
+template<class PROG>
+__global__ void __launch_bounds__(PS_GEOM_THREADS) geom_span_multi_kernel(const BatchView B)
+{
+	const uint32_t gb = B.blockList[blockIdx.x];
+	const DrawParams& P = B.items[B.blockDraw[gb] & 0xffffu];
+	const uint32_t tri = gb * PS_GEOM_THREADS + threadIdx.x;
+	uint32_t stageOff[16];
+#pragma unroll
+	for(int s = 0; s < 16; s++) stageOff[s] = 0;
+	GeomAcc acc = { 0, 0, 0, 0, 0 };
+	geomBatch<PROG, 0>(P, tri, threadIdx.x, tri < P.ntris, nullptr, stageOff, acc);
+	geomFinish(P, acc);
+}
+
+// one draw's DrawParams from the launch's parameter space into the batch's table (a kernel, not a copy: it can be recorded into a
+// captured frame with its source), and the draw's blocks into the block tables
+__global__ void __launch_bounds__(256) batch_item_kernel(const __grid_constant__ DrawParams item, DrawParams* dst, uint32_t* blockDraw, uint32_t* blockList,
+                                                        uint32_t firstBlock, uint32_t nBlocks, uint32_t listAt, uint32_t tag)
+{
+	static_assert(0 == sizeof(DrawParams) % 8, "copied as 8-byte words");
+	const uint2* src = (const uint2*)&item;
+	uint2* d = (uint2*)dst;
+	for(uint32_t i = threadIdx.x; i < sizeof(DrawParams) / 8; i += blockDim.x) d[i] = src[i];
+	for(uint32_t j = threadIdx.x; j < nBlocks; j += blockDim.x) { blockDraw[firstBlock + j] = tag; blockList[listAt + j] = firstBlock + j; }
+}
+
 // ======================================================================================================================
 // plan: lengths, verdict on the speculated capacities, tiles by descending list length, the draw's counters
 // ======================================================================================================================
@@ -1253,8 +1295,10 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK, MINB) tile_raster_spa
 // varyings): the stream words are read two iterations ahead and the span record one ahead, so only the last level's latency
 // is exposed. (Tried and dropped: that level staged through shared memory by 16-byte asynchronous copies, all issued together —
 // LDGSTS neither merges the lanes that name the same triangle nor uses L1, the kernel went 0.205 -> 0.355 ms.)
-template<class PROG, int MINB>
-__global__ void __launch_bounds__(PS_SHADE_THREADS, MINB) shade_span_kernel(const __grid_constant__ DrawParams P, const SurvivorStream2 Q)
+// MULTI: a batch of draws (BatchView above): this launch shades the survivors of its programme group's draws, with that draw's
+// uniforms, textures and varyings.
+template<class PROG, int MINB, bool MULTI = false>
+__global__ void __launch_bounds__(PS_SHADE_THREADS, MINB) shade_span_kernel(const __grid_constant__ DrawParams P, const SurvivorStream2 Q, const BatchView B)
 {
 	constexpr int NV = PROG::NV;
 	if(*P.poison) return;
@@ -1276,6 +1320,7 @@ __global__ void __launch_bounds__(PS_SHADE_THREADS, MINB) shade_span_kernel(cons
 	{
 		uint32_t xy;
 		F4 frag[NV > 0 ? NV : 1];
+		const DrawParams* D = &P;                                          // MULTI: the survivor's draw
 		if(NV > 0)
 		{
 			xy = xy0;
@@ -1290,9 +1335,15 @@ __global__ void __launch_bounds__(PS_SHADE_THREADS, MINB) shade_span_kernel(cons
 			}
 			if(PS_SV_HOLE == xy) continue;                                 // a reserved slot no survivor took
 			const uint32_t tri = (uint32_t)A.w & 0xffffffu;
+			if(MULTI)
+			{
+				const uint32_t bd = __ldg(B.blockDraw + tri / PS_GEOM_THREADS);
+				if((bd >> 16) != B.group) continue;                          // another programme's survivor
+				D = B.items + (bd & 0xffffu);
+			}
 			const uint4* src = (const uint4*)(P.hdr + tri);
 			const uint4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
-			const F4* v = P.vary + (size_t)tri * 3 * NV;
+			const F4* v = D->vary + (size_t)tri * 3 * NV;
 			const int x = (int)(xy & 0x1fff), y = (int)((xy >> 13) & 0x1fff);
 			const int left = A.x, right = A.y, e = (int)((uint32_t)A.w >> 24);
 			const float vx[3] = { __uint_as_float(q0.x), __uint_as_float(q0.z), __uint_as_float(q1.x) };
@@ -1327,11 +1378,22 @@ __global__ void __launch_bounds__(PS_SHADE_THREADS, MINB) shade_span_kernel(cons
 			for(int q = x1; q < x; q++) IP::stepForward(vStart, vStep, 1);    // interp.cpp:88, one rounded add per pixel
 			IP::correctInterpolation(frag, vStart, inv);
 		}
-		else { xy = Q.xy[i]; if(PS_SV_HOLE == xy) continue; }
+		else
+		{
+			xy = Q.xy[i];
+			if(PS_SV_HOLE == xy) continue;
+			if(MULTI)
+			{
+				const uint32_t tri = P.sp.rec[Q.span[i]].triEdges & 0xffffffu;
+				const uint32_t bd = __ldg(B.blockDraw + tri / PS_GEOM_THREADS);
+				if((bd >> 16) != B.group) continue;
+				D = B.items + (bd & 0xffffu);
+			}
+		}
 		const int x = (int)(xy & 0x1fff), y = (int)((xy >> 13) & 0x1fff);
 		FragmentProcessorOutput out;
 		out.discarded = false; out.wrote = false; out.blendable = false; out.bgra = 0;
-		PROG::F::process(frag, out, P);                                      // fragthrd.cpp:231
+		PROG::F::process(frag, out, *D);                                     // fragthrd.cpp:231
 		if(P.cap && x < P.capW && y < P.capH) atomicAdd(&P.cap[(size_t)y * P.capW + x], 1u);
 		if(out.wrote && (xy & PS_SV_WINNER) && y < P.colour.height && x < P.colour.width)
 		{

@@ -42,6 +42,8 @@ typedef void (*LaunchGeom)(const DrawParams&, cudaStream_t);
 typedef void (*LaunchTile)(const DrawParams&, const uint32_t*, const uint32_t*, cudaStream_t);
 typedef void (*LaunchShade)(const DrawParams&, const SurvivorStream&, cudaStream_t);
 typedef void (*LaunchShade2)(const DrawParams&, const SurvivorStream2&, cudaStream_t);
+typedef void (*LaunchGeomMulti)(const BatchView&, unsigned, cudaStream_t);
+typedef void (*LaunchShadeMulti)(const DrawParams&, const SurvivorStream2&, const BatchView&, cudaStream_t);
 
 struct ProgEntry
 {
@@ -57,6 +59,8 @@ struct ProgEntry
 	LaunchShade shade;
 	LaunchGeom geomSpan;        // span path (kernels_span.cuh)
 	LaunchShade2 shadeSpan;
+	LaunchGeomMulti geomSpanMulti;   // batches of small draws
+	LaunchShadeMulti shadeSpanMulti;
 };
 
 // PS3D_TILE_PATH=immediate|ordered|split forces one tile path for every draw (A/B checks); default: chosen per draw
@@ -210,9 +214,28 @@ template<class PROG> void launchShadeSpan(const DrawParams& P, const SurvivorStr
 		                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shade_span_kernel<PROG, 5>, PS_SHADE_THREADS, 0));
 		if(e != cudaSuccess || perSM <= 0) perSM = 4;
 	}
-	if(2 == minb) shade_span_kernel<PROG, 8><<<sms * perSM, PS_SHADE_THREADS, 0, s>>>(P, Q);
-	else if(1 == minb) shade_span_kernel<PROG, 7><<<sms * perSM, PS_SHADE_THREADS, 0, s>>>(P, Q);
-	else shade_span_kernel<PROG, 5><<<sms * perSM, PS_SHADE_THREADS, 0, s>>>(P, Q);
+	const BatchView none = { nullptr, nullptr, nullptr, 0 };
+	if(2 == minb) shade_span_kernel<PROG, 8><<<sms * perSM, PS_SHADE_THREADS, 0, s>>>(P, Q, none);
+	else if(1 == minb) shade_span_kernel<PROG, 7><<<sms * perSM, PS_SHADE_THREADS, 0, s>>>(P, Q, none);
+	else shade_span_kernel<PROG, 5><<<sms * perSM, PS_SHADE_THREADS, 0, s>>>(P, Q, none);
+}
+// ---- a batch of small draws (kernels_span.cuh: BatchView): one geometry and one shade launch per programme present ------------
+template<class PROG> void launchGeomSpanMulti(const BatchView& B, unsigned blocks, cudaStream_t s)
+{
+	geom_span_multi_kernel<PROG><<<blocks, PS_GEOM_THREADS, 0, s>>>(B);
+}
+template<class PROG> void launchShadeSpanMulti(const DrawParams& P, const SurvivorStream2& Q, const BatchView& B, cudaStream_t s)
+{
+	static int perSMs[PS_MAX_DEVICES] = { 0 }, smss[PS_MAX_DEVICES] = { 0 };
+	const int dev = currentDevice();
+	int& perSM = perSMs[dev];
+	int& sms = smss[dev];
+	if(0 == perSM)
+	{
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shade_span_kernel<PROG, 7, true>, PS_SHADE_THREADS, 0) != cudaSuccess || perSM <= 0) perSM = 4;
+	}
+	shade_span_kernel<PROG, 7, true><<<sms * perSM, PS_SHADE_THREADS, 0, s>>>(P, Q, B);
 }
 
 template<class PROG> ProgEntry makeEntry(int fnV, int fnI, int fnF)
@@ -232,6 +255,8 @@ template<class PROG> ProgEntry makeEntry(int fnV, int fnI, int fnF)
 	e.shade = launchShade<PROG>;
 	e.geomSpan = launchGeomSpan<PROG>;
 	e.shadeSpan = launchShadeSpan<PROG>;
+	e.geomSpanMulti = launchGeomSpanMulti<PROG>;
+	e.shadeSpanMulti = launchShadeSpanMulti<PROG>;
 	return e;
 }
 
@@ -339,6 +364,14 @@ struct ps3d_pipe
 	uint32_t* spanCountDev;
 	size_t spanHigh, listHigh;     // high-water marks of earlier draws: the next speculation
 	std::vector<uint8_t> vaoLegacy; // VAOs whose last draw needed the first path (a tile list too long for the shared-memory sort)
+	// batches of small draws (kernels_span.cuh: BatchView): `batch` collects draws until something other than a like draw arrives,
+	// `flight` is the batch whose launches are on the stream and whose verdict settle() has yet to read
+	struct BatchDraw { DrawParams P; const ProgEntry* pe; int vao; uint32_t firstBlock, nBlocks; };
+	struct Batch { std::vector<BatchDraw> draws; uint32_t blocks; void clear() { draws.clear(); blocks = 0; } };
+	Batch batch, flight;
+	DevBuf<DrawParams> batchItems;
+	DevBuf<uint32_t> batchBlockDraw, batchBlockList;
+	uint64_t batchesLaunched, drawsBatched;
 	// sort-first composite over peer memory (ps3d_peer_*): rank 0's display targets and flag block mapped into every rank
 	struct Peer
 	{
@@ -367,7 +400,7 @@ struct ps3d_pipe
 	cudaEvent_t scanEvent;
 	bool speculate;
 	size_t pairHigh, survivorHigh;   // high-water marks of earlier draws: the next speculation
-	struct Pending { bool valid; DrawParams P; const ProgEntry* pe; int path; bool radix; bool span; bool tailLaunched; int vao; } pending;
+	struct Pending { bool valid; DrawParams P; const ProgEntry* pe; int path; bool radix; bool span; bool tailLaunched; int vao; bool multi; } pending;
 	ps3d_stats stats;
 	uint32_t* capDev;
 	int capW, capH;
@@ -415,8 +448,9 @@ struct ProfScope
 
 static int settle(ps3d_pipe* p);
 static int peerFirstWrite(ps3d_pipe* p);
-static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe);
-static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao, size_t spans, size_t longest, size_t survivors);
+static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe, bool multi);
+static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao, size_t spans, size_t longest, size_t survivors, bool multi = false);
+static int flushBatch(ps3d_pipe* p);
 static int enqueueLegacy(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int path, int vao);
 
 // ---- NCCL, bound at run time ------------------------------------------------------------------------------------------
@@ -462,7 +496,8 @@ static const NcclApi* ncclApi()
 	return api.lib ? &api : nullptr;
 }
 #define NK(p, call) do { int r_ = (call); if(r_ != 0) { const NcclApi* a_ = ncclApi(); (p)->err = std::string(#call) + ": " + ((a_ && a_->GetErrorString) ? a_->GetErrorString(r_) : "nccl error"); return PS3D_ERR_DEVICE; } } while(0)
-#define SETTLE(p) do { int rc_ = settle(p); if(rc_) return rc_; } while(0)
+// (collected small draws are launched first: whatever calls this is about to touch the stream, the targets or device memory)
+#define SETTLE(p) do { int rc_ = flushBatch(p); if(rc_) return rc_; rc_ = settle(p); if(rc_) return rc_; } while(0)
 
 static int fail(ps3d_pipe* p, int code, const char* msg) { p->err = msg; return code; }
 static void freeVbo(Vbo& v)
@@ -628,21 +663,36 @@ static int settle(ps3d_pipe* p)
 		if(r.spans > p->spanHigh) p->spanHigh = r.spans;
 		if(r.longest > p->listHigh) p->listHigh = r.longest;
 		if(r.fragBound > p->survivorHigh) p->survivorHigh = (size_t)r.fragBound;
+		const bool multi = p->pending.multi;
 		if(!r.bad)
 		{
 			if(p->pending.tailLaunched) return PS3D_OK;
-			return launchSpanTail(p, P, pe);
+			return launchSpanTail(p, P, pe, multi);
 		}
 		CK(p, cudaMemsetAsync(p->poisonDev, 0, 4, p->stream));
 		const int vao = p->pending.vao;
 		if(r.longest > PS_SORT_LIMIT || r.fragBound >= 0xfffffff0ull || r.spans >= 0xfffffff0u)
 		{
+			const int path = r.fragBound >= 0xfffffff0ull ? 1 : 2;
+			if(multi)
+			{
+				// a batch whose lists outgrew the shared-memory sort: its draws one by one down the first path (nothing of the batch
+				// has touched the targets: the poisoned tail did not run)
+				const ps3d_pipe::Batch B = p->flight;
+				for(const ps3d_pipe::BatchDraw& d : B.draws)
+				{
+					int rc = enqueueLegacy(p, d.P, d.pe, path, d.vao);
+					if(!rc) rc = settle(p);
+					if(rc) return rc;
+				}
+				return PS3D_OK;
+			}
 			if(vao >= 0) { if((int)p->vaoLegacy.size() <= vao) p->vaoLegacy.resize(vao + 1, 0); p->vaoLegacy[vao] = 1; }
 			const DrawParams P2 = P;
-			return enqueueLegacy(p, P2, pe, r.fragBound >= 0xfffffff0ull ? 1 : 2, vao);
+			return enqueueLegacy(p, P2, pe, path, vao);
 		}
 		const DrawParams P2 = P;
-		return enqueueSpan(p, P2, pe, vao, r.spans, r.longest, (size_t)r.fragBound);
+		return enqueueSpan(p, P2, pe, vao, r.spans, r.longest, (size_t)r.fragBound, multi);
 	}
 	if(r.pairs > p->pairHigh) p->pairHigh = r.pairs;
 	if(2 == path && r.fragBound > p->survivorHigh) p->survivorHigh = (size_t)r.fragBound;
@@ -689,7 +739,15 @@ static int peerFirstWrite(ps3d_pipe* p)
 	return PS3D_OK;
 }
 
-static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe)
+// the programme groups of the batch in flight: distinct programmes in order of first appearance
+static void batchGroups(const ps3d_pipe::Batch& B, std::vector<const ProgEntry*>& groups)
+{
+	groups.clear();
+	for(const ps3d_pipe::BatchDraw& d : B.draws)
+		if(std::find(groups.begin(), groups.end(), d.pe) == groups.end()) groups.push_back(d.pe);
+}
+
+static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe, bool multi)
 {
 	const uint32_t ntiles = (uint32_t)(P.tilesX * P.tilesY);
 	SurvivorStream2 Q;
@@ -721,6 +779,19 @@ static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe
 		p->launches++;
 	}
 	{ const int rc = peerFirstWrite(p); if(rc) return rc; }
+	if(multi)
+	{
+		ProfScope ps(p, CLS_SHADE);
+		std::vector<const ProgEntry*> groups;
+		batchGroups(p->flight, groups);
+		for(size_t g = 0; g < groups.size(); g++)
+		{
+			const BatchView V = { p->batchItems.p, p->batchBlockDraw.p, p->batchBlockList.p, (uint32_t)g };
+			groups[g]->shadeSpanMulti(P, Q, V, p->stream);
+			p->launches++;
+		}
+	}
+	else
 	{
 		ProfScope ps(p, CLS_SHADE);
 		pe->shadeSpan(P, Q, p->stream);
@@ -732,13 +803,23 @@ static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe
 
 // The span path (kernels_span.cuh). spans / longest / survivors = 0: capacities speculated from the high-water marks of earlier
 // draws; otherwise the exact sizes a first attempt reported (settle()).
-static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao, size_t spans, size_t longest, size_t survivors)
+// multi: P is the batch-wide DrawParams of p->flight (ps3d_pipe::Batch), ntris = its blocks x PS_GEOM_THREADS ids.
+static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao, size_t spans, size_t longest, size_t survivors, bool multi)
 {
 	const uint32_t ntiles = (uint32_t)(P.tilesX * P.tilesY);
 	const size_t ntris = P.ntris;
 	const bool exact = spans || longest || survivors;
 	CK(p, p->hdr.ensure(ntris));
-	CK(p, p->vary.ensure(ntris * 3 * (size_t)(pe->nv > 0 ? pe->nv : 1)));
+	size_t varyCount = ntris * 3 * (size_t)(pe->nv > 0 ? pe->nv : 1);
+	if(multi)
+	{
+		varyCount = 1;
+		for(const ps3d_pipe::BatchDraw& d : p->flight.draws) varyCount += (size_t)d.nBlocks * PS_GEOM_THREADS * 3 * (size_t)d.pe->nv;
+		CK(p, p->batchItems.ensure(p->flight.draws.size()));
+		CK(p, p->batchBlockDraw.ensure(p->flight.blocks));
+		CK(p, p->batchBlockList.ensure(p->flight.blocks));
+	}
+	CK(p, p->vary.ensure(varyCount));
 	CK(p, p->spTri.ensure(ntris));
 	// (a frame being captured cannot allocate: it takes the buffers the same frame ran in a moment ago as they are — they hold
 	// its high-water marks — instead of asking for the usual 25 % of head-room)
@@ -773,13 +854,58 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 	P.sp.rec = p->spRec.p; P.sp.tri = p->spTri.p; P.sp.count = p->spanCountDev;
 	P.sp.capacity = (uint32_t)std::min<size_t>(p->spRec.cap, 0xfffffff0u);
 	P.tl.fill = p->tlFill.p; P.tl.len = p->tlLen.p; P.tl.ids = p->tlIds.p; P.tl.cap = (uint32_t)listCap;
+	if(multi)
 	{
+		// every draw's DrawParams into the table (shifted by its first id), its blocks into the block tables; then one geometry
+		// launch per programme over that programme's blocks
 		ProfScope ps(p, CLS_GEOM);
-		pe->geomSpan(P, p->stream);
-		p->launches++;
+		std::vector<const ProgEntry*> groups;
+		batchGroups(p->flight, groups);
+		std::vector<uint32_t> groupBlocks(groups.size(), 0), groupAt(groups.size(), 0), groupFill(groups.size(), 0);
+		for(const ps3d_pipe::BatchDraw& d : p->flight.draws)
+			groupBlocks[std::find(groups.begin(), groups.end(), d.pe) - groups.begin()] += d.nBlocks;
+		for(size_t g = 1; g < groups.size(); g++) groupAt[g] = groupAt[g - 1] + groupBlocks[g - 1];
+		size_t varyAt = 0;
+		for(size_t i = 0; i < p->flight.draws.size(); i++)
+		{
+			const ps3d_pipe::BatchDraw& d = p->flight.draws[i];
+			const size_t g = std::find(groups.begin(), groups.end(), d.pe) - groups.begin();
+			const size_t firstTri = (size_t)d.firstBlock * PS_GEOM_THREADS;
+			DrawParams item = P;                                    // targets, buffers, capacities: the batch's
+			for(int sl = 0; sl < 16; sl++)
+			{
+				item.stride[sl] = d.P.stride[sl];
+				item.slot[sl] = d.P.slot[sl] ? d.P.slot[sl] - firstTri * 3 * d.P.stride[sl] : nullptr;
+			}
+			memcpy(item.u, d.P.u, sizeof(item.u));
+			memcpy(item.tex, d.P.tex, sizeof(item.tex));
+			item.ntris = (uint32_t)(firstTri + d.P.ntris);
+			item.vary = p->vary.p + varyAt - firstTri * 3 * (size_t)d.pe->nv;
+			varyAt += (size_t)d.nBlocks * PS_GEOM_THREADS * 3 * (size_t)d.pe->nv;
+			batch_item_kernel<<<1, 256, 0, p->stream>>>(item, p->batchItems.p + i, p->batchBlockDraw.p, p->batchBlockList.p, d.firstBlock, d.nBlocks,
+			                                           groupAt[g] + groupFill[g], (uint32_t)i | ((uint32_t)g << 16));
+			groupFill[g] += d.nBlocks;
+			p->launches++;
+		}
+		for(size_t g = 0; g < groups.size(); g++)
+		{
+			const BatchView V = { p->batchItems.p, p->batchBlockDraw.p, p->batchBlockList.p + groupAt[g], (uint32_t)g };
+			groups[g]->geomSpanMulti(V, groupBlocks[g], p->stream);
+			p->launches++;
+		}
+		CK(p, cudaGetLastError());
+		for(const ps3d_pipe::BatchDraw& d : p->flight.draws) { const int rc = recordVboReads(p, d.vao); if(rc) return rc; }
 	}
-	CK(p, cudaGetLastError());
-	{ const int rc = recordVboReads(p, vao); if(rc) return rc; }
+	else
+	{
+		{
+			ProfScope ps(p, CLS_GEOM);
+			pe->geomSpan(P, p->stream);
+			p->launches++;
+		}
+		CK(p, cudaGetLastError());
+		{ const int rc = recordVboReads(p, vao); if(rc) return rc; }
+	}
 	{
 		ProfScope ps(p, CLS_BIN);
 		tile_plan_kernel<<<1, 1024, 0, p->stream>>>(P.tl, ntiles, p->statsDev, p->spanCountDev, P.sp.capacity,
@@ -791,17 +917,55 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 	{
 		// a captured frame cannot be judged by the host draw by draw: its tail is guarded by the poison word as always, and a
 		// replay that did not fit is reported through DrawReport::sticky at the next ps3d_finish
-		const int rc = launchSpanTail(p, P, pe);
+		const int rc = launchSpanTail(p, P, pe, multi);
 		return rc;
 	}
 	CK(p, cudaEventRecord(p->scanEvent, p->stream));
 	p->pending.valid = true; p->pending.P = P; p->pending.pe = pe; p->pending.path = 2; p->pending.span = true; p->pending.vao = vao;
+	p->pending.multi = multi;
 	p->pending.tailLaunched = false;
 	if(!p->speculate && !exact) return settle(p);      // sizes checked on the host before anything else is enqueued
 	p->pending.tailLaunched = true;
-	const int rc = launchSpanTail(p, P, pe);
+	const int rc = launchSpanTail(p, P, pe, multi);
 	if(rc) { p->pending.valid = false; return rc; }
 	return PS3D_OK;
+}
+
+// PS3D_BATCH=0: every draw is launched as it is submitted (A/B runs)
+static bool batchingOn() { static int on = -1; if(on < 0) { const char* e = getenv("PS3D_BATCH"); on = (e && e[0] == '0') ? 0 : 1; } return on == 1; }
+#define PS_BATCH_DRAW_TRIS 16384u     // a draw with more triangles than this fills the GPU by itself
+#define PS_BATCH_MAX_DRAWS 1024u
+#define PS_BATCH_MAX_BLOCKS 32768u
+
+// a draw can join the batch being collected: same targets, viewport, band and behaviour bits (any programme of the span path)
+static bool batchTakes(const ps3d_pipe* p, const DrawParams& P)
+{
+	if(p->batch.draws.empty()) return true;
+	const DrawParams& A = p->batch.draws[0].P;
+	return A.behavior == P.behavior && A.vpW == P.vpW && A.vpH == P.vpH && A.band0 == P.band0 && A.band1 == P.band1 && A.cap == P.cap
+	    && 0 == memcmp(&A.colour, &P.colour, sizeof(A.colour)) && 0 == memcmp(&A.depth, &P.depth, sizeof(A.depth))
+	    && p->batch.draws.size() < PS_BATCH_MAX_DRAWS && p->batch.blocks + (P.ntris + PS_GEOM_THREADS - 1) / PS_GEOM_THREADS <= PS_BATCH_MAX_BLOCKS;
+}
+
+// Launches the collected draws: one alone as any draw, several as one batch (kernels_span.cuh: BatchView).
+static int flushBatch(ps3d_pipe* p)
+{
+	if(p->batch.draws.empty()) return PS3D_OK;
+	{ const int rc = settle(p); if(rc) { p->batch.clear(); return rc; } }   // the verdict of what is on the stream first
+	if(1 == p->batch.draws.size())
+	{
+		const ps3d_pipe::BatchDraw d = p->batch.draws[0];
+		p->batch.clear();
+		return enqueueSpan(p, d.P, d.pe, d.vao, 0, 0, 0);
+	}
+	p->flight.draws.swap(p->batch.draws);
+	p->flight.blocks = p->batch.blocks;
+	p->batch.clear();
+	DrawParams P = p->flight.draws[0].P;
+	P.ntris = p->flight.blocks * PS_GEOM_THREADS;
+	for(int sl = 0; sl < 16; sl++) { P.slot[sl] = nullptr; P.stride[sl] = 0; }
+	p->batchesLaunched++; p->drawsBatched += p->flight.draws.size();
+	return enqueueSpan(p, P, p->flight.draws[0].pe, -1, 0, 0, 0, true);
 }
 
 // The first path (kernels.cuh): geometry with per-thread row walks, counted binning (tile scan + fill + sort), tile kernels that
@@ -871,7 +1035,7 @@ static int enqueueLegacy(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int pa
 		return launchTail(p, P, pe, path, false);
 	}
 	CK(p, cudaEventRecord(p->scanEvent, p->stream));
-	p->pending.valid = true; p->pending.P = P; p->pending.pe = pe; p->pending.path = path; p->pending.span = false; p->pending.tailLaunched = true; p->pending.vao = vao;
+	p->pending.valid = true; p->pending.P = P; p->pending.pe = pe; p->pending.path = path; p->pending.span = false; p->pending.tailLaunched = true; p->pending.vao = vao; p->pending.multi = false;
 	if(!speculate) return settle(p);          // exact sizes after a host sync in the middle of the draw
 	int rc = launchTail(p, P, pe, path, false);
 	if(rc) { p->pending.valid = false; return rc; }
@@ -935,6 +1099,7 @@ int ps3d_create(int width, int height, int device, ps3d_pipe** out)
 	ok = ok && cudaMalloc((void**)&p->peer.ctr, sizeof(PeerCounters)) == cudaSuccess;
 	if(ok) { cudaMemsetAsync(p->peer.flagsOwn, 0, sizeof(PeerFlags), p->stream); cudaMemsetAsync(p->peer.ctr, 0, sizeof(PeerCounters), p->stream); }
 	p->spanHigh = p->listHigh = 0;
+	p->batch.clear(); p->flight.clear(); p->batchesLaunched = p->drawsBatched = 0; p->pending.multi = false;
 	p->pending.span = false; p->pending.tailLaunched = false; p->pending.vao = -1;
 	if(ok)
 	{
@@ -982,6 +1147,7 @@ int ps3d_destroy(ps3d_pipe* p)
 		cudaGetLastError();
 		p->capturing = false; g_capturing = false;
 	}
+	p->batch.clear();                                  // draws nobody asked the result of
 	settle(p);
 	cudaStreamSynchronize(p->stream);
 	for(Texture* t : p->textures) if(t) { for(int i = 0; i < 6; i++) if(t->layer[i]) cudaFree(t->layer[i]); delete t; }
@@ -997,6 +1163,7 @@ int ps3d_destroy(ps3d_pipe* p)
 		cudaIpcCloseMemHandle(p->peer.display0[0]); cudaIpcCloseMemHandle(p->peer.display0[1]); cudaIpcCloseMemHandle(p->peer.flags0);
 	}
 	cudaFree(p->peer.flagsOwn); cudaFree(p->peer.ctr);
+	p->batchItems.release(); p->batchBlockDraw.release(); p->batchBlockList.release();
 	p->spRec.release(); p->spTri.release(); p->tlFill.release(); p->tlLen.release(); p->tlIds.release();
 	p->sv2Span.release(); p->sv2XY.release(); p->sv2Inv.release();
 	p->svTri.release(); p->svMisc.release(); p->svWinner.release(); p->svLeft.release(); p->svRight.release(); p->svInv.release();
@@ -1411,7 +1578,6 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	TRACE();
 	(void)callerThread;
 	cudaSetDevice(p->device);
-	SETTLE(p);
 	if(p->curProg < 0 || vao < 0 || vao >= (int)p->vaos.size() || !p->vaos[vao].alive) return PS3D_OK; // drawvao.cpp:12-15
 	const Prog pg = p->progs[p->curProg];
 	if(pg.vp < 0) return PS3D_OK;
@@ -1492,6 +1658,17 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	if(2 == path && (P.vpW > 8191 || P.vpH > 8191)) { path = 1; span = false; }      // the survivor record packs x and y in 13 bits each
 	if(radixBinningForced() || ntris >= PS_SPAN_MAX_TRIS) span = false;
 	if(span && vao < (int)p->vaoLegacy.size() && p->vaoLegacy[vao]) span = false;
+	// small draws of the span path are collected: consecutive ones into the same targets run as one batch (flushBatch)
+	if(span && batchingOn() && p->speculate && !p->profiling && ntris <= PS_BATCH_DRAW_TRIS && 0 == P.band0 && P.band1 >= P.vpH)
+	{
+		if(!batchTakes(p, P)) { const int rc = flushBatch(p); if(rc) return rc; }
+		ps3d_pipe::BatchDraw d;
+		d.P = P; d.pe = pe; d.vao = vao; d.firstBlock = p->batch.blocks; d.nBlocks = (uint32_t)((ntris + PS_GEOM_THREADS - 1) / PS_GEOM_THREADS);
+		p->batch.draws.push_back(d);
+		p->batch.blocks += d.nBlocks;
+		return PS3D_OK;
+	}
+	SETTLE(p);
 	if(span) return enqueueSpan(p, P, pe, vao, 0, 0, 0);
 	return enqueueLegacy(p, P, pe, path, vao);
 }
@@ -1839,6 +2016,7 @@ int ps3d_graph_end(ps3d_pipe* p, int* graph)
 	TRACE();
 	cudaSetDevice(p->device);
 	if(!p->capturing) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "no frame is being captured");
+	const int flushed = flushBatch(p);                 // small draws still being collected belong to the frame
 	p->capturing = false; g_capturing = false;
 	cudaGraph_t g = nullptr;
 	const cudaError_t e = cudaStreamEndCapture(p->stream, &g);
@@ -1849,6 +2027,7 @@ int ps3d_graph_end(ps3d_pipe* p, int* graph)
 	G.back = p->capBack; G.backAfter = p->back;
 	p->back = p->capBack;
 	G.vaos = p->capVaos; G.alive = true; G.exec = nullptr;
+	if(flushed) { if(g) cudaGraphDestroy(g); cudaGetLastError(); return flushed; }
 	if(e != cudaSuccess || !g) { cudaGetLastError(); p->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e); return PS3D_ERR_DEVICE; }
 	const cudaError_t e2 = cudaGraphInstantiate(&G.exec, g, 0);
 	cudaGraphDestroy(g);
@@ -1913,6 +2092,7 @@ int ps3d_device_colour_ptr(ps3d_pipe* p, void** devPtr, size_t* pitch) { SETTLE(
 int ps3d_device_depth_ptr(ps3d_pipe* p, void** devPtr, size_t* pitch) { SETTLE(p); *devPtr = p->defaultDepth; *pitch = (size_t)p->depthScanline; return PS3D_OK; }
 int ps3d_device_stream(ps3d_pipe* p, void** s) { SETTLE(p); *s = (void*)p->stream; return PS3D_OK; }
 int ps3d_device_launch_count(ps3d_pipe* p, uint64_t* n) { *n = p->launches; return PS3D_OK; }
+int ps3d_debug_batch_counts(ps3d_pipe* p, uint64_t* b, uint64_t* d) { if(b) *b = p->batchesLaunched; if(d) *d = p->drawsBatched; return PS3D_OK; }
 
 int ps3d_profile_enable(ps3d_pipe* p, int on)
 {

@@ -417,6 +417,12 @@ class PuresoftPipeline:
         self._lib.ps3d_host_approx_info(C.byref(a), C.byref(b))
         return a.value, b.value
 
+    def debugBatchCounts(self):
+        """(batches of small draws launched, draws that ran inside one) since creation — include/ps3d.h."""
+        b, d = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.ps3d_debug_batch_counts(self._h, C.byref(b), C.byref(d)))
+        return int(b.value), int(d.value)
+
     def deviceLaunchCount(self):
         n = C.c_uint64()
         self._check(self._lib.ps3d_device_launch_count(self._h, C.byref(n)))

@@ -1038,6 +1038,54 @@ def scene_crowded_tile(width=320, height=200, seed=22, crowd=3000):
     return sc
 
 
+def scene_small_draws(width=320, height=200, seed=31, draws=24, tris=40, crowd=0, big_every=0, flatid=True):
+    """Many small draws in a row into the same targets — what a frame of scene objects looks like (src/test2/puresoft.cpp:185-248:
+    54 draws of boxes) — cycling through three programmes with 3, 1 and 0 varyings (DEF02, FLATID, PositionOnly + single colour),
+    every draw with its own vertex streams and its own latched uniforms (a translation, a colour). The triangles of different
+    draws overlap with depths inside and around the 1e-4 dead band (fragthrd.cpp:227), so the order of the draws decides pixels.
+    `crowd` > 0: that many extra tiny triangles per draw inside one 16x16 tile (tile lists that outgrow one speculated capacity
+    after the other). `big_every` > 0: every such draw is one of 20000 triangles (too big to wait for its neighbours).
+    `flatid` False: without the parity-test functor FLATID the reference build does not have (DEF02 takes its turns)."""
+    rng = np.random.default_rng(seed)
+    sc = Scene("small-draws-%dx%d-%d-%d-%d" % (width, height, draws, tris, crowd), width, height)
+    progs = [sc.add_programme(K.FN_DEF02), sc.add_programme(K.FN_FLATID if flatid else K.FN_DEF02), sc.add_programme(K.FN_POSITIONONLY)]
+    ident = colmajor(mat_identity())
+    px, py = 2.0 / width, 2.0 / height
+    cx, cy = (40.0 - width // 2) / (width // 2), (72.0 - height // 2) / (height // 2)
+    sc.cmd("viewport", width, height); sc.cmd("depth", -1); sc.cmd("clearDepth", 1.0); sc.cmd("clearColour", 0xFF202020)
+    sc.cmd("uniform", 3, ident); sc.cmd("uniform", 5, ident)
+    sc.cmd("uniform", 7, vec4(0.3, 0.4, 2.0)); sc.cmd("uniform", 8, vec4(0.0, 0.0, 3.0))
+    sc.cmd("disable", K.BEHAVIOR_FACE_CULLING)
+    total = 0
+    for d in range(draws):
+        n = 20000 if (big_every and d % big_every == big_every - 1) else tris + int(rng.integers(0, 5))
+        c = rng.uniform(-0.9, 0.9, size=(n, 1, 2))
+        ext = rng.uniform(-0.25, 0.25, size=(n, 3, 2)) if n < 1000 else rng.uniform(-0.02, 0.02, size=(n, 3, 2))
+        xy = c + ext
+        z = (0.4 + 0.0002 * rng.integers(0, 6, size=(n, 1)) + rng.uniform(-0.00005, 0.00005, size=(n, 3)))[..., None]
+        pos = np.concatenate([xy, z, np.ones((n, 3, 1))], axis=-1)
+        if crowd:
+            cc = np.array([cx, cy]) + rng.uniform(-6, 6, size=(crowd, 1, 2)) * (px, py)
+            ce = rng.uniform(-2.5, 2.5, size=(crowd, 3, 2)) * (px, py)
+            cz = (0.3 - 0.0001 * (np.arange(crowd) % 7))[:, None, None] + rng.uniform(-0.00005, 0.00005, size=(crowd, 3, 1))
+            pos = np.concatenate([pos, np.concatenate([cc + ce, cz, np.ones((crowd, 3, 1))], axis=-1)], axis=0)
+            n += crowd
+        pos = pos.reshape(n * 3, 4).astype(F32)
+        nrm = np.tile(np.array([0.0, 0.0, 1.0, 0.0], F32), (n * 3, 1))
+        col = np.concatenate([rng.uniform(30, 255, size=(n * 3, 3)), np.full((n * 3, 1), 255.0)], axis=1).astype(F32)
+        ids = np.repeat(np.concatenate([rng.integers(0, 256, size=(n, 3)), np.full((n, 1), 255)], axis=1), 3, axis=0).astype(F32)
+        vao = sc.add_vao({0: (16, pos), 1: (16, nrm), 2: (16, col), 6: (16, ids)})
+        shift = mat_translation(float(rng.uniform(-0.05, 0.05)), float(rng.uniform(-0.05, 0.05)), 0.0)
+        sc.cmd("uniform", 4, colmajor(shift))           # DEF02 / FLATID: model; PositionOnly reads slot 5 (left alone)
+        sc.cmd("uniform", 31, vec4(*rng.uniform(0.1, 1.0, size=3)))
+        sc.cmd("use", progs[d % 3])
+        sc.cmd("draw", vao)
+        total += n
+    sc.cmd("enable", K.BEHAVIOR_FACE_CULLING)
+    sc.meta["triangles"] = total
+    return sc
+
+
 def scene_state_fuzz(seed, width=None, height=None, draws=None):
     """A seeded frame of several draws with the pipeline's state changing between them: behaviour bits (depth test / depth
     write / culling / blending; never 'test on, write off', where the reference reads a depth cursor it did not position,

@@ -39,6 +39,10 @@ SMALL = {
     "crowded_tile": lambda: scenes.scene_crowded_tile(320, 200, crowd=3000),
     # + the post-processing hook (PP_DepthofField through the reference's own postProcess)
     "demo2_post": lambda: _demo2_from_objx(post=True),
+    # many small draws in a row, programmes and uniforms changing from draw to draw, overlapping inside the depth dead band
+    # (the CUDA side runs them as batches: include/ps3d.h, ps3d_debug_batch_counts); with tile lists that outgrow the sort
+    "small_draws_mixed": lambda: scenes.scene_small_draws(320, 200, seed=31, draws=24, tris=40, flatid=False),
+    "small_draws_crowded": lambda: scenes.scene_small_draws(320, 200, seed=34, draws=12, tris=20, crowd=260, flatid=False),
 }
 
 # Extensions with no reference counterpart: checked CUDA-vs-oracle only, "parity unpinned".

@@ -70,7 +70,10 @@ def test_capture_without_a_sized_frame_fails_loudly(cuda_lib):
     up = scenes.upload(pipe, sc)
     pipe.graphBegin()
     with pytest.raises(Exception):
-        scenes.replay(pipe, sc, up, finish=False)    # nothing has sized the draw's buffers: a captured frame cannot allocate
+        # nothing has sized the draw's buffers: a captured frame cannot allocate. (A small draw is launched by the call that
+        # ends its batch — include/ps3d.h — which here is the end of the capture.)
+        scenes.replay(pipe, sc, up, finish=False)
+        pipe.graphEnd()
     try:
         pipe.graphEnd()
     except Exception:  # noqa: BLE001 — whether the truncated capture still ends cleanly is not the point
