@@ -161,4 +161,5 @@ struct DrawParams
 	int capW, capH;
 	SpanStreams sp;             // span path
 	TileLists tl;
+	uint32_t batchFirstBlock, batchTrisPerBlock;   // a draw inside a batch (kernels_span.cuh: BatchView): its first block of ids, triangles per block
 };

@@ -152,9 +152,10 @@ struct GeomAcc { unsigned rasterised, spans; unsigned long long frags; unsigned 
 
 // One batch of up to 128 triangles (one per thread; `candidate` false: none) through phases A, S and B. `orig` is the
 // triangle's place in the staged copy of the block's vertex range (STAGED only). Ends with a block barrier, so batches can
-// follow each other in one block.
+// follow each other in one block. `tri` indexes the draw's vertex streams and varyings; tri + idBias is the id the triangle
+// carries through records, lists and headers (a batch of draws numbers its triangles across the draws).
 template<class PROG, int STAGED>
-PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candidate, const uint8_t* stage, const uint32_t* stageOff, GeomAcc& acc)
+PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candidate, const uint8_t* stage, const uint32_t* stageOff, GeomAcc& acc, const uint32_t idBias = 0)
 {
 	constexpr int NV = PROG::NV;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -263,7 +264,7 @@ PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candi
 		sRowBase[slot] = rowBase + rowsIncl - (uint32_t)nrows;
 		sRow0[slot] = row0;
 		sOrig[slot] = (uint8_t)orig;
-		sTri[slot] = tri;
+		sTri[slot] = tri + idBias;
 	}
 	if(0 == threadIdx.x)
 	{
@@ -404,7 +405,8 @@ PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candi
 		{ TriSpan tsv; tsv.x = spanBase + myRows0; tsv.y = (uint32_t)sRow0[k] | ((uint32_t)(sRow0[k] + (int)(myRows1 - myRows0) - 1) << 16); P.sp.tri[wtri] = tsv; }
 		if(NV > 0)
 		{
-			float4* vd = (float4*)(P.vary + (size_t)wtri * 3 * NV);
+			const uint32_t ltri = wtri - idBias;                          // the triangle's place in its own draw
+			float4* vd = (float4*)(P.vary + (size_t)ltri * 3 * NV);
 #pragma unroll 1
 			for(int i = 0; i < 3; i++)
 			{
@@ -412,7 +414,7 @@ PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candi
 #pragma unroll
 				for(int s = 0; s < 16; s++)
 					in.data[s] = (PROG::V::SLOTS >> s) & 1 ? ((0 != ((stageMask<STAGED>(PROG::V::SLOTS) >> s) & 1)) ? stage + stageOff[s] + (size_t)(orig * 3 + i) * P.stride[s]
-					                                                  : P.slot[s] + (size_t)(wtri * 3 + i) * P.stride[s]) : nullptr;
+					                                                  : P.slot[s] + (size_t)(ltri * 3 + i) * P.stride[s]) : nullptr;
 				VertexProcessorOutput<NV> vo;
 				PROG::V::process(in, vo, P);
 #pragma unroll
@@ -606,25 +608,37 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_span_multi_kernel(const 
 {
 	const uint32_t gb = B.blockList[blockIdx.x];
 	const DrawParams& P = B.items[B.blockDraw[gb] & 0xffffu];
-	const uint32_t tri = gb * PS_GEOM_THREADS + threadIdx.x;
+	// a small draw spreads its triangles over many blocks (a block's rows are walked by its own threads: a dozen triangles that
+	// cover a 4096-row target are a dozen blocks' work, not one's): block gb takes batchTrisPerBlock of them
+	const uint32_t first = (gb - P.batchFirstBlock) * P.batchTrisPerBlock;
+	const uint32_t tri = first + threadIdx.x;
 	uint32_t stageOff[16];
 #pragma unroll
 	for(int s = 0; s < 16; s++) stageOff[s] = 0;
 	GeomAcc acc = { 0, 0, 0, 0, 0 };
-	geomBatch<PROG, 0>(P, tri, threadIdx.x, tri < P.ntris, nullptr, stageOff, acc);
+	geomBatch<PROG, 0>(P, tri, threadIdx.x, threadIdx.x < P.batchTrisPerBlock && tri < P.ntris, nullptr, stageOff, acc, gb * PS_GEOM_THREADS - first);
 	geomFinish(P, acc);
 }
 
-// one draw's DrawParams from the launch's parameter space into the batch's table (a kernel, not a copy: it can be recorded into a
-// captured frame with its source), and the draw's blocks into the block tables
-__global__ void __launch_bounds__(256) batch_item_kernel(const __grid_constant__ DrawParams item, DrawParams* dst, uint32_t* blockDraw, uint32_t* blockList,
-                                                        uint32_t firstBlock, uint32_t nBlocks, uint32_t listAt, uint32_t tag)
+// the draws' DrawParams from the launch's parameter space into the batch's table (a kernel, not a copy: it can be recorded into a
+// captured frame together with its source), and the draws' blocks into the block tables. Block = draw of the pack.
+#define PS_BATCH_PACK 7
+struct ItemPack
+{
+	DrawParams item[PS_BATCH_PACK];
+	uint32_t nBlocks[PS_BATCH_PACK], listAt[PS_BATCH_PACK], tag[PS_BATCH_PACK];
+	uint32_t first;             // place of item[0] in the table
+};
+static_assert(sizeof(ItemPack) <= 32000, "kernel parameters end at 32 764 bytes");
+__global__ void __launch_bounds__(256) batch_items_kernel(const __grid_constant__ ItemPack K, DrawParams* table, uint32_t* blockDraw, uint32_t* blockList)
 {
 	static_assert(0 == sizeof(DrawParams) % 8, "copied as 8-byte words");
-	const uint2* src = (const uint2*)&item;
-	uint2* d = (uint2*)dst;
-	for(uint32_t i = threadIdx.x; i < sizeof(DrawParams) / 8; i += blockDim.x) d[i] = src[i];
-	for(uint32_t j = threadIdx.x; j < nBlocks; j += blockDim.x) { blockDraw[firstBlock + j] = tag; blockList[listAt + j] = firstBlock + j; }
+	const uint32_t i = blockIdx.x;
+	const uint2* src = (const uint2*)&K.item[i];
+	uint2* d = (uint2*)(table + K.first + i);
+	for(uint32_t w = threadIdx.x; w < sizeof(DrawParams) / 8; w += blockDim.x) d[w] = src[w];
+	const uint32_t firstBlock = K.item[i].batchFirstBlock;
+	for(uint32_t j = threadIdx.x; j < K.nBlocks[i]; j += blockDim.x) { blockDraw[firstBlock + j] = K.tag[i]; blockList[K.listAt[i] + j] = firstBlock + j; }
 }
 
 // ======================================================================================================================
@@ -1343,7 +1357,9 @@ __global__ void __launch_bounds__(PS_SHADE_THREADS, MINB) shade_span_kernel(cons
 			}
 			const uint4* src = (const uint4*)(P.hdr + tri);
 			const uint4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
-			const F4* v = D->vary + (size_t)tri * 3 * NV;
+			// (a batch's draw keeps its varyings densely, by the triangle's place in the draw)
+			const uint32_t ltri = MULTI ? (tri % PS_GEOM_THREADS) + (tri / PS_GEOM_THREADS - D->batchFirstBlock) * D->batchTrisPerBlock : tri;
+			const F4* v = D->vary + (size_t)ltri * 3 * NV;
 			const int x = (int)(xy & 0x1fff), y = (int)((xy >> 13) & 0x1fff);
 			const int left = A.x, right = A.y, e = (int)((uint32_t)A.w >> 24);
 			const float vx[3] = { __uint_as_float(q0.x), __uint_as_float(q0.z), __uint_as_float(q1.x) };

@@ -366,7 +366,7 @@ struct ps3d_pipe
 	std::vector<uint8_t> vaoLegacy; // VAOs whose last draw needed the first path (a tile list too long for the shared-memory sort)
 	// batches of small draws (kernels_span.cuh: BatchView): `batch` collects draws until something other than a like draw arrives,
 	// `flight` is the batch whose launches are on the stream and whose verdict settle() has yet to read
-	struct BatchDraw { DrawParams P; const ProgEntry* pe; int vao; uint32_t firstBlock, nBlocks; };
+	struct BatchDraw { DrawParams P; const ProgEntry* pe; int vao; uint32_t firstBlock, nBlocks, trisPerBlock; };
 	struct Batch { std::vector<BatchDraw> draws; uint32_t blocks; void clear() { draws.clear(); blocks = 0; } };
 	Batch batch, flight;
 	DevBuf<DrawParams> batchItems;
@@ -814,7 +814,7 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 	if(multi)
 	{
 		varyCount = 1;
-		for(const ps3d_pipe::BatchDraw& d : p->flight.draws) varyCount += (size_t)d.nBlocks * PS_GEOM_THREADS * 3 * (size_t)d.pe->nv;
+		for(const ps3d_pipe::BatchDraw& d : p->flight.draws) varyCount += (size_t)d.P.ntris * 3 * (size_t)d.pe->nv;
 		CK(p, p->batchItems.ensure(p->flight.draws.size()));
 		CK(p, p->batchBlockDraw.ensure(p->flight.blocks));
 		CK(p, p->batchBlockList.ensure(p->flight.blocks));
@@ -866,26 +866,32 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 			groupBlocks[std::find(groups.begin(), groups.end(), d.pe) - groups.begin()] += d.nBlocks;
 		for(size_t g = 1; g < groups.size(); g++) groupAt[g] = groupAt[g - 1] + groupBlocks[g - 1];
 		size_t varyAt = 0;
+		static thread_local ItemPack pack;                         // (28 KB: not on the stack)
+		uint32_t packed = 0;
 		for(size_t i = 0; i < p->flight.draws.size(); i++)
 		{
 			const ps3d_pipe::BatchDraw& d = p->flight.draws[i];
 			const size_t g = std::find(groups.begin(), groups.end(), d.pe) - groups.begin();
-			const size_t firstTri = (size_t)d.firstBlock * PS_GEOM_THREADS;
-			DrawParams item = P;                                    // targets, buffers, capacities: the batch's
-			for(int sl = 0; sl < 16; sl++)
-			{
-				item.stride[sl] = d.P.stride[sl];
-				item.slot[sl] = d.P.slot[sl] ? d.P.slot[sl] - firstTri * 3 * d.P.stride[sl] : nullptr;
-			}
+			if(0 == packed) pack.first = (uint32_t)i;
+			DrawParams& item = pack.item[packed];
+			item = P;                                               // targets, buffers, capacities: the batch's
+			memcpy(item.slot, d.P.slot, sizeof(item.slot));
+			memcpy(item.stride, d.P.stride, sizeof(item.stride));
 			memcpy(item.u, d.P.u, sizeof(item.u));
 			memcpy(item.tex, d.P.tex, sizeof(item.tex));
-			item.ntris = (uint32_t)(firstTri + d.P.ntris);
-			item.vary = p->vary.p + varyAt - firstTri * 3 * (size_t)d.pe->nv;
-			varyAt += (size_t)d.nBlocks * PS_GEOM_THREADS * 3 * (size_t)d.pe->nv;
-			batch_item_kernel<<<1, 256, 0, p->stream>>>(item, p->batchItems.p + i, p->batchBlockDraw.p, p->batchBlockList.p, d.firstBlock, d.nBlocks,
-			                                           groupAt[g] + groupFill[g], (uint32_t)i | ((uint32_t)g << 16));
+			item.ntris = d.P.ntris;
+			item.batchFirstBlock = d.firstBlock; item.batchTrisPerBlock = d.trisPerBlock;
+			item.vary = p->vary.p + varyAt;
+			varyAt += (size_t)d.P.ntris * 3 * (size_t)d.pe->nv;
+			pack.nBlocks[packed] = d.nBlocks; pack.listAt[packed] = groupAt[g] + groupFill[g]; pack.tag[packed] = (uint32_t)i | ((uint32_t)g << 16);
 			groupFill[g] += d.nBlocks;
-			p->launches++;
+			packed++;
+			if(PS_BATCH_PACK == packed || i + 1 == p->flight.draws.size())
+			{
+				batch_items_kernel<<<packed, 256, 0, p->stream>>>(pack, p->batchItems.p, p->batchBlockDraw.p, p->batchBlockList.p);
+				p->launches++;
+				packed = 0;
+			}
 		}
 		for(size_t g = 0; g < groups.size(); g++)
 		{
@@ -935,7 +941,11 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 static bool batchingOn() { static int on = -1; if(on < 0) { const char* e = getenv("PS3D_BATCH"); on = (e && e[0] == '0') ? 0 : 1; } return on == 1; }
 #define PS_BATCH_DRAW_TRIS 16384u     // a draw with more triangles than this fills the GPU by itself
 #define PS_BATCH_MAX_DRAWS 1024u
-#define PS_BATCH_MAX_BLOCKS 32768u
+#define PS_BATCH_MAX_BLOCKS 8192u       // (every block is PS_GEOM_THREADS triangle ids: 64 B of header each)
+
+// a small draw spreads over up to 64 blocks (its triangles' rows are walked by the block's threads: kernels_span.cuh)
+static uint32_t batchTrisPerBlock(size_t ntris) { return (uint32_t)std::min<size_t>(std::max<size_t>((ntris + 63) / 64, 1), PS_GEOM_THREADS); }
+static uint32_t batchBlocks(size_t ntris) { const uint32_t per = batchTrisPerBlock(ntris); return (uint32_t)((ntris + per - 1) / per); }
 
 // a draw can join the batch being collected: same targets, viewport, band and behaviour bits (any programme of the span path)
 static bool batchTakes(const ps3d_pipe* p, const DrawParams& P)
@@ -944,7 +954,7 @@ static bool batchTakes(const ps3d_pipe* p, const DrawParams& P)
 	const DrawParams& A = p->batch.draws[0].P;
 	return A.behavior == P.behavior && A.vpW == P.vpW && A.vpH == P.vpH && A.band0 == P.band0 && A.band1 == P.band1 && A.cap == P.cap
 	    && 0 == memcmp(&A.colour, &P.colour, sizeof(A.colour)) && 0 == memcmp(&A.depth, &P.depth, sizeof(A.depth))
-	    && p->batch.draws.size() < PS_BATCH_MAX_DRAWS && p->batch.blocks + (P.ntris + PS_GEOM_THREADS - 1) / PS_GEOM_THREADS <= PS_BATCH_MAX_BLOCKS;
+	    && p->batch.draws.size() < PS_BATCH_MAX_DRAWS && p->batch.blocks + batchBlocks(P.ntris) <= PS_BATCH_MAX_BLOCKS;
 }
 
 // Launches the collected draws: one alone as any draw, several as one batch (kernels_span.cuh: BatchView).
@@ -1663,7 +1673,7 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	{
 		if(!batchTakes(p, P)) { const int rc = flushBatch(p); if(rc) return rc; }
 		ps3d_pipe::BatchDraw d;
-		d.P = P; d.pe = pe; d.vao = vao; d.firstBlock = p->batch.blocks; d.nBlocks = (uint32_t)((ntris + PS_GEOM_THREADS - 1) / PS_GEOM_THREADS);
+		d.P = P; d.pe = pe; d.vao = vao; d.firstBlock = p->batch.blocks; d.trisPerBlock = batchTrisPerBlock(ntris); d.nBlocks = batchBlocks(ntris);
 		p->batch.draws.push_back(d);
 		p->batch.blocks += d.nBlocks;
 		return PS3D_OK;
