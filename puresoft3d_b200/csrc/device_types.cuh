@@ -74,7 +74,7 @@ struct DrawReport
 	unsigned int spans;             // span path: span records the draw needs
 	unsigned long long fragBound;
 	unsigned int sticky;            // set with `bad`, cleared only by the host: a replayed captured frame (ps3d_graph_launch) is checked here
-	unsigned int pad;
+	unsigned int marks;             // span path: chain marks the draw's long spans ask for (SpanStreams::markZ)
 };
 
 // Survivors of the depth test, one record per FragmentProcessor::process call still to make (split path): structure of
@@ -111,7 +111,19 @@ struct SpanStreams
 	TriSpan* tri;         // per triangle: index of its first record, first row | last row << 16 of the records (inside band and targets)
 	uint32_t* count;      // records allocated so far in this draw (one atomicAdd per geometry block)
 	uint32_t capacity;
+	// Chain marks of long spans (more than PS_SPAN_BOUND_MAX pixels): the k-th pixel's depth and varyings are k ROUNDED additions
+	// from the span start (interp.cpp:88), which no closed form reproduces — a tile in the middle of a 4096-pixel span would replay
+	// thousands of them, every tile of the row again. The chain of a long span is walked ONCE instead and its state kept every
+	// PS_MARK_STEP pixels; tiles and fragments start from the nearest mark.
+	uint32_t* markAt;     // per record (long spans only): index of the span's first mark, ~0 = the marks did not fit (replay from the start)
+	float2* markZ;        // (cf2, z) after PS_MARK_STEP * k steps
+	F4* markV;            // the varyings after PS_MARK_STEP * k steps: [mark][NV]
+	uint32_t* longList;   // record indices of the long spans, any order
+	unsigned long long* longCount;   // long spans << 40 | marks asked for (one atomicAdd per long span)
+	uint32_t* longLatched;           // [0] long spans, [1] marks asked for: what the plan kernel read before it reset the counter
+	uint32_t markCap;     // marks that fit; 0: none are kept (only counted)
 };
+#define PS_MARK_STEP 16
 
 // per-tile triangle lists of fixed capacity, appended to directly by the geometry kernel (any order), sorted by the list sort
 struct TileLists

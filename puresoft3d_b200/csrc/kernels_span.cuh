@@ -323,6 +323,19 @@ PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candi
 				dst[0] = make_int4(sp.left, sp.right, __float_as_int(sp.zmin), (int)(sTri[o] | ((uint32_t)sp.edges << 24)));
 				dst[1] = make_int4(__float_as_int(sp.cf2), __float_as_int(sp.cf2Step), __float_as_int(sp.z0), __float_as_int(sp.zStep));
 			}
+			if(sp.x2 - sp.x1 > PS_SPAN_BOUND_MAX)
+			{
+				// a long span: room for its chain marks (SpanStreams), its record on the list the mark kernels walk
+				const uint32_t need = (uint32_t)(sp.x2 - sp.x1) / PS_MARK_STEP + 1u;
+				const unsigned long long old = atomicAdd(P.sp.longCount, (1ull << 40) | need);
+				if(fits && P.sp.markCap)
+				{
+					const uint32_t j = (uint32_t)(old >> 40);
+					const unsigned long long at = old & ((1ull << 40) - 1);
+					P.sp.markAt[spanBase + s] = at + need <= P.sp.markCap ? (uint32_t)at : 0xffffffffu;
+					if(j < P.sp.capacity) P.sp.longList[j] = spanBase + s;
+				}
+			}
 		}
 		__syncthreads();
 		// B's view of its triangle, row by row from what the lanes left in shared memory: the tile columns its spans reach in the
@@ -647,7 +660,7 @@ __global__ void __launch_bounds__(256) batch_items_kernel(const __grid_constant_
 
 __global__ void __launch_bounds__(1024) tile_plan_kernel(TileLists tl, uint32_t ntiles, DeviceStats* stats, uint32_t* spanCount, uint32_t spanCap,
                                                         unsigned long long survivorCap, uint32_t listLimit, uint32_t* poison, DrawReport* report,
-                                                        uint32_t* __restrict__ tileOrder)
+                                                        uint32_t* __restrict__ tileOrder, unsigned long long* longCount, uint32_t* longLatched)
 {
 	__shared__ uint32_t hist[256];                     // tiles per length class, longest lists first
 	// one histogram per warp: most tiles of a frame fall into a handful of classes, and ~8000 atomics of a whole block on five
@@ -771,6 +784,14 @@ __global__ void __launch_bounds__(1024) tile_plan_kernel(TileLists tl, uint32_t 
 		tileOrder[ntiles] = nonEmptyS;
 		const uint32_t lng = longestS, nspans = *spanCount;
 		*spanCount = 0;
+		// long spans and the chain marks they asked for (no verdict hangs on them: marks that did not fit are not kept, their spans
+		// replay from the start; the host sizes the next draw's buffer by the report)
+		const unsigned long long lc = *longCount;
+		*longCount = 0;
+		const unsigned long long marks = lc & ((1ull << 40) - 1);
+		longLatched[0] = (uint32_t)min(lc >> 40, (unsigned long long)spanCap);
+		longLatched[1] = (uint32_t)min(marks, 0xffffffffull);
+		report->marks = (unsigned int)min(marks, 0xffffffffull);
 		const unsigned long long bound = boundS;
 		const uint32_t bad = (lng > tl.cap || lng > listLimit || nspans > spanCap || bound > survivorCap) ? 1u : 0u;
 		if(!bad)
@@ -1073,7 +1094,8 @@ PS_D void pixelPass(const SurvivorStream2& Q, RasterSmem2& S, RasterCtx2& C, uin
 	}
 }
 
-template<int MINB>
+// MARKS: long spans start their chains from the nearest chain mark (SpanStreams::markZ, span_mark_depth_kernel)
+template<int MINB, bool MARKS = false>
 __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK, MINB) tile_raster_span_kernel(const __grid_constant__ DrawParams P, const SurvivorStream2 Q, int parts)
 {
 	__shared__ __align__(16) RasterSmem2 smem[PS_WARPS_PER_BLOCK];
@@ -1235,8 +1257,20 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK, MINB) tile_raster_spa
 				{
 					cf2 = __int_as_float(D.x); cf2Step = __int_as_float(D.y); z0 = __int_as_float(D.z); zStep = __int_as_float(D.w);
 					// the k-th pixel's value is k rounded additions from the span start (§9.6): replay them up to the tile
+					int xr = x1;
+					if(MARKS && zmin != zmin && xs - x1 >= PS_MARK_STEP)
+					{
+						const uint32_t at = __ldg(P.sp.markAt + idx);
+						if(at != 0xffffffffu)
+						{
+							const int k = (xs - x1) / PS_MARK_STEP;
+							const float2 m = __ldg(P.sp.markZ + at + k);
+							cf2 = m.x; z0 = m.y;
+							xr = x1 + k * PS_MARK_STEP;
+						}
+					}
 #pragma unroll 1
-					for(int x = x1; x < xs; x++)
+					for(int x = xr; x < xs; x++)
 					{
 						cf2 = fadd(cf2, cf2Step);
 						z0 = fadd(z0, zStep);
@@ -1309,9 +1343,46 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK, MINB) tile_raster_spa
 // varyings): the stream words are read two iterations ahead and the span record one ahead, so only the last level's latency
 // is exposed. (Tried and dropped: that level staged through shared memory by 16-byte asynchronous copies, all issued together —
 // LDGSTS neither merges the lanes that name the same triangle nor uses L1, the kernel went 0.205 -> 0.355 ms.)
+// The varyings' half of interpolateStartAndStep (interp.cpp:26-80) for one span: the chain's first value (at the clamped start x1,
+// which is returned) and its step.
+template<class PROG>
+PS_D int varyingChainStart(const uint4& q0, const uint4& q1, const uint4& q2, const F4* v, int left, int right, int e, int y,
+                           F4* vStart, F4* vStep)
+{
+	constexpr int NV = PROG::NV;
+	const float vx[3] = { __uint_as_float(q0.x), __uint_as_float(q0.z), __uint_as_float(q1.x) };
+	const float vy[3] = { __uint_as_float(q0.y), __uint_as_float(q0.w), __uint_as_float(q1.y) };
+	const float rw0 = __uint_as_float(q1.z), rw1 = __uint_as_float(q1.w), rw2 = __uint_as_float(q2.x);
+	float cl[3], cr[3];
+	edgeContrib(vx, vy, e & 3, (e >> 2) & 3, (float)left, (float)y, cl);
+	edgeContrib(vx, vy, (e >> 4) & 3, (e >> 6) & 3, (float)right, (float)y, cr);
+	cl[0] = fmul(cl[0], rw0); cl[1] = fmul(cl[1], rw1); cl[2] = fmul(cl[2], rw2);
+	cr[0] = fmul(cr[0], rw0); cr[1] = fmul(cr[1], rw1); cr[2] = fmul(cr[2], rw2);
+	const int stepCount = right - left;
+	const int x1 = left < 0 ? 0 : left;
+	const int skip = x1 - left;
+	// every varying is an independent float4 (the IP's methods are per-field loops, tex1light1.cpp:60-135)
+	typedef InterpolationProcessorVec4<1> IP1;
+	typedef typename PROG::I IP;
+	const float rStep = IP1::reciprocalStepCount(stepCount);        // one divide per span, as in calcStep (tex1light1.cpp:93-107)
+#pragma unroll
+	for(int q = 0; q < NV; q++)
+	{
+		const float4 a = __ldg((const float4*)(v + q)), b = __ldg((const float4*)(v + NV + q)), c = __ldg((const float4*)(v + 2 * NV + q));
+		const F4 v0 = f4(a.x, a.y, a.z, a.w), v1 = f4(b.x, b.y, b.z, b.w), v2 = f4(c.x, c.y, c.z, c.w);
+		F4 vEnd;
+		IP1::interpolateByContributes(&vStart[q], &v0, &v1, &v2, cl[0], cl[1], cl[2]);
+		IP1::interpolateByContributes(&vEnd, &v0, &v1, &v2, cr[0], cr[1], cr[2]);
+		IP1::calcStepR(&vStep[q], &vStart[q], &vEnd, rStep);
+	}
+	if(skip > 0) IP::stepForward(vStart, vStep, skip);               // interp.cpp:74-79
+	return x1;
+}
+
 // MULTI: a batch of draws (BatchView above): this launch shades the survivors of its programme group's draws, with that draw's
-// uniforms, textures and varyings.
-template<class PROG, int MINB, bool MULTI = false>
+// uniforms, textures and varyings. MARKS: fragments of long spans start their chains from the nearest chain mark
+// (SpanStreams::markV, span_mark_vary_kernel).
+template<class PROG, int MINB, bool MULTI = false, bool MARKS = false>
 __global__ void __launch_bounds__(PS_SHADE_THREADS, MINB) shade_span_kernel(const __grid_constant__ DrawParams P, const SurvivorStream2 Q, const BatchView B)
 {
 	constexpr int NV = PROG::NV;
@@ -1322,12 +1393,12 @@ __global__ void __launch_bounds__(PS_SHADE_THREADS, MINB) shade_span_kernel(cons
 	// pipeline registers: item i (xy, inv, record), item i + stride (stream words); item i + 2 * stride is read inside the loop.
 	// (Tried and dropped: the record two items ahead and the next item's header + varyings asked into L1 by prefetch
 	// instructions while this one is shaded: 0.186 -> 0.196 ms.)
-	uint32_t xy0 = PS_SV_HOLE, sp1 = 0, xy1 = PS_SV_HOLE;
+	uint32_t xy0 = PS_SV_HOLE, sp1 = 0, xy1 = PS_SV_HOLE, sp0 = 0;
 	float inv0 = 0, inv1 = 0;
 	int4 rec0 = make_int4(1, 0, 0, 0);
 	if(NV > 0)
 	{
-		if(i < n) { xy0 = Q.xy[i]; inv0 = Q.inv[i]; rec0 = __ldg((const int4*)(P.sp.rec + Q.span[i])); }
+		if(i < n) { xy0 = Q.xy[i]; inv0 = Q.inv[i]; sp0 = Q.span[i]; rec0 = __ldg((const int4*)(P.sp.rec + sp0)); }
 		if(i + stride < n && i + stride >= i) { xy1 = Q.xy[i + stride]; inv1 = Q.inv[i + stride]; sp1 = Q.span[i + stride]; }
 	}
 	for(; i < n; i += stride)
@@ -1340,10 +1411,11 @@ __global__ void __launch_bounds__(PS_SHADE_THREADS, MINB) shade_span_kernel(cons
 			xy = xy0;
 			const float inv = inv0;
 			const int4 A = rec0;
+			const uint32_t spCur = sp0;                                    // (MARKS only: the survivor's record index)
 			// the pipeline moves on
 			{
 				const uint32_t i1 = i + stride, i2 = i + 2 * stride;
-				xy0 = xy1; inv0 = inv1;
+				xy0 = xy1; inv0 = inv1; sp0 = sp1;
 				if(i1 < n && i1 >= i) rec0 = __ldg((const int4*)(P.sp.rec + sp1));
 				if(i2 < n && i2 >= i1 && i1 >= i) { xy1 = Q.xy[i2]; inv1 = Q.inv[i2]; sp1 = Q.span[i2]; }
 			}
@@ -1362,36 +1434,26 @@ __global__ void __launch_bounds__(PS_SHADE_THREADS, MINB) shade_span_kernel(cons
 			const F4* v = D->vary + (size_t)ltri * 3 * NV;
 			const int x = (int)(xy & 0x1fff), y = (int)((xy >> 13) & 0x1fff);
 			const int left = A.x, right = A.y, e = (int)((uint32_t)A.w >> 24);
-			const float vx[3] = { __uint_as_float(q0.x), __uint_as_float(q0.z), __uint_as_float(q1.x) };
-			const float vy[3] = { __uint_as_float(q0.y), __uint_as_float(q0.w), __uint_as_float(q1.y) };
-			const float rw0 = __uint_as_float(q1.z), rw1 = __uint_as_float(q1.w), rw2 = __uint_as_float(q2.x);
 			// interpolateStartAndStep, interp.cpp:26-80 (the varyings' half; the depth half ran in the geometry kernel)
-			float cl[3], cr[3];
-			edgeContrib(vx, vy, e & 3, (e >> 2) & 3, (float)left, (float)y, cl);
-			edgeContrib(vx, vy, (e >> 4) & 3, (e >> 6) & 3, (float)right, (float)y, cr);
-			cl[0] = fmul(cl[0], rw0); cl[1] = fmul(cl[1], rw1); cl[2] = fmul(cl[2], rw2);
-			cr[0] = fmul(cr[0], rw0); cr[1] = fmul(cr[1], rw1); cr[2] = fmul(cr[2], rw2);
-			const int stepCount = right - left;
-			const int x1 = left < 0 ? 0 : left;
-			const int skip = x1 - left;
 			F4 vStart[NV > 0 ? NV : 1], vStep[NV > 0 ? NV : 1];
-			// every varying is an independent float4 (the IP's methods are per-field loops, tex1light1.cpp:60-135)
-			typedef InterpolationProcessorVec4<1> IP1;
 			typedef typename PROG::I IP;
-			const float rStep = IP1::reciprocalStepCount(stepCount);        // one divide per span, as in calcStep (tex1light1.cpp:93-107)
-#pragma unroll
-			for(int q = 0; q < NV; q++)
+			const int x1 = varyingChainStart<PROG>(q0, q1, q2, v, left, right, e, y, vStart, vStep);
+			int xr = x1;
+			if(MARKS && ((uint32_t)A.z & 0x7fffffffu) > 0x7f800000u && x - x1 >= PS_MARK_STEP)
 			{
-				const float4 a = __ldg((const float4*)(v + q)), b = __ldg((const float4*)(v + NV + q)), c = __ldg((const float4*)(v + 2 * NV + q));
-				const F4 v0 = f4(a.x, a.y, a.z, a.w), v1 = f4(b.x, b.y, b.z, b.w), v2 = f4(c.x, c.y, c.z, c.w);
-				F4 vEnd;
-				IP1::interpolateByContributes(&vStart[q], &v0, &v1, &v2, cl[0], cl[1], cl[2]);
-				IP1::interpolateByContributes(&vEnd, &v0, &v1, &v2, cr[0], cr[1], cr[2]);
-				IP1::calcStepR(&vStep[q], &vStart[q], &vEnd, rStep);
+				// a long span (its depth bound is the NaN evalSpan left): from the nearest mark of its chain
+				const uint32_t at = __ldg(P.sp.markAt + spCur);
+				if(at != 0xffffffffu)
+				{
+					const int k = (x - x1) / PS_MARK_STEP;
+					const float4* m = (const float4*)(P.sp.markV + ((size_t)at + k) * NV);
+#pragma unroll
+					for(int q = 0; q < NV; q++) { const float4 t = __ldg(m + q); vStart[q] = f4(t.x, t.y, t.z, t.w); }
+					xr = x1 + k * PS_MARK_STEP;
+				}
 			}
-			if(skip > 0) IP::stepForward(vStart, vStep, skip);               // interp.cpp:74-79
 #pragma unroll 1
-			for(int q = x1; q < x; q++) IP::stepForward(vStart, vStep, 1);    // interp.cpp:88, one rounded add per pixel
+			for(int q = xr; q < x; q++) IP::stepForward(vStart, vStep, 1);    // interp.cpp:88, one rounded add per pixel
 			IP::correctInterpolation(frag, vStart, inv);
 		}
 		else
@@ -1416,6 +1478,93 @@ __global__ void __launch_bounds__(PS_SHADE_THREADS, MINB) shade_span_kernel(cons
 			// FBOBridge::write / write4 without ALPHABLEND: a plain store (fragthrd.cpp:54-82); later survivors of the pixel overwrite
 			uint8_t* row = P.colour.ptr + (size_t)(P.colour.topDown ? P.colour.height - 1 - y : y) * P.colour.scanline;
 			*(uint32_t*)(row + (size_t)x * 4) = out.bgra;
+		}
+	}
+}
+
+// ======================================================================================================================
+// chain marks of long spans (SpanStreams): each long span's chain walked once, its state kept every PS_MARK_STEP pixels
+// ======================================================================================================================
+
+#define PS_MARK_THREADS 128
+
+// lane = long span: the depth half's chain (cf2, z) — the same rounded additions, in the same order, as the replay in the
+// raster kernel they stand in for
+__global__ void __launch_bounds__(PS_MARK_THREADS) span_mark_depth_kernel(const __grid_constant__ DrawParams P)
+{
+	if(*P.poison) return;
+	const uint32_t n = min(P.sp.longLatched[0], P.sp.capacity);
+	const bool useDepth = 0 != (P.behavior & (PS_BEHAVIOR_TEST_DEPTH | PS_BEHAVIOR_UPDATE_DEPTH));
+	const int limitX = useDepth ? P.depth.width - 1 : 0x7fffffff;
+	for(uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+	{
+		const uint32_t idx = P.sp.longList[j];
+		const uint32_t at = P.sp.markAt[idx];
+		if(0xffffffffu == at) continue;
+		const int4* rec = (const int4*)(P.sp.rec + idx);
+		const int4 A = __ldg(rec), D = __ldg(rec + 1);
+		const int x1 = A.x < 0 ? 0 : A.x;
+		const int x2 = min(A.y >= P.vpW ? P.vpW - 1 : A.y, limitX);
+		const int steps = x2 - x1;
+		float cf2 = __int_as_float(D.x), z = __int_as_float(D.z);
+		const float cf2Step = __int_as_float(D.y), zStep = __int_as_float(D.w);
+		float2* out = P.sp.markZ + at;
+		for(int k = 0; ; k++)
+		{
+			out[k] = make_float2(cf2, z);
+			if((k + 1) * PS_MARK_STEP > steps) break;
+#pragma unroll
+			for(int i = 0; i < PS_MARK_STEP; i++)
+			{
+				cf2 = fadd(cf2, cf2Step);
+				z = fadd(z, zStep);
+			}
+		}
+	}
+}
+
+// lane = long span: the varyings' chain (shade_span_kernel's replay). MULTI: the spans of this launch's programme group.
+template<class PROG, bool MULTI>
+__global__ void __launch_bounds__(PS_MARK_THREADS) span_mark_vary_kernel(const __grid_constant__ DrawParams P, const BatchView B)
+{
+	constexpr int NV = PROG::NV > 0 ? PROG::NV : 1;
+	if(0 == PROG::NV || *P.poison) return;
+	const uint32_t n = min(P.sp.longLatched[0], P.sp.capacity);
+	const bool useDepth = 0 != (P.behavior & (PS_BEHAVIOR_TEST_DEPTH | PS_BEHAVIOR_UPDATE_DEPTH));
+	const int limitX = useDepth ? P.depth.width - 1 : 0x7fffffff;
+	typedef typename PROG::I IP;
+	for(uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+	{
+		const uint32_t idx = P.sp.longList[j];
+		const uint32_t at = P.sp.markAt[idx];
+		if(0xffffffffu == at) continue;
+		const int4 A = __ldg((const int4*)(P.sp.rec + idx));
+		const uint32_t tri = (uint32_t)A.w & 0xffffffu;
+		const DrawParams* D = &P;
+		if(MULTI)
+		{
+			const uint32_t bd = __ldg(B.blockDraw + tri / PS_GEOM_THREADS);
+			if((bd >> 16) != B.group) continue;
+			D = B.items + (bd & 0xffffu);
+		}
+		const TriSpan ts = P.sp.tri[tri];
+		const int y = (int)(ts.y & 0xffff) + (int)(idx - ts.x);         // records of a triangle are consecutive rows from its first
+		const uint4* src = (const uint4*)(P.hdr + tri);
+		const uint4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
+		const uint32_t ltri = MULTI ? (tri % PS_GEOM_THREADS) + (tri / PS_GEOM_THREADS - D->batchFirstBlock) * D->batchTrisPerBlock : tri;
+		const F4* v = D->vary + (size_t)ltri * 3 * PROG::NV;
+		F4 vStart[NV], vStep[NV];
+		const int x1 = varyingChainStart<PROG>(q0, q1, q2, v, A.x, A.y, (int)((uint32_t)A.w >> 24), y, vStart, vStep);
+		const int x2 = min(A.y >= P.vpW ? P.vpW - 1 : A.y, limitX);
+		const int steps = x2 - x1;
+		float4* out = (float4*)(P.sp.markV + (size_t)at * PROG::NV);
+		for(int k = 0; ; k++)
+		{
+#pragma unroll
+			for(int q = 0; q < PROG::NV; q++) out[(size_t)k * PROG::NV + q] = make_float4(vStart[q].x, vStart[q].y, vStart[q].z, vStart[q].w);
+			if((k + 1) * PS_MARK_STEP > steps) break;
+#pragma unroll 4
+			for(int i = 0; i < PS_MARK_STEP; i++) IP::stepForward(vStart, vStep, 1);
 		}
 	}
 }

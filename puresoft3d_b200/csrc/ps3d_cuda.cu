@@ -41,9 +41,10 @@ struct Prog { int vp, ip, fp; };
 typedef void (*LaunchGeom)(const DrawParams&, cudaStream_t);
 typedef void (*LaunchTile)(const DrawParams&, const uint32_t*, const uint32_t*, cudaStream_t);
 typedef void (*LaunchShade)(const DrawParams&, const SurvivorStream&, cudaStream_t);
-typedef void (*LaunchShade2)(const DrawParams&, const SurvivorStream2&, cudaStream_t);
+typedef void (*LaunchShade2)(const DrawParams&, const SurvivorStream2&, bool, cudaStream_t);
 typedef void (*LaunchGeomMulti)(const BatchView&, unsigned, cudaStream_t);
-typedef void (*LaunchShadeMulti)(const DrawParams&, const SurvivorStream2&, const BatchView&, cudaStream_t);
+typedef void (*LaunchShadeMulti)(const DrawParams&, const SurvivorStream2&, const BatchView&, bool, cudaStream_t);
+typedef void (*LaunchMarkVary)(const DrawParams&, const BatchView*, unsigned, cudaStream_t);
 
 struct ProgEntry
 {
@@ -61,6 +62,7 @@ struct ProgEntry
 	LaunchShade2 shadeSpan;
 	LaunchGeomMulti geomSpanMulti;   // batches of small draws
 	LaunchShadeMulti shadeSpanMulti;
+	LaunchMarkVary markVary;         // chain marks of long spans (the varyings' half)
 };
 
 // PS3D_TILE_PATH=immediate|ordered|split forces one tile path for every draw (A/B checks); default: chosen per draw
@@ -196,8 +198,22 @@ template<class PROG> void launchGeomSpan(const DrawParams& P, cudaStream_t s)
 	if(geomStagingOn() && launchGeomSpanStaged<PROG, 1>(P, blocks, s)) return;
 	geom_span_kernel<PROG, 0, false><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
 }
-template<class PROG> void launchShadeSpan(const DrawParams& P, const SurvivorStream2& Q, cudaStream_t s)
+template<class PROG> void launchShadeSpan(const DrawParams& P, const SurvivorStream2& Q, bool marks, cudaStream_t s)
 {
+	if(marks && PROG::NV > 0)
+	{
+		// long spans with chain marks (SpanStreams::markV): the variant that starts from them
+		static int perSMm[PS_MAX_DEVICES] = { 0 }, smsm[PS_MAX_DEVICES] = { 0 };
+		const int dev = currentDevice();
+		if(0 == perSMm[dev])
+		{
+			cudaDeviceGetAttribute(&smsm[dev], cudaDevAttrMultiProcessorCount, dev);
+			if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSMm[dev], shade_span_kernel<PROG, 7, false, true>, PS_SHADE_THREADS, 0) != cudaSuccess || perSMm[dev] <= 0) perSMm[dev] = 4;
+		}
+		const BatchView none = { nullptr, nullptr, nullptr, 0 };
+		shade_span_kernel<PROG, 7, false, true><<<smsm[dev] * perSMm[dev], PS_SHADE_THREADS, 0, s>>>(P, Q, none);
+		return;
+	}
 	// a flat grid-stride loop over the survivor stream: exactly one resident wave. PS3D_SHADE_MINB=5|7|8: the variant compiled for
 	// that many blocks per SM (A/B switch)
 	static int perSMs[PS_MAX_DEVICES][3] = { { 0 } }, smss[PS_MAX_DEVICES] = { 0 };
@@ -224,18 +240,30 @@ template<class PROG> void launchGeomSpanMulti(const BatchView& B, unsigned block
 {
 	geom_span_multi_kernel<PROG><<<blocks, PS_GEOM_THREADS, 0, s>>>(B);
 }
-template<class PROG> void launchShadeSpanMulti(const DrawParams& P, const SurvivorStream2& Q, const BatchView& B, cudaStream_t s)
+template<class PROG> void launchShadeSpanMulti(const DrawParams& P, const SurvivorStream2& Q, const BatchView& B, bool marks, cudaStream_t s)
 {
-	static int perSMs[PS_MAX_DEVICES] = { 0 }, smss[PS_MAX_DEVICES] = { 0 };
+	static int perSMs[PS_MAX_DEVICES][2] = { { 0 } }, smss[PS_MAX_DEVICES] = { 0 };
 	const int dev = currentDevice();
-	int& perSM = perSMs[dev];
+	const int m = (marks && PROG::NV > 0) ? 1 : 0;
+	int& perSM = perSMs[dev][m];
 	int& sms = smss[dev];
 	if(0 == perSM)
 	{
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shade_span_kernel<PROG, 7, true>, PS_SHADE_THREADS, 0) != cudaSuccess || perSM <= 0) perSM = 4;
+		const cudaError_t e = m ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shade_span_kernel<PROG, 7, true, true>, PS_SHADE_THREADS, 0)
+		                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shade_span_kernel<PROG, 7, true, false>, PS_SHADE_THREADS, 0);
+		if(e != cudaSuccess || perSM <= 0) perSM = 4;
 	}
-	shade_span_kernel<PROG, 7, true><<<sms * perSM, PS_SHADE_THREADS, 0, s>>>(P, Q, B);
+	if(m) shade_span_kernel<PROG, 7, true, true><<<sms * perSM, PS_SHADE_THREADS, 0, s>>>(P, Q, B);
+	else shade_span_kernel<PROG, 7, true, false><<<sms * perSM, PS_SHADE_THREADS, 0, s>>>(P, Q, B);
+}
+// chain marks of the varyings of long spans (kernels_span.cuh: span_mark_vary_kernel); B: a batch's programme group, or NULL
+template<class PROG> void launchMarkVary(const DrawParams& P, const BatchView* B, unsigned blocks, cudaStream_t s)
+{
+	if(0 == PROG::NV) return;
+	const BatchView none = { nullptr, nullptr, nullptr, 0 };
+	if(B) span_mark_vary_kernel<PROG, true><<<blocks, PS_MARK_THREADS, 0, s>>>(P, *B);
+	else span_mark_vary_kernel<PROG, false><<<blocks, PS_MARK_THREADS, 0, s>>>(P, none);
 }
 
 template<class PROG> ProgEntry makeEntry(int fnV, int fnI, int fnF)
@@ -257,6 +285,7 @@ template<class PROG> ProgEntry makeEntry(int fnV, int fnI, int fnF)
 	e.shadeSpan = launchShadeSpan<PROG>;
 	e.geomSpanMulti = launchGeomSpanMulti<PROG>;
 	e.shadeSpanMulti = launchShadeSpanMulti<PROG>;
+	e.markVary = launchMarkVary<PROG>;
 	return e;
 }
 
@@ -363,6 +392,14 @@ struct ps3d_pipe
 	DevBuf<float> sv2Inv;
 	uint32_t* spanCountDev;
 	size_t spanHigh, listHigh;     // high-water marks of earlier draws: the next speculation
+	// chain marks of long spans (device_types.cuh: SpanStreams): kept once a draw has asked for some
+	DevBuf<uint32_t> spMarkAt, spLongList;
+	DevBuf<float2> spMarkZ;
+	DevBuf<F4> spMarkV;
+	unsigned long long* longCountDev;
+	uint32_t* longLatchedDev;
+	size_t markHigh;
+	size_t marksMin;               // marks are kept for draws that ask for at least this many (PS3D_MARKS_MIN; two more launches per draw)
 	std::vector<uint8_t> vaoLegacy; // VAOs whose last draw needed the first path (a tile list too long for the shared-memory sort)
 	// batches of small draws (kernels_span.cuh: BatchView): `batch` collects draws until something other than a like draw arrives,
 	// `flight` is the batch whose launches are on the stream and whose verdict settle() has yet to read
@@ -451,6 +488,7 @@ static int peerFirstWrite(ps3d_pipe* p);
 static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe, bool multi);
 static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao, size_t spans, size_t longest, size_t survivors, bool multi = false);
 static int flushBatch(ps3d_pipe* p);
+static bool marksOn();
 static int enqueueLegacy(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int path, int vao);
 
 // ---- NCCL, bound at run time ------------------------------------------------------------------------------------------
@@ -663,6 +701,7 @@ static int settle(ps3d_pipe* p)
 		if(r.spans > p->spanHigh) p->spanHigh = r.spans;
 		if(r.longest > p->listHigh) p->listHigh = r.longest;
 		if(r.fragBound > p->survivorHigh) p->survivorHigh = (size_t)r.fragBound;
+		if(r.marks > p->markHigh) p->markHigh = r.marks;
 		const bool multi = p->pending.multi;
 		if(!r.bad)
 		{
@@ -759,6 +798,9 @@ static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe
 		p->launches++;
 	}
 	CK(p, cudaMemsetAsync(p->svCountDev, 0, 4, p->stream));
+	const bool marks = P.sp.markCap > 0;
+	// (lane = long span, grid-stride: the count is on the device; a draw's spans bound it)
+	const unsigned markBlocks = (unsigned)std::min<size_t>(((size_t)P.sp.capacity + PS_MARK_THREADS - 1) / PS_MARK_THREADS, (size_t)p->smCount * 8);
 	{
 		ProfScope ps(p, CLS_TILE);
 		// fewer tiles in play than warp slots on the GPU: cut every tile into 2 or 4 row groups, one warp each
@@ -773,7 +815,14 @@ static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe
 		// PS3D_RASTER_MINB=8|10|12: blocks per SM the kernel is compiled for (64 / 51 / 40 registers) — A/B switch
 		static int minb = -1;
 		if(minb < 0) { const char* e = getenv("PS3D_RASTER_MINB"); minb = e ? atoi(e) : 8; }
-		if(12 == minb) tile_raster_span_kernel<12><<<blocks, 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(P, Q, parts);
+		if(marks)
+		{
+			// the depth chains of the long spans, walked once (kernels_span.cuh: span_mark_depth_kernel), then the variant that uses them
+			span_mark_depth_kernel<<<markBlocks, PS_MARK_THREADS, 0, p->stream>>>(P);
+			p->launches++;
+			tile_raster_span_kernel<8, true><<<blocks, 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(P, Q, parts);
+		}
+		else if(12 == minb) tile_raster_span_kernel<12><<<blocks, 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(P, Q, parts);
 		else if(10 == minb) tile_raster_span_kernel<10><<<blocks, 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(P, Q, parts);
 		else tile_raster_span_kernel<8><<<blocks, 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(P, Q, parts);
 		p->launches++;
@@ -787,14 +836,16 @@ static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe
 		for(size_t g = 0; g < groups.size(); g++)
 		{
 			const BatchView V = { p->batchItems.p, p->batchBlockDraw.p, p->batchBlockList.p, (uint32_t)g };
-			groups[g]->shadeSpanMulti(P, Q, V, p->stream);
+			if(marks && groups[g]->nv > 0) { groups[g]->markVary(P, &V, markBlocks, p->stream); p->launches++; }
+			groups[g]->shadeSpanMulti(P, Q, V, marks, p->stream);
 			p->launches++;
 		}
 	}
 	else
 	{
 		ProfScope ps(p, CLS_SHADE);
-		pe->shadeSpan(P, Q, p->stream);
+		if(marks && pe->nv > 0) { pe->markVary(P, nullptr, markBlocks, p->stream); p->launches++; }
+		pe->shadeSpan(P, Q, marks, p->stream);
 		p->launches++;
 	}
 	CK(p, cudaGetLastError());
@@ -854,6 +905,31 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 	P.sp.rec = p->spRec.p; P.sp.tri = p->spTri.p; P.sp.count = p->spanCountDev;
 	P.sp.capacity = (uint32_t)std::min<size_t>(p->spRec.cap, 0xfffffff0u);
 	P.tl.fill = p->tlFill.p; P.tl.len = p->tlLen.p; P.tl.ids = p->tlIds.p; P.tl.cap = (uint32_t)listCap;
+	// chain marks of long spans: once some draw has asked for marks (its report said how many), room for them is kept; a draw
+	// whose marks do not fit replays those spans from their start, as every long span does while no marks are kept
+	P.sp.longCount = p->longCountDev; P.sp.longLatched = p->longLatchedDev;
+	P.sp.markAt = nullptr; P.sp.longList = nullptr; P.sp.markZ = nullptr; P.sp.markV = nullptr; P.sp.markCap = 0;
+	if(p->markHigh >= p->marksMin && p->markHigh > 0 && marksOn())
+	{
+		size_t nvMax = (size_t)pe->nv;
+		if(multi) for(const ps3d_pipe::BatchDraw& d : p->flight.draws) nvMax = std::max(nvMax, (size_t)d.pe->nv);
+		size_t markCap = std::min<size_t>(p->markHigh + p->markHigh / 4 + 1024, 0xfffffff0u);
+		bool room = true;
+		if(p->capturing)
+		{
+			// (a captured frame cannot allocate: what the same frame left behind a moment ago, or no marks)
+			room = p->spMarkAt.cap >= p->spRec.cap && p->spLongList.cap >= p->spRec.cap && p->spMarkZ.cap > 0 && (0 == nvMax || p->spMarkV.cap / nvMax > 0);
+			if(room) { markCap = std::min(markCap, p->spMarkZ.cap); if(nvMax) markCap = std::min(markCap, p->spMarkV.cap / nvMax); }
+		}
+		if(room)
+		{
+			CK(p, p->spMarkAt.ensure(p->spRec.cap)); CK(p, p->spLongList.ensure(p->spRec.cap));
+			CK(p, p->spMarkZ.ensure(markCap));
+			if(nvMax) CK(p, p->spMarkV.ensure(markCap * nvMax));
+			P.sp.markAt = p->spMarkAt.p; P.sp.longList = p->spLongList.p; P.sp.markZ = p->spMarkZ.p; P.sp.markV = p->spMarkV.p;
+			P.sp.markCap = (uint32_t)markCap;
+		}
+	}
 	if(multi)
 	{
 		// every draw's DrawParams into the table (shifted by its first id), its blocks into the block tables; then one geometry
@@ -916,7 +992,7 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 		ProfScope ps(p, CLS_BIN);
 		tile_plan_kernel<<<1, 1024, 0, p->stream>>>(P.tl, ntiles, p->statsDev, p->spanCountDev, P.sp.capacity,
 		                                          (unsigned long long)(std::min<size_t>(p->sv2Span.cap, 0xfffffff0u) - svSlack), PS_SORT_LIMIT,
-		                                          p->poisonDev, p->reportDev, p->tileOrder.p);
+		                                          p->poisonDev, p->reportDev, p->tileOrder.p, p->longCountDev, p->longLatchedDev);
 		p->launches++;
 	}
 	if(p->capturing)
@@ -937,6 +1013,8 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 	return PS3D_OK;
 }
 
+// PS3D_MARKS=0: no chain marks, long spans replay from their start (A/B runs)
+static bool marksOn() { static int on = -1; if(on < 0) { const char* e = getenv("PS3D_MARKS"); on = (e && e[0] == '0') ? 0 : 1; } return on == 1; }
 // PS3D_BATCH=0: every draw is launched as it is submitted (A/B runs)
 static bool batchingOn() { static int on = -1; if(on < 0) { const char* e = getenv("PS3D_BATCH"); on = (e && e[0] == '0') ? 0 : 1; } return on == 1; }
 #define PS_BATCH_DRAW_TRIS 16384u     // a draw with more triangles than this fills the GPU by itself
@@ -1103,17 +1181,23 @@ int ps3d_create(int width, int height, int device, ps3d_pipe** out)
 	}
 	ok = ok && cudaMalloc((void**)&p->svCountDev, 16) == cudaSuccess;
 	ok = ok && cudaMalloc((void**)&p->spanCountDev, 16) == cudaSuccess;
+	ok = ok && cudaMalloc((void**)&p->longCountDev, 16) == cudaSuccess;
+	ok = ok && cudaMalloc((void**)&p->longLatchedDev, 16) == cudaSuccess;
 	memset(&p->peer, 0, sizeof(p->peer));
 	p->capturing = false; p->graphLaunched = false; p->capBack = 0;
 	ok = ok && cudaMalloc((void**)&p->peer.flagsOwn, sizeof(PeerFlags)) == cudaSuccess;
 	ok = ok && cudaMalloc((void**)&p->peer.ctr, sizeof(PeerCounters)) == cudaSuccess;
 	if(ok) { cudaMemsetAsync(p->peer.flagsOwn, 0, sizeof(PeerFlags), p->stream); cudaMemsetAsync(p->peer.ctr, 0, sizeof(PeerCounters), p->stream); }
 	p->spanHigh = p->listHigh = 0;
+	p->markHigh = 0;
+	{ const char* e = getenv("PS3D_MARKS_MIN"); p->marksMin = e ? (size_t)atoll(e) : 16384; }
 	p->batch.clear(); p->flight.clear(); p->batchesLaunched = p->drawsBatched = 0; p->pending.multi = false;
 	p->pending.span = false; p->pending.tailLaunched = false; p->pending.vao = -1;
 	if(ok)
 	{
 		cudaMemsetAsync(p->spanCountDev, 0, 16, p->stream);
+		cudaMemsetAsync(p->longCountDev, 0, 16, p->stream);
+		cudaMemsetAsync(p->longLatchedDev, 0, 16, p->stream);
 		cudaMemsetAsync(p->display[0], 0, cbytes, p->stream);
 		cudaMemsetAsync(p->display[1], 0, cbytes, p->stream);
 		cudaMemsetAsync(p->defaultDepth, 0, dbytes, p->stream);
@@ -1166,7 +1250,8 @@ int ps3d_destroy(ps3d_pipe* p)
 	for(Vbo& v : p->vbos) if(v.alive) freeVbo(v);
 	cudaFree(p->display[0]); cudaFree(p->display[1]); cudaFree(p->defaultDepth);
 	cudaFree(p->totalDev); cudaFree(p->statsDev); cudaFree(p->svCountDev); cudaFree(p->poisonDev); cudaFreeHost(p->report); cudaEventDestroy(p->scanEvent);
-	cudaFree(p->spanCountDev);
+	cudaFree(p->spanCountDev); cudaFree(p->longCountDev); cudaFree(p->longLatchedDev);
+	p->spMarkAt.release(); p->spLongList.release(); p->spMarkZ.release(); p->spMarkV.release();
 	for(auto& g : p->graphs) if(g.alive) cudaGraphExecDestroy(g.exec);
 	if(p->peer.active && p->peer.rank != 0)
 	{
