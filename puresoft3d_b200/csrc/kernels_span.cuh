@@ -970,6 +970,7 @@ PS_D void flushEnd(const SurvivorStream2& Q, RasterSmem2& S, RasterCtx2& C)
 }
 PS_D void flushBegin(const SurvivorStream2& Q, RasterSmem2& S, RasterCtx2& C)
 {
+	if(nullptr == Q.span) return;                      // a draw whose fragment functor does nothing keeps no survivors (they are counted)
 	flushEnd(Q, S, C);
 	C.pSpan = S.qSpan[C.lane]; C.pXY = S.qXY[C.lane]; C.pInv = S.qInv[C.lane];
 	if(0 == C.lane) C.reserved = atomicAdd(Q.count, 32u);
@@ -978,6 +979,7 @@ PS_D void flushBegin(const SurvivorStream2& Q, RasterSmem2& S, RasterCtx2& C)
 // the last, partial group of a tile: n < 32 records, reserved and stored on the spot
 PS_D void flushRest(const SurvivorStream2& Q, RasterSmem2& S, RasterCtx2& C, uint32_t n)
 {
+	if(nullptr == Q.span) return;
 	flushEnd(Q, S, C);
 	const int lane = C.lane;
 	uint32_t base = 0;

@@ -55,6 +55,7 @@ struct ProgEntry
 	int ntex;
 	int texSlot[PS_MAX_BOUND_TEX];
 	bool mayDiscard, usesWrite4;
+	bool noop;                  // the fragment functor does nothing (FP_Null: depth-only passes)
 	LaunchGeom geom;
 	LaunchTile tileImmediate, tileOrdered;
 	LaunchShade shade;
@@ -266,6 +267,8 @@ template<class PROG> void launchMarkVary(const DrawParams& P, const BatchView* B
 	else span_mark_vary_kernel<PROG, false><<<blocks, PS_MARK_THREADS, 0, s>>>(P, none);
 }
 
+template<class F> constexpr auto fragmentNoop(int) -> decltype(F::NOOP) { return F::NOOP; }
+template<class F> constexpr bool fragmentNoop(...) { return false; }
 template<class PROG> ProgEntry makeEntry(int fnV, int fnI, int fnF)
 {
 	ProgEntry e;
@@ -277,6 +280,7 @@ template<class PROG> ProgEntry makeEntry(int fnV, int fnI, int fnF)
 	for(int i = 0; i < PS_MAX_BOUND_TEX; i++) e.texSlot[i] = i < e.ntex ? PROG::F::texSlot(i) : -1;
 	e.mayDiscard = PROG::F::MAY_DISCARD;
 	e.usesWrite4 = PROG::F::USES_WRITE4;
+	e.noop = fragmentNoop<typename PROG::F>(0);
 	e.geom = launchGeom<PROG>;
 	e.tileImmediate = launchTileImmediate<PROG>;
 	e.tileOrdered = launchTileOrdered<PROG>;
@@ -489,6 +493,7 @@ static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe
 static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao, size_t spans, size_t longest, size_t survivors, bool multi = false);
 static int flushBatch(ps3d_pipe* p);
 static bool marksOn();
+static bool spanNoShade(const ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe, bool multi);
 static int enqueueLegacy(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int path, int vao);
 
 // ---- NCCL, bound at run time ------------------------------------------------------------------------------------------
@@ -700,9 +705,9 @@ static int settle(ps3d_pipe* p)
 		// and counts were reset by the plan kernel); a list too long for the shared-memory sort sends the draw down the first path
 		if(r.spans > p->spanHigh) p->spanHigh = r.spans;
 		if(r.longest > p->listHigh) p->listHigh = r.longest;
-		if(r.fragBound > p->survivorHigh) p->survivorHigh = (size_t)r.fragBound;
-		if(r.marks > p->markHigh) p->markHigh = r.marks;
 		const bool multi = p->pending.multi;
+		if(r.fragBound > p->survivorHigh && !spanNoShade(p, P, pe, multi)) p->survivorHigh = (size_t)r.fragBound;
+		if(r.marks > p->markHigh) p->markHigh = r.marks;
 		if(!r.bad)
 		{
 			if(p->pending.tailLaunched) return PS3D_OK;
@@ -786,12 +791,25 @@ static void batchGroups(const ps3d_pipe::Batch& B, std::vector<const ProgEntry*>
 		if(std::find(groups.begin(), groups.end(), d.pe) == groups.end()) groups.push_back(d.pe);
 }
 
+// a draw (a batch) whose fragment functors do nothing — the depth-only pass of a shadow map — has no shade kernel to run and
+// keeps no survivor stream; the raster kernel still counts its survivors. (Not while the per-pixel counts of the parity hook
+// are on: they are taken by the shade kernel.)
+static bool spanNoShade(const ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe, bool multi)
+{
+	if(P.cap) return false;
+	if(!multi) return pe->noop;
+	for(const ps3d_pipe::BatchDraw& d : p->flight.draws) if(!d.pe->noop) return false;
+	return true;
+}
+
 static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe, bool multi)
 {
 	const uint32_t ntiles = (uint32_t)(P.tilesX * P.tilesY);
 	SurvivorStream2 Q;
 	Q.span = p->sv2Span.p; Q.xy = p->sv2XY.p; Q.inv = p->sv2Inv.p; Q.count = p->svCountDev;
 	Q.capacity = (uint32_t)std::min<size_t>(p->sv2Span.cap, 0xfffffff0u);
+	const bool noShade = spanNoShade(p, P, pe, multi);
+	if(noShade) { Q.span = nullptr; Q.xy = nullptr; Q.inv = nullptr; Q.capacity = 0; }
 	{
 		ProfScope ps(p, CLS_BIN);
 		tile_list_sort_cap_kernel<<<(ntiles + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK, 32 * PS_WARPS_PER_BLOCK, 0, p->stream>>>(P.tl, ntiles, p->poisonDev, p->tileOrder.p);
@@ -828,6 +846,7 @@ static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe
 		p->launches++;
 	}
 	{ const int rc = peerFirstWrite(p); if(rc) return rc; }
+	if(noShade) { CK(p, cudaGetLastError()); return PS3D_OK; }
 	if(multi)
 	{
 		ProfScope ps(p, CLS_SHADE);
@@ -892,9 +911,13 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 		if(p->tlFill.p != before) CK(p, cudaMemsetAsync(p->tlFill.p, 0, p->tlFill.cap * 4, p->stream));
 	}
 	const size_t svSlack = 0;
-	size_t svCap = (exact ? survivors + 1 : std::max(p->survivorHigh + p->survivorHigh / 4, (size_t)P.vpW * P.vpH * 2)) + svSlack;
-	if(p->capturing && p->sv2Span.cap >= p->survivorHigh) svCap = std::min(svCap, p->sv2Span.cap);
-	CK(p, p->sv2Span.ensure(svCap)); CK(p, p->sv2XY.ensure(svCap)); CK(p, p->sv2Inv.ensure(svCap));
+	const bool noShade = spanNoShade(p, P, pe, multi);
+	if(!noShade)
+	{
+		size_t svCap = (exact ? survivors + 1 : std::max(p->survivorHigh + p->survivorHigh / 4, (size_t)P.vpW * P.vpH * 2)) + svSlack;
+		if(p->capturing && p->sv2Span.cap >= p->survivorHigh) svCap = std::min(svCap, p->sv2Span.cap);
+		CK(p, p->sv2Span.ensure(svCap)); CK(p, p->sv2XY.ensure(svCap)); CK(p, p->sv2Inv.ensure(svCap));
+	}
 	P.hdr = p->hdr.p; P.vary = p->vary.p; P.tileOrder = p->tileOrder.p; P.poison = p->poisonDev;
 	if(P.band0 > 0 || P.band1 < P.vpH)
 	{
@@ -991,7 +1014,7 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 	{
 		ProfScope ps(p, CLS_BIN);
 		tile_plan_kernel<<<1, 1024, 0, p->stream>>>(P.tl, ntiles, p->statsDev, p->spanCountDev, P.sp.capacity,
-		                                          (unsigned long long)(std::min<size_t>(p->sv2Span.cap, 0xfffffff0u) - svSlack), PS_SORT_LIMIT,
+		                                          noShade ? 0xffffffffffull : (unsigned long long)(std::min<size_t>(p->sv2Span.cap, 0xfffffff0u) - svSlack), PS_SORT_LIMIT,
 		                                          p->poisonDev, p->reportDev, p->tileOrder.p, p->longCountDev, p->longLatchedDev);
 		p->launches++;
 	}

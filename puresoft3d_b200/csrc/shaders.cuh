@@ -680,6 +680,7 @@ struct VP_Shadow // testproc.cpp:510-516 — 0.9 shrink (xyz), then PVM
 // IP_Null (testproc.cpp:26-45) declares 16 bytes of user data and never touches them: no varying reaches the fragment functor
 struct FP_Null // testproc.cpp:520-524
 {
+	static constexpr bool NOOP = true;   // process() does nothing: a depth-only pass needs no shade kernel and no survivor stream
 	static constexpr uint64_t UNIFORMS = 0;
 	static constexpr bool MAY_DISCARD = false;
 	static constexpr bool USES_WRITE4 = false;

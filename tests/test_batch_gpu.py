@@ -83,3 +83,22 @@ def test_captured_frame_of_small_draws(cuda_lib, oracle_lib):
     assert np.array_equal(pipe.readDepth().view(np.uint32), want["depth"].view(np.uint32))
     pipe.graphDestroy(g)
     pipe.close()
+
+
+@pytest.mark.parametrize("name", ["c3_demo2_desk", "demo2_objx_file", "demo1_planets"])
+def test_depth_only_passes_without_the_parity_hook(name, cuda_lib, oracle_lib):
+    """Without the per-pixel count hook a pass whose fragment functor does nothing (FP_Null: the shadow maps) runs no shade kernel and
+    keeps no survivor stream: the shadow map it leaves (seen through the lit pass), the frame and the counters must not change."""
+    sc = SMALL[name]()
+    want = render_all(oracle_lib, sc, capture=False)
+    pipe = PuresoftPipeline(sc.width, sc.height, lib=cuda_lib)
+    up = scenes.upload(pipe, sc)
+    for frame in range(3):
+        pipe.resetStats()
+        scenes.replay(pipe, sc, up)
+        st = pipe.getStats()
+        assert np.array_equal(pipe.readDepth().view(np.uint32), want["depth"].view(np.uint32)), frame
+        assert np.array_equal(pipe.readColour().view(np.uint32)[:-1], want["colour"].view(np.uint32)[:-1]), frame
+        for key in ("draws", "triangles_submitted", "triangles_rasterised", "spans", "fragments_tested", "fragments_shaded"):
+            assert st[key] == want["stats"][key], (frame, key)
+    pipe.close()
