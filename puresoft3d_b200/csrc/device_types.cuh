@@ -142,8 +142,19 @@ struct SurvivorStream2
 	float* inv;           // 1 / correctionFactor2 at the pixel (interp.cpp:85)
 	uint32_t* count;
 	uint32_t capacity;
+	// draws that blend (blend4 is not commutative: a pixel's survivors must land in submission order). A warp of the raster kernel
+	// appends its tile's survivors in groups of 32 consecutive stream slots, in submission order pixel by pixel; the groups of a
+	// tile (of a row group of a tile) are chained: chain[2 u] = 1 + first slot of the first group of unit u (0: none),
+	// chain[2 u + 1] = size of its last group, next[first slot of a group] = 1 + first slot of the next (0: last). The shade kernel
+	// leaves every survivor's colour in `colour` instead of storing it, and shade_resolve_kernel walks each unit's groups in order.
+	// NULL for every other draw.
+	uint32_t* next;
+	uint32_t* chain;
+	uint32_t* colour;
 };
 #define PS_SV_WINNER 0x80000000u   // the LAST survivor of its pixel: the only one whose colour lands
+#define PS_SV_WROTE 0x40000000u    // (blending draws) the fragment functor wrote a colour ...
+#define PS_SV_BLEND 0x20000000u    // ... through write4 (blend4 under ALPHABLEND) rather than write
 
 struct DrawParams
 {

@@ -587,6 +587,12 @@ __global__ void __launch_bounds__(PS_GEOM_THREADS) geom_span_kernel(const __grid
 	const uint32_t orig = threadIdx.x;
 	uint32_t tri = tri0 + threadIdx.x;
 	bool candidate = tri < P.ntris;
+	if(!STAGED && !LISTED && P.batchTrisPerBlock)
+	{
+		// a small draw: fewer triangles per block, more blocks (a block's rows and whole-rectangle appends are its own threads' work)
+		tri = blockIdx.x * P.batchTrisPerBlock + threadIdx.x;
+		candidate = threadIdx.x < P.batchTrisPerBlock && tri < P.ntris;
+	}
 	if(LISTED)
 	{
 		const uint32_t nList = *P.workCount;
@@ -933,7 +939,10 @@ struct RasterSmem2
 	// staging queue of survivors
 	uint32_t qSpan[PS_RQCAP], qXY[PS_RQCAP];   // px | row << 4 while queued
 	float qInv[PS_RQCAP];
+	uint32_t chainUnit, chainLast;             // blending draws: this warp's unit, 1 + first slot of the last group it appended
+	uint32_t chainPad[2];                      // (the array of these is walked with 16-byte accesses)
 };
+static_assert(0 == sizeof(RasterSmem2) % 16, "one per warp, 16-byte accesses");
 
 struct RasterCtx2
 {
@@ -955,11 +964,23 @@ struct RasterCtx2
 // trip (7 % of this kernel's stall samples when waited for on the spot) passes while the next pixels are tested, and the stream
 // stays dense. (Tried: slots reserved 32 at a time ahead of need, the last partial group padded with holes the shade kernel
 // skips — same gain here, but 4 % more warps for the shade kernel.)
+// a blending draw (SurvivorStream2::next): one lane hangs the group of `n` survivors at stream slot `base` onto its unit's chain
+PS_D void chainGroup(const SurvivorStream2& Q, RasterSmem2& S, uint32_t base, uint32_t n)
+{
+	if(base >= Q.capacity) return;                     // (the draw is poisoned: nothing reads the chain)
+	Q.next[base] = 0;
+	if(S.chainLast) Q.next[S.chainLast - 1] = base + 1;
+	else Q.chain[2 * S.chainUnit] = base + 1;
+	Q.chain[2 * S.chainUnit + 1] = n;
+	S.chainLast = base + 1;
+}
+
 PS_D void flushEnd(const SurvivorStream2& Q, RasterSmem2& S, RasterCtx2& C)
 {
 	if(!C.pending) return;                             // (warp-uniform)
 	C.pending = false;
-	const uint32_t i = __shfl_sync(PS_FULL, C.reserved, 0) + (uint32_t)C.lane;
+	const uint32_t base = __shfl_sync(PS_FULL, C.reserved, 0);
+	const uint32_t i = base + (uint32_t)C.lane;
 	if(i < Q.capacity)
 	{
 		Q.span[i] = C.pSpan; Q.inv[i] = C.pInv;
@@ -967,6 +988,7 @@ PS_D void flushEnd(const SurvivorStream2& Q, RasterSmem2& S, RasterCtx2& C)
 	}
 	// queue order = submission order inside a pixel and a warp's reservations grow with time: the latest record has the highest index
 	atomicMax(&S.lastIdx[C.pXY & 0xff], i + 1);
+	if(Q.next && 0 == C.lane) chainGroup(Q, S, base, 32u);
 }
 PS_D void flushBegin(const SurvivorStream2& Q, RasterSmem2& S, RasterCtx2& C)
 {
@@ -996,6 +1018,7 @@ PS_D void flushRest(const SurvivorStream2& Q, RasterSmem2& S, RasterCtx2& C, uin
 		}
 		atomicMax(&S.lastIdx[m & 0xff], i + 1);
 	}
+	if(Q.next && 0 == lane && n) chainGroup(Q, S, base, n);
 	__syncwarp();
 }
 
@@ -1149,6 +1172,7 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK, MINB) tile_raster_spa
 	}
 	__syncwarp();
 
+	if(Q.next && 0 == lane) { S.chainUnit = (uint32_t)warpSlot; S.chainLast = 0; Q.chain[2 * warpSlot] = 0; }
 	RasterCtx2 C;
 	C.lane = lane; C.tx0 = tx0; C.ty0 = ty0;
 	C.testDepth = testDepth; C.updateDepth = updateDepth;
@@ -1384,7 +1408,8 @@ PS_D int varyingChainStart(const uint4& q0, const uint4& q1, const uint4& q2, co
 // MULTI: a batch of draws (BatchView above): this launch shades the survivors of its programme group's draws, with that draw's
 // uniforms, textures and varyings. MARKS: fragments of long spans start their chains from the nearest chain mark
 // (SpanStreams::markV, span_mark_vary_kernel).
-template<class PROG, int MINB, bool MULTI = false, bool MARKS = false>
+// ORDERED: a draw that blends — the colour is left in the stream for shade_resolve_kernel (SurvivorStream2::colour).
+template<class PROG, int MINB, bool MULTI = false, bool MARKS = false, bool ORDERED = false>
 __global__ void __launch_bounds__(PS_SHADE_THREADS, MINB) shade_span_kernel(const __grid_constant__ DrawParams P, const SurvivorStream2 Q, const BatchView B)
 {
 	constexpr int NV = PROG::NV;
@@ -1441,7 +1466,7 @@ __global__ void __launch_bounds__(PS_SHADE_THREADS, MINB) shade_span_kernel(cons
 			typedef typename PROG::I IP;
 			const int x1 = varyingChainStart<PROG>(q0, q1, q2, v, left, right, e, y, vStart, vStep);
 			int xr = x1;
-			if(MARKS && ((uint32_t)A.z & 0x7fffffffu) > 0x7f800000u && x - x1 >= PS_MARK_STEP)
+			if(MARKS && P.sp.markCap && ((uint32_t)A.z & 0x7fffffffu) > 0x7f800000u && x - x1 >= PS_MARK_STEP)
 			{
 				// a long span (its depth bound is the NaN evalSpan left): from the nearest mark of its chain
 				const uint32_t at = __ldg(P.sp.markAt + spCur);
@@ -1475,7 +1500,12 @@ __global__ void __launch_bounds__(PS_SHADE_THREADS, MINB) shade_span_kernel(cons
 		out.discarded = false; out.wrote = false; out.blendable = false; out.bgra = 0;
 		PROG::F::process(frag, out, *D);                                     // fragthrd.cpp:231
 		if(P.cap && x < P.capW && y < P.capH) atomicAdd(&P.cap[(size_t)y * P.capW + x], 1u);
-		if(out.wrote && (xy & PS_SV_WINNER) && y < P.colour.height && x < P.colour.width)
+		if(ORDERED)
+		{
+			Q.colour[i] = out.bgra;
+			if(out.wrote) Q.xy[i] = xy | PS_SV_WROTE | (out.blendable ? PS_SV_BLEND : 0u);
+		}
+		else if(out.wrote && (xy & PS_SV_WINNER) && y < P.colour.height && x < P.colour.width)
 		{
 			// FBOBridge::write / write4 without ALPHABLEND: a plain store (fragthrd.cpp:54-82); later survivors of the pixel overwrite
 			uint8_t* row = P.colour.ptr + (size_t)(P.colour.topDown ? P.colour.height - 1 - y : y) * P.colour.scanline;
@@ -1568,5 +1598,57 @@ __global__ void __launch_bounds__(PS_MARK_THREADS) span_mark_vary_kernel(const _
 #pragma unroll 4
 			for(int i = 0; i < PS_MARK_STEP; i++) IP::stepForward(vStart, vStep, 1);
 		}
+	}
+}
+
+// ======================================================================================================================
+// draws that blend: a pixel's colours applied first to last (FBOBridge::write4 -> blend4 under ALPHABLEND, fragthrd.cpp:54-82)
+// ======================================================================================================================
+
+// warp = unit of the raster kernel (a tile, or a row group of one): its groups of survivors first to last; lane = survivor of the
+// group; survivors of one pixel inside a group land in lane order.
+__global__ void __launch_bounds__(128) shade_resolve_kernel(const __grid_constant__ DrawParams P, const SurvivorStream2 Q, int parts)
+{
+	if(*P.poison) return;
+	const int lane = threadIdx.x & 31;
+	const uint32_t u = blockIdx.x * 4 + (threadIdx.x >> 5);
+	if(u >= P.tileOrder[P.tilesX * P.tilesY] * (uint32_t)parts) return;       // the units the raster kernel ran (same test)
+	if(0 == P.tl.len[P.tileOrder[u / (uint32_t)parts]]) return;
+	const bool alphaBlend = 0 != (P.behavior & PS_BEHAVIOR_ALPHABLEND);
+	const uint32_t ltMask = (1u << lane) - 1;
+	const uint32_t lastN = Q.chain[2 * u + 1];
+	uint32_t at = Q.chain[2 * u];
+	while(at)
+	{
+		const uint32_t base = at - 1;
+		const uint32_t nextAt = Q.next[base];
+		const uint32_t n = nextAt ? 32u : lastN;
+		uint32_t xy = 0, c = 0;
+		bool act = false;
+		if((uint32_t)lane < n)
+		{
+			xy = Q.xy[base + lane];
+			c = Q.colour[base + lane];
+			const int x = (int)(xy & 0x1fff), y = (int)((xy >> 13) & 0x1fff);
+			act = (xy & PS_SV_WROTE) && y < P.colour.height && x < P.colour.width;
+		}
+		const uint32_t peers = __match_any_sync(PS_FULL, act ? (xy & 0x3ffffffu) : 0x80000000u + (uint32_t)lane);
+		const int rank = __popc(peers & ltMask);
+		const int maxRank = __reduce_max_sync(PS_FULL, act ? rank : 0);
+		uint32_t* dst = nullptr;
+		if(act)
+		{
+			const int x = (int)(xy & 0x1fff), y = (int)((xy >> 13) & 0x1fff);
+			uint8_t* row = P.colour.ptr + (size_t)(P.colour.topDown ? P.colour.height - 1 - y : y) * P.colour.scanline;
+			dst = (uint32_t*)(row + (size_t)x * 4);
+		}
+#pragma unroll 1
+		for(int r = 0; r <= maxRank; r++)
+		{
+			// FBOBridge::write4 -> blend4 under ALPHABLEND, FBOBridge::write -> plain store (fragthrd.cpp:54-82)
+			if(act && rank == r) *(volatile uint32_t*)dst = ((xy & PS_SV_BLEND) && alphaBlend) ? blend4(c, *(volatile uint32_t*)dst) : c;
+			__syncwarp();
+		}
+		at = nextAt;
 	}
 }

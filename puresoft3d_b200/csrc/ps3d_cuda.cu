@@ -194,6 +194,11 @@ template<class PROG> void launchGeomSpan(const DrawParams& P, cudaStream_t s)
 		geom_span_kernel<PROG, 0, true><<<blocks, PS_GEOM_THREADS, 0, s>>>(P);
 		return;
 	}
+	if(P.batchTrisPerBlock)
+	{
+		geom_span_kernel<PROG, 0, false><<<(P.ntris + P.batchTrisPerBlock - 1) / P.batchTrisPerBlock, PS_GEOM_THREADS, 0, s>>>(P);
+		return;
+	}
 	// PS3D_GEOM_STAGE=0: nothing staged (A/B runs); default: the position slot staged in shared memory by one TMA bulk copy per block.
 	// (Every slot staged — STAGED = 2, 28 KB per block for DEF03, phase B off global memory — measured 0.194 -> 0.215 ms on C2: dropped.)
 	if(geomStagingOn() && launchGeomSpanStaged<PROG, 1>(P, blocks, s)) return;
@@ -201,6 +206,23 @@ template<class PROG> void launchGeomSpan(const DrawParams& P, cudaStream_t s)
 }
 template<class PROG> void launchShadeSpan(const DrawParams& P, const SurvivorStream2& Q, bool marks, cudaStream_t s)
 {
+	if(Q.colour)
+	{
+		// a draw that blends: colours left in the stream for shade_resolve_kernel (the variant with chain marks serves both cases)
+		if constexpr(PROG::F::USES_WRITE4)
+		{
+			static int perSMo[PS_MAX_DEVICES] = { 0 }, smso[PS_MAX_DEVICES] = { 0 };
+			const int dev = currentDevice();
+			if(0 == perSMo[dev])
+			{
+				cudaDeviceGetAttribute(&smso[dev], cudaDevAttrMultiProcessorCount, dev);
+				if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSMo[dev], shade_span_kernel<PROG, 7, false, true, true>, PS_SHADE_THREADS, 0) != cudaSuccess || perSMo[dev] <= 0) perSMo[dev] = 4;
+			}
+			const BatchView none = { nullptr, nullptr, nullptr, 0 };
+			shade_span_kernel<PROG, 7, false, true, true><<<smso[dev] * perSMo[dev], PS_SHADE_THREADS, 0, s>>>(P, Q, none);
+		}
+		return;
+	}
 	if(marks && PROG::NV > 0)
 	{
 		// long spans with chain marks (SpanStreams::markV): the variant that starts from them
@@ -394,6 +416,7 @@ struct ps3d_pipe
 	DevBuf<uint32_t> tlFill, tlLen, tlIds;
 	DevBuf<uint32_t> sv2Span, sv2XY;
 	DevBuf<float> sv2Inv;
+	DevBuf<uint32_t> sv2Next, sv2Chain, sv2Colour;   // draws that blend (device_types.cuh: SurvivorStream2)
 	uint32_t* spanCountDev;
 	size_t spanHigh, listHigh;     // high-water marks of earlier draws: the next speculation
 	// chain marks of long spans (device_types.cuh: SpanStreams): kept once a draw has asked for some
@@ -441,7 +464,7 @@ struct ps3d_pipe
 	cudaEvent_t scanEvent;
 	bool speculate;
 	size_t pairHigh, survivorHigh;   // high-water marks of earlier draws: the next speculation
-	struct Pending { bool valid; DrawParams P; const ProgEntry* pe; int path; bool radix; bool span; bool tailLaunched; int vao; bool multi; } pending;
+	struct Pending { bool valid; DrawParams P; const ProgEntry* pe; int path; bool radix; bool span; bool tailLaunched; int vao; bool multi; bool blend; } pending;
 	ps3d_stats stats;
 	uint32_t* capDev;
 	int capW, capH;
@@ -489,9 +512,18 @@ struct ProfScope
 
 static int settle(ps3d_pipe* p);
 static int peerFirstWrite(ps3d_pipe* p);
-static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe, bool multi);
-static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao, size_t spans, size_t longest, size_t survivors, bool multi = false);
+static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe, bool multi, bool blend);
+static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao, size_t spans, size_t longest, size_t survivors, bool multi = false, bool blend = false);
 static int flushBatch(ps3d_pipe* p);
+#define PS_BATCH_DRAW_TRIS 16384u     // a draw with more triangles than this fills the GPU by itself
+#define PS_BATCH_MAX_DRAWS 1024u
+#define PS_BATCH_MAX_BLOCKS 8192u       // (every block is PS_GEOM_THREADS triangle ids: 64 B of header each)
+
+// a small draw spreads over up to 2048 blocks (a block's rows and whole-rectangle tile appends are its own threads' work: twenty
+// full-screen triangles in one block are half a millisecond of appends, in twenty blocks 25 us: kernels_span.cuh)
+static uint32_t batchTrisPerBlock(size_t ntris) { return (uint32_t)std::min<size_t>(std::max<size_t>((ntris + 2047) / 2048, 1), PS_GEOM_THREADS); }
+static uint32_t batchBlocks(size_t ntris) { const uint32_t per = batchTrisPerBlock(ntris); return (uint32_t)((ntris + per - 1) / per); }
+
 static bool marksOn();
 static bool spanNoShade(const ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe, bool multi);
 static int enqueueLegacy(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int path, int vao);
@@ -708,16 +740,17 @@ static int settle(ps3d_pipe* p)
 		const bool multi = p->pending.multi;
 		if(r.fragBound > p->survivorHigh && !spanNoShade(p, P, pe, multi)) p->survivorHigh = (size_t)r.fragBound;
 		if(r.marks > p->markHigh) p->markHigh = r.marks;
+		const bool blend = p->pending.blend;
 		if(!r.bad)
 		{
 			if(p->pending.tailLaunched) return PS3D_OK;
-			return launchSpanTail(p, P, pe, multi);
+			return launchSpanTail(p, P, pe, multi, blend);
 		}
 		CK(p, cudaMemsetAsync(p->poisonDev, 0, 4, p->stream));
 		const int vao = p->pending.vao;
 		if(r.longest > PS_SORT_LIMIT || r.fragBound >= 0xfffffff0ull || r.spans >= 0xfffffff0u)
 		{
-			const int path = r.fragBound >= 0xfffffff0ull ? 1 : 2;
+			const int path = (blend || r.fragBound >= 0xfffffff0ull) ? 1 : 2;
 			if(multi)
 			{
 				// a batch whose lists outgrew the shared-memory sort: its draws one by one down the first path (nothing of the batch
@@ -736,7 +769,7 @@ static int settle(ps3d_pipe* p)
 			return enqueueLegacy(p, P2, pe, path, vao);
 		}
 		const DrawParams P2 = P;
-		return enqueueSpan(p, P2, pe, vao, r.spans, r.longest, (size_t)r.fragBound, multi);
+		return enqueueSpan(p, P2, pe, vao, r.spans, r.longest, (size_t)r.fragBound, multi, blend);
 	}
 	if(r.pairs > p->pairHigh) p->pairHigh = r.pairs;
 	if(2 == path && r.fragBound > p->survivorHigh) p->survivorHigh = (size_t)r.fragBound;
@@ -802,13 +835,14 @@ static bool spanNoShade(const ps3d_pipe* p, const DrawParams& P, const ProgEntry
 	return true;
 }
 
-static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe, bool multi)
+static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe, bool multi, bool blend)
 {
 	const uint32_t ntiles = (uint32_t)(P.tilesX * P.tilesY);
 	SurvivorStream2 Q;
 	Q.span = p->sv2Span.p; Q.xy = p->sv2XY.p; Q.inv = p->sv2Inv.p; Q.count = p->svCountDev;
 	Q.capacity = (uint32_t)std::min<size_t>(p->sv2Span.cap, 0xfffffff0u);
-	const bool noShade = spanNoShade(p, P, pe, multi);
+	Q.next = blend ? p->sv2Next.p : nullptr; Q.chain = blend ? p->sv2Chain.p : nullptr; Q.colour = blend ? p->sv2Colour.p : nullptr;
+	const bool noShade = !blend && spanNoShade(p, P, pe, multi);
 	if(noShade) { Q.span = nullptr; Q.xy = nullptr; Q.inv = nullptr; Q.capacity = 0; }
 	{
 		ProfScope ps(p, CLS_BIN);
@@ -817,6 +851,7 @@ static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe
 	}
 	CK(p, cudaMemsetAsync(p->svCountDev, 0, 4, p->stream));
 	const bool marks = P.sp.markCap > 0;
+	int partsUsed = 1;
 	// (lane = long span, grid-stride: the count is on the device; a draw's spans bound it)
 	const unsigned markBlocks = (unsigned)std::min<size_t>(((size_t)P.sp.capacity + PS_MARK_THREADS - 1) / PS_MARK_THREADS, (size_t)p->smCount * 8);
 	{
@@ -829,6 +864,7 @@ static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe
 		// GPU's warp slots about twice over, shorter chains win — 2, 4 or 8 row groups per tile)
 		int parts = rasterPartsForced();
 		if(parts <= 0) parts = tilesInPlay * 4 <= warpSlots ? 8 : (tilesInPlay * 2 <= warpSlots ? 4 : (tilesInPlay <= warpSlots * 2 ? 2 : 1));
+		partsUsed = parts;
 		const unsigned blocks = (ntiles * (unsigned)parts + PS_WARPS_PER_BLOCK - 1) / PS_WARPS_PER_BLOCK;
 		// PS3D_RASTER_MINB=8|10|12: blocks per SM the kernel is compiled for (64 / 51 / 40 registers) — A/B switch
 		static int minb = -1;
@@ -866,6 +902,12 @@ static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe
 		if(marks && pe->nv > 0) { pe->markVary(P, nullptr, markBlocks, p->stream); p->launches++; }
 		pe->shadeSpan(P, Q, marks, p->stream);
 		p->launches++;
+		if(blend)
+		{
+			// every pixel's colours applied in submission order (kernels_span.cuh: shade_resolve_kernel)
+			shade_resolve_kernel<<<(ntiles * (unsigned)partsUsed + 3) / 4, 128, 0, p->stream>>>(P, Q, partsUsed);
+			p->launches++;
+		}
 	}
 	CK(p, cudaGetLastError());
 	return PS3D_OK;
@@ -874,7 +916,7 @@ static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe
 // The span path (kernels_span.cuh). spans / longest / survivors = 0: capacities speculated from the high-water marks of earlier
 // draws; otherwise the exact sizes a first attempt reported (settle()).
 // multi: P is the batch-wide DrawParams of p->flight (ps3d_pipe::Batch), ntris = its blocks x PS_GEOM_THREADS ids.
-static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao, size_t spans, size_t longest, size_t survivors, bool multi)
+static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao, size_t spans, size_t longest, size_t survivors, bool multi, bool blend)
 {
 	const uint32_t ntiles = (uint32_t)(P.tilesX * P.tilesY);
 	const size_t ntris = P.ntris;
@@ -911,12 +953,13 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 		if(p->tlFill.p != before) CK(p, cudaMemsetAsync(p->tlFill.p, 0, p->tlFill.cap * 4, p->stream));
 	}
 	const size_t svSlack = 0;
-	const bool noShade = spanNoShade(p, P, pe, multi);
+	const bool noShade = !blend && spanNoShade(p, P, pe, multi);
 	if(!noShade)
 	{
 		size_t svCap = (exact ? survivors + 1 : std::max(p->survivorHigh + p->survivorHigh / 4, (size_t)P.vpW * P.vpH * 2)) + svSlack;
 		if(p->capturing && p->sv2Span.cap >= p->survivorHigh) svCap = std::min(svCap, p->sv2Span.cap);
 		CK(p, p->sv2Span.ensure(svCap)); CK(p, p->sv2XY.ensure(svCap)); CK(p, p->sv2Inv.ensure(svCap));
+		if(blend) { CK(p, p->sv2Next.ensure(p->sv2Span.cap)); CK(p, p->sv2Colour.ensure(p->sv2Span.cap)); CK(p, p->sv2Chain.ensure((size_t)ntiles * 16)); }
 	}
 	P.hdr = p->hdr.p; P.vary = p->vary.p; P.tileOrder = p->tileOrder.p; P.poison = p->poisonDev;
 	if(P.band0 > 0 || P.band1 < P.vpH)
@@ -925,6 +968,8 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 		P.workList = p->workList.p + 4; P.workCount = p->workList.p;      // the counter lives in front of the list
 		CK(p, cudaMemsetAsync(P.workCount, 0, 4, p->stream));
 	}
+	P.batchFirstBlock = 0;
+	P.batchTrisPerBlock = (!multi && !P.workList && ntris <= PS_BATCH_DRAW_TRIS) ? batchTrisPerBlock(ntris) : 0;
 	P.sp.rec = p->spRec.p; P.sp.tri = p->spTri.p; P.sp.count = p->spanCountDev;
 	P.sp.capacity = (uint32_t)std::min<size_t>(p->spRec.cap, 0xfffffff0u);
 	P.tl.fill = p->tlFill.p; P.tl.len = p->tlLen.p; P.tl.ids = p->tlIds.p; P.tl.cap = (uint32_t)listCap;
@@ -1022,16 +1067,16 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 	{
 		// a captured frame cannot be judged by the host draw by draw: its tail is guarded by the poison word as always, and a
 		// replay that did not fit is reported through DrawReport::sticky at the next ps3d_finish
-		const int rc = launchSpanTail(p, P, pe, multi);
+		const int rc = launchSpanTail(p, P, pe, multi, blend);
 		return rc;
 	}
 	CK(p, cudaEventRecord(p->scanEvent, p->stream));
 	p->pending.valid = true; p->pending.P = P; p->pending.pe = pe; p->pending.path = 2; p->pending.span = true; p->pending.vao = vao;
-	p->pending.multi = multi;
+	p->pending.multi = multi; p->pending.blend = blend;
 	p->pending.tailLaunched = false;
 	if(!p->speculate && !exact) return settle(p);      // sizes checked on the host before anything else is enqueued
 	p->pending.tailLaunched = true;
-	const int rc = launchSpanTail(p, P, pe, multi);
+	const int rc = launchSpanTail(p, P, pe, multi, blend);
 	if(rc) { p->pending.valid = false; return rc; }
 	return PS3D_OK;
 }
@@ -1040,14 +1085,6 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 static bool marksOn() { static int on = -1; if(on < 0) { const char* e = getenv("PS3D_MARKS"); on = (e && e[0] == '0') ? 0 : 1; } return on == 1; }
 // PS3D_BATCH=0: every draw is launched as it is submitted (A/B runs)
 static bool batchingOn() { static int on = -1; if(on < 0) { const char* e = getenv("PS3D_BATCH"); on = (e && e[0] == '0') ? 0 : 1; } return on == 1; }
-#define PS_BATCH_DRAW_TRIS 16384u     // a draw with more triangles than this fills the GPU by itself
-#define PS_BATCH_MAX_DRAWS 1024u
-#define PS_BATCH_MAX_BLOCKS 8192u       // (every block is PS_GEOM_THREADS triangle ids: 64 B of header each)
-
-// a small draw spreads over up to 64 blocks (its triangles' rows are walked by the block's threads: kernels_span.cuh)
-static uint32_t batchTrisPerBlock(size_t ntris) { return (uint32_t)std::min<size_t>(std::max<size_t>((ntris + 63) / 64, 1), PS_GEOM_THREADS); }
-static uint32_t batchBlocks(size_t ntris) { const uint32_t per = batchTrisPerBlock(ntris); return (uint32_t)((ntris + per - 1) / per); }
-
 // a draw can join the batch being collected: same targets, viewport, band and behaviour bits (any programme of the span path)
 static bool batchTakes(const ps3d_pipe* p, const DrawParams& P)
 {
@@ -1146,7 +1183,7 @@ static int enqueueLegacy(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int pa
 		return launchTail(p, P, pe, path, false);
 	}
 	CK(p, cudaEventRecord(p->scanEvent, p->stream));
-	p->pending.valid = true; p->pending.P = P; p->pending.pe = pe; p->pending.path = path; p->pending.span = false; p->pending.tailLaunched = true; p->pending.vao = vao; p->pending.multi = false;
+	p->pending.valid = true; p->pending.P = P; p->pending.pe = pe; p->pending.path = path; p->pending.span = false; p->pending.tailLaunched = true; p->pending.vao = vao; p->pending.multi = false; p->pending.blend = false;
 	if(!speculate) return settle(p);          // exact sizes after a host sync in the middle of the draw
 	int rc = launchTail(p, P, pe, path, false);
 	if(rc) { p->pending.valid = false; return rc; }
@@ -1214,7 +1251,7 @@ int ps3d_create(int width, int height, int device, ps3d_pipe** out)
 	p->spanHigh = p->listHigh = 0;
 	p->markHigh = 0;
 	{ const char* e = getenv("PS3D_MARKS_MIN"); p->marksMin = e ? (size_t)atoll(e) : 16384; }
-	p->batch.clear(); p->flight.clear(); p->batchesLaunched = p->drawsBatched = 0; p->pending.multi = false;
+	p->batch.clear(); p->flight.clear(); p->batchesLaunched = p->drawsBatched = 0; p->pending.multi = false; p->pending.blend = false;
 	p->pending.span = false; p->pending.tailLaunched = false; p->pending.vao = -1;
 	if(ok)
 	{
@@ -1283,7 +1320,7 @@ int ps3d_destroy(ps3d_pipe* p)
 	cudaFree(p->peer.flagsOwn); cudaFree(p->peer.ctr);
 	p->batchItems.release(); p->batchBlockDraw.release(); p->batchBlockList.release();
 	p->spRec.release(); p->spTri.release(); p->tlFill.release(); p->tlLen.release(); p->tlIds.release();
-	p->sv2Span.release(); p->sv2XY.release(); p->sv2Inv.release();
+	p->sv2Span.release(); p->sv2XY.release(); p->sv2Inv.release(); p->sv2Next.release(); p->sv2Chain.release(); p->sv2Colour.release();
 	p->svTri.release(); p->svMisc.release(); p->svWinner.release(); p->svLeft.release(); p->svRight.release(); p->svInv.release();
 	if(p->capDev) cudaFree(p->capDev);
 	if(p->rcpDev) cudaFree(p->rcpDev);
@@ -1771,13 +1808,18 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 	// everything else -> split: raster + depth kernel, survivor stream, flat shade kernel — over span records computed once
 	// by the geometry kernel (kernels_span.cuh, the default) or, PS3D_TILE_PATH=split, re-derived per tile (kernels.cuh)
 	int path = pe->mayDiscard ? 0 : (((p->behavior & PS3D_BEHAVIOR_ALPHABLEND) && pe->usesWrite4) ? 1 : 2);
-	bool span = 2 == path;
+	// (a draw that blends takes the span path too — its colours resolved in submission order behind the shade kernel — unless
+	// PS3D_SPAN_BLEND=0 keeps it on the one-kernel ordered tile path)
+	static int spanBlendOn = -1;
+	if(spanBlendOn < 0) { const char* e = getenv("PS3D_SPAN_BLEND"); spanBlendOn = (e && e[0] == '0') ? 0 : 1; }
+	const bool blend = 1 == path && spanBlendOn && !p->peer.active;
+	bool span = 2 == path || blend;
 	if(tilePathForced() >= 0 && !(pe->mayDiscard)) { path = tilePathForced() == 2 && 1 == path ? 1 : tilePathForced(); span = false; }
-	if(2 == path && (P.vpW > 8191 || P.vpH > 8191)) { path = 1; span = false; }      // the survivor record packs x and y in 13 bits each
+	if(path != 0 && (P.vpW > 8191 || P.vpH > 8191)) { path = 1; span = false; }      // the survivor record packs x and y in 13 bits each
 	if(radixBinningForced() || ntris >= PS_SPAN_MAX_TRIS) span = false;
 	if(span && vao < (int)p->vaoLegacy.size() && p->vaoLegacy[vao]) span = false;
 	// small draws of the span path are collected: consecutive ones into the same targets run as one batch (flushBatch)
-	if(span && batchingOn() && p->speculate && !p->profiling && ntris <= PS_BATCH_DRAW_TRIS && 0 == P.band0 && P.band1 >= P.vpH)
+	if(span && !blend && batchingOn() && p->speculate && !p->profiling && ntris <= PS_BATCH_DRAW_TRIS && 0 == P.band0 && P.band1 >= P.vpH)
 	{
 		if(!batchTakes(p, P)) { const int rc = flushBatch(p); if(rc) return rc; }
 		ps3d_pipe::BatchDraw d;
@@ -1787,7 +1829,7 @@ int ps3d_draw_vao(ps3d_pipe* p, int vao, int callerThread)
 		return PS3D_OK;
 	}
 	SETTLE(p);
-	if(span) return enqueueSpan(p, P, pe, vao, 0, 0, 0);
+	if(span) return enqueueSpan(p, P, pe, vao, 0, 0, 0, false, blend);
 	return enqueueLegacy(p, P, pe, path, vao);
 }
 
@@ -1976,7 +2018,9 @@ int ps3d_comm_init(ps3d_pipe* p, int rank, int world, const void* id256)
 }
 int ps3d_comm_destroy(ps3d_pipe* p)
 {
-	const NcclApi* a = ncclApi();
+	// (only a pipe that has communicators touches the NCCL library: loading libnccl.so.2 into a process that imports torch
+	// LATER would put the system's NCCL in front of the one torch bundles)
+	const NcclApi* a = (p->commFrame || p->commUpload) ? ncclApi() : nullptr;
 	if(p->gatherStream) { cudaStreamSynchronize(p->gatherStream); }
 	if(a && p->commFrame) { cudaStreamSynchronize(p->stream); a->CommDestroy(p->commFrame); }
 	if(a && p->commUpload) a->CommDestroy(p->commUpload);

@@ -38,7 +38,8 @@ def _same(got, want, what):
 
 
 @pytest.mark.parametrize("name", ["c1_cube_640", "c1_cube_def03", "soup_def02", "soup_nocull", "soup_odd_size", "c3_demo2_desk",
-                                  "demo2_objx_file", "crowded_tile", "ragged_streams", "small_draws_mixed", "c2_heightfield_small"])
+                                  "demo2_objx_file", "crowded_tile", "ragged_streams", "small_draws_mixed", "c2_heightfield_small",
+                                  "c4_blend_overdraw", "demo1_planets"])
 def test_later_frames_of_a_pipe_equal_the_first(name, cuda_lib, oracle_lib):
     sc = SMALL[name]()
     want = render_all(oracle_lib, sc)

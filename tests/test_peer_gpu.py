@@ -36,3 +36,18 @@ def test_peer_import_of_garbage_handles_fails_loudly(cuda_lib):
         pipe.peerImport(1, 2, bad)
     pipe.peerReset()
     pipe.peerImport(0, 1, blob)                      # the pipe is still usable
+
+
+def test_a_pipe_without_communicators_never_loads_nccl():
+    """ps3d_destroy used to ask for libnccl.so.2 (to destroy communicators it did not have): in a process that imports torch LATER
+    that puts the system's NCCL in front of the one torch bundles, and `import torch` fails on a missing symbol."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = ("from puresoft3d_b200.pipeline import PuresoftPipeline\n"
+            "p = PuresoftPipeline(64, 64, device=0)\np.clearColour(0)\np.finish()\np.close()\n"
+            "import torch\nassert torch.cuda.is_available()\nprint('ok')\n")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, PYTHONPATH=ROOT))
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
