@@ -132,7 +132,14 @@ struct TileLists
 	uint32_t* len;        // per tile: the finished count, written by the plan kernel
 	uint32_t* ids;        // tile * cap + slot
 	uint32_t cap;
+	// triangles whose tile rectangle is PS_BIG_AREA tiles or more (a 4096^2 shadow map's ground quad: 65 536 each): the geometry
+	// kernel only notes them (3 words: tx0 | tx1 << 16, ty0 | ty1 << 16, id), tile_append_big_kernel appends them with the whole
+	// grid instead of one block. NULL: every block appends its own.
+	uint32_t* bigList;
+	uint32_t* bigCount;   // zeroed by the plan kernel
+	uint32_t bigCap;
 };
+#define PS_BIG_AREA 2048u
 
 // survivors of the depth test on the span path: 12 bytes each
 struct SurvivorStream2

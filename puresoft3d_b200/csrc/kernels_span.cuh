@@ -475,6 +475,20 @@ PS_D void geomBatch(const DrawParams& P, uint32_t tri, uint32_t orig, bool candi
 	// whole-rectangle triangles: the BLOCK appends one's id to its tiles, every thread four tiles per step, so that hundreds of the
 	// (returning) atomics are in flight instead of one lane's one (a 4096^2 shadow map's ground quad is 2 x 65 536 tiles: a
 	// millisecond per triangle when one warp did it, an atomic's round trip per 32 tiles)
+	if(bigPending && P.tl.bigList)
+	{
+		// a very large rectangle goes to the grid-wide append (TileLists::bigList), if the list has room
+		const uint32_t area = ((rect0 >> 16) - (rect0 & 0xffff) + 1u) * ((rect1 >> 16) - (rect1 & 0xffff) + 1u);
+		if(area >= PS_BIG_AREA)
+		{
+			const uint32_t j = atomicAdd(P.tl.bigCount, 1u);
+			if(j < P.tl.bigCap)
+			{
+				P.tl.bigList[3 * j] = rect0; P.tl.bigList[3 * j + 1] = rect1; P.tl.bigList[3 * j + 2] = wtri;
+				bigPending = false;
+			}
+		}
+	}
 	if(bigPending)
 	{
 		const uint32_t q = atomicAdd(&sTallCount, 0x10000u) >> 16;   // (the tall list's counter: low half tall survivors, high half big ones)
@@ -660,6 +674,25 @@ __global__ void __launch_bounds__(256) batch_items_kernel(const __grid_constant_
 	for(uint32_t j = threadIdx.x; j < K.nBlocks[i]; j += blockDim.x) { blockDraw[firstBlock + j] = K.tag[i]; blockList[K.listAt[i] + j] = firstBlock + j; }
 }
 
+// the noted very large rectangles (TileLists::bigList), appended by the whole grid: thread = tile of a rectangle
+__global__ void __launch_bounds__(256) tile_append_big_kernel(TileLists tl, int tilesX)
+{
+	const uint32_t n = min(*tl.bigCount, tl.bigCap);
+	const uint32_t threads = gridDim.x * blockDim.x, me = blockIdx.x * blockDim.x + threadIdx.x;
+	for(uint32_t e = 0; e < n; e++)
+	{
+		const uint32_t r0 = tl.bigList[3 * e], r1 = tl.bigList[3 * e + 1], t = tl.bigList[3 * e + 2];
+		const int tx0 = (int)(r0 & 0xffff), tx1 = (int)(r0 >> 16), ty0 = (int)(r1 & 0xffff), ty1 = (int)(r1 >> 16);
+		const uint32_t w = (uint32_t)(tx1 - tx0 + 1), total = w * (uint32_t)(ty1 - ty0 + 1);
+		for(uint32_t i = me; i < total; i += threads)
+		{
+			const uint32_t tile = (uint32_t)((ty0 + (int)(i / w)) * tilesX + tx0 + (int)(i % w));
+			const uint32_t at = atomicAdd(&tl.fill[tile], 1u);
+			if(at < tl.cap) tl.ids[(size_t)tile * tl.cap + at] = t;
+		}
+	}
+}
+
 // ======================================================================================================================
 // plan: lengths, verdict on the speculated capacities, tiles by descending list length, the draw's counters
 // ======================================================================================================================
@@ -794,6 +827,7 @@ __global__ void __launch_bounds__(1024) tile_plan_kernel(TileLists tl, uint32_t 
 		// replay from the start; the host sizes the next draw's buffer by the report)
 		const unsigned long long lc = *longCount;
 		*longCount = 0;
+		if(tl.bigCount) *tl.bigCount = 0;
 		const unsigned long long marks = lc & ((1ull << 40) - 1);
 		longLatched[0] = (uint32_t)min(lc >> 40, (unsigned long long)spanCap);
 		longLatched[1] = (uint32_t)min(marks, 0xffffffffull);

@@ -425,6 +425,8 @@ struct ps3d_pipe
 	DevBuf<F4> spMarkV;
 	unsigned long long* longCountDev;
 	uint32_t* longLatchedDev;
+	uint32_t* bigListDev;          // TileLists::bigList: [0] the counter, from [4] the entries
+
 	size_t markHigh;
 	size_t marksMin;               // marks are kept for draws that ask for at least this many (PS3D_MARKS_MIN; two more launches per draw)
 	std::vector<uint8_t> vaoLegacy; // VAOs whose last draw needed the first path (a tile list too long for the shared-memory sort)
@@ -515,6 +517,7 @@ static int peerFirstWrite(ps3d_pipe* p);
 static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe, bool multi, bool blend);
 static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao, size_t spans, size_t longest, size_t survivors, bool multi = false, bool blend = false);
 static int flushBatch(ps3d_pipe* p);
+#define PS_BIG_LIST 4096u            // very large tile rectangles a draw may hand to the grid-wide append (more: their blocks append them)
 #define PS_BATCH_DRAW_TRIS 16384u     // a draw with more triangles than this fills the GPU by itself
 #define PS_BATCH_MAX_DRAWS 1024u
 #define PS_BATCH_MAX_BLOCKS 8192u       // (every block is PS_GEOM_THREADS triangle ids: 64 B of header each)
@@ -973,6 +976,10 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 	P.sp.rec = p->spRec.p; P.sp.tri = p->spTri.p; P.sp.count = p->spanCountDev;
 	P.sp.capacity = (uint32_t)std::min<size_t>(p->spRec.cap, 0xfffffff0u);
 	P.tl.fill = p->tlFill.p; P.tl.len = p->tlLen.p; P.tl.ids = p->tlIds.p; P.tl.cap = (uint32_t)listCap;
+	// very large tile rectangles are appended by a kernel of their own — for draws that follow one with many long spans (the
+	// same scenes have both; one more launch per draw does not pay elsewhere)
+	const bool bigAppend = p->markHigh >= p->marksMin && p->markHigh > 0 && marksOn();
+	P.tl.bigList = bigAppend ? p->bigListDev + 4 : nullptr; P.tl.bigCount = p->bigListDev; P.tl.bigCap = PS_BIG_LIST;
 	// chain marks of long spans: once some draw has asked for marks (its report said how many), room for them is kept; a draw
 	// whose marks do not fit replays those spans from their start, as every long span does while no marks are kept
 	P.sp.longCount = p->longCountDev; P.sp.longLatched = p->longLatchedDev;
@@ -1055,6 +1062,12 @@ static int enqueueSpan(ps3d_pipe* p, DrawParams P, const ProgEntry* pe, int vao,
 		}
 		CK(p, cudaGetLastError());
 		{ const int rc = recordVboReads(p, vao); if(rc) return rc; }
+	}
+	if(bigAppend)
+	{
+		ProfScope ps(p, CLS_GEOM);
+		tile_append_big_kernel<<<p->smCount * 4, 256, 0, p->stream>>>(P.tl, P.tilesX);
+		p->launches++;
 	}
 	{
 		ProfScope ps(p, CLS_BIN);
@@ -1243,6 +1256,7 @@ int ps3d_create(int width, int height, int device, ps3d_pipe** out)
 	ok = ok && cudaMalloc((void**)&p->spanCountDev, 16) == cudaSuccess;
 	ok = ok && cudaMalloc((void**)&p->longCountDev, 16) == cudaSuccess;
 	ok = ok && cudaMalloc((void**)&p->longLatchedDev, 16) == cudaSuccess;
+	ok = ok && cudaMalloc((void**)&p->bigListDev, (4 + 3 * PS_BIG_LIST) * sizeof(uint32_t)) == cudaSuccess;
 	memset(&p->peer, 0, sizeof(p->peer));
 	p->capturing = false; p->graphLaunched = false; p->capBack = 0;
 	ok = ok && cudaMalloc((void**)&p->peer.flagsOwn, sizeof(PeerFlags)) == cudaSuccess;
@@ -1258,6 +1272,7 @@ int ps3d_create(int width, int height, int device, ps3d_pipe** out)
 		cudaMemsetAsync(p->spanCountDev, 0, 16, p->stream);
 		cudaMemsetAsync(p->longCountDev, 0, 16, p->stream);
 		cudaMemsetAsync(p->longLatchedDev, 0, 16, p->stream);
+		cudaMemsetAsync(p->bigListDev, 0, 16, p->stream);
 		cudaMemsetAsync(p->display[0], 0, cbytes, p->stream);
 		cudaMemsetAsync(p->display[1], 0, cbytes, p->stream);
 		cudaMemsetAsync(p->defaultDepth, 0, dbytes, p->stream);
@@ -1310,7 +1325,7 @@ int ps3d_destroy(ps3d_pipe* p)
 	for(Vbo& v : p->vbos) if(v.alive) freeVbo(v);
 	cudaFree(p->display[0]); cudaFree(p->display[1]); cudaFree(p->defaultDepth);
 	cudaFree(p->totalDev); cudaFree(p->statsDev); cudaFree(p->svCountDev); cudaFree(p->poisonDev); cudaFreeHost(p->report); cudaEventDestroy(p->scanEvent);
-	cudaFree(p->spanCountDev); cudaFree(p->longCountDev); cudaFree(p->longLatchedDev);
+	cudaFree(p->spanCountDev); cudaFree(p->longCountDev); cudaFree(p->longLatchedDev); cudaFree(p->bigListDev);
 	p->spMarkAt.release(); p->spLongList.release(); p->spMarkZ.release(); p->spMarkV.release();
 	for(auto& g : p->graphs) if(g.alive) cudaGraphExecDestroy(g.exec);
 	if(p->peer.active && p->peer.rank != 0)

@@ -83,3 +83,16 @@ def test_captured_frame_with_marks(cuda_lib, oracle_lib):
     assert np.array_equal(pipe.readColour().view(np.uint32), want["colour"].view(np.uint32))
     pipe.graphDestroy(g)
     pipe.close()
+
+
+def test_very_large_rectangles_appended_by_the_grid(cuda_lib, oracle_lib):
+    """A target of 64 x 48 tiles and triangles far larger than it: once the pipe keeps marks, rectangles of 2048 tiles or more are
+    handed to tile_append_big_kernel instead of being appended by their geometry block."""
+    sc = scenes.scene_crowded_tile(1024, 768, crowd=150)
+    want = render_all(oracle_lib, sc)
+    pipe = PuresoftPipeline(sc.width, sc.height, lib=cuda_lib)
+    pipe.debugCapture(sc.width, sc.height)
+    up = scenes.upload(pipe, sc)
+    for frame in range(3):
+        _same(_frame(pipe, sc, up), want, "frame %d" % frame)
+    pipe.close()

@@ -80,6 +80,8 @@ def main():
         ms = e0.elapsed_time(e1) / steps
         st = pipe.getStats()
         frags = st["fragments_shaded"] / steps
+        # the frames that were timed (warm speculation, chain marks, batches, captured): the last one must be the frame a fresh pipe renders
+        steady = dict(colour=pipe.readColour(), depth=pipe.readDepth())
         pipe.close()
         # the parity frame on a FRESH pipe, like the reference's below: clear4 never touches the last buffer row (fbo.cpp:336),
         # so on a long-lived target a blending scene accumulates there from frame to frame — on both sides
@@ -120,7 +122,10 @@ def main():
                        "coverage_bit_exact": bool(np.array_equal(g["counts"] > 0, r["counts"] > 0)),
                        "depth_bit_exact": bool(np.array_equal(g["depth"].view(np.uint32), r["depth"].view(np.uint32))), "depth_max_ulp": ulp,
                        "colour_within_1_of_255": frac, "colour_max_diff": maxd,
-                       "fragments_shaded_equal": bool(int(frags) == int(r["stats"]["fragments_shaded"]))},
+                       "fragments_shaded_equal": bool(int(frags) == int(r["stats"]["fragments_shaded"])),
+                       # (clear4 leaves the last buffer row alone, fbo.cpp:336: a blending scene accumulates there on a long-lived pipe)
+                       "timed_frames_equal_first_frame": bool(np.array_equal(steady["depth"].view(np.uint32), g["depth"].view(np.uint32))
+                                                              and np.array_equal(steady["colour"].view(np.uint32)[:-1], g["colour"].view(np.uint32)[:-1]))},
         }
         print(json.dumps(line), flush=True)
 
