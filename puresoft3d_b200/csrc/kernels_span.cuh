@@ -1074,8 +1074,7 @@ PS_D void flushEnd(const SurvivorStream2& Q, RasterSmem2& S, RasterCtx2& C)
 {
 	if(!C.pending) return;                             // (warp-uniform)
 	C.pending = false;
-	const uint32_t base = __shfl_sync(PS_FULL, C.reserved, 0);
-	const uint32_t i = base + (uint32_t)C.lane;
+	const uint32_t i = __shfl_sync(PS_FULL, C.reserved, 0) + (uint32_t)C.lane;
 	if(i < Q.capacity)
 	{
 		Q.span[i] = C.pSpan; Q.inv[i] = C.pInv;
@@ -1083,7 +1082,7 @@ PS_D void flushEnd(const SurvivorStream2& Q, RasterSmem2& S, RasterCtx2& C)
 	}
 	// queue order = submission order inside a pixel and a warp's reservations grow with time: the latest record has the highest index
 	atomicMax(&S.lastIdx[C.pXY & 0xff], i + 1);
-	if(Q.next && 0 == C.lane) chainGroup(Q, S, base, 32u);
+	if(Q.next && 0 == C.lane) chainGroup(Q, S, i, 32u);      // (lane 0's slot is the group's first)
 }
 PS_D void flushBegin(const SurvivorStream2& Q, RasterSmem2& S, RasterCtx2& C)
 {
