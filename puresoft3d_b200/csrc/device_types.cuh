@@ -105,6 +105,7 @@ struct alignas(32) SpanRec
 };
 #define PS_SPAN_MAX_TRIS 0x1000000u   // triangle ids must fit 24 bits on the span path
 struct alignas(8) TriSpan { uint32_t x, y; };   // (a plain struct: this header is also compiled for the host by the functor tests)
+struct alignas(8) MarkZ { float cf2, z; };   // (a plain struct: this header is also compiled for the host by the functor tests)
 struct SpanStreams
 {
 	SpanRec* rec;
@@ -116,7 +117,7 @@ struct SpanStreams
 	// thousands of them, every tile of the row again. The chain of a long span is walked ONCE instead and its state kept every
 	// PS_MARK_STEP pixels; tiles and fragments start from the nearest mark.
 	uint32_t* markAt;     // per record (long spans only): index of the span's first mark, ~0 = the marks did not fit (replay from the start)
-	float2* markZ;        // (cf2, z) after PS_MARK_STEP * k steps
+	MarkZ* markZ;         // (cf2, z) after PS_MARK_STEP * k steps
 	F4* markV;            // the varyings after PS_MARK_STEP * k steps: [mark][NV]
 	uint32_t* longList;   // record indices of the long spans, any order
 	unsigned long long* longCount;   // long spans << 40 | marks asked for (one atomicAdd per long span)

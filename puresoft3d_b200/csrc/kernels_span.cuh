@@ -1384,7 +1384,7 @@ __global__ void __launch_bounds__(32 * PS_WARPS_PER_BLOCK, MINB) tile_raster_spa
 						if(at != 0xffffffffu)
 						{
 							const int k = (xs - x1) / PS_MARK_STEP;
-							const float2 m = __ldg(P.sp.markZ + at + k);
+							const float2 m = __ldg((const float2*)(P.sp.markZ + at + k));
 							cf2 = m.x; z0 = m.y;
 							xr = x1 + k * PS_MARK_STEP;
 						}
@@ -1634,7 +1634,7 @@ __global__ void __launch_bounds__(PS_MARK_THREADS) span_mark_depth_kernel(const 
 		const int steps = x2 - x1;
 		float cf2 = __int_as_float(D.x), z = __int_as_float(D.z);
 		const float cf2Step = __int_as_float(D.y), zStep = __int_as_float(D.w);
-		float2* out = P.sp.markZ + at;
+		float2* out = (float2*)(P.sp.markZ + at);
 		for(int k = 0; ; k++)
 		{
 			out[k] = make_float2(cf2, z);

@@ -421,7 +421,7 @@ struct ps3d_pipe
 	size_t spanHigh, listHigh;     // high-water marks of earlier draws: the next speculation
 	// chain marks of long spans (device_types.cuh: SpanStreams): kept once a draw has asked for some
 	DevBuf<uint32_t> spMarkAt, spLongList;
-	DevBuf<float2> spMarkZ;
+	DevBuf<MarkZ> spMarkZ;
 	DevBuf<F4> spMarkV;
 	unsigned long long* longCountDev;
 	uint32_t* longLatchedDev;
