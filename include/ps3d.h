@@ -244,7 +244,8 @@ int ps3d_composite_peer(ps3d_pipe* p);
  * unchanged between launches (uniform values are latched at capture), and capture once per (VBO set, display target)
  * combination the frame is launched with. Vertex data may change between launches (ps3d_vbo_update*): the streams are read
  * through the same pointers. A replayed frame whose intermediates no longer fit the buffers it was captured with is reported
- * by the next ps3d_finish as PS3D_ERR_INVALID_ARGUMENT ("re-capture"). */
+ * by the next ps3d_finish as PS3D_ERR_INVALID_ARGUMENT ("re-capture"); a launch after a draw submitted normally has outgrown
+ * (reallocated) one of the pipe's scratch buffers is refused with the same code: the recorded kernels point into the old one. */
 int ps3d_graph_begin(ps3d_pipe* p);
 int ps3d_graph_end(ps3d_pipe* p, int* graph);
 int ps3d_graph_launch(ps3d_pipe* p, int graph);

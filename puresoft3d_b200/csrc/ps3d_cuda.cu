@@ -449,7 +449,7 @@ struct ps3d_pipe
 		bool needTake;              // no colour write since the last composite: the next one takes (rank 0: hands out) the target first
 	} peer;
 	// captured frames (ps3d_graph_*)
-	struct Graph { cudaGraphExec_t exec; uint64_t launches; uint64_t draws, tris; std::vector<int> vaos; int back, backAfter; bool alive; };
+	struct Graph { cudaGraphExec_t exec; uint64_t launches; uint64_t draws, tris; std::vector<int> vaos; int back, backAfter; bool alive; uint64_t scratch; };
 	std::vector<Graph> graphs;
 	bool capturing, graphLaunched;
 	int capBack;
@@ -2173,6 +2173,22 @@ int ps3d_composite_peer(ps3d_pipe* p)
 
 // ---- captured frames (include/ps3d.h) ---------------------------------------------------------------------------------------
 
+// The recorded kernels hold the addresses of the pipe's scratch buffers. A draw submitted normally AFTER the capture may outgrow
+// one of them (freed, allocated anew): a replay would then write through a dangling pointer. The addresses are folded into one
+// word at the end of the capture and compared at every launch.
+static uint64_t scratchSignature(const ps3d_pipe* p)
+{
+	const void* ptrs[] = {
+		p->hdr.p, p->vary.p, p->triCount.p, p->triOffset.p, p->triRect.p, p->scanSums.p, p->keysA.p, p->valsA.p, p->keysB.p, p->valsB.p,
+		p->tileCount.p, p->tileStart.p, p->tileFill.p, p->tileOrder.p, p->sortCounts.p, p->workList.p,
+		p->svTri.p, p->svMisc.p, p->svWinner.p, p->svLeft.p, p->svRight.p, p->svInv.p,
+		p->spRec.p, p->spTri.p, p->tlFill.p, p->tlLen.p, p->tlIds.p, p->sv2Span.p, p->sv2XY.p, p->sv2Inv.p, p->sv2Next.p, p->sv2Chain.p, p->sv2Colour.p,
+		p->spMarkAt.p, p->spLongList.p, p->spMarkZ.p, p->spMarkV.p, p->batchItems.p, p->batchBlockDraw.p, p->batchBlockList.p };
+	uint64_t h = 1469598103934665603ull;
+	for(const void* q : ptrs) { h ^= (uint64_t)(uintptr_t)q; h *= 1099511628211ull; }
+	return h;
+}
+
 int ps3d_graph_begin(ps3d_pipe* p)
 {
 	TRACE();
@@ -2203,7 +2219,7 @@ int ps3d_graph_end(ps3d_pipe* p, int* graph)
 	p->launches = p->capLaunches0; p->stats.draws = p->capDraws0; p->stats.triangles_submitted = p->capTris0;
 	G.back = p->capBack; G.backAfter = p->back;
 	p->back = p->capBack;
-	G.vaos = p->capVaos; G.alive = true; G.exec = nullptr;
+	G.vaos = p->capVaos; G.alive = true; G.exec = nullptr; G.scratch = scratchSignature(p);
 	if(flushed) { if(g) cudaGraphDestroy(g); cudaGetLastError(); return flushed; }
 	if(e != cudaSuccess || !g) { cudaGetLastError(); p->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e); return PS3D_ERR_DEVICE; }
 	const cudaError_t e2 = cudaGraphInstantiate(&G.exec, g, 0);
@@ -2224,6 +2240,7 @@ int ps3d_graph_launch(ps3d_pipe* p, int graph)
 	if(p->capturing) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "a frame is being captured");
 	ps3d_pipe::Graph& G = p->graphs[graph];
 	if(p->back != G.back) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "the frame was captured with the other display target current");
+	if(G.scratch != scratchSignature(p)) return fail(p, PS3D_ERR_INVALID_ARGUMENT, "a draw submitted since the capture outgrew a scratch buffer the captured frame points into: capture the frame again");
 	// what the recorded calls would have waited for one by one: asynchronous uploads of the streams the frame reads, and an
 	// asynchronous read-back still leaving the target it writes
 	for(int vao : G.vaos)
