@@ -894,6 +894,8 @@ static int launchSpanTail(ps3d_pipe* p, const DrawParams& P, const ProgEntry* pe
 		for(size_t g = 0; g < groups.size(); g++)
 		{
 			const BatchView V = { p->batchItems.p, p->batchBlockDraw.p, p->batchBlockList.p, (uint32_t)g };
+			// (markV is indexed mark * NV with the programme's own NV: two programmes' marks may share bytes — each group's marks are
+			// written and consumed before the next group's are written, in stream order)
 			if(marks && groups[g]->nv > 0) { groups[g]->markVary(P, &V, markBlocks, p->stream); p->launches++; }
 			groups[g]->shadeSpanMulti(P, Q, V, marks, p->stream);
 			p->launches++;
