@@ -269,12 +269,15 @@ public:
 	// composite over NVLink peer memory: every rank renders straight into rank 0's colour target (include/ps3d.h)
 	void peerExport(void* blob) { check(ps3d_peer_export(m_pipe, blob)); }
 	void peerImport(int rank, int world, const void* blobs) { check(ps3d_peer_import(m_pipe, rank, world, blobs)); }
+	void peerReset() { check(ps3d_peer_import(m_pipe, 0, 0, NULL)); }   // undo an import (fall back to another composite)
 	void compositePeer() { check(ps3d_composite_peer(m_pipe)); }
 	// captured frames: record the calls of one frame once, replay them as one launch (include/ps3d.h)
 	void graphBegin() { check(ps3d_graph_begin(m_pipe)); }
 	int graphEnd() { int g = -1; check(ps3d_graph_end(m_pipe, &g)); return g; }
 	void graphLaunch(int graph) { check(ps3d_graph_launch(m_pipe, graph)); }
 	void graphDestroy(int graph) { check(ps3d_graph_destroy(m_pipe, graph)); }
+	// batches of small draws (include/ps3d.h): how many were launched, how many draws ran inside one
+	void debugBatchCounts(uint64_t* batches, uint64_t* draws) { check(ps3d_debug_batch_counts(m_pipe, batches, draws)); }
 
 	int deviceWidth() const { return m_width; }
 	int deviceHeight() const { return m_height; }
