@@ -117,7 +117,7 @@ def test_launch_after_the_scratch_buffers_moved_is_refused(cuda_lib):
     """The recorded kernels hold the addresses of the pipe's scratch buffers: once a bigger draw, submitted normally, has made
     one of them grow (freed and allocated anew), replaying the captured frame would write through a dangling pointer."""
     small = SMALL["c1_cube_def01"]()
-    big = scenes.scene_soup(small.width, small.height, seed=3, count=6000)
+    big = scenes.scene_soup(small.width, small.height, seed=3, count=30000)
     pipe = PuresoftPipeline(small.width, small.height, lib=cuda_lib)
     up_small, up_big = scenes.upload(pipe, small), scenes.upload(pipe, big)
     for _ in range(2):
@@ -127,7 +127,7 @@ def test_launch_after_the_scratch_buffers_moved_is_refused(cuda_lib):
     g = pipe.graphEnd()
     pipe.graphLaunch(g)
     pipe.finish()
-    scenes.replay(pipe, big, up_big)                 # 6000 triangles: headers, varyings, span records outgrow the cube's
+    scenes.replay(pipe, big, up_big)                 # 30 000 triangles: headers, varyings, span records outgrow the cube's (megabytes: new address ranges)
     with pytest.raises(ValueError):
         pipe.graphLaunch(g)
     pipe.graphDestroy(g)
