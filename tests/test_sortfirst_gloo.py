@@ -61,3 +61,24 @@ def test_sort_first_frame_over_gloo(world, scene, tmp_path, built):
         logs.append(o)
         assert pr.returncode == 0, o[-2000:]
     assert out.read_text() == "ok", out.read_text() + "\n" + "\n".join(l[-500:] for l in logs)
+
+
+@pytest.mark.parametrize("mode", ["ok", "export_fails", "import_fails"])
+def test_peer_composite_agreement_over_gloo(mode, tmp_path):
+    """sortfirst.init_peer_composite with a stand-in pipe: whatever fails on whichever rank, every rank ends with the same answer
+    (and a rank that had already mapped rank 0's targets lets go of them)."""
+    out = tmp_path / "result.txt"
+    world = 3
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(free_port()), WORLD_SIZE=str(world), OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_gloo_peer_worker.py"), mode, str(out)],
+                              env=dict(env, RANK=str(rank), LOCAL_RANK=str(rank)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for rank in range(world)]
+    for pr in procs:
+        try:
+            o, _ = pr.communicate(timeout=240)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        assert pr.returncode == 0, o[-2000:]
+    assert out.read_text() == "ok", out.read_text()
